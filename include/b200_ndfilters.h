@@ -1,0 +1,128 @@
+/*
+ * b200_ndfilters.h -- C ABI of the B200-native ndfilters correlation path.
+ *
+ * This is the drop-in boundary for the hot path of dask-image's ndfilters: the
+ * per-chunk arithmetic that the reference reaches through scipy's three
+ * compiled entry points
+ *
+ *   _nd_image.correlate1d(input, weights, axis, output, mode, cval, origin)
+ *        scipy/ndimage/_filters.py:610   (reached from dask-image via
+ *        dask_image/dispatch/_dispatch_ndfilters.py:129,145,161 ->
+ *        gaussian_filter / gaussian_gradient_magnitude / gaussian_laplace)
+ *   _nd_image.uniform_filter1d(input, size, axis, output, mode, cval, origin)
+ *        scipy/ndimage/_filters.py:1542  (via _dispatch_ndfilters.py:273)
+ *   _nd_image.correlate(input, weights, output, mode, cval, origins)
+ *        scipy/ndimage/_filters.py:1305  (via _dispatch_ndfilters.py:49,65)
+ *
+ * plus the numpy ufunc epilogues scipy applies between passes
+ * (scipy/ndimage/_filters.py:1025-1030 and :1184-1193).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every array is C-contiguous, `shape` has
+ *    `ndim` int64 entries, element type given by a b200_dtype code;
+ *  - `in` / `out` are DEVICE pointers on the current CUDA device, `weights`,
+ *    `shape`, `wshape`, `origins` are HOST pointers (copied before return);
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *    calls are asynchronous on that stream and re-entrant (no global mutable
+ *    state besides a thread-local error string);
+ *  - `in` and `out` must not overlap;
+ *  - mode codes are scipy's (scipy/ndimage/_ni_support.py:37-49);
+ *  - every function returns 0 on success or a B200_E* code; the message is
+ *    available from b200_last_error() on the calling thread.
+ *
+ * Slab halos (multi-GPU axis-0 decomposition, replaces dask's map_overlap):
+ * `pad_lo` / `pad_hi` say how many REAL planes of the global volume are
+ * resident in memory directly before `in` plane 0 / after plane n-1 along
+ * `axis` 0 (received from the neighbouring rank).  Positions inside
+ * [-pad_lo, n + pad_hi) are read as they are; positions outside are resolved
+ * by `mode` against this array's own extent [0, n).  pad_lo = pad_hi = 0 gives
+ * exactly scipy's behaviour on a whole array.  Pads are only meaningful for
+ * the filtered axis 0 (1-D passes with axis == 0, and the N-D correlate).
+ */
+#ifndef B200_NDFILTERS_H
+#define B200_NDFILTERS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_MAXDIM 8
+
+typedef enum {
+    B200_U8 = 0, B200_I8 = 1, B200_U16 = 2, B200_I16 = 3, B200_U32 = 4,
+    B200_I32 = 5, B200_U64 = 6, B200_I64 = 7, B200_F32 = 8, B200_F64 = 9
+} b200_dtype;
+
+typedef enum {
+    B200_MODE_NEAREST = 0, B200_MODE_WRAP = 1, B200_MODE_REFLECT = 2,
+    B200_MODE_MIRROR = 3, B200_MODE_CONSTANT = 4
+} b200_mode;
+
+/* status codes */
+#define B200_OK            0
+#define B200_EINVAL        1   /* bad argument (maps to RuntimeError)        */
+#define B200_EORIGIN       2   /* origin outside the footprint (ValueError)  */
+#define B200_EMODE         3   /* boundary mode not supported (RuntimeError) */
+#define B200_EDTYPE        4   /* data type not supported (RuntimeError)     */
+#define B200_ECUDA         5   /* CUDA runtime / driver error                */
+#define B200_ENODEVICE     6   /* no sm_100 device / kernels unavailable     */
+
+/* flags */
+#define B200_FLAG_EXACT      1u  /* force the scipy-order fp64 path (bit-exact) */
+#define B200_FLAG_NO_TMA     2u  /* never pick a TMA-tiled kernel (debug/tests) */
+#define B200_FLAG_FORCE_FAST 4u  /* fail instead of falling back to generic     */
+
+/* epilogue applied when a 1-D pass stores its result r (already rounded to
+ * the array dtype, as scipy stores every pass) into out: */
+typedef enum {
+    B200_EPI_STORE = 0,        /* out  = r                          */
+    B200_EPI_ACC = 1,          /* out += r            (laplace sum) */
+    B200_EPI_SQ_STORE = 2,     /* out  = r*r          (ggm first)   */
+    B200_EPI_SQ_ACC = 3,       /* out += r*r          (ggm middle)  */
+    B200_EPI_SQ_ACC_SQRT = 4   /* out  = sqrt(out + r*r) (ggm last) */
+} b200_epilogue;
+
+/* replaces _nd_image.correlate1d (scipy/ndimage/_filters.py:610):
+ *   out[i] = sum_j weights[j] * ext(in)[i + j - nw/2 - origin] along `axis` */
+int b200_correlate1d(const void *in, void *out, int dtype, int ndim,
+                     const int64_t *shape, int axis, const double *weights,
+                     int64_t nw, int mode, double cval, int64_t origin,
+                     int64_t pad_lo, int64_t pad_hi, int epilogue,
+                     unsigned flags, void *stream);
+
+/* replaces _nd_image.uniform_filter1d (scipy/ndimage/_filters.py:1542) */
+int b200_uniform_filter1d(const void *in, void *out, int dtype, int ndim,
+                          const int64_t *shape, int axis, int64_t size,
+                          int mode, double cval, int64_t origin,
+                          int64_t pad_lo, int64_t pad_hi, unsigned flags,
+                          void *stream);
+
+/* replaces _nd_image.correlate (scipy/ndimage/_filters.py:1305); `weights` has
+ * shape `wshape` (ndim entries, C order), taps with |w| <= DBL_EPSILON are
+ * skipped as scipy does; convolve = flipped weights + adjusted origins,
+ * prepared by the caller exactly as scipy/ndimage/_filters.py:1282-1287. */
+int b200_correlate_nd(const void *in, void *out, int dtype, int ndim,
+                      const int64_t *shape, const double *weights,
+                      const int64_t *wshape, const int64_t *origins, int mode,
+                      double cval, int64_t pad_lo, int64_t pad_hi,
+                      unsigned flags, void *stream);
+
+/* replaces the numpy ufuncs of scipy/ndimage/_filters.py:1025-1030,1184-1193:
+ * acc (op)= src elementwise over n elements, in the array dtype. */
+int b200_combine(void *acc, const void *src, int dtype, int64_t n, int op,
+                 void *stream);
+
+/* name of the kernel family the last successful call on this thread chose
+ * ("corr1d_tma_strided_f32", "corr1d_generic", ...); for tests and profiling */
+const char *b200_last_kernel(void);
+const char *b200_last_error(void);
+const char *b200_version(void);
+/* number of kernel launches issued by this thread since the last reset */
+int64_t b200_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_NDFILTERS_H */
