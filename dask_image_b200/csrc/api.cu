@@ -1,0 +1,195 @@
+// api.cu -- extern "C" entry points declared in include/b200_ndfilters.h:
+// argument validation (same conditions and error classes as the scipy drivers
+// the reference calls), kernel-family selection, thread-local diagnostics.
+#include "common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+
+namespace b200 {
+
+static thread_local char tl_error[512] = "";
+static thread_local char tl_kernel[128] = "";
+static thread_local int64_t tl_launches = 0;
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void note_kernel(const char *name)
+{
+    strncpy(tl_kernel, name, sizeof(tl_kernel) - 1);
+    tl_kernel[sizeof(tl_kernel) - 1] = 0;
+}
+
+void count_launch(int n) { tl_launches += n; }
+
+int check_cuda(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return B200_OK;
+    return set_error(B200_ECUDA, "CUDA error in %s: %s (%s)", what, cudaGetErrorName(e),
+                     cudaGetErrorString(e));
+}
+
+int device_sm_count()
+{
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cached[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+static int check_common(const void *in, const void *out, int dtype, int ndim, const int64_t *shape,
+                        int mode, int64_t *total)
+{
+    if (dtype < B200_U8 || dtype > B200_F64) return set_error(B200_EDTYPE, "data type not supported");
+    if (ndim < 1 || ndim > B200_MAXDIM) return set_error(B200_EINVAL, "ndim must be in [1, %d]", B200_MAXDIM);
+    if (mode < B200_MODE_NEAREST || mode > B200_MODE_CONSTANT)
+        return set_error(B200_EMODE, "boundary mode not supported");
+    int64_t t = 1;
+    for (int d = 0; d < ndim; ++d) {
+        if (shape[d] < 0) return set_error(B200_EINVAL, "negative extent");
+        t *= shape[d];
+    }
+    *total = t;
+    if (t > 0 && (!in || !out)) return set_error(B200_EINVAL, "null device pointer");
+    if (t > 0 && in == out) return set_error(B200_EINVAL, "input and output must not alias");
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_correlate1d(const void *in, void *out, int dtype, int ndim, const int64_t *shape, int axis,
+                     const double *weights, int64_t nw, int mode, double cval, int64_t origin,
+                     int64_t pad_lo, int64_t pad_hi, int epilogue, unsigned flags, void *stream)
+{
+    int64_t total;
+    if (int rc = check_common(in, out, dtype, ndim, shape, mode, &total)) return rc;
+    if (axis < 0 || axis >= ndim) return set_error(B200_EINVAL, "axis out of range");
+    if (!weights || nw < 1) return set_error(B200_EINVAL, "no filter weights given");
+    if (nw > (1 << 20)) return set_error(B200_EINVAL, "too many filter weights");
+    if (origin < -(nw / 2) || origin > (nw - 1) / 2)
+        return set_error(B200_EORIGIN, "Invalid origin; origin must satisfy "
+                                       "-(len(weights) // 2) <= origin <= (len(weights)-1) // 2");
+    if (epilogue < B200_EPI_STORE || epilogue > B200_EPI_SQ_ACC_SQRT)
+        return set_error(B200_EINVAL, "unknown epilogue");
+    if (pad_lo < 0 || pad_hi < 0 || ((pad_lo || pad_hi) && axis != 0))
+        return set_error(B200_EINVAL, "halo pads are only defined for axis 0");
+    if (total == 0) return B200_OK;
+
+    Corr1dArgs a;
+    a.in = in; a.out = out; a.dtype = dtype;
+    a.g = line_geometry(ndim, shape, axis);
+    a.w = weights; a.nw = (int)nw; a.mode = mode; a.cval = cval; a.origin = (int)origin;
+    a.pad_lo = pad_lo; a.pad_hi = pad_hi; a.epilogue = epilogue; a.flags = flags;
+    a.stream = (cudaStream_t)stream;
+
+    const bool is_float = dtype == B200_F32 || dtype == B200_F64;
+    if (is_float && !(flags & (B200_FLAG_EXACT | B200_FLAG_NO_TMA))) {
+        int rc = launch_corr1d_tma(a);
+        if (rc >= 0) return rc;
+    }
+    if (flags & B200_FLAG_FORCE_FAST)
+        return set_error(B200_EINVAL, "no tiled kernel is eligible for this call");
+    return launch_corr1d_generic(a);
+}
+
+int b200_uniform_filter1d(const void *in, void *out, int dtype, int ndim, const int64_t *shape, int axis,
+                          int64_t size, int mode, double cval, int64_t origin, int64_t pad_lo,
+                          int64_t pad_hi, unsigned flags, void *stream)
+{
+    int64_t total;
+    if (int rc = check_common(in, out, dtype, ndim, shape, mode, &total)) return rc;
+    if (axis < 0 || axis >= ndim) return set_error(B200_EINVAL, "axis out of range");
+    if (size < 1 || size > (1 << 20)) return set_error(B200_EINVAL, "incorrect filter size");
+    if (size / 2 + origin < 0 || size / 2 + origin >= size) return set_error(B200_EORIGIN, "invalid origin");
+    if (pad_lo < 0 || pad_hi < 0 || ((pad_lo || pad_hi) && axis != 0))
+        return set_error(B200_EINVAL, "halo pads are only defined for axis 0");
+    if (total == 0) return B200_OK;
+
+    Uniform1dArgs a;
+    a.in = in; a.out = out; a.dtype = dtype;
+    a.g = line_geometry(ndim, shape, axis);
+    a.size = (int)size; a.mode = mode; a.cval = cval; a.origin = (int)origin;
+    a.pad_lo = pad_lo; a.pad_hi = pad_hi; a.flags = flags; a.stream = (cudaStream_t)stream;
+    if (!(flags & (B200_FLAG_EXACT | B200_FLAG_NO_TMA))) {
+        int rc = launch_uniform1d_fast(a);
+        if (rc >= 0) return rc;
+    }
+    if (flags & B200_FLAG_FORCE_FAST)
+        return set_error(B200_EINVAL, "no tiled kernel is eligible for this call");
+    return launch_uniform1d_generic(a);
+}
+
+int b200_correlate_nd(const void *in, void *out, int dtype, int ndim, const int64_t *shape,
+                      const double *weights, const int64_t *wshape, const int64_t *origins, int mode,
+                      double cval, int64_t pad_lo, int64_t pad_hi, unsigned flags, void *stream)
+{
+    int64_t total;
+    if (int rc = check_common(in, out, dtype, ndim, shape, mode, &total)) return rc;
+    if (!weights || !wshape || !origins) return set_error(B200_EINVAL, "no filter weights given");
+    int64_t wtotal = 1;
+    for (int d = 0; d < ndim; ++d) {
+        if (wshape[d] < 1) return set_error(B200_EINVAL, "weights must have non-zero extents");
+        wtotal *= wshape[d];
+        if (wtotal > (1 << 24)) return set_error(B200_EINVAL, "too many filter weights");
+        if (origins[d] < -(wshape[d] / 2) || origins[d] > (wshape[d] - 1) / 2)
+            return set_error(B200_EORIGIN, "Invalid origin; origin must satisfy "
+                                           "-(weights.shape[k] // 2) <= origin[k] <= (weights.shape[k]-1) // 2");
+    }
+    if (pad_lo < 0 || pad_hi < 0) return set_error(B200_EINVAL, "negative halo pad");
+    if (total == 0) return B200_OK;
+
+    CorrNdArgs a;
+    a.in = in; a.out = out; a.dtype = dtype; a.ndim = ndim;
+    for (int d = 0; d < ndim; ++d) {
+        a.shape[d] = shape[d]; a.wshape[d] = wshape[d]; a.origins[d] = origins[d];
+    }
+    a.w = weights; a.mode = mode; a.cval = cval; a.pad_lo = pad_lo; a.pad_hi = pad_hi;
+    a.flags = flags; a.stream = (cudaStream_t)stream;
+    const bool is_float = dtype == B200_F32 || dtype == B200_F64;
+    if (is_float && !(flags & (B200_FLAG_EXACT | B200_FLAG_NO_TMA))) {
+        int rc = launch_corrnd_tiled(a);
+        if (rc >= 0) return rc;
+    }
+    if (flags & B200_FLAG_FORCE_FAST)
+        return set_error(B200_EINVAL, "no tiled kernel is eligible for this call");
+    return launch_corrnd_generic(a);
+}
+
+int b200_combine(void *acc, const void *src, int dtype, int64_t n, int op, void *stream)
+{
+    if (dtype < B200_U8 || dtype > B200_F64) return set_error(B200_EDTYPE, "data type not supported");
+    if (op < B200_EPI_STORE || op > B200_EPI_SQ_ACC_SQRT) return set_error(B200_EINVAL, "unknown combine op");
+    if (n < 0) return set_error(B200_EINVAL, "negative length");
+    if (n > 0 && (!acc || !src)) return set_error(B200_EINVAL, "null device pointer");
+    return launch_combine(acc, src, dtype, n, op, (cudaStream_t)stream);
+}
+
+const char *b200_last_kernel(void) { return tl_kernel; }
+const char *b200_last_error(void) { return tl_error; }
+const char *b200_version(void) { return "b200-ndfilters 0.1.0 (sm_100a)"; }
+
+int64_t b200_launch_count(int reset)
+{
+    int64_t v = tl_launches;
+    if (reset) tl_launches = 0;
+    return v;
+}
+
+}  // extern "C"

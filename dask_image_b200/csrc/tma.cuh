@@ -1,0 +1,83 @@
+// tma.cuh -- thin inline-PTX wrappers for TMA tile loads + mbarrier (sm_100a),
+// and the host-side tensor-map encoder (driver entry point fetched at run time
+// so the library has no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+// make the barrier initialisation visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1,
+                                            int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// Host: encode a tiled tensor map (rank <= 3) over a dense row-major view.
+// dims[0] is the contiguous dimension; strides_bytes[i] is the byte stride of
+// dims[i+1].  Returns 0 on success, -1 if the driver entry point is missing or
+// the encoder rejects the geometry (caller falls back to a non-TMA kernel).
+int encode_tensor_map(CUtensorMap *map, int dtype /* b200_dtype */, void *base, int rank,
+                      const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box);
+
+}  // namespace b200

@@ -1,0 +1,18 @@
+"""Drop-in for the correlation family of ``dask_image.ndfilters``: same names,
+signatures, validation and exception classes (dask_image/ndfilters/__init__.py)."""
+from ._conv import convolve, correlate
+from ._diff import laplace
+from ._edge import prewitt, sobel
+from ._gaussian import (gaussian, gaussian_filter, gaussian_gradient_magnitude,
+                        gaussian_laplace)
+from ._smooth import uniform_filter
+
+__all__ = [
+    "convolve", "correlate", "laplace", "prewitt", "sobel", "gaussian", "gaussian_filter",
+    "gaussian_gradient_magnitude", "gaussian_laplace", "uniform_filter",
+]
+
+for _f in (convolve, correlate, laplace, prewitt, sobel, gaussian, gaussian_filter,
+           gaussian_gradient_magnitude, gaussian_laplace, uniform_filter):
+    _f.__module__ = __name__
+del _f

@@ -1,0 +1,513 @@
+"""Per-chunk filter functions on :class:`B200Array` with ``scipy.ndimage``'s
+signatures -- what the dispatch factories hand to ``map_overlap`` in place of
+``scipy.ndimage.*`` / ``cupyx.scipy.ndimage.*``
+(dask_image/dispatch/_dispatch_ndfilters.py:47-59,63-75,127-171,271-283).
+
+Each function decomposes into the same sequence of 1-D passes / ufunc steps as
+scipy's Python drivers (scipy/ndimage/_filters.py, cited per function) and runs
+every step as a hand-written sm_100a kernel through the C ABI
+(include/b200_ndfilters.h).  Intermediate passes are stored in the array dtype
+exactly as scipy does, so integer results are bit-identical.
+"""
+import numbers
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._array import B200Array, as_b200
+
+__all__ = [
+    "correlate1d", "convolve1d", "gaussian_filter1d", "gaussian_filter",
+    "uniform_filter1d", "uniform_filter", "correlate", "convolve",
+    "gaussian_gradient_magnitude", "gaussian_laplace", "laplace", "prewitt", "sobel",
+]
+
+_default_flags = _lib.FLAG_EXACT if os.environ.get("B200_NDFILTERS_EXACT", "") not in ("", "0") else 0
+
+
+def set_default_flags(flags):
+    """Set library-wide kernel selection flags (``_lib.FLAG_*``); returns the old value."""
+    global _default_flags
+    old, _default_flags = _default_flags, int(flags)
+    return old
+
+
+# --------------------------------------------------------------------------
+# argument helpers (scipy/ndimage/_ni_support.py:62-80 semantics)
+# --------------------------------------------------------------------------
+def _per_axis(value, rank):
+    if isinstance(value, str) or not np.iterable(value):
+        return [value] * rank
+    seq = list(value)
+    if len(seq) != rank:
+        raise RuntimeError("sequence argument must have length equal to input rank")
+    return seq
+
+
+def _axis_index(axis, ndim):
+    if not isinstance(axis, numbers.Integral):
+        raise TypeError("axis must be an integer")
+    if axis < -ndim or axis >= ndim:
+        raise np.exceptions.AxisError(axis, ndim)
+    return int(axis) % ndim if ndim else 0
+
+
+def _stream_ptr(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _new_like(x):
+    return torch.empty_like(x.tensor)
+
+
+def _check_output(output, x):
+    if output is None:
+        return None
+    out = as_b200(output)
+    if out.shape != x.shape or out.dtype != x.dtype:
+        raise RuntimeError("output shape / dtype not correct")
+    if out.tensor.data_ptr() == x.tensor.data_ptr() and x.size:
+        raise RuntimeError("input and output must not share memory")
+    return out
+
+
+# --------------------------------------------------------------------------
+# raw launches
+# --------------------------------------------------------------------------
+def _launch_correlate1d(src, dst, shape, np_dtype, axis, weights, mode, cval, origin,
+                        pad=(0, 0), epilogue=_lib.EPI_STORE, flags=None):
+    """src/dst: torch tensors (device pointers are taken at element 0 of the
+    UNPADDED array; ``pad`` planes of real data precede/follow it on axis 0)."""
+    lib = _lib.load()
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    with torch.cuda.device(src.device):
+        rc = lib.b200_correlate1d(
+            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape),
+            _lib.i64_array(shape), int(axis), _lib.f64_pointer(w), int(w.shape[0]),
+            _lib.mode_code(mode), float(cval), int(origin), int(pad[0]), int(pad[1]),
+            int(epilogue), int(_default_flags if flags is None else flags), _stream_ptr(src))
+    _lib.check(rc)
+
+
+def _launch_uniform1d(src, dst, shape, np_dtype, axis, size, mode, cval, origin, pad=(0, 0),
+                      flags=None):
+    lib = _lib.load()
+    with torch.cuda.device(src.device):
+        rc = lib.b200_uniform_filter1d(
+            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape),
+            _lib.i64_array(shape), int(axis), int(size), _lib.mode_code(mode), float(cval),
+            int(origin), int(pad[0]), int(pad[1]),
+            int(_default_flags if flags is None else flags), _stream_ptr(src))
+    _lib.check(rc)
+
+
+def _launch_correlate_nd(src, dst, shape, np_dtype, weights, origins, mode, cval, pad=(0, 0),
+                         flags=None):
+    lib = _lib.load()
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    with torch.cuda.device(src.device):
+        rc = lib.b200_correlate_nd(
+            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape),
+            _lib.i64_array(shape), _lib.f64_pointer(w), _lib.i64_array(w.shape),
+            _lib.i64_array(origins), _lib.mode_code(mode), float(cval), int(pad[0]), int(pad[1]),
+            int(_default_flags if flags is None else flags), _stream_ptr(src))
+    _lib.check(rc)
+
+
+def _launch_combine(acc, src, np_dtype, op):
+    lib = _lib.load()
+    with torch.cuda.device(acc.device):
+        rc = lib.b200_combine(acc.data_ptr(), src.data_ptr(), _lib.DTYPE_CODES[np_dtype.name],
+                              int(acc.numel()), int(op), _stream_ptr(acc))
+    _lib.check(rc)
+
+
+def _zero_dim_guard(x):
+    if x.ndim == 0:
+        raise RuntimeError("0-d arrays are not supported")
+
+
+# --------------------------------------------------------------------------
+# 1-D primitives
+# --------------------------------------------------------------------------
+def correlate1d(input, weights, axis=-1, output=None, mode="reflect", cval=0.0, origin=0):
+    """scipy.ndimage.correlate1d (scipy/ndimage/_filters.py:556-612)."""
+    x = as_b200(input)
+    _zero_dim_guard(x)
+    w = np.asarray(weights if not isinstance(weights, B200Array) else weights.to_numpy())
+    if w.dtype.kind == "c" or x.dtype.kind == "c":
+        raise RuntimeError("complex data is not supported")
+    w = np.asarray(w, dtype=np.float64)
+    if w.ndim != 1 or w.shape[0] < 1:
+        raise RuntimeError("no filter weights given")
+    axis = _axis_index(axis, x.ndim)
+    out = _check_output(output, x) or x.empty_like()
+    _launch_correlate1d(x.tensor, out.tensor, x.shape, x.dtype, axis, w, mode, cval, origin)
+    return out
+
+
+def convolve1d(input, weights, axis=-1, output=None, mode="reflect", cval=0.0, origin=0):
+    """scipy.ndimage.convolve1d (scipy/ndimage/_filters.py:645-653)."""
+    w = np.asarray(weights if not isinstance(weights, B200Array) else weights.to_numpy())
+    w = w[::-1]
+    origin = -origin
+    if not w.shape[0] & 1:
+        origin -= 1
+    return correlate1d(input, w, axis, output, mode, cval, origin)
+
+
+def _gaussian_kernel1d(sigma, order, radius):
+    """Sampled Gaussian (derivative) kernel, built the way scipy builds it
+    (scipy/ndimage/_filters.py:656-684): normalised phi(x) times a polynomial
+    q_order(x) obtained by applying (d/dx - x/sigma^2) `order` times to 1.
+    The same numpy primitives are used so the taps are bit-identical to
+    scipy's (integer outputs depend on it)."""
+    if order < 0:
+        raise ValueError("order must be non-negative")
+    var = sigma * sigma
+    xs = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / var * xs ** 2)
+    phi = phi / phi.sum()
+    if order == 0:
+        return phi
+    powers = np.arange(order + 1)
+    # operator on polynomial coefficients: differentiate + multiply by -x/sigma^2
+    step = np.diag(powers[1:], 1) + np.diag(np.ones(order) / -var, -1)
+    coeff = np.zeros(order + 1)
+    coeff[0] = 1
+    for _ in range(order):
+        coeff = step.dot(coeff)
+    poly = (xs[:, None] ** powers).dot(coeff)
+    return poly * phi
+
+
+def _gaussian_weights(sigma, order, truncate, radius=None):
+    """Taps handed to correlate1d by scipy's gaussian_filter1d (:745-754)."""
+    sd = float(sigma)
+    lw = int(truncate * sd + 0.5)
+    if radius is not None:
+        lw = radius
+    if not isinstance(lw, numbers.Integral) or lw < 0:
+        raise ValueError("Radius must be a nonnegative integer.")
+    return _gaussian_kernel1d(sigma, order, lw)[::-1]
+
+
+def gaussian_filter1d(input, sigma, axis=-1, order=0, output=None, mode="reflect", cval=0.0,
+                      truncate=4.0, *, radius=None):
+    """scipy.ndimage.gaussian_filter1d (scipy/ndimage/_filters.py:688-754)."""
+    weights = _gaussian_weights(sigma, order, truncate, radius)
+    return correlate1d(input, weights, axis, output, mode, cval, 0)
+
+
+def uniform_filter1d(input, size, axis=-1, output=None, mode="reflect", cval=0.0, origin=0):
+    """scipy.ndimage.uniform_filter1d (scipy/ndimage/_filters.py:1502-1549)."""
+    x = as_b200(input)
+    _zero_dim_guard(x)
+    axis = _axis_index(axis, x.ndim)
+    if size < 1:
+        raise RuntimeError("incorrect filter size")
+    if (size // 2 + origin < 0) or (size // 2 + origin >= size):
+        raise ValueError("invalid origin")
+    out = _check_output(output, x) or x.empty_like()
+    _launch_uniform1d(x.tensor, out.tensor, x.shape, x.dtype, axis, size, mode, cval, origin)
+    return out
+
+
+# --------------------------------------------------------------------------
+# pass chains
+# --------------------------------------------------------------------------
+class _Pass:
+    __slots__ = ("kind", "axis", "weights", "size", "origin", "mode")
+
+    def __init__(self, kind, axis, mode, weights=None, size=0, origin=0):
+        self.kind, self.axis, self.mode = kind, axis, mode
+        self.weights, self.size, self.origin = weights, size, origin
+
+
+def _run_chain(x_tensor, shape, np_dtype, passes, cval, out_tensor, final_epilogue=_lib.EPI_STORE,
+               pad=(0, 0), scratch=None, flags=None):
+    """Run 1-D passes in order (input -> s0 -> s1 -> ... -> out), never writing
+    the input; the last pass applies ``final_epilogue`` into ``out_tensor``.
+    ``pad`` describes axis-0 halo planes around ``x_tensor`` (slab engine) and
+    only the first pass may consume it -- later passes read scratch buffers
+    that hold the slab interior only."""
+    scratch = scratch if scratch is not None else []
+    src, src_pad = x_tensor, pad
+    for i, ps in enumerate(passes):
+        last = i == len(passes) - 1
+        if last:
+            dst = out_tensor
+        else:
+            k = i % 2
+            while len(scratch) <= k:
+                scratch.append(torch.empty(tuple(shape), dtype=out_tensor.dtype,
+                                           device=out_tensor.device))
+            dst = scratch[k]
+        use_pad = src_pad if ps.axis == 0 else (0, 0)
+        epi = final_epilogue if last else _lib.EPI_STORE
+        if ps.kind == "corr":
+            _launch_correlate1d(src, dst, shape, np_dtype, ps.axis, ps.weights, ps.mode, cval,
+                                ps.origin, use_pad, epi, flags)
+        else:
+            if epi != _lib.EPI_STORE:
+                raise RuntimeError("uniform passes have no fused epilogue")
+            _launch_uniform1d(src, dst, shape, np_dtype, ps.axis, ps.size, ps.mode, cval,
+                              ps.origin, use_pad, flags)
+        src, src_pad = dst, (0, 0)
+    return scratch
+
+
+def _gaussian_passes(ndim, sigma, order, mode, truncate, radius=None, axes=None):
+    """Pass list of scipy.ndimage.gaussian_filter (:838-858): axes in order,
+    those with sigma <= 1e-15 skipped."""
+    axes = _check_axes(axes, ndim)
+    k = len(axes)
+    sigmas, orders = _per_axis(sigma, k), _per_axis(order, k)
+    modes, radiuses = _per_axis(mode, k), _per_axis(radius, k)
+    passes = []
+    for i, ax in enumerate(axes):
+        if sigmas[i] > 1e-15:
+            w = _gaussian_weights(sigmas[i], orders[i], truncate, radiuses[i])
+            _lib.mode_code(modes[i])
+            passes.append(_Pass("corr", ax, modes[i], weights=w))
+    return passes
+
+
+def _check_axes(axes, ndim):
+    if axes is None:
+        return tuple(range(ndim))
+    if np.isscalar(axes):
+        axes = (axes,)
+    out = []
+    for ax in axes:
+        if not isinstance(ax, numbers.Integral):
+            raise ValueError("axes must be integers")
+        if ax < -ndim or ax >= ndim:
+            raise ValueError("specified axis: %d is out of range" % ax)
+        out.append(int(ax) % ndim)
+    if len(set(out)) != len(out):
+        raise ValueError("axes must be unique")
+    return tuple(out)
+
+
+def gaussian_filter(input, sigma, order=0, output=None, mode="reflect", cval=0.0, truncate=4.0,
+                    *, radius=None, axes=None):
+    """scipy.ndimage.gaussian_filter (scipy/ndimage/_filters.py:758-862)."""
+    x = as_b200(input)
+    _zero_dim_guard(x)
+    passes = _gaussian_passes(x.ndim, sigma, order, mode, truncate, radius, axes)
+    out = _check_output(output, x) or x.empty_like()
+    if not passes or x.size == 0:
+        out.tensor.copy_(x.tensor)
+        return out
+    _run_chain(x.tensor, x.shape, x.dtype, passes, cval, out.tensor)
+    return out
+
+
+def uniform_filter(input, size=3, output=None, mode="reflect", cval=0.0, origin=0, *, axes=None):
+    """scipy.ndimage.uniform_filter (scipy/ndimage/_filters.py:1553-1622)."""
+    x = as_b200(input)
+    _zero_dim_guard(x)
+    axes = _check_axes(axes, x.ndim)
+    k = len(axes)
+    sizes, origins, modes = _per_axis(size, k), _per_axis(origin, k), _per_axis(mode, k)
+    passes = []
+    for i, ax in enumerate(axes):
+        if sizes[i] > 1:
+            sz, og = int(sizes[i]), int(origins[i])
+            if (sz // 2 + og < 0) or (sz // 2 + og >= sz):
+                raise ValueError("invalid origin")
+            _lib.mode_code(modes[i])
+            passes.append(_Pass("uniform", ax, modes[i], size=sz, origin=og))
+    out = _check_output(output, x) or x.empty_like()
+    if not passes or x.size == 0:
+        out.tensor.copy_(x.tensor)
+        return out
+    _run_chain(x.tensor, x.shape, x.dtype, passes, cval, out.tensor)
+    return out
+
+
+# --------------------------------------------------------------------------
+# N-D correlate / convolve
+# --------------------------------------------------------------------------
+def _weights_to_host(weights):
+    if isinstance(weights, B200Array):
+        return weights.to_numpy()
+    if isinstance(weights, torch.Tensor):
+        return weights.cpu().numpy()
+    return np.asarray(weights)
+
+
+def _prepare_nd_weights(x, weights, origin, convolution):
+    """scipy/ndimage/_filters.py:1271-1292: float64 weights; for convolution
+    flip every axis and negate origins (one more on even-length axes)."""
+    w = _weights_to_host(weights)
+    if w.dtype.kind == "c" or x.dtype.kind == "c":
+        raise RuntimeError("complex data is not supported")
+    w = np.asarray(w, dtype=np.float64)
+    wshape = [s for s in w.shape if s > 0]
+    if len(wshape) != x.ndim or w.ndim != x.ndim:
+        raise RuntimeError("weights.ndim (%d) must match len(axes) (%d)" % (len(wshape), x.ndim))
+    origins = [int(o) for o in _per_axis(origin, x.ndim)]
+    if convolution:
+        w = w[tuple([slice(None, None, -1)] * w.ndim)]
+        for i in range(x.ndim):
+            origins[i] = -origins[i]
+            if not w.shape[i] & 1:
+                origins[i] -= 1
+    for og, lenw in zip(origins, wshape):
+        if (og < -(lenw // 2)) or (og > (lenw - 1) // 2):
+            raise ValueError("Invalid origin; origin must satisfy "
+                             "-(weights.shape[k] // 2) <= origin[k] <= (weights.shape[k]-1) // 2")
+    return np.ascontiguousarray(w), origins
+
+
+def _correlate_or_convolve(input, weights, output, mode, cval, origin, convolution):
+    x = as_b200(input)
+    _zero_dim_guard(x)
+    if not isinstance(mode, str) and np.iterable(mode):
+        raise RuntimeError("A sequence of modes is not supported")
+    w, origins = _prepare_nd_weights(x, weights, origin, convolution)
+    out = _check_output(output, x) or x.empty_like()
+    _launch_correlate_nd(x.tensor, out.tensor, x.shape, x.dtype, w, origins, mode, cval)
+    return out
+
+
+def correlate(input, weights, output=None, mode="reflect", cval=0.0, origin=0):
+    """scipy.ndimage.correlate (scipy/ndimage/_filters.py:1312-1380)."""
+    return _correlate_or_convolve(input, weights, output, mode, cval, origin, False)
+
+
+def convolve(input, weights, output=None, mode="reflect", cval=0.0, origin=0):
+    """scipy.ndimage.convolve (scipy/ndimage/_filters.py:1383-1499)."""
+    return _correlate_or_convolve(input, weights, output, mode, cval, origin, True)
+
+
+# --------------------------------------------------------------------------
+# derivative compositions
+# --------------------------------------------------------------------------
+def _combine_chains(x, chains, ops, cval, output):
+    """Run one pass chain per entry, folding each chain's result into the
+    output with the matching epilogue (fused into the chain's last pass)."""
+    out = _check_output(output, x) or x.empty_like()
+    scratch = []
+    for passes, op in zip(chains, ops):
+        if passes:
+            scratch = _run_chain(x.tensor, x.shape, x.dtype, passes, cval, out.tensor,
+                                 final_epilogue=op, scratch=scratch)
+        else:
+            # all sigmas ~ 0: the "derivative" is the input itself
+            _launch_combine(out.tensor, x.tensor, x.dtype, op)
+    return out
+
+
+def gaussian_gradient_magnitude(input, sigma, output=None, mode="reflect", cval=0.0, *,
+                                axes=None, **kwargs):
+    """scipy.ndimage.gaussian_gradient_magnitude (scipy/ndimage/_filters.py:1142-1250):
+    sqrt(sum_a gaussian_filter(order = e_a)^2), squares/adds/sqrt in the array
+    dtype; fused here as epilogues of the last pass of each chain."""
+    x = as_b200(input)
+    _zero_dim_guard(x)
+    truncate = kwargs.pop("truncate", 4.0)
+    radius = kwargs.pop("radius", None)
+    if kwargs:
+        raise TypeError("unexpected keyword arguments: %s" % sorted(kwargs))
+    axes = _check_axes(axes, x.ndim)
+    if len(axes) != x.ndim:
+        raise NotImplementedError("axes subsets are not supported (the reference never passes them)")
+    if x.size == 0:
+        out = _check_output(output, x) or x.empty_like()
+        return out
+    modes = _per_axis(mode, len(axes))
+    sigmas = _per_axis(sigma, len(axes))
+    chains, ops = [], []
+    for i, ax in enumerate(axes):
+        order = [0] * len(axes)
+        order[i] = 1
+        chains.append(_gaussian_passes(x.ndim, sigmas, order, modes[i], truncate, radius, axes))
+        if len(axes) == 1:
+            ops.append(_lib.EPI_SQ_ACC_SQRT)
+        elif i == 0:
+            ops.append(_lib.EPI_SQ_STORE)
+        elif i == len(axes) - 1:
+            ops.append(_lib.EPI_SQ_ACC_SQRT)
+        else:
+            ops.append(_lib.EPI_SQ_ACC)
+    out = _check_output(output, x) or x.empty_like()
+    if len(axes) == 1:
+        out.tensor.zero_()
+    return _combine_chains(x, chains, ops, cval, out)
+
+
+def gaussian_laplace(input, sigma, output=None, mode="reflect", cval=0.0, *, axes=None, **kwargs):
+    """scipy.ndimage.gaussian_laplace (scipy/ndimage/_filters.py:984-1030,1075-1139):
+    sum_a gaussian_filter(order = 2 e_a)."""
+    x = as_b200(input)
+    _zero_dim_guard(x)
+    truncate = kwargs.pop("truncate", 4.0)
+    radius = kwargs.pop("radius", None)
+    if kwargs:
+        raise TypeError("unexpected keyword arguments: %s" % sorted(kwargs))
+    axes = _check_axes(axes, x.ndim)
+    if len(axes) != x.ndim:
+        raise NotImplementedError("axes subsets are not supported (the reference never passes them)")
+    if x.size == 0:
+        out = _check_output(output, x) or x.empty_like()
+        return out
+    modes = _per_axis(mode, len(axes))
+    sigmas = _per_axis(sigma, len(axes))
+    chains, ops = [], []
+    for i, ax in enumerate(axes):
+        order = [0] * len(axes)
+        order[i] = 2
+        chains.append(_gaussian_passes(x.ndim, sigmas, order, modes[i], truncate, radius, axes))
+        ops.append(_lib.EPI_STORE if i == 0 else _lib.EPI_ACC)
+    return _combine_chains(x, chains, ops, cval, output)
+
+
+# --------------------------------------------------------------------------
+# 3-tap correlate1d compositions
+# --------------------------------------------------------------------------
+def laplace(input, output=None, mode="reflect", cval=0.0, *, axes=None):
+    """scipy.ndimage.laplace (scipy/ndimage/_filters.py:1037-1071): sum over
+    axes of correlate1d with [1, -2, 1]."""
+    x = as_b200(input)
+    _zero_dim_guard(x)
+    axes = _check_axes(axes, x.ndim)
+    if not axes or x.size == 0:
+        out = _check_output(output, x) or x.empty_like()
+        out.tensor.copy_(x.tensor)
+        return out
+    modes = _per_axis(mode, len(axes))
+    chains = [[_Pass("corr", ax, modes[i], weights=np.array([1.0, -2.0, 1.0]))]
+              for i, ax in enumerate(axes)]
+    ops = [_lib.EPI_STORE if i == 0 else _lib.EPI_ACC for i in range(len(axes))]
+    return _combine_chains(x, chains, ops, cval, output)
+
+
+def _edge_filter(input, axis, output, mode, cval, smooth):
+    """prewitt / sobel (scipy/ndimage/_filters.py:865-982): [-1,0,1] along
+    ``axis`` then ``smooth`` along every other axis, in axis order."""
+    x = as_b200(input)
+    _zero_dim_guard(x)
+    axis = _axis_index(axis, x.ndim)
+    modes = _per_axis(mode, x.ndim)
+    passes = [_Pass("corr", axis, modes[axis], weights=np.array([-1.0, 0.0, 1.0]))]
+    for ax in range(x.ndim):
+        if ax != axis:
+            passes.append(_Pass("corr", ax, modes[ax], weights=np.array(smooth, dtype=np.float64)))
+    out = _check_output(output, x) or x.empty_like()
+    if x.size == 0:
+        return out
+    _run_chain(x.tensor, x.shape, x.dtype, passes, cval, out.tensor)
+    return out
+
+
+def prewitt(input, axis=-1, output=None, mode="reflect", cval=0.0):
+    return _edge_filter(input, axis, output, mode, cval, [1.0, 1.0, 1.0])
+
+
+def sobel(input, axis=-1, output=None, mode="reflect", cval=0.0):
+    return _edge_filter(input, axis, output, mode, cval, [1.0, 2.0, 1.0])

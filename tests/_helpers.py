@@ -1,0 +1,65 @@
+"""Shared helpers of the test-suite: golden fixtures, tolerances, oracle access."""
+import json
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN_NPZ = os.path.join(HERE, "golden", "ndfilters_golden.npz")
+GOLDEN_JSON = os.path.join(HERE, "golden", "ndfilters_golden.json")
+
+# north_star tolerances (BASELINE.json): fp32 <= 1e-5 relative with fp32
+# accumulation, fp64 <= 1e-12, integers bit-exact.  Derivative / laplace
+# outputs cross zero, so "relative" is taken against the output's magnitude as
+# well as elementwise:
+#     |got - ref| <= rtol * |ref| + rtol * max|ref|
+RTOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+
+_golden = None
+
+
+def golden_cases():
+    with open(GOLDEN_JSON) as f:
+        return json.load(f)["cases"]
+
+
+def golden_arrays():
+    global _golden
+    if _golden is None:
+        _golden = dict(np.load(GOLDEN_NPZ))
+    return _golden
+
+
+def golden_case(i):
+    spec = golden_cases()[i]
+    arrs = golden_arrays()
+    kwargs = {}
+    for k, v in spec["kwargs"].items():
+        if v == "@array":
+            kwargs[k] = arrs["kw_%d_%s" % (i, k)]
+        elif isinstance(v, list):
+            kwargs[k] = tuple(v)
+        else:
+            kwargs[k] = v
+    return spec["func"], arrs[spec["input"]], kwargs, arrs["out_%d" % i]
+
+
+def assert_parity(got, ref, exact=False, what=""):
+    got = np.asarray(got)
+    ref = np.asarray(ref)
+    assert got.shape == ref.shape, "%s shape %s != %s" % (what, got.shape, ref.shape)
+    assert got.dtype == ref.dtype, "%s dtype %s != %s" % (what, got.dtype, ref.dtype)
+    if exact or ref.dtype.kind != "f":
+        if not np.array_equal(got, ref, equal_nan=True):
+            bad = np.argwhere(got != ref)
+            raise AssertionError("%s: %d / %d elements differ (first at %s: got %r, ref %r)" % (
+                what, len(bad), ref.size, tuple(bad[0]), got[tuple(bad[0])], ref[tuple(bad[0])]))
+        return
+    rtol = RTOL[ref.dtype]
+    scale = float(np.max(np.abs(ref))) if ref.size else 0.0
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    bound = rtol * np.abs(ref.astype(np.float64)) + rtol * scale
+    if not np.all(err <= bound):
+        i = np.unravel_index(np.argmax(err - bound), err.shape)
+        raise AssertionError("%s: |got-ref|=%g exceeds %g at %s (got %r, ref %r, rtol %g)" % (
+            what, err[i], bound[i], i, got[i], ref[i], rtol))

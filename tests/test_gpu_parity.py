@@ -1,0 +1,283 @@
+"""GPU parity tests (``-m gpu``): the CUDA path, called through the C ABI by the
+host mirror of the reference interface, against the CPU oracle, the committed
+golden vectors and scipy (the arithmetic the reference runs per chunk).
+
+Parametrisations follow the reference's own tests
+(tests/test_dask_image/test_ndfilters/test__gaussian.py, test__smooth.py,
+test__conv.py) with ``HaloChunked`` standing in for ``dask.array.from_array``.
+"""
+import numpy as np
+import pytest
+import scipy.ndimage as ndi
+
+from _helpers import assert_parity, golden_case, golden_cases
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CASES = golden_cases()
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import dask_image_b200
+
+    return dask_image_b200
+
+
+def dev(b200, a):
+    return b200.B200Array.from_numpy(np.asarray(a))
+
+
+def host_kwargs(b200, kwargs):
+    return dict(kwargs)
+
+
+# ---------------------------------------------------------------------------
+# golden vectors (all dtypes, all modes, origins, even sizes, long radii)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("i", range(len(CASES)), ids=[c["name"] for c in CASES])
+def test_golden(b200, i):
+    func, a, kwargs, expected = golden_case(i)
+    got = getattr(b200.ndimage, func)(dev(b200, a), **kwargs)
+    assert type(got) is b200.B200Array
+    assert_parity(got.to_numpy(), expected, what=CASES[i]["name"])
+
+
+@pytest.mark.parametrize("i", range(0, len(CASES), 3), ids=[c["name"] for c in CASES[::3]])
+def test_golden_exact_mode_is_bitwise(b200, i):
+    """B200_FLAG_EXACT: fp64 accumulation in scipy's order -> bit-identical for floats too."""
+    from dask_image_b200 import _lib
+
+    func, a, kwargs, expected = golden_case(i)
+    old = b200.ndimage.set_default_flags(_lib.FLAG_EXACT)
+    try:
+        got = getattr(b200.ndimage, func)(dev(b200, a), **kwargs)
+    finally:
+        b200.ndimage.set_default_flags(old)
+    if func in ("uniform_filter", "uniform_filter1d") and a.dtype.kind == "f":
+        # scipy carries a running sum along each line; the kernel sums each
+        # window directly -- same value up to fp64 rounding, not bitwise
+        assert_parity(got.to_numpy(), expected, what=CASES[i]["name"])
+    else:
+        assert_parity(got.to_numpy(), expected, exact=True, what=CASES[i]["name"])
+
+
+def test_scipy_docstring_known_answers(b200):
+    nd = b200.ndimage
+    assert nd.correlate1d(dev(b200, np.array([2, 8, 0, 4, 1, 9, 9, 0])), [1, 3]).to_numpy().tolist() == \
+        [8, 26, 8, 12, 7, 28, 36, 9]
+    assert nd.convolve1d(dev(b200, np.array([2, 8, 0, 4, 1, 9, 9, 0])), [1, 3]).to_numpy().tolist() == \
+        [14, 24, 4, 13, 12, 36, 27, 0]
+    assert nd.uniform_filter1d(dev(b200, np.array([2, 8, 0, 4, 1, 9, 9, 0])), size=3).to_numpy().tolist() == \
+        [4, 3, 4, 1, 4, 6, 6, 3]
+    np.testing.assert_allclose(
+        nd.gaussian_filter1d(dev(b200, np.array([1.0, 2.0, 3.0, 4.0, 5.0])), 1).to_numpy(),
+        [1.42704095, 2.06782203, 3.0, 3.93217797, 4.57295905], atol=1e-8)
+    # scipy/ndimage/_filters.py:824-829 (integer gaussian_filter)
+    a = np.arange(50, step=2).reshape((5, 5))
+    assert_parity(nd.gaussian_filter(dev(b200, a), sigma=1).to_numpy(), ndi.gaussian_filter(a, sigma=1))
+
+
+# ---------------------------------------------------------------------------
+# the reference's tests, through the public wrappers, chunked like dask would
+# ---------------------------------------------------------------------------
+GAUSS_FUNCS = [("gaussian_filter", "gaussian"), ("gaussian_filter", "gaussian_filter"),
+               ("gaussian_gradient_magnitude", "gaussian_gradient_magnitude"),
+               ("gaussian_laplace", "gaussian_laplace")]
+
+
+@pytest.mark.parametrize("sigma, truncate", [(1.0, 2.0), (1.0, 4.0), (2.0, 2.0), (2.0, 4.0), ((1.0, 2.0), 4.0)])
+@pytest.mark.parametrize("sp_name, da_name", GAUSS_FUNCS)
+@pytest.mark.parametrize("chunks", [None, (50, 55)])
+def test_gaussian_filters_compare(b200, sp_name, da_name, sigma, truncate, chunks):
+    # reference: test__gaussian.py:125-154
+    s = (100, 110)
+    a = np.arange(float(np.prod(s))).reshape(s)
+    d = dev(b200, a) if chunks is None else b200.from_array(a, chunks=chunks)
+    got = getattr(b200.ndfilters, da_name)(d, sigma, truncate=truncate)
+    ref = getattr(orc, sp_name)(a, sigma, truncate=truncate)
+    assert all(type(x) is int for x in got.shape)
+    assert_parity(np.asarray(got), ref)
+    assert_parity(np.asarray(got), getattr(ndi, sp_name)(a, sigma, truncate=truncate))
+
+
+@pytest.mark.parametrize("sigma, truncate", [(0.0, 0.0), (1.0, 0.0), (0.0, 1.0), (1.0, 2.0), (1.0, 4.0),
+                                             (2.0, 2.0), (2.0, 4.0), ((1.0, 2.0), 4.0)])
+@pytest.mark.parametrize("order", [0, 1, 2, 3, (0, 1), (2, 3)])
+@pytest.mark.parametrize("da_name", ["gaussian", "gaussian_filter"])
+def test_gaussian_derivative_filters_compare(b200, da_name, order, sigma, truncate):
+    # reference: test__gaussian.py:157-196
+    s = (100, 110)
+    a = np.arange(float(np.prod(s))).reshape(s)
+    d = b200.from_array(a, chunks=(50, 55))
+    got = getattr(b200.ndfilters, da_name)(d, sigma, order, truncate=truncate)
+    assert_parity(np.asarray(got), orc.gaussian_filter(a, sigma, order, truncate=truncate))
+
+
+@pytest.mark.parametrize("sigma, truncate", [(0.0, 0.0), (0.0, 1.0), (0.0, 4.0), (1.0, 0.0)])
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
+def test_gaussian_filters_identity(b200, order, sigma, truncate):
+    # reference: test__gaussian.py:38-75
+    a = np.arange(140.0).reshape(10, 14)
+    d = b200.from_array(a, chunks=(5, 7))
+    if order % 2 == 1 and sigma != 0 and truncate == 0:
+        pytest.skip("SciPy zeros the result for odd derivatives with truncate == 0 (scipy#7364)")
+    got = b200.ndfilters.gaussian_filter(d, sigma, order, truncate=truncate)
+    assert_parity(np.asarray(got), a)
+    assert_parity(np.asarray(got), ndi.gaussian_filter(a, sigma, order, truncate=truncate))
+
+
+@pytest.mark.parametrize("da_name", ["gaussian", "gaussian_filter", "gaussian_gradient_magnitude",
+                                     "gaussian_laplace", "uniform_filter"])
+def test_filter_comprehensions(b200, da_name):
+    # reference: test__gaussian.py:101-122, test__smooth.py:45-57
+    np.random.seed(0)
+    a = np.random.random((3, 12, 14))
+    d = b200.from_array(a, chunks=(3, 6, 7))
+    f = getattr(b200.ndfilters, da_name)
+    args = (1,) if da_name == "uniform_filter" else (1.0,)
+    sp = getattr(ndi, "gaussian_filter" if da_name == "gaussian" else da_name)
+    for i in range(len(a)):
+        assert_parity(np.asarray(f(d[i], *args)), sp(a[i], *args))
+
+
+@pytest.mark.parametrize("size, origin", [(1, 0), (2, 0), (3, 0), (3, 1), (3, (1, 0)), ((1, 2), 0),
+                                          ((3, 2), (1, 0))])
+@pytest.mark.parametrize("chunks", [None, (50, 55)])
+def test_uniform_compare(b200, size, origin, chunks):
+    # reference: test__smooth.py:60-99
+    s = (100, 110)
+    a = np.arange(float(np.prod(s))).reshape(s)
+    d = dev(b200, a) if chunks is None else b200.from_array(a, chunks=chunks)
+    got = b200.ndfilters.uniform_filter(d, size, origin=origin)
+    assert_parity(np.asarray(got), orc.uniform_filter(a, size, origin=origin))
+    assert_parity(np.asarray(got), ndi.uniform_filter(a, size, origin=origin))
+
+
+DISC = (np.mgrid[-2:3, -2:3] ** 2).sum(axis=0) < 2.5 ** 2
+CONV_W = [(np.ones((1, 1)), 0), (np.ones((2, 2)), 0), (np.ones((2, 3)), 0), (np.ones((2, 3)), (0, 1)),
+          (np.ones((2, 3)), (0, -1)), (DISC, 0), (DISC, (1, 2)), (DISC, (-1, -2)), (np.ones((5, 5)), 0),
+          (np.ones((7, 7)), 0), (np.ones((8, 8)), 0), (np.ones((10, 10)), 0), (np.ones((5, 5)), 2),
+          (np.ones((5, 5)), -2)]
+
+
+@pytest.mark.parametrize("name", ["convolve", "correlate"])
+@pytest.mark.parametrize("wi", range(len(CONV_W)))
+@pytest.mark.parametrize("chunks", [None, (5, 7)])
+def test_convolutions_compare(b200, name, wi, chunks):
+    # reference: test__conv.py:88-156 (weights are a B200Array: array types must match)
+    weights, origin = CONV_W[wi]
+    a = np.arange(140.0).reshape(10, 14)
+    d = dev(b200, a) if chunks is None else b200.from_array(a, chunks=chunks)
+    got = getattr(b200.ndfilters, name)(d, dev(b200, weights.astype(float)), origin=origin)
+    assert_parity(np.asarray(got), getattr(orc, name)(a, weights, origin=origin))
+
+
+@pytest.mark.parametrize("name", ["convolve", "correlate"])
+@pytest.mark.parametrize("wshape", [(1, 5), (5, 1)])
+@pytest.mark.parametrize("mode", ["reflect", "wrap", "nearest", "constant", "mirror"])
+@pytest.mark.parametrize("chunks", [None, (5, 7)])
+def test_convolutions_modes(b200, name, wshape, mode, chunks):
+    # reference: test__conv.py:159-191 -- INTEGER array, all five modes; the
+    # chunked run goes through the wrap -> periodic rewrite (_conv.py:23-25)
+    a = np.arange(140).reshape(10, 14)
+    d = dev(b200, a) if chunks is None else b200.from_array(a, chunks=chunks)
+    if chunks is not None and mode != "wrap":
+        # the reference's own per-chunk semantics for non-wrap modes equal whole-array scipy
+        pass
+    got = getattr(b200.ndfilters, name)(d, dev(b200, np.ones(wshape)), mode=mode)
+    assert_parity(np.asarray(got), getattr(orc, name)(a, np.ones(wshape), mode=mode))
+    assert_parity(np.asarray(got), getattr(ndi, name)(a, np.ones(wshape), mode=mode))
+
+
+@pytest.mark.parametrize("name", ["convolve", "correlate"])
+@pytest.mark.parametrize("err_type, weights, origin", [
+    (ValueError, np.ones((1,)), 0), (ValueError, np.ones((1, 0)), 0), (RuntimeError, np.ones((1, 1)), (0,)),
+    (RuntimeError, np.ones((1, 1)), [(0,)]), (ValueError, np.ones((1, 1)), 1), (TypeError, np.ones((1, 1)), 0.0),
+    (TypeError, np.ones((1, 1)), (0.0, 0.0)), (TypeError, np.ones((1, 1)), 1 + 0j),
+    (TypeError, np.ones((1, 1)), (0 + 0j, 1 + 0j)),
+])
+def test_convolutions_params(b200, name, err_type, weights, origin):
+    # reference: test__conv.py:12-43
+    d = b200.from_array(np.arange(140.0).reshape(10, 14), chunks=(5, 7))
+    with pytest.raises(err_type):
+        getattr(b200.ndfilters, name)(d, dev(b200, weights), origin=origin)
+
+
+def test_numpy_input_has_no_cpu_fallback(b200):
+    with pytest.raises((TypeError, AttributeError)):
+        b200.ndfilters.gaussian_filter(np.zeros((4, 4)), 1.0)
+
+
+# ---------------------------------------------------------------------------
+# edge cases the reference never exercises
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(0, 5), (5, 0), (1, 1), (1, 7), (7, 1), (2, 3, 1, 4)])
+def test_empty_and_degenerate_shapes(b200, shape):
+    a = np.random.default_rng(0).random(shape)
+    nd = b200.ndimage
+    assert_parity(nd.gaussian_filter(dev(b200, a), 1.5).to_numpy(), ndi.gaussian_filter(a, 1.5))
+    assert_parity(nd.uniform_filter(dev(b200, a), 3).to_numpy(), ndi.uniform_filter(a, 3))
+    if a.size:
+        w = np.ones((3,) * a.ndim)
+        assert_parity(nd.correlate(dev(b200, a), w).to_numpy(), ndi.correlate(a, w))
+
+
+@pytest.mark.parametrize("mode", ["reflect", "wrap", "nearest", "constant", "mirror"])
+def test_radius_much_larger_than_axis(b200, mode):
+    a = np.random.default_rng(1).random((3, 5))
+    got = b200.ndimage.gaussian_filter(dev(b200, a), 6.0, mode=mode, cval=0.25)
+    assert_parity(got.to_numpy(), ndi.gaussian_filter(a, 6.0, mode=mode, cval=0.25))
+    got = b200.ndimage.uniform_filter(dev(b200, a), 17, mode=mode, cval=0.25)
+    assert_parity(got.to_numpy(), ndi.uniform_filter(a, 17, mode=mode, cval=0.25))
+
+
+def test_unsigned_wrap_and_truncation(b200):
+    # truncation toward zero, negative -> unsigned wraps modulo 2^bits
+    a = np.random.default_rng(2).integers(0, 65536, (40, 50), dtype=np.uint16)
+    for order in (1, 2):
+        got = b200.ndimage.gaussian_filter(dev(b200, a), 2.0, order=order)
+        assert_parity(got.to_numpy(), ndi.gaussian_filter(a, 2.0, order=order))
+    w = np.array([[-1.5, 2.0], [0.25, -3.0]])
+    assert_parity(b200.ndimage.correlate(dev(b200, a), w).to_numpy(), ndi.correlate(a, w))
+    a8 = a.astype(np.int8)
+    assert_parity(b200.ndimage.correlate(dev(b200, a8), w * 40).to_numpy(), ndi.correlate(a8, w * 40))
+
+
+def test_grid_mode_aliases(b200):
+    a = np.random.default_rng(3).random((9, 11))
+    for alias, mode in [("grid-wrap", "wrap"), ("grid-constant", "constant"), ("grid-mirror", "reflect")]:
+        got = b200.ndimage.gaussian_filter(dev(b200, a), 2.0, mode=alias, cval=1.0)
+        assert_parity(got.to_numpy(), ndi.gaussian_filter(a, 2.0, mode=mode, cval=1.0))
+    with pytest.raises(RuntimeError, match="boundary mode not supported"):
+        b200.ndimage.gaussian_filter(dev(b200, a), 2.0, mode="bogus")
+
+
+def test_input_is_not_mutated_and_output_is_new(b200):
+    a = np.random.default_rng(4).random((33, 47)).astype(np.float32)
+    d = dev(b200, a)
+    out = b200.ndimage.gaussian_filter(d, 1.0)
+    assert out.tensor.data_ptr() != d.tensor.data_ptr()
+    assert np.array_equal(d.to_numpy(), a)
+
+
+def test_per_axis_modes_and_axes(b200):
+    a = np.random.default_rng(5).random((20, 30))
+    got = b200.ndimage.gaussian_filter(dev(b200, a), (1.0, 2.0), mode=("wrap", "mirror"))
+    assert_parity(got.to_numpy(), ndi.gaussian_filter(a, (1.0, 2.0), mode=("wrap", "mirror")))
+    got = b200.ndimage.uniform_filter(dev(b200, a), 5, axes=(1,))
+    assert_parity(got.to_numpy(), ndi.uniform_filter(a, 5, axes=(1,)))
+
+
+@pytest.mark.parametrize("name", ["laplace", "prewitt", "sobel"])
+@pytest.mark.parametrize("dt", ["float64", "float32", "int16", "uint8"])
+def test_three_tap_compositions(b200, name, dt):
+    # SURVEY.md 8(f) rank 1; reference: tests/.../test__diff.py, test__edge.py
+    a = (np.random.default_rng(6).random((24, 30)) * 100).astype(dt)
+    d = b200.from_array(a, chunks=(12, 10))
+    got = getattr(b200.ndfilters, name)(d)
+    assert_parity(np.asarray(got), getattr(ndi, name)(a))
+    if name != "laplace":
+        got = getattr(b200.ndfilters, name)(d, axis=0, mode="mirror")
+        assert_parity(np.asarray(got), getattr(ndi, name)(a, axis=0, mode="mirror"))

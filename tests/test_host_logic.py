@@ -1,0 +1,293 @@
+"""CPU tests of the host side: argument validation tables of the reference's
+tests (tests/test_dask_image/test_ndfilters/test__utils.py:63-189,
+test__gaussian.py:12-35, test__conv.py:19-43, test__smooth.py:12-28), the
+dispatch mechanism, the gaussian tap generator and the C-ABI library's export
+table.  No kernel is launched here."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.ndimage
+
+import dask_image_b200
+from dask_image_b200 import _lib, ndimage
+from dask_image_b200.dispatch import Dispatcher, check_arraytypes_compatible, get_type
+from dask_image_b200.ndfilters import _gaussian, _utils
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C ABI -----------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "b200_ndfilters.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header))
+    assert {"b200_correlate1d", "b200_uniform_filter1d", "b200_correlate_nd", "b200_combine"} <= declared
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "missing export %s" % name
+    assert declared == set(_lib.EXPORTS)
+    assert "sm_100a" in _lib.version()
+
+
+def test_abi_argument_errors_without_gpu():
+    """Validation happens before any CUDA call, with scipy's exception classes."""
+    lib = _lib.load()
+    shape = _lib.i64_array([4, 4])
+    w = np.ones(3)
+    fake = ctypes.c_void_p(256)
+    fake2 = ctypes.c_void_p(512)
+    rc = lib.b200_correlate1d(fake, fake2, 9, 2, shape, 0, _lib.f64_pointer(w), 3, 2, 0.0, 2, 0, 0, 0, 0, None)
+    assert rc == _lib.EORIGIN
+    with pytest.raises(ValueError, match="Invalid origin"):
+        _lib.check(rc)
+    rc = lib.b200_correlate1d(fake, fake2, 9, 2, shape, 0, _lib.f64_pointer(w), 3, 7, 0.0, 0, 0, 0, 0, 0, None)
+    with pytest.raises(RuntimeError, match="boundary mode not supported"):
+        _lib.check(rc)
+    rc = lib.b200_correlate1d(fake, fake2, 42, 2, shape, 0, _lib.f64_pointer(w), 3, 2, 0.0, 0, 0, 0, 0, 0, None)
+    with pytest.raises(RuntimeError, match="data type not supported"):
+        _lib.check(rc)
+    rc = lib.b200_correlate1d(fake, fake2, 9, 2, shape, 0, _lib.f64_pointer(w), 0, 2, 0.0, 0, 0, 0, 0, 0, None)
+    with pytest.raises(RuntimeError, match="no filter weights given"):
+        _lib.check(rc)
+    rc = lib.b200_uniform_filter1d(fake, fake2, 9, 2, shape, 0, 0, 2, 0.0, 0, 0, 0, 0, None)
+    with pytest.raises(RuntimeError, match="incorrect filter size"):
+        _lib.check(rc)
+    rc = lib.b200_uniform_filter1d(fake, fake2, 9, 2, shape, 0, 3, 2, 0.0, 2, 0, 0, 0, None)
+    with pytest.raises(ValueError, match="invalid origin"):
+        _lib.check(rc)
+    rc = lib.b200_correlate1d(fake, fake, 9, 2, shape, 0, _lib.f64_pointer(w), 3, 2, 0.0, 0, 0, 0, 0, 0, None)
+    with pytest.raises(RuntimeError, match="alias"):
+        _lib.check(rc)
+    # empty arrays are a no-op
+    rc = lib.b200_correlate1d(None, None, 9, 2, _lib.i64_array([0, 4]), 0, _lib.f64_pointer(w), 3, 2, 0.0, 0,
+                              0, 0, 0, 0, None)
+    assert rc == 0
+    with pytest.raises(RuntimeError, match="boundary mode not supported"):
+        _lib.mode_code("bogus")
+
+
+# ---- gaussian taps -----------------------------------------------------------
+@pytest.mark.parametrize("order", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("sigma", [0.5, 1.0, 2.0, 3.0, 4.0, 7.3])
+def test_gaussian_taps_bit_identical_to_scipy(sigma, order):
+    for truncate in (0.0, 2.0, 4.0):
+        radius = int(truncate * sigma + 0.5)
+        ref = scipy.ndimage._filters._gaussian_kernel1d(sigma, order, radius)
+        got = ndimage._gaussian_kernel1d(sigma, order, radius)
+        assert np.array_equal(ref, got)
+        assert np.array_equal(ref[::-1], ndimage._gaussian_weights(sigma, order, truncate))
+
+
+# ---- wrapper metadata (reference test__utils.py:11-60) -----------------------
+def test__get_docstring_and_update_wrapper():
+    f = lambda: 0  # noqa: E731
+    expected = """
+    Wrapped copy of "{mod_name}.{func_name}"
+
+
+    Excludes the output parameter as it would not work with Dask arrays.
+
+
+    Original docstring:
+
+    {doc}
+    """.format(mod_name=inspect.getmodule(f).__name__, func_name=f.__name__, doc="")
+    assert _utils._get_docstring(f) == expected
+
+    @_utils._update_wrapper(f)
+    def g():
+        return f()
+
+    assert g.__name__ == f.__name__
+    assert g.__doc__ == expected
+
+
+def test_public_surface():
+    nf = dask_image_b200.ndfilters
+    for name in ["convolve", "correlate", "gaussian", "gaussian_filter", "gaussian_gradient_magnitude",
+                 "gaussian_laplace", "uniform_filter", "laplace", "prewitt", "sobel"]:
+        f = getattr(nf, name)
+        assert f.__module__ == "dask_image_b200.ndfilters"
+    assert 'Wrapped copy of "scipy.ndimage' in nf.gaussian_filter.__doc__
+
+    def fake(input, output=None):
+        """Summary of input.
+
+        Parameters
+        ----------
+    input : array_like
+        The input array.
+    output : array, optional
+        Dropped.
+    mode : str
+        Kept.
+
+        Examples
+        --------
+        >>> gone
+        """
+
+    doc = _utils._get_docstring(fake)
+    assert "output :" not in doc and "Dropped" not in doc and "gone" not in doc
+    assert "image : array_like" in doc and "mode : str" in doc
+    sig = inspect.signature(nf.gaussian_filter)
+    assert list(sig.parameters) == ["image", "sigma", "order", "mode", "cval", "truncate"]
+    assert list(inspect.signature(nf.uniform_filter).parameters) == ["image", "size", "mode", "cval", "origin"]
+    assert list(inspect.signature(nf.convolve).parameters) == ["image", "weights", "mode", "cval", "origin"]
+
+
+# ---- validation tables -------------------------------------------------------
+@pytest.mark.parametrize("err_type, ndim, depth, boundary", [
+    (TypeError, lambda: 0, 1, None), (TypeError, 1.0, 1, None), (ValueError, -1, 1, None),
+    (TypeError, 1, lambda: 0, None), (TypeError, 1, 1.0, None), (ValueError, 1, -1, None),
+    (ValueError, 1, (1, 1), None), (ValueError, 1, {0: 1, 1: 1}, None), (TypeError, 1, {1}, None),
+    (TypeError, 1, 1, 1), (ValueError, 1, 1, (None, None)), (ValueError, 1, 1, {0: None, 1: None}),
+    (TypeError, 1, 1, (1,)), (TypeError, 1, 1, {1}),
+])
+def test_errs__get_depth_boundary(err_type, ndim, depth, boundary):
+    with pytest.raises(err_type):
+        _utils._get_depth_boundary(ndim, depth, boundary)
+
+
+@pytest.mark.parametrize("err_type, ndim, size", [
+    (TypeError, 1.0, 1), (RuntimeError, 1, [[1]]), (TypeError, 1, 1.0), (TypeError, 1, [1.0]),
+    (RuntimeError, 1, [1, 1]),
+])
+def test_errs__get_size(err_type, ndim, size):
+    with pytest.raises(err_type):
+        _utils._get_size(ndim, size)
+
+
+@pytest.mark.parametrize("err_type, size, origin", [
+    (TypeError, [1], 1.0), (TypeError, [1], [1.0]), (RuntimeError, [1], [[1]]),
+    (RuntimeError, [1], [1, 1]), (ValueError, [1], [2]),
+])
+def test_errs__get_origin(err_type, size, origin):
+    with pytest.raises(err_type):
+        _utils._get_origin(size, origin)
+
+
+@pytest.mark.parametrize("err_type, ndim, size, footprint", [
+    (RuntimeError, 1, None, None), (RuntimeError, 1, [2], np.ones((2,), dtype=bool)),
+    (RuntimeError, 1, None, np.ones((1, 2), dtype=bool)), (RuntimeError, 1, None, np.ones([0], dtype=bool)),
+])
+def test_errs__get_footprint(err_type, ndim, size, footprint):
+    with pytest.raises(err_type):
+        _utils._get_footprint(ndim, size=size, footprint=footprint)
+
+
+@pytest.mark.parametrize("expected, ndim, depth, boundary", [
+    (({0: 0}, {0: "none"}), 1, 0, "none"), (({0: 0}, {0: "reflect"}), 1, 0, "reflect"),
+    (({0: 0}, {0: "periodic"}), 1, 0, "periodic"), (({0: 1}, {0: "none"}), 1, 1, "none"),
+])
+def test__get_depth_boundary(expected, ndim, depth, boundary):
+    assert expected == _utils._get_depth_boundary(ndim, depth, boundary)
+
+
+@pytest.mark.parametrize("expected, ndim, size", [((1,), 1, 1), ((3, 3), 2, 3), ((2, 4), 2, (2, 4))])
+def test__get_size(expected, ndim, size):
+    assert expected == _utils._get_size(ndim, size)
+
+
+@pytest.mark.parametrize("expected, size, origin", [((0,), (1,), 0), ((1,), (3,), 1), ((1, 2), (3, 5), (1, 2))])
+def test__get_origin(expected, size, origin):
+    assert expected == _utils._get_origin(size, origin)
+
+
+@pytest.mark.parametrize("expected, size, origin", [
+    ((0,), (1,), 0), ((1,), (3,), 0), ((2,), (3,), 1), ((2, 4), (3, 5), (1, 2))])
+def test__get_depth(expected, size, origin):
+    assert expected == _utils._get_depth(size, origin)
+
+
+@pytest.mark.parametrize("expected, ndim, size, footprint", [
+    (np.ones((2,), dtype=bool), 1, 2, None), (np.ones((2,), dtype=bool), 1, None, np.ones((2,), dtype=bool))])
+def test__get_footprint(expected, ndim, size, footprint):
+    assert (expected == _utils._get_footprint(ndim, size, footprint)).all()
+
+
+class _Shape2D:
+    ndim = 2
+    shape = (10, 14)
+    dtype = np.dtype(float)
+
+
+@pytest.mark.parametrize("err_type, sigma, truncate", [
+    (RuntimeError, [[1.0]], 4.0), (RuntimeError, [1.0], 4.0), (TypeError, 1.0 + 0.0j, 4.0),
+    (TypeError, 1.0, 4.0 + 0.0j),
+])
+@pytest.mark.parametrize("name", ["gaussian", "gaussian_filter", "gaussian_gradient_magnitude",
+                                  "gaussian_laplace"])
+def test_gaussian_filters_params(name, err_type, sigma, truncate):
+    # reference: test__gaussian.py:12-35 -- raised before any dispatch / compute
+    with pytest.raises(err_type):
+        getattr(dask_image_b200.ndfilters, name)(_Shape2D(), sigma, truncate=truncate)
+
+
+def test_gaussian_halo_is_ceil_sigma_truncate():
+    assert _gaussian._get_border(_Shape2D(), (1.0, 2.3), 4.0) == (4, 10)
+    sig = _gaussian._get_sigmas(_Shape2D(), 2)
+    assert len(sig) == 2 and all(s == 2 for s in sig)
+
+
+@pytest.mark.parametrize("err_type, size, origin", [
+    (TypeError, 3.0, 0), (TypeError, 3, 0.0), (RuntimeError, [3], 0), (RuntimeError, 3, [0]),
+    (RuntimeError, [[3]], 0), (RuntimeError, 3, [[0]]),
+])
+def test_uniform_filter_params(err_type, size, origin):
+    # reference: test__smooth.py:12-28
+    with pytest.raises(err_type):
+        dask_image_b200.ndfilters.uniform_filter(_Shape2D(), size, origin=origin)
+
+
+# ---- dispatch ----------------------------------------------------------------
+def test_dispatcher_semantics():
+    d = Dispatcher(name="demo")
+
+    class A:
+        pass
+
+    class B(A):
+        pass
+
+    class Meta:
+        def __init__(self, m):
+            self._meta = m
+
+    @d.register(A)
+    def factory_a(*args, **kwargs):
+        return "chunk-func-for-A"
+
+    assert d(A()) == "chunk-func-for-A"
+    assert d(B()) == "chunk-func-for-A"          # MRO walk
+    assert d(Meta(B())) == "chunk-func-for-A"    # dask arrays dispatch on type(_meta)
+    assert get_type(Meta(A())) is A
+    with pytest.raises(TypeError):
+        d(3.0)
+    check_arraytypes_compatible(A(), Meta(A()))
+    with pytest.raises(ValueError, match="Array types must be compatible"):
+        check_arraytypes_compatible(A(), np.ones(3))
+
+
+def test_b200array_is_registered_and_numpy_is_not():
+    from dask_image_b200 import B200Array
+    from dask_image_b200.dispatch import _dispatch_ndfilters as t
+
+    for name in ["convolve", "correlate", "gaussian_filter", "gaussian_gradient_magnitude",
+                 "gaussian_laplace", "uniform_filter", "laplace", "prewitt", "sobel"]:
+        disp = getattr(t, "dispatch_" + name)
+        assert disp.dispatch(B200Array)() is getattr(ndimage, name)
+        with pytest.raises(TypeError):      # no CPU fallback registered
+            disp.dispatch(np.ndarray)
+
+
+def test_conv_params_host_side():
+    # reference: test__conv.py:19-43 (conditions that do not need device data)
+    nf = dask_image_b200.ndfilters
+    img = _Shape2D()
+    for f in (nf.convolve, nf.correlate):
+        with pytest.raises(ValueError):   # array types differ
+            f(img, np.ones((1, 1)))
