@@ -265,7 +265,7 @@ def run_b200(args, wl, rank, world, local_rank):
 
     # ---- end to end: pinned host in -> device -> filter -> pinned host out ---
     e2e = None
-    if world == 1:
+    if world == 1 and not args.no_e2e:
         try:
             h_in = torch.empty(shape, dtype=torch.float32).pin_memory()
             h_out = torch.empty(shape, dtype=torch.float32).pin_memory()
@@ -324,6 +324,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -57,8 +57,10 @@ class HaloChunked:
 
     def map_overlap(self, func, depth, boundary, dtype=None, meta=None, **kwargs):
         nd = self.ndim
-        depth = [int(depth[d]) for d in range(nd)]
-        bnd = [boundary[d] for d in range(nd)]
+        # dask accepts a scalar or a per-axis mapping for both arguments
+        depth = [int(depth[d]) if hasattr(depth, "__getitem__") else int(depth) for d in range(nd)]
+        bnd = [boundary if (boundary is None or isinstance(boundary, str)) else boundary[d]
+               for d in range(nd)]
         src = self._array.tensor
         shift = [0] * nd
         for d in range(nd):

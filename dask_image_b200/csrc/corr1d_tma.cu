@@ -86,7 +86,8 @@ int encode_tensor_map(CUtensorMap *map, int dtype, void *base, int rank, const u
 }
 
 // ---------------------------------------------------------------------------
-constexpr int kMaxTapsTma = 200;
+constexpr int kMaxTapsTma = 208;
+constexpr int kMaxStages = 6;
 
 template <typename T>
 struct Corr1dTmaParams {
@@ -94,11 +95,16 @@ struct Corr1dTmaParams {
     T *out;
     int64_t outer, n, inner;
     int64_t pad_lo, pad_hi;
+    int64_t num_tiles;
     int nw, lo, mode, epilogue;
-    int tile_rows;   // strided: outputs per CTA along the filtered axis
+    int tile_rows;   // strided: outputs per CTA tile along the filtered axis
     int smem_rows;   // strided: tile_rows + nw - 1
     int nb;          // strided: row blocks per thread
     int pitch;       // contig: smem row pitch in elements (V * odd)
+    int shift;       // contig: leading taps to skip (box start aligned down to 16 bytes)
+    int ncg;         // contig: 4*R-column groups per tile
+    int stages;      // smem ring depth (1 or 2)
+    int stage_elems; // elements per stage
     int n_tiles, c_tiles;
     T cval;
     T w[kMaxTapsTma];
@@ -109,15 +115,62 @@ struct alignas(16) Vec {
     T v[V];
 };
 
-template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
-template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
-template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
+// ---------------------------------------------------------------------------
+// Accumulator blocks.  Acc<T, N> holds N accumulators and consumes 16-byte
+// vectors.  The float specialisation keeps them as float2 pairs and issues the
+// sm_100 packed FFMA2 (fma.rn.f32x2, broadcast weight from a uniform
+// register): half the issue slots of scalar FFMA for the same math.
+// ---------------------------------------------------------------------------
+template <typename T, int V>
+struct VecAcc {
+    T a[V];
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[i] = T(0);
+    }
+    __device__ __forceinline__ void fma(const Vec<T, V> &x, T w)
+    {
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[i] = ::fma(w, x.v[i], a[i]);
+    }
+    __device__ __forceinline__ T get(int i) const { return a[i]; }
+};
+
+template <>
+struct VecAcc<float, 4> {
+    float2 a[2];
+    __device__ __forceinline__ void zero() { a[0] = a[1] = make_float2(0.f, 0.f); }
+    __device__ __forceinline__ void fma(const Vec<float, 4> &x, float w)
+    {
+        const float2 w2 = make_float2(w, w);
+        a[0] = __ffma2_rn(make_float2(x.v[0], x.v[1]), w2, a[0]);
+        a[1] = __ffma2_rn(make_float2(x.v[2], x.v[3]), w2, a[1]);
+    }
+    __device__ __forceinline__ float get(int i) const
+    {
+        return i == 0 ? a[0].x : i == 1 ? a[0].y : i == 2 ? a[1].x : a[1].y;
+    }
+};
+
+// 16-byte aligned base of the dynamic shared memory (TMA destinations need
+// 128-byte alignment; the launcher over-allocates by 128).  Pointer arithmetic
+// on the __shared__ array keeps the shared address space (LDS, not LD).
+template <typename T>
+__device__ __forceinline__ T *aligned_smem(unsigned char *raw)
+{
+    const uint32_t pad = (128u - (smem_u32(raw) & 127u)) & 127u;
+    return reinterpret_cast<T *>(raw + pad);
+}
 
 // ===========================================================================
-// strided-axis pass
+// strided-axis pass: one tile per CTA, 3 CTAs resident per SM
 // ===========================================================================
-template <typename T, int W, int TY, int R>
-__global__ void __launch_bounds__((W / (16 / (int)sizeof(T))) * TY, 2)
+// REM = taps % R is a template parameter so that the tap tail is straight-line
+// code; nothing in the tap loops is divergent, which lets ptxas keep the
+// weights on the uniform datapath (LDCU -> FFMA2 with a UR operand).
+template <typename T, int W, int TY, int R, int MINB, int REM>
+__global__ void __launch_bounds__((W / (16 / (int)sizeof(T))) * TY, MINB)
 corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T> p)
 {
     constexpr int V = 16 / (int)sizeof(T);
@@ -125,30 +178,33 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
     constexpr int NTHREADS = TX * TY;
     using VecT = Vec<T, V>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // TMA destinations must be 128-byte aligned; the launcher over-allocates by 128
-    T *tile = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    __shared__ __align__(8) uint64_t bar;
+    T *tile = aligned_smem<T>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar;
 
     const int tid = threadIdx.x;
-    int64_t b = blockIdx.x;
-    const int tn = (int)(b % p.n_tiles);
-    b /= p.n_tiles;
-    const int tc = (int)(b % p.c_tiles);
-    const int64_t o = b / p.c_tiles;
-    const int64_t row0 = (int64_t)tn * p.tile_rows;  // first output row of this CTA
+    const int tx = tid % TX, ty = tid / TX;
+    const int L = p.nw;
+    const bool reads_out = epilogue_reads_out(p.epilogue);
+
+    const int64_t t = blockIdx.x;
+    const int tn = (int)(t % p.n_tiles);
+    const int64_t q = t / p.n_tiles;
+    const int tc = (int)(q % p.c_tiles);
+    const int64_t o = q / p.c_tiles;
+    const int64_t row0 = (int64_t)tn * p.tile_rows;  // first output row of this tile
     const int64_t col0 = (int64_t)tc * W;
     const int64_t g0 = row0 - p.lo;                  // array row held by smem row 0
 
     if (tid == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&full_bar, 1);
         fence_barrier_init();
+        mbar_arrive_expect_tx(&full_bar, (uint32_t)(p.smem_rows * W * (int)sizeof(T)));
+        tma_load_3d(tile, &tmap, &full_bar, (int)col0, (int)(g0 + p.pad_lo), (int)o);
     }
     __syncthreads();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(&bar, (uint32_t)(p.smem_rows * W * (int)sizeof(T)));
-        tma_load_3d(tile, &tmap, &bar, (int)col0, (int)(g0 + p.pad_lo), (int)o);
-    }
-    mbar_wait(&bar, 0);
+    // one warp polls the mbarrier; the others sleep at the CTA barrier
+    if (tid < 32) mbar_wait(&full_bar, 0);
+    __syncthreads();
 
     // rows of the tile that lie outside the resident range: patch through the
     // extension map (TMA left zeros there, which is already right for
@@ -171,61 +227,51 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
         __syncthreads();
     }
 
-    const int tx = tid % TX, ty = tid / TX;
-    const int L = p.nw;
-    const bool reads_out = epilogue_reads_out(p.epilogue);
+    const int Lfull = L - REM;
+    const int64_t col = col0 + tx * V;
+    T *const out_col = p.out + (o * p.n * p.inner + col);
     for (int blk = 0; blk < p.nb; ++blk) {
         const int r0 = (blk * TY + ty) * R;
-        if (row0 + r0 >= p.n) break;
         const T *sbase = tile + r0 * W + tx * V;
         VecT win[R];
-        T acc[R][V];
+        VecAcc<T, V> acc[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc[j][v] = T(0);
+        for (int j = 0; j < R; ++j) acc[j].zero();
 #pragma unroll
         for (int j = 0; j < R - 1; ++j) win[j] = *reinterpret_cast<const VecT *>(sbase + j * W);
-        int k = 0;
-        for (; k + R <= L; k += R) {
+        const T *sk = sbase + (R - 1) * W;
+        for (int k = 0; k < Lfull; k += R, sk += R * W) {
 #pragma unroll
             for (int u = 0; u < R; ++u) {
-                win[(u + R - 1) % R] = *reinterpret_cast<const VecT *>(sbase + (k + u + R - 1) * W);
+                win[(u + R - 1) % R] = *reinterpret_cast<const VecT *>(sk + u * W);
                 const T wk = p.w[k + u];
 #pragma unroll
-                for (int j = 0; j < R; ++j)
-#pragma unroll
-                    for (int v = 0; v < V; ++v) acc[j][v] = fma_t<T>(wk, win[(u + j) % R].v[v], acc[j][v]);
+                for (int j = 0; j < R; ++j) acc[j].fma(win[(u + j) % R], wk);
             }
         }
 #pragma unroll
-        for (int u = 0; u < R; ++u) {
-            if (k + u < L) {
-                win[(u + R - 1) % R] = *reinterpret_cast<const VecT *>(sbase + (k + u + R - 1) * W);
-                const T wk = p.w[k + u];
+        for (int u = 0; u < REM; ++u) {
+            win[(u + R - 1) % R] = *reinterpret_cast<const VecT *>(sk + u * W);
+            const T wk = p.w[Lfull + u];
 #pragma unroll
-                for (int j = 0; j < R; ++j)
-#pragma unroll
-                    for (int v = 0; v < V; ++v) acc[j][v] = fma_t<T>(wk, win[(u + j) % R].v[v], acc[j][v]);
-            }
+            for (int j = 0; j < R; ++j) acc[j].fma(win[(u + j) % R], wk);
         }
-        const int64_t col = col0 + tx * V;
         if (col < p.inner) {
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const int64_t row = row0 + r0 + j;
                 if (row < p.n) {
-                    T *dst = p.out + ((o * p.n + row) * p.inner + col);
+                    T *dst = out_col + row * p.inner;
                     VecT res;
                     if (p.epilogue == B200_EPI_STORE) {
 #pragma unroll
-                        for (int v = 0; v < V; ++v) res.v[v] = acc[j][v];
+                        for (int v = 0; v < V; ++v) res.v[v] = acc[j].get(v);
                     } else {
                         VecT prev;
                         if (reads_out) prev = *reinterpret_cast<const VecT *>(dst);
 #pragma unroll
                         for (int v = 0; v < V; ++v)
-                            res.v[v] = apply_epilogue<T>(p.epilogue, reads_out ? prev.v[v] : T(0), acc[j][v]);
+                            res.v[v] = apply_epilogue<T>(p.epilogue, reads_out ? prev.v[v] : T(0), acc[j].get(v));
                     }
                     *reinterpret_cast<VecT *>(dst) = res;
                 }
@@ -235,43 +281,138 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
 }
 
 // ===========================================================================
-// contiguous-axis pass
+// contiguous-axis pass: one tile per CTA
 // ===========================================================================
-template <typename T, int TR>
+// Per-thread state: R = 2V consecutive outputs of one row, three rotating
+// 16-byte register blocks B (12 floats / 6 doubles of the row).
+//
+// double: scalar FMAs.  float: packed FFMA2 on aligned register pairs.  A tap
+// at even data offset t pairs outputs (0,1)(2,3)(4,5)(6,7) with the aligned
+// data pairs {v[j+t], v[j+t+1]}; a tap at odd offset would need misaligned
+// pairs, so odd taps accumulate into a second set paired at ODD outputs
+// (-1,0)(1,2)(3,4)(5,6)(7,8) -- aligned again -- and the two sets are summed at
+// the end (the two half-wasted end pairs cost 1 extra FFMA2 per odd tap).
+template <typename T, int V>
+struct ContigAcc {
+    static constexpr int R = 2 * V;
+    T a[R];
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int j = 0; j < R; ++j) a[j] = T(0);
+    }
+    // tap at static data offset TT (0..V-1) inside the current group; U = group slot
+    template <int U, int TT>
+    __device__ __forceinline__ void tap(const Vec<T, V> (&B)[3], T w)
+    {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int m = j + TT;
+            a[j] = ::fma(w, B[(U + m / V) % 3].v[m % V], a[j]);
+        }
+    }
+    __device__ __forceinline__ T get(int j) const { return a[j]; }
+};
+
+template <>
+struct ContigAcc<float, 4> {
+    static constexpr int R = 8;
+    float2 e[4];   // outputs (0,1)(2,3)(4,5)(6,7): even data offsets
+    float2 o[5];   // outputs (-1,0)(1,2)(3,4)(5,6)(7,8): odd data offsets
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) o[i] = make_float2(0.f, 0.f);
+    }
+    template <int U, int TT>
+    __device__ __forceinline__ void tap(const Vec<float, 4> (&B)[3], float w)
+    {
+        const float2 w2 = make_float2(w, w);
+        if constexpr ((TT & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = 2 * i + TT;   // even
+                const Vec<float, 4> &b = B[(U + m / 4) % 3];
+                e[i] = __ffma2_rn(make_float2(b.v[m % 4], b.v[m % 4 + 1]), w2, e[i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int m = 2 * i - 1 + TT;   // even, 0..10
+                const Vec<float, 4> &b = B[(U + m / 4) % 3];
+                o[i] = __ffma2_rn(make_float2(b.v[m % 4], b.v[m % 4 + 1]), w2, o[i]);
+            }
+        }
+    }
+    __device__ __forceinline__ float get(int j) const
+    {
+        const float ev = (j & 1) ? e[j >> 1].y : e[j >> 1].x;
+        const float od = (j & 1) ? o[(j + 1) >> 1].x : o[j >> 1].y;
+        return ev + od;
+    }
+};
+
+// One group of V taps starting at tap index kb (a multiple of V): loads the
+// 16-byte block two ahead into rotating slot (U+2)%3 and applies taps
+// [T0, T1) of the group.  U = (kb / V) % 3 is static so the register rotation
+// is free; T0/T1 are static so partial groups have no per-tap tests.
+template <typename T, int V, int U, int T0, int T1, typename ACC>
+__device__ __forceinline__ void contig_group(Vec<T, V> (&B)[3], ACC &acc, const T *srow, const T *w, int kb)
+{
+    B[(U + 2) % 3] = *reinterpret_cast<const Vec<T, V> *>(srow + kb + 2 * V);
+    auto one = [&]<int TT>() {
+        if constexpr (TT >= T0 && TT < T1) acc.template tap<U, TT>(B, w[kb + TT]);
+    };
+    one.template operator()<0>();
+    one.template operator()<1>();
+    if constexpr (V == 4) {
+        one.template operator()<2>();
+        one.template operator()<3>();
+    }
+}
+
+// SH = leading taps to skip (box start aligned down to 16 bytes), REM = taps % V
+template <typename T, int SH, int REM>
 __global__ void __launch_bounds__(256, 2)
 corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T> p)
 {
     constexpr int V = 16 / (int)sizeof(T);
     constexpr int R = 2 * V;        // outputs per thread
     constexpr int PC = 4 * R;       // patch columns (4 lanes along x)
-    constexpr int SX = 4 * PC;      // tile columns (128 floats / 64 doubles = 512 B)
-    constexpr int NPATCH = (TR / 8) * 4;
     using VecT = Vec<T, V>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // TMA destinations must be 128-byte aligned; the launcher over-allocates by 128
-    T *tile = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    __shared__ __align__(8) uint64_t bar;
+    T *tile = aligned_smem<T>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar;
 
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int P = p.pitch;
-    int64_t b = blockIdx.x;
-    const int tcx = (int)(b % p.c_tiles);      // tile index along the filtered (contiguous) axis
-    const int64_t trow = b / p.c_tiles;
-    const int64_t x0t = (int64_t)tcx * SX;     // first output column of this CTA
-    const int64_t row0 = trow * TR;
-    const int64_t g0 = x0t - p.lo;             // array column held by smem column 0
+    const int TR = p.tile_rows;      // rows per tile (multiple of 8)
+    const int SX = p.ncg * PC;       // tile columns
+    const int nrg = TR / 8;
+    const int npatch = nrg * p.ncg;
+    const int L = p.nw;              // taps incl. the SH alignment taps
     const int64_t nrows = p.outer;
+    const bool reads_out = epilogue_reads_out(p.epilogue);
+
+    const int64_t t = blockIdx.x;
+    const int tcx = (int)(t % p.c_tiles);      // tile index along the filtered (contiguous) axis
+    const int64_t trow = t / p.c_tiles;
+    const int64_t x0t = (int64_t)tcx * SX;     // first output column of this tile
+    const int64_t row0 = trow * TR;
+    const int64_t g0 = x0t - p.lo;             // array column held by smem column 0 (16-byte aligned)
 
     if (tid == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&full_bar, 1);
         fence_barrier_init();
+        mbar_arrive_expect_tx(&full_bar, (uint32_t)(TR * P * (int)sizeof(T)));
+        tma_load_2d(tile, &tmap, &full_bar, (int)g0, (int)row0);
     }
     __syncthreads();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(&bar, (uint32_t)(TR * P * (int)sizeof(T)));
-        tma_load_2d(tile, &tmap, &bar, (int)g0, (int)row0);
-    }
-    mbar_wait(&bar, 0);
+    if (tid < 32) mbar_wait(&full_bar, 0);
+    __syncthreads();
 
     const bool low_edge = g0 < 0;
     const bool high_edge = g0 + P > p.n;
@@ -293,56 +434,57 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         __syncthreads();
     }
 
-    const int warp = tid >> 5, lane = tid & 31;
-    const int L = p.nw;
-    const bool reads_out = epilogue_reads_out(p.epilogue);
-    for (int q = warp; q < NPATCH; q += 8) {
-        const int rg = q % (TR / 8), cg = q / (TR / 8);
+    // group schedule (all warp-uniform): group 0 skips the SH alignment taps;
+    // full groups follow in slot order 1,2,0,...; the last group has REM taps
+    const int Lfull = L - REM;          // multiple of V, >= V when REM == 0 ... see launcher
+    // uniform trip count (every warp runs the same number of patches, surplus
+    // ones recompute the last patch and skip the store): keeps the tap loops
+    // free of divergence so the weights stay on the uniform datapath
+    const int patch_iters = (npatch + 7) / 8;
+    for (int qi = 0; qi < patch_iters; ++qi) {
+        const int q_raw = qi * 8 + warp;
+        const bool patch_live = q_raw < npatch;
+        const int q = patch_live ? q_raw : npatch - 1;
+        const int rg = q % nrg, cg = q / nrg;
         const int r = rg * 8 + (lane >> 2);
         const int xl = cg * PC + (lane & 3) * R;
         const int64_t row = row0 + r;
         const int64_t x = x0t + xl;
         const T *srow = tile + r * P + xl;
         VecT B[3];
-        T acc[R];
-#pragma unroll
-        for (int j = 0; j < R; ++j) acc[j] = T(0);
+        ContigAcc<T, V> acc;
+        acc.zero();
         B[0] = *reinterpret_cast<const VecT *>(srow);
         B[1] = *reinterpret_cast<const VecT *>(srow + V);
         int k = 0;
-        for (; k + 3 * V <= L; k += 3 * V) {
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                B[(u + 2) % 3] = *reinterpret_cast<const VecT *>(srow + k + (u + 2) * V);
-#pragma unroll
-                for (int t = 0; t < V; ++t) {
-                    const T wk = p.w[k + u * V + t];
-#pragma unroll
-                    for (int j = 0; j < R; ++j) {
-                        const int m = j + t;
-                        acc[j] = fma_t<T>(wk, B[(u + m / V) % 3].v[m % V], acc[j]);
-                    }
-                }
+        if (Lfull >= V) {
+            contig_group<T, V, 0, SH, V>(B, acc, srow, p.w, 0);
+            k = V;
+            for (; k + 3 * V <= Lfull; k += 3 * V) {
+                contig_group<T, V, 1, 0, V>(B, acc, srow, p.w, k);
+                contig_group<T, V, 2, 0, V>(B, acc, srow, p.w, k + V);
+                contig_group<T, V, 0, 0, V>(B, acc, srow, p.w, k + 2 * V);
             }
-        }
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            if (k + u * V < L) {
-                B[(u + 2) % 3] = *reinterpret_cast<const VecT *>(srow + k + (u + 2) * V);
-#pragma unroll
-                for (int t = 0; t < V; ++t) {
-                    if (k + u * V + t < L) {
-                        const T wk = p.w[k + u * V + t];
-#pragma unroll
-                        for (int j = 0; j < R; ++j) {
-                            const int m = j + t;
-                            acc[j] = fma_t<T>(wk, B[(u + m / V) % 3].v[m % V], acc[j]);
-                        }
-                    }
+            // 0, 1 or 2 full groups left, then the partial one
+            if (k + V <= Lfull) {
+                contig_group<T, V, 1, 0, V>(B, acc, srow, p.w, k);
+                k += V;
+                if (k + V <= Lfull) {
+                    contig_group<T, V, 2, 0, V>(B, acc, srow, p.w, k);
+                    k += V;
+                    if constexpr (REM > 0) contig_group<T, V, 0, 0, REM>(B, acc, srow, p.w, k);
+                } else {
+                    if constexpr (REM > 0) contig_group<T, V, 2, 0, REM>(B, acc, srow, p.w, k);
                 }
+            } else {
+                if constexpr (REM > 0) contig_group<T, V, 1, 0, REM>(B, acc, srow, p.w, k);
             }
+        } else {
+            // fewer than V taps in total: a single partial group (REM > SH here)
+            if constexpr (REM > 0) contig_group<T, V, 0, SH, REM>(B, acc, srow, p.w, 0);
         }
-        if (row < nrows) {
+
+        if (patch_live && row < nrows) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int64_t xx = x + h * V;
@@ -351,13 +493,13 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                     VecT res;
                     if (p.epilogue == B200_EPI_STORE) {
 #pragma unroll
-                        for (int v = 0; v < V; ++v) res.v[v] = acc[h * V + v];
+                        for (int v = 0; v < V; ++v) res.v[v] = acc.get(h * V + v);
                     } else {
                         VecT prev;
                         if (reads_out) prev = *reinterpret_cast<const VecT *>(dst);
 #pragma unroll
                         for (int v = 0; v < V; ++v)
-                            res.v[v] = apply_epilogue<T>(p.epilogue, reads_out ? prev.v[v] : T(0), acc[h * V + v]);
+                            res.v[v] = apply_epilogue<T>(p.epilogue, reads_out ? prev.v[v] : T(0), acc.get(h * V + v));
                     }
                     *reinterpret_cast<VecT *>(dst) = res;
                 }
@@ -375,69 +517,56 @@ static int env_int(const char *name, int dflt)
     return (s && *s) ? atoi(s) : dflt;
 }
 
-template <typename T>
-static int launch_strided(const Corr1dArgs &a)
+constexpr size_t kSmemPerSm = 227 * 1024;
+
+template <typename T, int R, int MINB, int REM>
+static int launch_strided_cfg(const Corr1dArgs &a, int nb)
 {
     constexpr int V = 16 / (int)sizeof(T);
     constexpr int W = 32 * V;   // 512-byte tile rows: one warp spans a row with 16-byte vectors
-    constexpr int TY = 8, R = 8;
-    constexpr int ROWS_PER_BLK = TY * R;   // 64
+    constexpr int TY = 8;
+    constexpr int ROWS_PER_BLK = TY * R;
     const int es = (int)sizeof(T);
     const LineGeom &g = a.g;
     const int L = a.nw;
-    if (L > kMaxTapsTma || ROWS_PER_BLK + L - 1 > 256) return -1;
-    if ((g.inner * es) % 16 != 0) return -1;
     const int64_t n_tot = a.pad_lo + g.n + a.pad_hi;
-    if (g.inner >= (1ll << 31) || n_tot >= (1ll << 31) || g.outer >= (1ll << 31)) return -1;
     const char *base = (const char *)a.in - a.pad_lo * g.inner * es;
-    if (((uintptr_t)base & 15) || ((uintptr_t)a.out & 15)) return -1;
 
-    // row blocks per CTA: as tall as shared memory (2 CTAs/SM), the 256-row TMA
-    // box limit and the need for >= ~4 waves of CTAs allow
     const int c_tiles = (int)((g.inner + W - 1) / W);
-    int nb = env_int("B200_TMA_NB", 0);
-    if (nb <= 0) {
-        nb = 1;
-        const int sms = device_sm_count();
-        for (int cand = 2; cand <= 3; ++cand) {
-            const int rows = cand * ROWS_PER_BLK + L - 1;
-            if (rows > 256 || (size_t)rows * W * es > 110 * 1024) break;
-            const int64_t ctas = ((g.n + cand * ROWS_PER_BLK - 1) / (cand * ROWS_PER_BLK)) * c_tiles * g.outer;
-            if (ctas < 4ll * sms) break;
-            nb = cand;
-        }
-    }
     while (nb > 1 && (nb * ROWS_PER_BLK + L - 1 > 256)) --nb;
+    if (nb * ROWS_PER_BLK + L - 1 > 256) return -1;
+    // do not make tiles taller than the axis
+    while (nb > 1 && (int64_t)(nb - 1) * ROWS_PER_BLK >= g.n) --nb;
     const int tile_rows = nb * ROWS_PER_BLK;
     const int smem_rows = tile_rows + L - 1;
+    const size_t stage_bytes = (size_t)smem_rows * W * es;
+    if (stage_bytes + 256 > kSmemPerSm - 1024) return -1;
     const int64_t n_tiles = (g.n + tile_rows - 1) / tile_rows;
-    const int64_t grid = n_tiles * c_tiles * g.outer;
-    if (grid >= (1ll << 31)) return -1;
+    const int64_t num_tiles = n_tiles * c_tiles * g.outer;
+    if (num_tiles >= (1ll << 31)) return -1;
 
     CUtensorMap tmap;
     uint64_t dims[3] = {(uint64_t)g.inner, (uint64_t)n_tot, (uint64_t)g.outer};
     uint64_t strides[2] = {(uint64_t)g.inner * es, (uint64_t)g.inner * es * (uint64_t)n_tot};
     uint32_t box[3] = {(uint32_t)W, (uint32_t)smem_rows, 1u};
-    if (a.pad_lo || a.pad_hi) {
-        // pads exist only for axis 0, where outer == 1
-        if (g.outer != 1) return -1;
-    }
     if (encode_tensor_map(&tmap, a.dtype, (void *)base, 3, dims, strides, box) != 0) return -1;
 
     Corr1dTmaParams<T> p;
     p.in = (const T *)a.in; p.out = (T *)a.out;
     p.outer = g.outer; p.n = g.n; p.inner = g.inner;
     p.pad_lo = a.pad_lo; p.pad_hi = a.pad_hi;
+    p.num_tiles = num_tiles;
     p.nw = L; p.lo = L / 2 + a.origin; p.mode = a.mode; p.epilogue = a.epilogue;
-    p.tile_rows = tile_rows; p.smem_rows = smem_rows; p.nb = nb; p.pitch = W;
+    p.tile_rows = tile_rows; p.smem_rows = smem_rows; p.nb = nb; p.pitch = W; p.shift = 0; p.ncg = 0;
+    p.stages = 1; p.stage_elems = (int)(stage_bytes / es);
     p.n_tiles = (int)n_tiles; p.c_tiles = c_tiles;
     p.cval = (T)a.cval;
     for (int i = 0; i < L; ++i) p.w[i] = (T)a.w[i];
 
-    auto kern = corr1d_strided_tma_kernel<T, W, TY, R>;
-    const size_t smem = (size_t)smem_rows * W * es + 128;
+    auto kern = corr1d_strided_tma_kernel<T, W, TY, R, MINB, REM>;
+    const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, (W / V) * TY, smem, a.stream>>>(tmap, p);
+    kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
     note_kernel(sizeof(T) == 4 ? "corr1d_tma_strided_f32" : "corr1d_tma_strided_f64");
@@ -445,53 +574,142 @@ static int launch_strided(const Corr1dArgs &a)
 }
 
 template <typename T>
-static int launch_contig(const Corr1dArgs &a)
+static int launch_strided(const Corr1dArgs &a)
 {
-    constexpr int V = 16 / (int)sizeof(T);
-    constexpr int R = 2 * V, SX = 16 * R, TR = 32;
+    constexpr int R = 4, MINB = 3;
     const int es = (int)sizeof(T);
     const LineGeom &g = a.g;
     const int L = a.nw;
-    if (a.pad_lo || a.pad_hi) return -1;
-    if (L > kMaxTapsTma) return -1;
-    // pitch: smallest odd multiple of 16 bytes covering SX + L + V - 1 elements
-    int pitch = SX + L + V - 1;
-    pitch = (pitch + V - 1) / V;        // in 16-byte units
-    if (!(pitch & 1)) ++pitch;
-    pitch *= V;
+    if (L > kMaxTapsTma || 8 * R + L - 1 > 256) return -1;
+    if ((g.inner * es) % 16 != 0) return -1;
+    const int64_t n_tot = a.pad_lo + g.n + a.pad_hi;
+    if (g.inner >= (1ll << 31) || n_tot >= (1ll << 31) || g.outer >= (1ll << 31)) return -1;
+    if ((a.pad_lo || a.pad_hi) && g.outer != 1) return -1;   // pads exist only for axis 0
+    const char *base = (const char *)a.in - a.pad_lo * g.inner * es;
+    if (((uintptr_t)base & 15) || ((uintptr_t)a.out & 15)) return -1;
+
+    // nb = row blocks (of 8*R rows) per CTA tile: the tallest tile that still
+    // leaves MINB CTAs resident per SM (B200 sweeps in profiles/: more, smaller
+    // CTAs beat a deeper per-CTA pipeline for this streaming kernel)
+    int nb = env_int("B200_TMA_NB", 0);
+    if (nb <= 0) {
+        const int per_cta = (int)((kSmemPerSm - 3072) / MINB);
+        const int max_rows = per_cta / 512;
+        nb = (max_rows - (L - 1)) / (8 * R);
+        nb = nb < 1 ? 1 : nb;
+    }
+    switch (L % R) {
+    case 0: return launch_strided_cfg<T, R, MINB, 0>(a, nb);
+    case 1: return launch_strided_cfg<T, R, MINB, 1>(a, nb);
+    case 2: return launch_strided_cfg<T, R, MINB, 2>(a, nb);
+    default: return launch_strided_cfg<T, R, MINB, 3>(a, nb);
+    }
+}
+
+template <typename T, int SH, int REM>
+static int launch_contig_cfg(const Corr1dArgs &a, int lo_al, int L)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int R = 2 * V, PC = 4 * R;
+    const int es = (int)sizeof(T);
+    const LineGeom &g = a.g;
+    // tile width: ncg column groups of 4*R outputs; pitch = smallest odd multiple
+    // of 16 bytes covering SX + L + 2V - 1 elements (the float path's odd-offset
+    // pairs read one block further); TMA boxes are at most 256 elements wide.
+    auto pitch_for = [&](int cand) {
+        int pt = cand * PC + L + 2 * V - 1;
+        pt = (pt + V - 1) / V;   // 16-byte units
+        if (!(pt & 1)) ++pt;
+        return pt * V;
+    };
+    int ncg = env_int("B200_TMA_NCG", 4);
+    ncg = ncg < 1 ? 1 : (ncg > 7 ? 7 : ncg);
+    while (ncg > 1 && pitch_for(ncg) > 256) --ncg;
+    const int pitch = pitch_for(ncg);
     if (pitch > 256) return -1;
-    if ((g.n * es) % 16 != 0) return -1;
-    if (g.n >= (1ll << 31) || g.outer >= (1ll << 31)) return -1;
-    if (((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15)) return -1;
+    const int SX = ncg * PC;
+
+    // tile rows: as many as keep 2 CTAs/SM resident (more bytes in flight per
+    // CTA), without exceeding the array
+    int tr = env_int("B200_TMA_TR", 192);
+    tr = (tr + 7) / 8 * 8;
+    tr = tr < 8 ? 8 : (tr > 256 ? 256 : tr);
+    while (tr > 8 && (size_t)tr * pitch * es + 384 > (kSmemPerSm - 2048) / 2) tr -= 8;
+    const int64_t rows8 = (g.outer + 7) / 8 * 8;
+    if (tr > rows8) tr = (int)rows8;
     const int64_t c_tiles = (g.n + SX - 1) / SX;
-    const int64_t r_tiles = (g.outer + TR - 1) / TR;
-    const int64_t grid = c_tiles * r_tiles;
-    if (grid >= (1ll << 31)) return -1;
+    const int64_t r_tiles = (g.outer + tr - 1) / tr;
+    const int64_t num_tiles = c_tiles * r_tiles;
+    if (num_tiles >= (1ll << 31)) return -1;
+    const size_t stage_bytes = (size_t)tr * pitch * es;
 
     CUtensorMap tmap;
     uint64_t dims[2] = {(uint64_t)g.n, (uint64_t)g.outer};
     uint64_t strides[1] = {(uint64_t)g.n * es};
-    uint32_t box[2] = {(uint32_t)pitch, (uint32_t)TR};
+    uint32_t box[2] = {(uint32_t)pitch, (uint32_t)tr};
     if (encode_tensor_map(&tmap, a.dtype, (void *)a.in, 2, dims, strides, box) != 0) return -1;
 
     Corr1dTmaParams<T> p;
     p.in = (const T *)a.in; p.out = (T *)a.out;
     p.outer = g.outer; p.n = g.n; p.inner = 1;
     p.pad_lo = 0; p.pad_hi = 0;
-    p.nw = L; p.lo = L / 2 + a.origin; p.mode = a.mode; p.epilogue = a.epilogue;
-    p.tile_rows = TR; p.smem_rows = TR; p.nb = 1; p.pitch = pitch;
+    p.num_tiles = num_tiles;
+    p.nw = L; p.lo = lo_al; p.mode = a.mode; p.epilogue = a.epilogue;
+    p.tile_rows = tr; p.smem_rows = tr; p.nb = 1; p.pitch = pitch; p.shift = SH; p.ncg = ncg;
+    p.stages = 1; p.stage_elems = (int)(stage_bytes / es);
     p.n_tiles = (int)r_tiles; p.c_tiles = (int)c_tiles;
     p.cval = (T)a.cval;
-    for (int i = 0; i < L; ++i) p.w[i] = (T)a.w[i];
+    for (int i = 0; i < SH; ++i) p.w[i] = T(0);
+    for (int i = 0; i < a.nw; ++i) p.w[SH + i] = (T)a.w[i];
 
-    auto kern = corr1d_contig_tma_kernel<T, TR>;
-    const size_t smem = (size_t)TR * pitch * es + 128;
+    auto kern = corr1d_contig_tma_kernel<T, SH, REM>;
+    const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, 256, smem, a.stream>>>(tmap, p);
+    kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
     note_kernel(sizeof(T) == 4 ? "corr1d_tma_contig_f32" : "corr1d_tma_contig_f64");
     return B200_OK;
+}
+
+template <typename T, int SH>
+static int launch_contig_sh(const Corr1dArgs &a, int lo_al, int L)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    switch (L % V) {
+    case 0: return launch_contig_cfg<T, SH, 0>(a, lo_al, L);
+    case 1: return launch_contig_cfg<T, SH, 1>(a, lo_al, L);
+    case 2: if constexpr (V == 4) return launch_contig_cfg<T, SH, 2>(a, lo_al, L);
+    case 3: if constexpr (V == 4) return launch_contig_cfg<T, SH, 3>(a, lo_al, L);
+    }
+    return -1;
+}
+
+template <typename T>
+static int launch_contig(const Corr1dArgs &a)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    const int es = (int)sizeof(T);
+    const LineGeom &g = a.g;
+    if (a.pad_lo || a.pad_hi) return -1;
+    if ((g.n * es) % 16 != 0) return -1;
+    if (g.n >= (1ll << 31) || g.outer >= (1ll << 31)) return -1;
+    if (((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15)) return -1;
+    // TMA needs the box's innermost start coordinate on a 16-byte boundary
+    // (cp.async.bulk.tensor faults otherwise): start the box `shift` elements
+    // early and skip `shift` leading taps in the kernel instead.
+    const int lo = a.nw / 2 + a.origin;
+    const int lo_al = (lo + V - 1) / V * V;
+    const int shift = lo_al - lo;
+    const int L = a.nw + shift;
+    if (L > kMaxTapsTma) return -1;
+    switch (shift) {
+    case 0: return launch_contig_sh<T, 0>(a, lo_al, L);
+    case 1: return launch_contig_sh<T, 1>(a, lo_al, L);
+    case 2: if constexpr (V == 4) return launch_contig_sh<T, 2>(a, lo_al, L);
+    case 3: if constexpr (V == 4) return launch_contig_sh<T, 3>(a, lo_al, L);
+    }
+    return -1;
 }
 
 int launch_corr1d_tma(const Corr1dArgs &a)
