@@ -103,7 +103,8 @@ struct Corr1dTmaParams {
     int pitch;       // contig: smem row pitch in elements (V * odd)
     int shift;       // contig: leading taps to skip (box start aligned down to 16 bytes)
     int ncg;         // contig: 4*R-column groups per tile
-    int stages;      // smem ring depth (1 or 2)
+    int stages;      // (unused: one tile per CTA)
+    int wide_store;  // contig: rows and base are 32-byte aligned -> 256-bit stores
     int stage_elems; // elements per stage
     int n_tiles, c_tiles;
     T cval;
@@ -280,6 +281,32 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
     }
 }
 
+
+// 32-byte global stores/loads (sm_100 STG.E.256 / LDG.E.256): a contiguous-axis
+// thread owns 8 consecutive floats (4 doubles) of a row; one 256-bit store
+// writes whole 32-byte sectors instead of two half-sector 128-bit stores.
+__device__ __forceinline__ void st_global_256(float *dst, const float (&v)[8])
+{
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void st_global_256(double *dst, const double (&v)[4])
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const float *src, float (&v)[8])
+{
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(src));
+}
+__device__ __forceinline__ void ld_global_256(const double *src, double (&v)[4])
+{
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(src));
+}
+
 // ===========================================================================
 // contiguous-axis pass: one tile per CTA
 // ===========================================================================
@@ -375,7 +402,7 @@ __device__ __forceinline__ void contig_group(Vec<T, V> (&B)[3], ACC &acc, const 
 
 // SH = leading taps to skip (box start aligned down to 16 bytes), REM = taps % V
 template <typename T, int SH, int REM>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T> p)
 {
     constexpr int V = 16 / (int)sizeof(T);
@@ -485,23 +512,41 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         }
 
         if (patch_live && row < nrows) {
+            T *dst0 = p.out + (row * p.n + x);
+            if (p.wide_store && x + R <= p.n) {
+                // whole 32-byte sector(s) in one store
+                T res[R];
+                if (p.epilogue == B200_EPI_STORE) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int64_t xx = x + h * V;
-                if (xx < p.n) {
-                    T *dst = p.out + (row * p.n + xx);
-                    VecT res;
-                    if (p.epilogue == B200_EPI_STORE) {
+                    for (int j = 0; j < R; ++j) res[j] = acc.get(j);
+                } else {
+                    T prev[R];
+                    if (reads_out) ld_global_256(dst0, prev);
 #pragma unroll
-                        for (int v = 0; v < V; ++v) res.v[v] = acc.get(h * V + v);
-                    } else {
-                        VecT prev;
-                        if (reads_out) prev = *reinterpret_cast<const VecT *>(dst);
+                    for (int j = 0; j < R; ++j)
+                        res[j] = apply_epilogue<T>(p.epilogue, reads_out ? prev[j] : T(0), acc.get(j));
+                }
+                st_global_256(dst0, res);
+            } else {
 #pragma unroll
-                        for (int v = 0; v < V; ++v)
-                            res.v[v] = apply_epilogue<T>(p.epilogue, reads_out ? prev.v[v] : T(0), acc.get(h * V + v));
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t xx = x + h * V;
+                    if (xx < p.n) {
+                        T *dst = dst0 + h * V;
+                        VecT res;
+                        if (p.epilogue == B200_EPI_STORE) {
+#pragma unroll
+                            for (int v = 0; v < V; ++v) res.v[v] = acc.get(h * V + v);
+                        } else {
+                            VecT prev;
+                            if (reads_out) prev = *reinterpret_cast<const VecT *>(dst);
+#pragma unroll
+                            for (int v = 0; v < V; ++v)
+                                res.v[v] =
+                                    apply_epilogue<T>(p.epilogue, reads_out ? prev.v[v] : T(0), acc.get(h * V + v));
+                        }
+                        *reinterpret_cast<VecT *>(dst) = res;
                     }
-                    *reinterpret_cast<VecT *>(dst) = res;
                 }
             }
         }
@@ -558,7 +603,7 @@ static int launch_strided_cfg(const Corr1dArgs &a, int nb)
     p.num_tiles = num_tiles;
     p.nw = L; p.lo = L / 2 + a.origin; p.mode = a.mode; p.epilogue = a.epilogue;
     p.tile_rows = tile_rows; p.smem_rows = smem_rows; p.nb = nb; p.pitch = W; p.shift = 0; p.ncg = 0;
-    p.stages = 1; p.stage_elems = (int)(stage_bytes / es);
+    p.stages = 1; p.stage_elems = (int)(stage_bytes / es); p.wide_store = 0;
     p.n_tiles = (int)n_tiles; p.c_tiles = c_tiles;
     p.cval = (T)a.cval;
     for (int i = 0; i < L; ++i) p.w[i] = (T)a.w[i];
@@ -622,19 +667,20 @@ static int launch_contig_cfg(const Corr1dArgs &a, int lo_al, int L)
         if (!(pt & 1)) ++pt;
         return pt * V;
     };
-    int ncg = env_int("B200_TMA_NCG", 4);
+    // Geometry from the B200 sweeps (profiles/): ~42 KB tiles so that 4 CTAs stay
+    // resident per SM; 2 column groups for short filters (taller tiles), 4 for
+    // long ones (less halo re-read per output).
+    int ncg = env_int("B200_TMA_NCG", L <= 24 ? 2 : 4);
     ncg = ncg < 1 ? 1 : (ncg > 7 ? 7 : ncg);
     while (ncg > 1 && pitch_for(ncg) > 256) --ncg;
     const int pitch = pitch_for(ncg);
     if (pitch > 256) return -1;
     const int SX = ncg * PC;
-
-    // tile rows: as many as keep 2 CTAs/SM resident (more bytes in flight per
-    // CTA), without exceeding the array
-    int tr = env_int("B200_TMA_TR", 192);
-    tr = (tr + 7) / 8 * 8;
+    int tr = env_int("B200_TMA_TR", 0);
+    if (tr <= 0) tr = (int)(43 * 1024 / ((size_t)pitch * es));
+    tr = tr / 8 * 8;
     tr = tr < 8 ? 8 : (tr > 256 ? 256 : tr);
-    while (tr > 8 && (size_t)tr * pitch * es + 384 > (kSmemPerSm - 2048) / 2) tr -= 8;
+    while (tr > 8 && (size_t)tr * pitch * es + 512 > kSmemPerSm - 3072) tr -= 8;
     const int64_t rows8 = (g.outer + 7) / 8 * 8;
     if (tr > rows8) tr = (int)rows8;
     const int64_t c_tiles = (g.n + SX - 1) / SX;
@@ -657,6 +703,7 @@ static int launch_contig_cfg(const Corr1dArgs &a, int lo_al, int L)
     p.nw = L; p.lo = lo_al; p.mode = a.mode; p.epilogue = a.epilogue;
     p.tile_rows = tr; p.smem_rows = tr; p.nb = 1; p.pitch = pitch; p.shift = SH; p.ncg = ncg;
     p.stages = 1; p.stage_elems = (int)(stage_bytes / es);
+    p.wide_store = (((g.n * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
     p.n_tiles = (int)r_tiles; p.c_tiles = (int)c_tiles;
     p.cval = (T)a.cval;
     for (int i = 0; i < SH; ++i) p.w[i] = T(0);
