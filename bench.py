@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """Benchmark of the ndfilters hot path (BASELINE.json metric: gaussian_filter
-GVoxels/s on fp32 volumes, % of HBM roofline).
+GVoxels/s on a 2048^3 fp32 volume at 1/2/4/8 B200, % of HBM roofline).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # reference CPU path
+    torchrun --nproc-per-node N bench.py --gpus N ...        # N > 1 (one rank per GPU)
 
-One "step" = one whole gaussian_filter over the synthetic volume (every 1-D
-pass of scipy's chain).  ``value`` is device-resident throughput, ``e2e`` is
-the same call fed from / drained to pinned HOST buffers inside the timed
-region.  Prints exactly one JSON line on rank 0.
+One "step" = one whole ``gaussian_filter`` over the synthetic volume (every 1-D
+pass of scipy's chain; for N > 1 including the NCCL halo exchange).  ``value``
+is device-resident throughput (inputs already in HBM), ``e2e`` is the same
+public call fed from / drained to pinned HOST buffers inside the timed region.
+The volume is the same for every N ("strong" scaling: fixed total work).
+Prints exactly one JSON line on rank 0.
 """
 import argparse
 import json
@@ -27,16 +30,15 @@ if ROOT not in sys.path:
 METRIC = "gaussian_filter_gvoxels_per_s"
 UNIT = "GVoxels/s"
 
-# name -> (per-GPU-or-global shape, sigma, mode, description)
 WORKLOADS = {
-    # BASELINE.json configs[1]
-    "c2": dict(shape=(1024, 1024, 1024), sigma=(4.0, 4.0, 4.0), mode="reflect",
-               desc="gaussian_filter sigma=(4,4,4) mode=reflect on 1024^3 float32"),
-    # SURVEY.md 8(d) headline
+    # BASELINE.json `metric` (SURVEY.md 8(d) headline): fits one B200 (96 GiB)
     "headline": dict(shape=(2048, 2048, 2048), sigma=(2.0, 2.0, 2.0), mode="reflect",
                      desc="gaussian_filter sigma=2 mode=reflect on 2048^3 float32"),
     "headline_s4": dict(shape=(2048, 2048, 2048), sigma=(4.0, 4.0, 4.0), mode="reflect",
                         desc="gaussian_filter sigma=4 mode=reflect on 2048^3 float32"),
+    # BASELINE.json configs[1]
+    "c2": dict(shape=(1024, 1024, 1024), sigma=(4.0, 4.0, 4.0), mode="reflect",
+               desc="gaussian_filter sigma=(4,4,4) mode=reflect on 1024^3 float32"),
     "small": dict(shape=(256, 256, 256), sigma=(2.0, 2.0, 2.0), mode="reflect",
                   desc="gaussian_filter sigma=2 mode=reflect on 256^3 float32 (debug)"),
 }
@@ -49,6 +51,17 @@ def measured_peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic(kernel, voxels_per_launch):
+    """DRAM bytes per launch of ``kernel`` from the committed ncu --set full
+    capture (profiles/traffic.json: bytes per voxel), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            per_voxel = json.load(f)["dram_bytes_per_voxel"][kernel]
+        return float(per_voxel) * voxels_per_launch
+    except Exception:
+        return None
 
 
 # ---------------------------------------------------------------------------
@@ -70,8 +83,9 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.3)          # let the first samples land before the timed region
         except Exception:
             self.proc = None
 
@@ -79,7 +93,7 @@ class ClockSampler:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -113,16 +127,16 @@ class ClockSampler:
 # exactly: halo = ceil(sigma*truncate), boundary "none", trim; verified
 # bit-identical to whole-array scipy in tests/test_oracle.py)
 # ---------------------------------------------------------------------------
-def cpu_reference_run(wl, steps, warmup, target_seconds=12.0):
+def cpu_reference_run(wl, steps, warmup, budget_seconds=60.0):
     import scipy.ndimage as ndi
     from oracle import oracle as orc
 
     cores = len(os.sched_getaffinity(0))
     sigma, mode = wl["sigma"], wl["mode"]
-    # bounded sample of the same workload: a cube sized for ~target_seconds of
-    # CPU work per step at ~0.012 GVox/s/core (SURVEY.md section 6 probes)
+    # bounded sample of the same workload: a cube sized so that warmup + steps
+    # passes of it cost ~budget_seconds at ~0.012 GVox/s/core
     rate = 0.012e9 * cores * (2.0 / max(sigma)) ** 0.5
-    side = int(round((rate * target_seconds / max(1, steps + warmup)) ** (1.0 / 3) / 64.0)) * 64
+    side = int((rate * budget_seconds / max(1, steps + warmup)) ** (1.0 / 3) / 64.0) * 64
     side = int(min(max(side, 128), min(wl["shape"])))
     chunk = max(64, side // 4) if cores > 1 else side
     rng = np.random.default_rng(1234)
@@ -170,9 +184,11 @@ def run_b200(args, wl, rank, world, local_rank):
 
     import dask_image_b200 as b200
     from dask_image_b200 import _lib, ndimage
+    from dask_image_b200.sharded import ShardedVolume, slab_bounds
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
 
@@ -180,30 +196,23 @@ def run_b200(args, wl, rank, world, local_rank):
     shape = tuple(wl["shape"])
     sigma, mode = wl["sigma"], wl["mode"]
     voxels = int(np.prod(shape))
+    warmup = max(args.warmup, 3)
 
-    if world > 1:
-        from dask_image_b200.sharded import ShardedVolume
+    def barrier():
+        if dist is not None:
+            dist.barrier()
 
-        vol = ShardedVolume.random(shape, np.float32, seed=1234)
-        def step():
-            return b200.ndfilters.gaussian_filter(vol, sigma, mode=mode)
-        barrier = dist.barrier
-    else:
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(1234)
-        x = b200.B200Array(torch.rand(shape, dtype=torch.float32, device=dev, generator=gen))
-        out = x.empty_like()
-        scratch = []
+    # ---- device-resident: the public call on a (sharded) resident volume ---
+    halo = max(int(4.0 * s + 0.5) for s in sigma)
+    vol = ShardedVolume.random(shape, np.float32, seed=1234, device=dev, halo=halo)
+    res = None
 
-        def step():
-            passes = ndimage._gaussian_passes(3, sigma, 0, mode, 4.0)
-            ndimage._run_chain(x.tensor, x.shape, x.dtype, passes, 0.0, out.tensor, scratch=scratch)
-            return out
+    def step():
+        nonlocal res
+        res = None                      # release the previous result first
+        res = b200.ndfilters.gaussian_filter(vol, sigma, mode=mode)
 
-        def barrier():
-            return None
-
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     barrier()
@@ -223,76 +232,89 @@ def run_b200(args, wl, rank, world, local_rank):
     launches = _lib.launch_count()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
+    if dist is not None:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
     ms_per_step = ms / args.steps
     value = voxels / (ms_per_step * 1e-3) / 1e9
 
-    # ---- per-kernel timing for the roofline (single GPU, same buffers) ------
-    roofline = None
-    passes_info = []
-    if world == 1:
-        passes = ndimage._gaussian_passes(3, sigma, 0, mode, 4.0)
-        per_pass = []
-        for pi, ps in enumerate(passes):
-            src, dst = x.tensor, out.tensor      # timing only: contents do not matter
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-            ndimage._launch_correlate1d(src, dst, x.shape, x.dtype, ps.axis, ps.weights, ps.mode, 0.0, 0)
-            torch.cuda.synchronize()
-            evs[0].record()
-            for k in range(args.steps):
-                ndimage._launch_correlate1d(src, dst, x.shape, x.dtype, ps.axis, ps.weights, ps.mode, 0.0, 0)
-                evs[k + 1].record()
-            torch.cuda.synchronize()
-            t = np.mean([evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)])
-            per_pass.append((_lib.last_kernel(), ps.axis, len(ps.weights), float(t)))
-        peak, peak_src = measured_peaks()
-        alg_bytes = 2 * 4 * voxels           # one read + one write of the f32 volume per pass
-        by_kernel = {}
-        for name, ax, taps, t in per_pass:
-            by_kernel.setdefault(name, []).append(t)
-            passes_info.append({"kernel": name, "axis": ax, "taps": taps, "ms": t,
-                                "gb_s": alg_bytes / (t * 1e-3) / 1e9})
-        dom = max(by_kernel, key=lambda k: sum(by_kernel[k]))
-        t_dom = float(np.mean(by_kernel[dom]))
-        achieved = alg_bytes / (t_dom * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "frac_of_8000": achieved / 8000.0, "traffic": None,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                    "launch_ms": t_dom}
+    # ---- per-kernel launch durations (CUDA events, same stream, same slab) --
+    n_loc = vol.n_local
+    lshape = (n_loc,) + shape[1:]
+    lvox = int(np.prod(lshape))
+    x_t, out_t = vol.local, res.local
+    passes = ndimage._gaussian_passes(3, sigma, 0, mode, 4.0)
+    per_pass = []
+    for ps in passes:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        ndimage._launch_correlate1d(x_t, out_t, lshape, np.dtype(np.float32), ps.axis, ps.weights, ps.mode, 0.0, 0)
+        torch.cuda.synchronize()
+        evs[0].record()
+        for k in range(args.steps):
+            ndimage._launch_correlate1d(x_t, out_t, lshape, np.dtype(np.float32), ps.axis, ps.weights, ps.mode,
+                                        0.0, 0)
+            evs[k + 1].record()
+        torch.cuda.synchronize()
+        t = float(np.mean([evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]))
+        per_pass.append((_lib.last_kernel(), ps.axis, len(ps.weights), t))
+    peak, peak_src = measured_peaks()
+    alg_bytes = 2 * 4 * lvox               # one read + one write of the f32 slab per pass
+    by_kernel, passes_info = {}, []
+    for name, ax, taps, t in per_pass:
+        by_kernel.setdefault(name, []).append(t)
+        passes_info.append({"kernel": name, "axis": ax, "taps": taps, "ms": t,
+                            "gb_s": alg_bytes / (t * 1e-3) / 1e9})
+    dom = max(by_kernel, key=lambda k: sum(by_kernel[k]))
+    t_dom = float(np.mean(by_kernel[dom]))
+    achieved = alg_bytes / (t_dom * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "frac_of_8000": achieved / 8000.0,
+                "traffic": measured_traffic(dom, lvox), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": t_dom,
+                "launches_per_step": {k: len(v) for k, v in by_kernel.items()},
+                "kernel_share_of_step": sum(by_kernel[dom]) / sum(t for _, _, _, t in per_pass)}
 
-    # ---- end to end: pinned host in -> device -> filter -> pinned host out ---
+    # ---- end to end: pinned host in -> device -> public call -> pinned host out
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if not args.no_e2e:
         try:
-            h_in = torch.empty(shape, dtype=torch.float32).pin_memory()
-            h_out = torch.empty(shape, dtype=torch.float32).pin_memory()
-            h_in.copy_(x.tensor)          # realistic content
-            torch.cuda.synchronize()
+            s0, s1 = slab_bounds(shape[0], world)[rank]
+            h_in = torch.empty(lshape, dtype=torch.float32).pin_memory()
+            h_out = torch.empty(lshape, dtype=torch.float32).pin_memory()
+            h_in.copy_(vol.local)                     # realistic content
+            res = None
+            vol = None
+            x_t = out_t = None
+            torch.cuda.empty_cache()
 
             def e2e_step():
-                d_in = b200.B200Array(h_in.to(dev, non_blocking=True))
-                res = b200.ndfilters.gaussian_filter(d_in, sigma, mode=mode)
-                h_out.copy_(res.tensor, non_blocking=True)
+                d = ShardedVolume.empty(shape, np.float32, device=dev, halo=halo)
+                d.local.copy_(h_in, non_blocking=True)
+                r = b200.ndfilters.gaussian_filter(d, sigma, mode=mode)
+                h_out.copy_(r.local, non_blocking=True)
 
-            # free the device-resident buffers of the first measurement
             e2e_step()
             torch.cuda.synchronize()
+            barrier()
             n_e2e = max(1, min(args.steps, 5))
             t0 = time.perf_counter()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
             for _ in range(n_e2e):
                 e2e_step()
-            a1.record()
             torch.cuda.synchronize()
-            wall = (time.perf_counter() - t0) / n_e2e
-            dev_ms = a0.elapsed_time(a1) / n_e2e
-            t_e2e = max(wall, dev_ms * 1e-3)
+            barrier()
+            t_e2e = (time.perf_counter() - t0) / n_e2e
+            if dist is not None:
+                t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                t_e2e = float(t.item())
             e2e = {"value": voxels / t_e2e / 1e9, "unit": UNIT, "h2d_bytes_per_step": voxels * 4,
-                   "d2h_bytes_per_step": voxels * 4, "ms_per_step": t_e2e * 1e3, "steps": n_e2e}
+                   "d2h_bytes_per_step": voxels * 4, "ms_per_step": t_e2e * 1e3, "steps": n_e2e,
+                   "how": "pinned host slab -> H2D -> ndfilters.gaussian_filter -> D2H into pinned host, "
+                          "wall clock with device sync, max over ranks"}
         except Exception as exc:  # e.g. not enough pinnable host memory
             e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:200]}
 
@@ -300,18 +322,20 @@ def run_b200(args, wl, rank, world, local_rank):
         return
     cpu = None
     if world == 1 and not args.no_cpu:
-        gv, dt, cores, sample = cpu_reference_run(wl, 1, 1)
+        gv, dt, cores, sample = cpu_reference_run(wl, 1, 1, budget_seconds=25.0)
         cpu = {"value": gv, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "shape": list(shape), "sigma": list(sigma), "mode": mode,
-                   "passes": 3, "l2": "inputs (%.1f GiB) larger than L2; no flush needed" % (voxels * 4 / 2 ** 30),
-                   "decomposition": "axis-0 slabs, NCCL halo exchange" if world > 1 else "single GPU"},
+                   "passes": len(passes),
+                   "l2": "per-GPU slab (%.1f GiB) larger than L2; no flush needed" % (lvox * 4 / 2 ** 30),
+                   "decomposition": ("axis-0 slabs (%d planes/GPU), NCCL send/recv halo exchange overlapped "
+                                     "with interior compute" % n_loc) if world > 1 else "single GPU"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "passes": passes_info,
-        "op_level_roofline_frac": (24.0 * voxels / (ms_per_step * 1e-3) / 1e9) / measured_peaks()[0],
+        "op_level_roofline_frac": (8.0 * len(passes) * voxels / world / (ms_per_step * 1e-3) / 1e9) / peak,
     }
     print(json.dumps(line))
 
@@ -329,7 +353,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = WORKLOADS[args.workload or os.environ.get("B200_BENCH_WORKLOAD", "c2")]
+    wl = WORKLOADS[args.workload or os.environ.get("B200_BENCH_WORKLOAD", "headline")]
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
     else:

@@ -6,5 +6,6 @@ and an NCCL slab engine replacing ``map_overlap`` for multi-GPU volumes."""
 from ._array import B200Array, as_b200  # noqa: F401
 from . import ndimage, ndfilters, dispatch  # noqa: F401
 from ._overlap import HaloChunked, from_array  # noqa: F401
+from .sharded import ShardedVolume  # noqa: F401
 
 __version__ = "0.1.0"

@@ -87,16 +87,21 @@ __host__ __device__ __forceinline__ int64_t ext_index(int64_t i, int64_t n, int 
     }
 }
 
-// Same map, but positions inside the resident halo [-pad_lo, n + pad_hi) are
-// returned unchanged (they address real neighbour planes, possibly negative).
-// Returns INT64_MIN for "use cval".
+// Slab form of the same map.  `pad_lo` / `pad_hi` real planes of the global
+// volume are resident directly before / after the n planes this call produces
+// output for, so the RESIDENT range is [-pad_lo, n + pad_hi).  Positions inside
+// it are returned unchanged (possibly negative: they address neighbour planes);
+// positions outside are folded by `mode` at the ends of the resident range --
+// on an end slab that end is the global volume's boundary, on every other slab
+// it is never reached (the pads cover the filter's reach).  pad_lo = pad_hi = 0
+// is exactly ext_index().  Returns B200_USE_CVAL for "use cval".
 #define B200_USE_CVAL INT64_MIN
 __host__ __device__ __forceinline__ int64_t ext_index_padded(int64_t i, int64_t n, int mode,
                                                             int64_t pad_lo, int64_t pad_hi)
 {
     if (i >= -pad_lo && i < n + pad_hi) return i;
-    int64_t s = ext_index(i, n, mode);
-    return s < 0 ? B200_USE_CVAL : s;
+    int64_t s = ext_index(i + pad_lo, n + pad_lo + pad_hi, mode);
+    return s < 0 ? B200_USE_CVAL : s - pad_lo;
 }
 
 // ---------------------------------------------------------------------------

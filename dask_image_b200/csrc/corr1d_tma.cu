@@ -761,9 +761,9 @@ static int launch_contig(const Corr1dArgs &a)
 
 int launch_corr1d_tma(const Corr1dArgs &a)
 {
-    const int64_t total = a.g.outer * a.g.n * a.g.inner;
-    // tiny arrays: one generic launch is as good, and keeps odd shapes simple
-    if (!(a.flags & B200_FLAG_FORCE_FAST) && total < (1 << 16)) return -1;
+    // NB the choice of kernel family must not depend on the number of planes
+    // of the call: slabs of one volume (any GPU count) have to take the same
+    // arithmetic path so that the whole-volume result is partition-invariant.
     if (a.dtype == B200_F32)
         return a.g.inner == 1 ? launch_contig<float>(a) : launch_strided<float>(a);
     if (a.dtype == B200_F64)

@@ -12,6 +12,7 @@ tables too, so unmodified ``dask_image.ndfilters.*`` calls route ``B200Array``
 chunks to the CUDA kernels.
 """
 from .. import ndimage as _b200_ndimage
+from .. import sharded as _b200_sharded
 from .._array import B200Array
 from ._dispatcher import Dispatcher
 
@@ -48,6 +49,8 @@ def register_b200(dispatchers):
         d = dispatchers.get(name)
         if d is not None:
             d.register(B200Array)(_factory(getattr(_b200_ndimage, name)))
+            # a whole multi-GPU volume: the slab engine plays map_overlap's part
+            d.register(_b200_sharded.ShardedVolume)(_factory(_b200_sharded.FUNCTIONS[name]))
 
 
 _OWN = {n: globals()["dispatch_" + n] for n in _NAMES}

@@ -144,14 +144,12 @@ def _map_chunks(image, dispatcher, depth, boundary, **kwargs):
 
     * dask arrays (anything with ``map_overlap``): exactly the reference's call,
       e.g. dask_image/ndfilters/_gaussian.py:70-81 -- dask assembles halos.
-    * ``ShardedVolume``: the NCCL slab engine assembles axis-0 halos instead.
+    * ``ShardedVolume``: the dispatcher returns the slab-engine function
+      (sharded.py), which exchanges axis-0 halo planes over NCCL instead.
     * a bare ``B200Array`` is one chunk: the chunk function is applied directly
       (``map_overlap`` on a single chunk with ``boundary="none"`` adds nothing).
     """
     if hasattr(image, "map_overlap"):
         return image.map_overlap(dispatcher(image), depth=depth, boundary=boundary,
                                  dtype=image.dtype, meta=image._meta, **kwargs)
-    func = dispatcher(image)
-    if hasattr(image, "_run_sharded"):
-        return image._run_sharded(func.__name__, **kwargs)
-    return func(image, **kwargs)
+    return dispatcher(image)(image, **kwargs)

@@ -226,21 +226,32 @@ class _Pass:
         self.weights, self.size, self.origin = weights, size, origin
 
 
+def _chain_targets(n_passes, epilogue):
+    """Destination of every pass of a chain: ``"out"`` or a scratch index.
+    The last pass lands in the output.  When the final epilogue does not read
+    the output (store / square-store) the intermediate passes ping-pong between
+    the output and ONE scratch volume; an accumulating epilogue needs the
+    output intact, so they ping-pong between two scratch volumes instead."""
+    if epilogue in (_lib.EPI_STORE, _lib.EPI_SQ_STORE):
+        return ["out" if (n_passes - 1 - i) % 2 == 0 else 0 for i in range(n_passes)]
+    return [i % 2 for i in range(n_passes - 1)] + ["out"]
+
+
 def _run_chain(x_tensor, shape, np_dtype, passes, cval, out_tensor, final_epilogue=_lib.EPI_STORE,
                pad=(0, 0), scratch=None, flags=None):
-    """Run 1-D passes in order (input -> s0 -> s1 -> ... -> out), never writing
-    the input; the last pass applies ``final_epilogue`` into ``out_tensor``.
-    ``pad`` describes axis-0 halo planes around ``x_tensor`` (slab engine) and
-    only the first pass may consume it -- later passes read scratch buffers
-    that hold the slab interior only."""
+    """Run 1-D passes in order (input -> ... -> out), never writing the input;
+    the last pass applies ``final_epilogue`` into ``out_tensor``.  ``pad``
+    describes axis-0 halo planes around ``x_tensor`` and only the first pass
+    may consume it -- later passes read buffers that hold the interior only."""
     scratch = scratch if scratch is not None else []
     src, src_pad = x_tensor, pad
+    targets = _chain_targets(len(passes), final_epilogue)
     for i, ps in enumerate(passes):
         last = i == len(passes) - 1
-        if last:
+        if targets[i] == "out":
             dst = out_tensor
         else:
-            k = i % 2
+            k = targets[i]
             while len(scratch) <= k:
                 scratch.append(torch.empty(tuple(shape), dtype=out_tensor.dtype,
                                            device=out_tensor.device))
@@ -292,25 +303,56 @@ def _check_axes(axes, ndim):
     return tuple(out)
 
 
-def gaussian_filter(input, sigma, order=0, output=None, mode="reflect", cval=0.0, truncate=4.0,
-                    *, radius=None, axes=None):
-    """scipy.ndimage.gaussian_filter (scipy/ndimage/_filters.py:758-862)."""
-    x = as_b200(input)
-    _zero_dim_guard(x)
-    passes = _gaussian_passes(x.ndim, sigma, order, mode, truncate, radius, axes)
-    out = _check_output(output, x) or x.empty_like()
-    if not passes or x.size == 0:
+class _Plan:
+    """What one public filter call decomposes into -- shared by the single
+    array executor below and the multi-GPU slab engine (sharded.py):
+
+    * ``chains``: list of ``(passes, epilogue)``; every chain starts from the
+      INPUT, runs its 1-D passes in order and folds its result into the output
+      with ``epilogue`` (fused into the chain's last pass).  An empty list is
+      the identity (scipy skips every axis); an empty ``passes`` folds the
+      input itself.
+    * ``nd``: ``(weights, origins, mode)`` of a direct N-D correlate instead.
+    * ``zero_out``: clear the output first (1-axis gradient magnitude).
+    """
+    __slots__ = ("chains", "nd", "cval", "zero_out")
+
+    def __init__(self, chains=(), nd=None, cval=0.0, zero_out=False):
+        self.chains, self.nd, self.cval, self.zero_out = list(chains), nd, cval, zero_out
+
+
+def _execute(plan, x, out):
+    """Run ``plan`` on one resident array: x (B200Array) -> out (B200Array)."""
+    if x.size == 0:
+        return out
+    if plan.nd is not None:
+        w, origins, mode = plan.nd
+        _launch_correlate_nd(x.tensor, out.tensor, x.shape, x.dtype, w, origins, mode, plan.cval)
+        return out
+    if not plan.chains:
         out.tensor.copy_(x.tensor)
         return out
-    _run_chain(x.tensor, x.shape, x.dtype, passes, cval, out.tensor)
+    if plan.zero_out:
+        out.tensor.zero_()
+    scratch = []
+    for passes, op in plan.chains:
+        if passes:
+            scratch = _run_chain(x.tensor, x.shape, x.dtype, passes, plan.cval, out.tensor,
+                                 final_epilogue=op, scratch=scratch)
+        else:
+            # all sigmas ~ 0: the "derivative" is the input itself
+            _launch_combine(out.tensor, x.tensor, x.dtype, op)
     return out
 
 
-def uniform_filter(input, size=3, output=None, mode="reflect", cval=0.0, origin=0, *, axes=None):
-    """scipy.ndimage.uniform_filter (scipy/ndimage/_filters.py:1553-1622)."""
-    x = as_b200(input)
-    _zero_dim_guard(x)
-    axes = _check_axes(axes, x.ndim)
+def _plan_gaussian_filter(ndim, sigma, order=0, mode="reflect", cval=0.0, truncate=4.0,
+                          radius=None, axes=None):
+    passes = _gaussian_passes(ndim, sigma, order, mode, truncate, radius, axes)
+    return _Plan([(passes, _lib.EPI_STORE)] if passes else [], cval=cval)
+
+
+def _plan_uniform_filter(ndim, size=3, mode="reflect", cval=0.0, origin=0, axes=None):
+    axes = _check_axes(axes, ndim)
     k = len(axes)
     sizes, origins, modes = _per_axis(size, k), _per_axis(origin, k), _per_axis(mode, k)
     passes = []
@@ -321,12 +363,106 @@ def uniform_filter(input, size=3, output=None, mode="reflect", cval=0.0, origin=
                 raise ValueError("invalid origin")
             _lib.mode_code(modes[i])
             passes.append(_Pass("uniform", ax, modes[i], size=sz, origin=og))
+    return _Plan([(passes, _lib.EPI_STORE)] if passes else [], cval=cval)
+
+
+def _derivative_kwargs(kwargs):
+    truncate = kwargs.pop("truncate", 4.0)
+    radius = kwargs.pop("radius", None)
+    if kwargs:
+        raise TypeError("unexpected keyword arguments: %s" % sorted(kwargs))
+    return truncate, radius
+
+
+def _plan_gaussian_gradient_magnitude(ndim, sigma, mode="reflect", cval=0.0, axes=None, **kwargs):
+    truncate, radius = _derivative_kwargs(kwargs)
+    axes = _check_axes(axes, ndim)
+    if len(axes) != ndim:
+        raise NotImplementedError("axes subsets are not supported (the reference never passes them)")
+    modes = _per_axis(mode, len(axes))
+    sigmas = _per_axis(sigma, len(axes))
+    chains = []
+    for i, ax in enumerate(axes):
+        order = [0] * len(axes)
+        order[i] = 1
+        passes = _gaussian_passes(ndim, sigmas, order, modes[i], truncate, radius, axes)
+        if len(axes) == 1 or i == len(axes) - 1:
+            op = _lib.EPI_SQ_ACC_SQRT
+        elif i == 0:
+            op = _lib.EPI_SQ_STORE
+        else:
+            op = _lib.EPI_SQ_ACC
+        chains.append((passes, op))
+    return _Plan(chains, cval=cval, zero_out=len(axes) == 1)
+
+
+def _plan_gaussian_laplace(ndim, sigma, mode="reflect", cval=0.0, axes=None, **kwargs):
+    truncate, radius = _derivative_kwargs(kwargs)
+    axes = _check_axes(axes, ndim)
+    if len(axes) != ndim:
+        raise NotImplementedError("axes subsets are not supported (the reference never passes them)")
+    modes = _per_axis(mode, len(axes))
+    sigmas = _per_axis(sigma, len(axes))
+    chains = []
+    for i, ax in enumerate(axes):
+        order = [0] * len(axes)
+        order[i] = 2
+        passes = _gaussian_passes(ndim, sigmas, order, modes[i], truncate, radius, axes)
+        chains.append((passes, _lib.EPI_STORE if i == 0 else _lib.EPI_ACC))
+    return _Plan(chains, cval=cval)
+
+
+def _plan_laplace(ndim, mode="reflect", cval=0.0, axes=None):
+    axes = _check_axes(axes, ndim)
+    modes = _per_axis(mode, len(axes))
+    chains = [([_Pass("corr", ax, modes[i], weights=np.array([1.0, -2.0, 1.0]))],
+               _lib.EPI_STORE if i == 0 else _lib.EPI_ACC) for i, ax in enumerate(axes)]
+    return _Plan(chains, cval=cval)
+
+
+def _plan_edge(ndim, axis, mode, cval, smooth):
+    axis = _axis_index(axis, ndim)
+    modes = _per_axis(mode, ndim)
+    passes = [_Pass("corr", axis, modes[axis], weights=np.array([-1.0, 0.0, 1.0]))]
+    for ax in range(ndim):
+        if ax != axis:
+            passes.append(_Pass("corr", ax, modes[ax], weights=np.array(smooth, dtype=np.float64)))
+    return _Plan([(passes, _lib.EPI_STORE)], cval=cval)
+
+
+def _plan_prewitt(ndim, axis=-1, mode="reflect", cval=0.0):
+    return _plan_edge(ndim, axis, mode, cval, [1.0, 1.0, 1.0])
+
+
+def _plan_sobel(ndim, axis=-1, mode="reflect", cval=0.0):
+    return _plan_edge(ndim, axis, mode, cval, [1.0, 2.0, 1.0])
+
+
+def _plan_correlate_nd(ndim, np_dtype, weights, mode="reflect", cval=0.0, origin=0, convolution=False):
+    if not isinstance(mode, str) and np.iterable(mode):
+        raise RuntimeError("A sequence of modes is not supported")
+    w, origins = _prepare_nd_weights(ndim, np_dtype, weights, origin, convolution)
+    _lib.mode_code(mode)
+    return _Plan(nd=(w, origins, mode), cval=cval)
+
+
+def _run(plan_fn, input, output, *args, **kwargs):
+    x = as_b200(input)
+    _zero_dim_guard(x)
+    plan = plan_fn(x.ndim, *args, **kwargs)
     out = _check_output(output, x) or x.empty_like()
-    if not passes or x.size == 0:
-        out.tensor.copy_(x.tensor)
-        return out
-    _run_chain(x.tensor, x.shape, x.dtype, passes, cval, out.tensor)
-    return out
+    return _execute(plan, x, out)
+
+
+def gaussian_filter(input, sigma, order=0, output=None, mode="reflect", cval=0.0, truncate=4.0,
+                    *, radius=None, axes=None):
+    """scipy.ndimage.gaussian_filter (scipy/ndimage/_filters.py:758-862)."""
+    return _run(_plan_gaussian_filter, input, output, sigma, order, mode, cval, truncate, radius, axes)
+
+
+def uniform_filter(input, size=3, output=None, mode="reflect", cval=0.0, origin=0, *, axes=None):
+    """scipy.ndimage.uniform_filter (scipy/ndimage/_filters.py:1553-1622)."""
+    return _run(_plan_uniform_filter, input, output, size, mode, cval, origin, axes)
 
 
 # --------------------------------------------------------------------------
@@ -340,20 +476,20 @@ def _weights_to_host(weights):
     return np.asarray(weights)
 
 
-def _prepare_nd_weights(x, weights, origin, convolution):
+def _prepare_nd_weights(ndim, np_dtype, weights, origin, convolution):
     """scipy/ndimage/_filters.py:1271-1292: float64 weights; for convolution
     flip every axis and negate origins (one more on even-length axes)."""
     w = _weights_to_host(weights)
-    if w.dtype.kind == "c" or x.dtype.kind == "c":
+    if w.dtype.kind == "c" or np_dtype.kind == "c":
         raise RuntimeError("complex data is not supported")
     w = np.asarray(w, dtype=np.float64)
     wshape = [s for s in w.shape if s > 0]
-    if len(wshape) != x.ndim or w.ndim != x.ndim:
-        raise RuntimeError("weights.ndim (%d) must match len(axes) (%d)" % (len(wshape), x.ndim))
-    origins = [int(o) for o in _per_axis(origin, x.ndim)]
+    if len(wshape) != ndim or w.ndim != ndim:
+        raise RuntimeError("weights.ndim (%d) must match len(axes) (%d)" % (len(wshape), ndim))
+    origins = [int(o) for o in _per_axis(origin, ndim)]
     if convolution:
         w = w[tuple([slice(None, None, -1)] * w.ndim)]
-        for i in range(x.ndim):
+        for i in range(ndim):
             origins[i] = -origins[i]
             if not w.shape[i] & 1:
                 origins[i] -= 1
@@ -367,12 +503,9 @@ def _prepare_nd_weights(x, weights, origin, convolution):
 def _correlate_or_convolve(input, weights, output, mode, cval, origin, convolution):
     x = as_b200(input)
     _zero_dim_guard(x)
-    if not isinstance(mode, str) and np.iterable(mode):
-        raise RuntimeError("A sequence of modes is not supported")
-    w, origins = _prepare_nd_weights(x, weights, origin, convolution)
+    plan = _plan_correlate_nd(x.ndim, x.dtype, weights, mode, cval, origin, convolution)
     out = _check_output(output, x) or x.empty_like()
-    _launch_correlate_nd(x.tensor, out.tensor, x.shape, x.dtype, w, origins, mode, cval)
-    return out
+    return _execute(plan, x, out)
 
 
 def correlate(input, weights, output=None, mode="reflect", cval=0.0, origin=0):
@@ -388,83 +521,18 @@ def convolve(input, weights, output=None, mode="reflect", cval=0.0, origin=0):
 # --------------------------------------------------------------------------
 # derivative compositions
 # --------------------------------------------------------------------------
-def _combine_chains(x, chains, ops, cval, output):
-    """Run one pass chain per entry, folding each chain's result into the
-    output with the matching epilogue (fused into the chain's last pass)."""
-    out = _check_output(output, x) or x.empty_like()
-    scratch = []
-    for passes, op in zip(chains, ops):
-        if passes:
-            scratch = _run_chain(x.tensor, x.shape, x.dtype, passes, cval, out.tensor,
-                                 final_epilogue=op, scratch=scratch)
-        else:
-            # all sigmas ~ 0: the "derivative" is the input itself
-            _launch_combine(out.tensor, x.tensor, x.dtype, op)
-    return out
-
-
 def gaussian_gradient_magnitude(input, sigma, output=None, mode="reflect", cval=0.0, *,
                                 axes=None, **kwargs):
     """scipy.ndimage.gaussian_gradient_magnitude (scipy/ndimage/_filters.py:1142-1250):
     sqrt(sum_a gaussian_filter(order = e_a)^2), squares/adds/sqrt in the array
     dtype; fused here as epilogues of the last pass of each chain."""
-    x = as_b200(input)
-    _zero_dim_guard(x)
-    truncate = kwargs.pop("truncate", 4.0)
-    radius = kwargs.pop("radius", None)
-    if kwargs:
-        raise TypeError("unexpected keyword arguments: %s" % sorted(kwargs))
-    axes = _check_axes(axes, x.ndim)
-    if len(axes) != x.ndim:
-        raise NotImplementedError("axes subsets are not supported (the reference never passes them)")
-    if x.size == 0:
-        out = _check_output(output, x) or x.empty_like()
-        return out
-    modes = _per_axis(mode, len(axes))
-    sigmas = _per_axis(sigma, len(axes))
-    chains, ops = [], []
-    for i, ax in enumerate(axes):
-        order = [0] * len(axes)
-        order[i] = 1
-        chains.append(_gaussian_passes(x.ndim, sigmas, order, modes[i], truncate, radius, axes))
-        if len(axes) == 1:
-            ops.append(_lib.EPI_SQ_ACC_SQRT)
-        elif i == 0:
-            ops.append(_lib.EPI_SQ_STORE)
-        elif i == len(axes) - 1:
-            ops.append(_lib.EPI_SQ_ACC_SQRT)
-        else:
-            ops.append(_lib.EPI_SQ_ACC)
-    out = _check_output(output, x) or x.empty_like()
-    if len(axes) == 1:
-        out.tensor.zero_()
-    return _combine_chains(x, chains, ops, cval, out)
+    return _run(_plan_gaussian_gradient_magnitude, input, output, sigma, mode, cval, axes, **kwargs)
 
 
 def gaussian_laplace(input, sigma, output=None, mode="reflect", cval=0.0, *, axes=None, **kwargs):
     """scipy.ndimage.gaussian_laplace (scipy/ndimage/_filters.py:984-1030,1075-1139):
     sum_a gaussian_filter(order = 2 e_a)."""
-    x = as_b200(input)
-    _zero_dim_guard(x)
-    truncate = kwargs.pop("truncate", 4.0)
-    radius = kwargs.pop("radius", None)
-    if kwargs:
-        raise TypeError("unexpected keyword arguments: %s" % sorted(kwargs))
-    axes = _check_axes(axes, x.ndim)
-    if len(axes) != x.ndim:
-        raise NotImplementedError("axes subsets are not supported (the reference never passes them)")
-    if x.size == 0:
-        out = _check_output(output, x) or x.empty_like()
-        return out
-    modes = _per_axis(mode, len(axes))
-    sigmas = _per_axis(sigma, len(axes))
-    chains, ops = [], []
-    for i, ax in enumerate(axes):
-        order = [0] * len(axes)
-        order[i] = 2
-        chains.append(_gaussian_passes(x.ndim, sigmas, order, modes[i], truncate, radius, axes))
-        ops.append(_lib.EPI_STORE if i == 0 else _lib.EPI_ACC)
-    return _combine_chains(x, chains, ops, cval, output)
+    return _run(_plan_gaussian_laplace, input, output, sigma, mode, cval, axes, **kwargs)
 
 
 # --------------------------------------------------------------------------
@@ -473,41 +541,16 @@ def gaussian_laplace(input, sigma, output=None, mode="reflect", cval=0.0, *, axe
 def laplace(input, output=None, mode="reflect", cval=0.0, *, axes=None):
     """scipy.ndimage.laplace (scipy/ndimage/_filters.py:1037-1071): sum over
     axes of correlate1d with [1, -2, 1]."""
-    x = as_b200(input)
-    _zero_dim_guard(x)
-    axes = _check_axes(axes, x.ndim)
-    if not axes or x.size == 0:
-        out = _check_output(output, x) or x.empty_like()
-        out.tensor.copy_(x.tensor)
-        return out
-    modes = _per_axis(mode, len(axes))
-    chains = [[_Pass("corr", ax, modes[i], weights=np.array([1.0, -2.0, 1.0]))]
-              for i, ax in enumerate(axes)]
-    ops = [_lib.EPI_STORE if i == 0 else _lib.EPI_ACC for i in range(len(axes))]
-    return _combine_chains(x, chains, ops, cval, output)
-
-
-def _edge_filter(input, axis, output, mode, cval, smooth):
-    """prewitt / sobel (scipy/ndimage/_filters.py:865-982): [-1,0,1] along
-    ``axis`` then ``smooth`` along every other axis, in axis order."""
-    x = as_b200(input)
-    _zero_dim_guard(x)
-    axis = _axis_index(axis, x.ndim)
-    modes = _per_axis(mode, x.ndim)
-    passes = [_Pass("corr", axis, modes[axis], weights=np.array([-1.0, 0.0, 1.0]))]
-    for ax in range(x.ndim):
-        if ax != axis:
-            passes.append(_Pass("corr", ax, modes[ax], weights=np.array(smooth, dtype=np.float64)))
-    out = _check_output(output, x) or x.empty_like()
-    if x.size == 0:
-        return out
-    _run_chain(x.tensor, x.shape, x.dtype, passes, cval, out.tensor)
-    return out
+    return _run(_plan_laplace, input, output, mode, cval, axes)
 
 
 def prewitt(input, axis=-1, output=None, mode="reflect", cval=0.0):
-    return _edge_filter(input, axis, output, mode, cval, [1.0, 1.0, 1.0])
+    """scipy.ndimage.prewitt (scipy/ndimage/_filters.py:865-921): [-1,0,1] along
+    ``axis`` then [1,1,1] along every other axis, in axis order."""
+    return _run(_plan_prewitt, input, output, axis, mode, cval)
 
 
 def sobel(input, axis=-1, output=None, mode="reflect", cval=0.0):
-    return _edge_filter(input, axis, output, mode, cval, [1.0, 2.0, 1.0])
+    """scipy.ndimage.sobel (scipy/ndimage/_filters.py:924-982): as prewitt with
+    [1,2,1] smoothing."""
+    return _run(_plan_sobel, input, output, axis, mode, cval)

@@ -1,0 +1,478 @@
+"""Multi-GPU slab engine: ``ShardedVolume`` + halo exchange over NCCL.
+
+This replaces the step dask performs around the reference's per-chunk calls --
+``image.map_overlap(func, depth, boundary)`` (dask_image/ndfilters/_gaussian.py:70-81,
+_smooth.py:28-38, _conv.py:27-37: cut into chunks, attach ``depth`` voxels of
+every neighbour, run ``func``, trim) -- for the GPUs of one 8xB200 box:
+
+* one process per GPU (``torch.distributed``, backend ``nccl``); the volume is
+  cut into contiguous slabs along axis 0, ``N0 / G`` planes per rank;
+* only passes that filter along axis 0 (and the N-D correlate) read across slab
+  faces.  Before such a pass the ``lo`` planes below and ``hi`` planes above the
+  slab are fetched from the two axis-0 neighbours with one grouped
+  ``ncclSend``/``ncclRecv`` exchange (``mode='wrap'`` closes the ring, which is
+  the reference's ``boundary="periodic"`` rewrite, _conv.py:23-25).  Faces are
+  contiguous ``depth x N1 x N2`` blocks and are received straight into the pad
+  planes that every slab buffer carries in front of / behind its interior: no
+  pack/unpack kernels, no trim copies;
+* the exchange overlaps compute: planes whose window lies inside the slab are
+  filtered while the faces are in flight, the ``lo + hi`` edge planes follow
+  once the exchange has completed (stream-ordered, no host sync);
+* the kernels see the received planes through the ``pad_lo`` / ``pad_hi``
+  arguments of the C ABI (include/b200_ndfilters.h) and fold positions by
+  ``mode`` only at the ends of the resident range, i.e. only at the GLOBAL
+  volume boundary.  Every voxel therefore goes through exactly the operation
+  sequence it would on one GPU: results are identical for every GPU count.
+
+The arithmetic backend is pluggable (``backend=``): the product one launches
+the CUDA kernels through the C ABI; the CPU test-suite injects the oracle to
+check partitioning, exchange and boundary handling on ``gloo``.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import ndimage as _nd
+from ._array import _NP_TO_TORCH, _TORCH_TO_NP, torch_dtype
+
+__all__ = ["ShardedVolume", "slab_bounds", "FUNCTIONS"]
+
+
+def slab_bounds(n0, world):
+    """``[(start, stop)]`` of every rank's planes: as even as possible, the
+    first ``n0 % world`` ranks hold one plane more."""
+    base, rem = divmod(int(n0), int(world))
+    out, s = [], 0
+    for r in range(world):
+        e = s + base + (1 if r < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+# --------------------------------------------------------------------------
+# arithmetic backends
+# --------------------------------------------------------------------------
+class CudaBackend:
+    """Launches the sm_100a kernels through the C ABI.  ``src_full`` /
+    ``dst_full`` are whole slab buffers (pads included); ``s0`` / ``d0`` index
+    the first plane of the call inside them."""
+
+    name = "cuda"
+
+    @staticmethod
+    def correlate1d(src_full, s0, dst_full, d0, n, pad, shape, np_dtype, ps, cval, epilogue, flags=None):
+        _nd._launch_correlate1d(src_full[s0:s0 + n], dst_full[d0:d0 + n], (n,) + tuple(shape[1:]),
+                                np_dtype, ps.axis, ps.weights, ps.mode, cval, ps.origin, pad, epilogue,
+                                flags)
+
+    @staticmethod
+    def uniform1d(src_full, s0, dst_full, d0, n, pad, shape, np_dtype, ps, cval, flags=None):
+        _nd._launch_uniform1d(src_full[s0:s0 + n], dst_full[d0:d0 + n], (n,) + tuple(shape[1:]),
+                              np_dtype, ps.axis, ps.size, ps.mode, cval, ps.origin, pad, flags)
+
+    @staticmethod
+    def correlate_nd(src_full, s0, dst_full, d0, n, pad, shape, np_dtype, w, origins, mode, cval,
+                     flags=None):
+        _nd._launch_correlate_nd(src_full[s0:s0 + n], dst_full[d0:d0 + n], (n,) + tuple(shape[1:]),
+                                 np_dtype, w, origins, mode, cval, pad, flags)
+
+    @staticmethod
+    def combine(dst, src, np_dtype, op):
+        _nd._launch_combine(dst, src, np_dtype, op)
+
+
+# --------------------------------------------------------------------------
+# slab buffers
+# --------------------------------------------------------------------------
+class _SlabBuf:
+    """``cap`` pad planes + ``n`` interior planes + ``cap`` pad planes, one
+    allocation; ``full[cap + p]`` is local plane ``p`` (``p`` may be negative
+    or >= n: a received neighbour plane)."""
+    __slots__ = ("full", "cap", "n")
+
+    def __init__(self, n, tail_shape, dtype, device, cap):
+        self.cap, self.n = int(cap), int(n)
+        self.full = torch.empty((self.n + 2 * self.cap,) + tuple(tail_shape), dtype=dtype, device=device)
+
+    def planes(self, p0, p1):
+        return self.full[self.cap + p0:self.cap + p1]
+
+    @property
+    def interior(self):
+        return self.planes(0, self.n)
+
+
+class ShardedVolume:
+    """An N-D volume cut into axis-0 slabs, one per rank of ``group``.
+
+    Construct with :meth:`from_global` (every rank passes the same host array
+    and keeps its slab), :meth:`from_local` (each rank passes its own planes),
+    or :meth:`random` (device-side synthetic data that does not depend on the
+    number of ranks).  The filters of ``dask_image_b200.ndfilters`` accept a
+    ``ShardedVolume`` wherever they accept a ``B200Array`` / dask array and
+    return a new ``ShardedVolume``.
+    """
+
+    DEFAULT_HALO = 16
+
+    def __init__(self, buf, global_shape, group=None, backend=None):
+        self._buf = buf
+        self.shape = tuple(int(s) for s in global_shape)
+        self.group = group
+        self.backend = backend or CudaBackend
+        self.rank = dist.get_rank(group) if _dist_on() else 0
+        self.world = dist.get_world_size(group) if _dist_on() else 1
+        self.bounds = slab_bounds(self.shape[0], self.world)
+        lo, hi = self.bounds[self.rank]
+        if hi - lo != buf.n:
+            raise ValueError("rank %d holds %d planes, expected %d" % (self.rank, buf.n, hi - lo))
+
+    # ---- construction ---------------------------------------------------
+    @classmethod
+    def _alloc(cls, global_shape, torch_dt, device, group, backend, halo):
+        world = dist.get_world_size(group) if _dist_on() else 1
+        rank = dist.get_rank(group) if _dist_on() else 0
+        s, e = slab_bounds(global_shape[0], world)[rank]
+        cap = 0 if world == 1 else int(halo)
+        buf = _SlabBuf(e - s, global_shape[1:], torch_dt, device, cap)
+        return cls(buf, global_shape, group, backend)
+
+    @classmethod
+    def empty(cls, global_shape, dtype, device=None, group=None, backend=None, halo=None):
+        device = _default_device() if device is None else torch.device(device)
+        return cls._alloc(tuple(global_shape), torch_dtype(dtype), device, group, backend,
+                          cls.DEFAULT_HALO if halo is None else halo)
+
+    @classmethod
+    def from_global(cls, array, device=None, group=None, backend=None, halo=None):
+        a = np.ascontiguousarray(array)
+        vol = cls.empty(a.shape, a.dtype, device, group, backend, halo)
+        s, e = vol.bounds[vol.rank]
+        vol.local.copy_(torch.from_numpy(a[s:e].copy()))
+        return vol
+
+    @classmethod
+    def from_local(cls, tensor, global_shape, group=None, backend=None, halo=None):
+        vol = cls.empty(global_shape, _TORCH_TO_NP[tensor.dtype], tensor.device, group, backend, halo)
+        vol.local.copy_(tensor)
+        return vol
+
+    @classmethod
+    def random(cls, global_shape, dtype, seed=1234, device=None, group=None, backend=None, halo=None):
+        """Synthetic volume (uniform [0,1) floats / full-range integers) from a
+        counter hash of the GLOBAL voxel index: the same volume for any number
+        of ranks, generated in place on the device."""
+        vol = cls.empty(global_shape, dtype, device, group, backend, halo)
+        s, _ = vol.bounds[vol.rank]
+        plane = int(np.prod(vol.shape[1:], dtype=np.int64))
+        loc = vol.local
+        step = max(1, (1 << 26) // max(1, plane))
+        for p0 in range(0, vol.n_local, step):
+            p1 = min(vol.n_local, p0 + step)
+            idx = torch.arange((s + p0) * plane, (s + p1) * plane, dtype=torch.int64, device=loc.device)
+            loc[p0:p1] = _hash_values(idx, seed, loc.dtype).reshape(loc[p0:p1].shape)
+        return vol
+
+    # ---- numpy-like surface -----------------------------------------------
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def dtype(self):
+        return _TORCH_TO_NP[self._buf.full.dtype]
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape, dtype=np.int64))
+
+    @property
+    def device(self):
+        return self._buf.full.device
+
+    @property
+    def n_local(self):
+        return self._buf.n
+
+    @property
+    def local(self):
+        """This rank's planes (a view; no pads)."""
+        return self._buf.interior
+
+    def gather(self):
+        """The whole volume as a host array on every rank (tests / small data)."""
+        loc = self.local.contiguous()
+        if self.world == 1:
+            return loc.cpu().numpy()
+        nmax = max(e - s for s, e in self.bounds)
+        padded = torch.zeros((nmax,) + tuple(self.shape[1:]), dtype=loc.dtype, device=loc.device)
+        padded[:loc.shape[0]] = loc
+        # gloo has no unsigned 16/32/64 support: ship raw bytes
+        raw = padded.view(torch.uint8) if padded.numel() else padded.to(torch.uint8)
+        parts = [torch.empty_like(raw) for _ in range(self.world)]
+        dist.all_gather(parts, raw, group=self.group)
+        out = [p.view(loc.dtype).reshape(padded.shape)[:e - s].cpu().numpy()
+               for p, (s, e) in zip(parts, self.bounds)]
+        return np.concatenate(out, axis=0)
+
+    def __repr__(self):
+        return "ShardedVolume(shape=%s, dtype=%s, rank=%d/%d, planes=%s)" % (
+            self.shape, self.dtype, self.rank, self.world, self.bounds[self.rank])
+
+    # ---- engine -------------------------------------------------------------
+    def _like(self, halo):
+        cap = 0 if self.world == 1 else max(int(halo), self._buf.cap)
+        buf = _SlabBuf(self.n_local, self.shape[1:], self._buf.full.dtype, self.device, cap)
+        return buf
+
+    def _ensure_cap(self, depth):
+        """Grow the pad capacity of the input buffer (one copy) if a filter
+        reaches further than the buffer was allocated for."""
+        if self.world > 1 and depth > self._buf.cap:
+            new = _SlabBuf(self.n_local, self.shape[1:], self._buf.full.dtype, self.device, depth)
+            new.interior.copy_(self._buf.interior)
+            self._buf = new
+
+    def _exchange(self, buf, lo, hi, ring):
+        """Start the face exchange for a pass that reaches ``lo`` planes below
+        and ``hi`` planes above.  Returns ``(pad_lo, pad_hi, requests)``."""
+        G, r, n = self.world, self.rank, buf.n
+        if G == 1 or (lo == 0 and hi == 0):
+            return 0, 0, []
+        nmin = min(e - s for s, e in self.bounds)
+        if max(lo, hi) > nmin:
+            raise ValueError("halo depth %d exceeds the thinnest slab (%d planes on %d ranks)"
+                             % (max(lo, hi), nmin, G))
+        has_prev = ring or r > 0
+        has_next = ring or r < G - 1
+        prev, nxt = (r - 1) % G, (r + 1) % G
+        if self.group is not None:
+            prev, nxt = dist.get_global_rank(self.group, prev), dist.get_global_rank(self.group, nxt)
+        def face(p0, p1):
+            # raw bytes: gloo (CPU tests) has no unsigned 16/32/64-bit types
+            return buf.planes(p0, p1).view(torch.uint8)
+
+        ops = []
+        # "down" faces first, then "up" faces, on every rank: NCCL matches the
+        # sends and receives of a pair in posting order (tags are a gloo thing)
+        if hi > 0:
+            if has_prev:
+                ops.append(dist.P2POp(dist.isend, face(0, hi), prev, self.group, tag=0))
+            if has_next:
+                ops.append(dist.P2POp(dist.irecv, face(n, n + hi), nxt, self.group, tag=0))
+        if lo > 0:
+            if has_next:
+                ops.append(dist.P2POp(dist.isend, face(n - lo, n), nxt, self.group, tag=1))
+            if has_prev:
+                ops.append(dist.P2POp(dist.irecv, face(-lo, 0), prev, self.group, tag=1))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        return (lo if has_prev else 0), (hi if has_next else 0), reqs
+
+    def _axis0_call(self, src, lo, hi, ring, call, cache=None):
+        """Run an axis-0-reaching kernel over the slab with the exchange
+        overlapped: ``call(p0, p1, pad)`` filters local planes [p0, p1).
+        ``cache`` (a dict) remembers the faces already resident around the
+        plan's INPUT buffer, so that the chains of one plan (gradient
+        magnitude / laplace: three chains that all start along axis 0) share
+        ONE exchange."""
+        n = src.n
+        if cache is not None and cache.get("ring") == ring and cache.get("lo", -1) >= lo \
+                and cache.get("hi", -1) >= hi:
+            call(0, n, (cache["pad_lo"], cache["pad_hi"]))
+            return
+        pad_lo, pad_hi, reqs = self._exchange(src, lo, hi, ring)
+        if cache is not None:
+            cache.update(ring=ring, lo=lo, hi=hi, pad_lo=pad_lo, pad_hi=pad_hi)
+        i0, i1 = pad_lo, n - pad_hi          # planes whose window stays inside the slab
+        if not reqs:
+            call(0, n, (0, 0))
+            return
+        if i1 > i0:
+            call(i0, i1, (i0, n - i1))
+        for rq in reqs:
+            rq.wait()                        # stream-ordered on NCCL; blocking on gloo
+        if i1 > i0:
+            if i0 > 0:
+                call(0, i0, (pad_lo, n - i0 + pad_hi))
+            if i1 < n:
+                call(i1, n, (i1 + pad_lo, pad_hi))
+        else:
+            call(0, n, (pad_lo, pad_hi))
+
+    def _run_plan(self, plan):
+        be, dt, shape = self.backend, self.dtype, (self.n_local,) + self.shape[1:]
+        # a 1-D volume's only axis is the contiguous one, whose tiled kernel
+        # takes no pads: keep every GPU count on the same (generic) arithmetic
+        flags = _lib.FLAG_NO_TMA if self.ndim == 1 else None
+        cache0 = {}
+        # deepest axis-0 reach of the plan -> pad capacity of every buffer
+        depth = 0
+        if plan.nd is not None:
+            w, origins, mode = plan.nd
+            depth = max(w.shape[0] // 2 + origins[0], w.shape[0] - 1 - w.shape[0] // 2 - origins[0])
+        for passes, _ in plan.chains:
+            for ps in passes:
+                if ps.axis == 0:
+                    lo, hi = _reach(ps)
+                    depth = max(depth, lo, hi)
+        self._ensure_cap(depth)
+        out = self._like(depth)
+        result = ShardedVolume(out, self.shape, self.group, self.backend)
+        if self.size == 0:
+            return result
+        src0 = self._buf
+
+        if plan.nd is not None:
+            w, origins, mode = plan.nd
+            lo = w.shape[0] // 2 + origins[0]
+            hi = w.shape[0] - 1 - w.shape[0] // 2 - origins[0]
+            self._axis0_call(src0, lo, hi, mode in ("wrap", "grid-wrap"),
+                             lambda p0, p1, pad: be.correlate_nd(
+                                 src0.full, src0.cap + p0, out.full, out.cap + p0, p1 - p0, pad,
+                                 shape, dt, w, origins, mode, plan.cval, flags))
+            return result
+        if not plan.chains:
+            out.interior.copy_(src0.interior)
+            return result
+        if plan.zero_out:
+            out.interior.zero_()
+        scratch = []
+        for passes, op in plan.chains:
+            if not passes:
+                be.combine(out.interior, src0.interior, dt, op)
+                continue
+            src = src0
+            targets = _nd._chain_targets(len(passes), op)
+            for i, ps in enumerate(passes):
+                last = i == len(passes) - 1
+                if targets[i] == "out":
+                    dst = out
+                else:
+                    k = targets[i]
+                    while len(scratch) <= k:
+                        scratch.append(self._like(depth))
+                    dst = scratch[k]
+                epi = op if last else _lib.EPI_STORE
+                if ps.kind != "corr" and epi != _lib.EPI_STORE:
+                    raise RuntimeError("uniform passes have no fused epilogue")
+
+                def call(p0, p1, pad, src=src, dst=dst, ps=ps, epi=epi):
+                    if ps.kind == "corr":
+                        be.correlate1d(src.full, src.cap + p0, dst.full, dst.cap + p0, p1 - p0, pad,
+                                       shape, dt, ps, plan.cval, epi, flags)
+                    else:
+                        be.uniform1d(src.full, src.cap + p0, dst.full, dst.cap + p0, p1 - p0, pad,
+                                     shape, dt, ps, plan.cval, flags)
+
+                if ps.axis == 0:
+                    lo, hi = _reach(ps)
+                    self._axis0_call(src, lo, hi, ps.mode in ("wrap", "grid-wrap"), call,
+                                     cache0 if src is src0 else None)
+                else:
+                    call(0, self.n_local, (0, 0))
+                src = dst
+        return result
+
+
+def _reach(ps):
+    """Planes a 1-D pass reads below / above an output position
+    (SURVEY.md Appendix A1)."""
+    L = len(ps.weights) if ps.kind == "corr" else ps.size
+    lo = L // 2 + ps.origin
+    return lo, L - 1 - lo
+
+
+def _dist_on():
+    return dist.is_available() and dist.is_initialized()
+
+
+def _default_device():
+    if torch.cuda.is_available():
+        return torch.device("cuda", torch.cuda.current_device())
+    raise RuntimeError("dask_image_b200 needs a CUDA device (sm_100a); none is visible "
+                       "and there is no CPU fallback")
+
+
+def _hash_values(idx, seed, torch_dt):
+    """splitmix-style 64-bit mix of the global voxel index (int64 arithmetic
+    wraps), mapped to the dtype's synthetic range."""
+    h = idx * -7046029254386353131 + (int(seed) * 2 + 1) * 0x2545F4914F6CDD1D % (1 << 62)
+    h = (h ^ ((h >> 31) & 0x1FFFFFFFF)) * -4658895280553007687
+    h = h ^ ((h >> 29) & 0x7FFFFFFFF)
+    if torch_dt in (torch.float32, torch.float64):
+        return (((h >> 24) & 0xFFFFFF).to(torch.float32) * (1.0 / (1 << 24))).to(torch_dt)
+    np_dt = _TORCH_TO_NP[torch_dt]
+    bits = np_dt.itemsize * 8
+    v = (h >> 8) & ((1 << min(bits, 48)) - 1)
+    if np_dt.kind == "i":
+        v = v - (1 << (min(bits, 48) - 1))
+    return v.to(torch_dt)
+
+
+# --------------------------------------------------------------------------
+# the per-"chunk" functions the dispatchers hand out for a ShardedVolume
+# (same names / kwargs as dask_image_b200.ndimage, i.e. as scipy.ndimage)
+# --------------------------------------------------------------------------
+def _check(vol):
+    if not isinstance(vol, ShardedVolume):
+        raise TypeError("expected a ShardedVolume")
+    if vol.ndim == 0:
+        raise RuntimeError("0-d arrays are not supported")
+    return vol
+
+
+def gaussian_filter(input, sigma, order=0, mode="reflect", cval=0.0, truncate=4.0, *,
+                    radius=None, axes=None):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_gaussian_filter(vol.ndim, sigma, order, mode, cval, truncate,
+                                                   radius, axes))
+
+
+def uniform_filter(input, size=3, mode="reflect", cval=0.0, origin=0, *, axes=None):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_uniform_filter(vol.ndim, size, mode, cval, origin, axes))
+
+
+def gaussian_gradient_magnitude(input, sigma, mode="reflect", cval=0.0, *, axes=None, **kwargs):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_gaussian_gradient_magnitude(vol.ndim, sigma, mode, cval, axes,
+                                                               **kwargs))
+
+
+def gaussian_laplace(input, sigma, mode="reflect", cval=0.0, *, axes=None, **kwargs):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_gaussian_laplace(vol.ndim, sigma, mode, cval, axes, **kwargs))
+
+
+def correlate(input, weights, mode="reflect", cval=0.0, origin=0):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_correlate_nd(vol.ndim, vol.dtype, weights, mode, cval, origin, False))
+
+
+def convolve(input, weights, mode="reflect", cval=0.0, origin=0):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_correlate_nd(vol.ndim, vol.dtype, weights, mode, cval, origin, True))
+
+
+def laplace(input, mode="reflect", cval=0.0, *, axes=None):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_laplace(vol.ndim, mode, cval, axes))
+
+
+def prewitt(input, axis=-1, mode="reflect", cval=0.0):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_prewitt(vol.ndim, axis, mode, cval))
+
+
+def sobel(input, axis=-1, mode="reflect", cval=0.0):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_sobel(vol.ndim, axis, mode, cval))
+
+
+FUNCTIONS = {f.__name__: f for f in (
+    convolve, correlate, laplace, prewitt, sobel, gaussian_filter, gaussian_gradient_magnitude,
+    gaussian_laplace, uniform_filter)}
+
+assert set(_NP_TO_TORCH)  # dtype tables shared with B200Array

@@ -31,13 +31,17 @@
  *    available from b200_last_error() on the calling thread.
  *
  * Slab halos (multi-GPU axis-0 decomposition, replaces dask's map_overlap):
- * `pad_lo` / `pad_hi` say how many REAL planes of the global volume are
+ * `in` / `out` point at the first of the `shape[0]` planes this call produces,
+ * and `pad_lo` / `pad_hi` say how many REAL planes of the global volume are
  * resident in memory directly before `in` plane 0 / after plane n-1 along
- * `axis` 0 (received from the neighbouring rank).  Positions inside
- * [-pad_lo, n + pad_hi) are read as they are; positions outside are resolved
- * by `mode` against this array's own extent [0, n).  pad_lo = pad_hi = 0 gives
- * exactly scipy's behaviour on a whole array.  Pads are only meaningful for
- * the filtered axis 0 (1-D passes with axis == 0, and the N-D correlate).
+ * axis 0 (own planes of the slab, or planes received from the neighbouring
+ * rank).  Positions inside the resident range [-pad_lo, n + pad_hi) are read
+ * as they are; positions outside it are folded by `mode` at the ends of the
+ * resident range (on an end slab that end is the global boundary; elsewhere
+ * the pads cover the filter's reach and it is never touched).  pad_lo =
+ * pad_hi = 0 gives exactly scipy's behaviour on a whole array.  Pads are only
+ * meaningful for the filtered axis 0 (1-D passes with axis == 0, and the N-D
+ * correlate).
  */
 #ifndef B200_NDFILTERS_H
 #define B200_NDFILTERS_H

@@ -1,0 +1,176 @@
+"""GPU tests of the slab contract (pad_lo / pad_hi of the C ABI) and of the
+NCCL slab engine.  The invariant under test is north_star's: the whole-volume
+result is IDENTICAL (bit for bit) regardless of how many slabs / GPUs it was
+computed on -- on top of parity with the oracle."""
+import os
+import socket
+import sys
+import traceback
+
+import numpy as np
+import pytest
+
+from _helpers import assert_parity
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["reflect", "mirror", "nearest", "constant", "wrap"]
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import dask_image_b200
+
+    return dask_image_b200
+
+
+def _slabs(n, parts):
+    from dask_image_b200.sharded import slab_bounds
+
+    return [b for b in slab_bounds(n, parts) if b[1] > b[0]]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.uint16, np.int32])
+def test_slab_calls_equal_whole_call(b200, dtype, mode):
+    """Filtering plane ranges [s, e) of a resident volume with pad = (s, N - e)
+    must reproduce the whole-array call exactly, for the axis-0 1-D pass, the
+    box filter and the N-D correlate."""
+    import torch
+    from dask_image_b200 import ndimage as nd
+
+    rng = np.random.default_rng(11)
+    shape = (37, 12, 64)
+    if np.dtype(dtype).kind == "f":
+        a = (rng.random(shape) - 0.3).astype(dtype)
+    else:
+        a = rng.integers(0, 1000, shape).astype(dtype)
+    x = torch.from_numpy(a).cuda() if a.dtype != np.uint16 else torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
+    w1 = rng.random(9) - 0.2
+    w3 = rng.random((4, 3, 5)) - 0.4
+    dt = np.dtype(dtype)
+
+    def run(kind, src, dst, n, pad):
+        shp = (n,) + shape[1:]
+        if kind == "corr":
+            nd._launch_correlate1d(src, dst, shp, dt, 0, w1, mode, 0.7, 1, pad)
+        elif kind == "uniform":
+            nd._launch_uniform1d(src, dst, shp, dt, 0, 6, mode, 0.7, -1, pad)
+        else:
+            nd._launch_correlate_nd(src, dst, shp, dt, w3, (1, 0, -2), mode, 0.7, pad)
+
+    for kind in ("corr", "uniform", "nd"):
+        whole = torch.empty_like(x)
+        run(kind, x, whole, shape[0], (0, 0))
+        for parts in (2, 3, 5):
+            out = torch.zeros_like(x)
+            for s, e in _slabs(shape[0], parts):
+                run(kind, x[s:e], out[s:e], e - s, (s, shape[0] - e))
+            assert torch.equal(out.view(torch.uint8), whole.view(torch.uint8)), (kind, parts, mode, dt)
+    # and the whole call itself is right
+    got = b200.B200Array(whole).to_numpy()
+    assert_parity(got, orc.correlate(a, w3, mode, 0.7, (1, 0, -2)), what="nd")
+
+
+def test_sharded_single_rank_equals_array_path(b200):
+    rng = np.random.default_rng(5)
+    a = rng.random((40, 24, 64), dtype=np.float32)
+    vol = b200.ShardedVolume.from_global(a)
+    arr = b200.B200Array.from_numpy(a)
+    for name, kw in [("gaussian_filter", dict(sigma=1.5)),
+                     ("gaussian_gradient_magnitude", dict(sigma=1.0, mode="nearest")),
+                     ("uniform_filter", dict(size=5, mode="wrap")),
+                     ("convolve", dict(weights=rng.random((3, 3, 3)), mode="wrap"))]:
+        f = getattr(b200.ndfilters, name)
+        kw2 = dict(kw)
+        if "weights" in kw2:
+            kw2["weights"] = b200.B200Array.from_numpy(kw2["weights"])
+        got = f(vol, **kw).gather()
+        one = f(arr, **kw2).to_numpy()
+        assert np.array_equal(got, one), name
+        assert_parity(got, getattr(orc, name)(a, **kw), what=name)
+
+
+def test_random_volume_is_partition_free(b200):
+    import torch
+
+    v = b200.ShardedVolume.random((16, 8, 32), np.float32, seed=9)
+    g = v.gather()
+    assert g.min() >= 0.0 and g.max() < 1.0 and abs(g.mean() - 0.5) < 0.05
+    u = b200.ShardedVolume.random((16, 8, 32), np.uint16, seed=9).gather()
+    assert u.dtype == np.uint16 and u.max() > 60000 and u.min() < 5000
+    assert torch.cuda.is_available()
+
+
+# ---------------------------------------------------------------------------
+# NCCL: one process per GPU
+# ---------------------------------------------------------------------------
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, q):
+    try:
+        import torch
+        import torch.distributed as dist
+
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", rank))
+        import dask_image_b200 as b200
+
+        rng = np.random.default_rng(21)
+        f32 = rng.random((50, 20, 64), dtype=np.float32)
+        u16 = rng.integers(0, 65536, (45, 16, 24), dtype=np.uint16)
+        w3 = rng.random((3, 5, 4)) - 0.3
+        failures = []
+        cases = []
+        for mode in MODES:
+            cases += [
+                ("gaussian_filter", f32, dict(sigma=2.0, mode=mode, cval=0.2)),
+                ("gaussian_gradient_magnitude", f32, dict(sigma=1.5, mode=mode)),
+                ("gaussian_laplace", f32, dict(sigma=1.0, mode=mode)),
+                ("uniform_filter", u16, dict(size=7, mode=mode)),
+                ("gaussian_filter", u16, dict(sigma=1.0, mode=mode)),
+                ("convolve", f32, dict(weights=w3, mode=mode, origin=(0, 1, -1))),
+                ("sobel", f32, dict(axis=0, mode=mode)),
+            ]
+        for name, a, kw in cases:
+            f = getattr(b200.ndfilters, name)
+            got = f(b200.ShardedVolume.from_global(a, halo=4), **kw).gather()
+            kw1 = dict(kw)
+            if "weights" in kw1:
+                kw1["weights"] = b200.B200Array.from_numpy(kw1["weights"])
+            one = f(b200.B200Array.from_numpy(a), **kw1).to_numpy()
+            if not np.array_equal(got, one):
+                failures.append("%s %s %s: %d voxels differ from the 1-GPU result" % (
+                    name, a.dtype, kw["mode"], int((got != one).sum())))
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, failures))
+    except Exception:
+        q.put((rank, ["EXC " + traceback.format_exc()]))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_engine_nccl(world):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, failures in results:
+        assert not failures, "rank %d: %s" % (rank, "\n".join(failures))
