@@ -13,6 +13,11 @@ GOLDEN_JSON = os.path.join(HERE, "golden", "ndfilters_golden.json")
 # outputs cross zero, so "relative" is taken against the output's magnitude as
 # well as elementwise:
 #     |got - ref| <= rtol * |ref| + rtol * max|ref|
+# Where the caller passes the filter's input (``data=``) the scale is
+# max(max|ref|, max|data|): a derivative kernel applied to a constant image is
+# EXACTLY zero in scipy (it folds x[-j] - x[j] first) while any direct-form
+# kernel leaves rounding noise of order eps * sum|w| * |data| -- an error
+# relative to the data, not to an all-zero reference.
 RTOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
 
 _golden = None
@@ -44,7 +49,7 @@ def golden_case(i):
     return spec["func"], arrs[spec["input"]], kwargs, arrs["out_%d" % i]
 
 
-def assert_parity(got, ref, exact=False, what=""):
+def assert_parity(got, ref, exact=False, what="", data=None):
     got = np.asarray(got)
     ref = np.asarray(ref)
     assert got.shape == ref.shape, "%s shape %s != %s" % (what, got.shape, ref.shape)
@@ -57,6 +62,8 @@ def assert_parity(got, ref, exact=False, what=""):
         return
     rtol = RTOL[ref.dtype]
     scale = float(np.max(np.abs(ref))) if ref.size else 0.0
+    if data is not None and np.size(data):
+        scale = max(scale, float(np.max(np.abs(np.asarray(data, dtype=np.float64)))))
     err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
     bound = rtol * np.abs(ref.astype(np.float64)) + rtol * scale
     if not np.all(err <= bound):

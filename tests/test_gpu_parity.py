@@ -41,7 +41,7 @@ def test_golden(b200, i):
     func, a, kwargs, expected = golden_case(i)
     got = getattr(b200.ndimage, func)(dev(b200, a), **kwargs)
     assert type(got) is b200.B200Array
-    assert_parity(got.to_numpy(), expected, what=CASES[i]["name"])
+    assert_parity(got.to_numpy(), expected, what=CASES[i]["name"], data=a)
 
 
 @pytest.mark.parametrize("i", range(0, len(CASES), 3), ids=[c["name"] for c in CASES[::3]])
