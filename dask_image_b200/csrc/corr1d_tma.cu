@@ -28,6 +28,8 @@
 #include "tma.cuh"
 #include <mutex>
 #include <cstdlib>
+#include <cstring>
+#include <cmath>
 
 namespace b200 {
 
@@ -89,10 +91,13 @@ int encode_tensor_map(CUtensorMap *map, int dtype, void *base, int rank, const u
 constexpr int kMaxTapsTma = 208;
 constexpr int kMaxStages = 6;
 
-template <typename T>
+// T = arithmetic type (float / double), TS = storage type of the array: TS == T
+// for the float passes; TS = uint8_t / uint16_t with T = float for the exact
+// integer box filter (see the integer epilogue below).
+template <typename T, typename TS = T>
 struct Corr1dTmaParams {
-    const T *in;   // plane/row 0 of the array (edge patch-up loads)
-    T *out;
+    const TS *in;   // plane/row 0 of the array (edge patch-up loads)
+    TS *out;
     int64_t outer, n, inner;
     int64_t pad_lo, pad_hi;
     int64_t num_tiles;
@@ -107,7 +112,8 @@ struct Corr1dTmaParams {
     int wide_store;  // contig: rows and base are 32-byte aligned -> 256-bit stores
     int stage_elems; // elements per stage
     int n_tiles, c_tiles;
-    T cval;
+    TS cval;
+    T qinv, qc0;     // integer box filter: 1/size and the (0.5 - size/2) offset
     T w[kMaxTapsTma];
 };
 
@@ -164,22 +170,104 @@ __device__ __forceinline__ T *aligned_smem(unsigned char *raw)
     return reinterpret_cast<T *>(raw + pad);
 }
 
+// ---------------------------------------------------------------------------
+// Storage <-> arithmetic vectors.  A thread-level block is V elements: 16 bytes
+// when TS == T, 4 elements (8 / 4 bytes) when TS is uint16_t / uint8_t.
+// Integer elements are widened with one PRMT each (bits 0x4B000000 | v are the
+// float 2^23 + v) and a packed subtract of 2^23 -- exact, no I2F.
+// ---------------------------------------------------------------------------
+template <typename T, typename TS>
+struct StorageV {
+    static constexpr int V = sizeof(TS) == sizeof(T) ? 16 / (int)sizeof(T) : 4;
+};
+
+template <typename T, typename TS, int V>
+__device__ __forceinline__ Vec<T, V> load_block(const TS *ptr)
+{
+    if constexpr (sizeof(TS) == sizeof(T)) {
+        return *reinterpret_cast<const Vec<T, V> *>(ptr);
+    } else {
+        static_assert(V == 4 && sizeof(T) == 4, "integer storage widens to 4 floats");
+        uint32_t f[4];
+        if constexpr (sizeof(TS) == 2) {
+            const uint2 raw = *reinterpret_cast<const uint2 *>(ptr);
+            f[0] = __byte_perm(raw.x, 0x4B000000u, 0x7410);
+            f[1] = __byte_perm(raw.x, 0x4B000000u, 0x7432);
+            f[2] = __byte_perm(raw.y, 0x4B000000u, 0x7410);
+            f[3] = __byte_perm(raw.y, 0x4B000000u, 0x7432);
+        } else {
+            const uint32_t raw = *reinterpret_cast<const uint32_t *>(ptr);
+            f[0] = __byte_perm(raw, 0x4B000000u, 0x7440);
+            f[1] = __byte_perm(raw, 0x4B000000u, 0x7441);
+            f[2] = __byte_perm(raw, 0x4B000000u, 0x7442);
+            f[3] = __byte_perm(raw, 0x4B000000u, 0x7443);
+        }
+        const float2 bias = make_float2(-8388608.f, -8388608.f);
+        const float2 a = __fadd2_rn(make_float2(__uint_as_float(f[0]), __uint_as_float(f[1])), bias);
+        const float2 b = __fadd2_rn(make_float2(__uint_as_float(f[2]), __uint_as_float(f[3])), bias);
+        Vec<T, V> r;
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+        return r;
+    }
+}
+
+// Integer box filter epilogue.  s is the exact window sum (an integer below
+// 2^23 held in a float); the result is trunc(s / size) as the reference
+// computes it (double division, C cast).  With s2 = s + 0.5 - size/2,
+//     fma(s2, 1/size, 1.5 * 2^23)
+// rounds (s + 0.5)/size - 0.5 to the nearest integer in ONE rounding, which is
+// floor(s/size); the low bits of the float's bit pattern are that integer.
+// The launcher proves the identity for every reachable sum before it selects
+// this kernel (uniform_int_exact()).
+template <typename T>
+__device__ __forceinline__ uint32_t box_quotient_bits(T s, T qinv, T qc0)
+{
+    return __float_as_uint(fmaf((float)s + (float)qc0, (float)qinv, 12582912.f));
+}
+
+template <typename T, typename TS, int N>
+__device__ __forceinline__ void store_box_quotients(TS *dst, const T (&s)[N], T qinv, T qc0)
+{
+    static_assert(N == 4 || N == 8, "4 or 8 outputs per store");
+    uint32_t q[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = box_quotient_bits<T>(s[i], qinv, qc0);
+    if constexpr (sizeof(TS) == 2) {
+        uint32_t w[N / 2];
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) w[i] = __byte_perm(q[2 * i], q[2 * i + 1], 0x5410);
+        if constexpr (N == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+        else *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        uint32_t w[N / 4];
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            const uint32_t lo = __byte_perm(q[4 * i], q[4 * i + 1], 0x0040);
+            const uint32_t hi = __byte_perm(q[4 * i + 2], q[4 * i + 3], 0x0040);
+            w[i] = __byte_perm(lo, hi, 0x5410);
+        }
+        if constexpr (N == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
+        else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+    }
+}
+
 // ===========================================================================
 // strided-axis pass: one tile per CTA, 3 CTAs resident per SM
 // ===========================================================================
 // REM = taps % R is a template parameter so that the tap tail is straight-line
 // code; nothing in the tap loops is divergent, which lets ptxas keep the
 // weights on the uniform datapath (LDCU -> FFMA2 with a UR operand).
-template <typename T, int W, int TY, int R, int MINB, int REM>
-__global__ void __launch_bounds__((W / (16 / (int)sizeof(T))) * TY, MINB)
-corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T> p)
+template <typename T, typename TS, int W, int TY, int R, int MINB, int REM>
+__global__ void __launch_bounds__((W / StorageV<T, TS>::V) * TY, MINB)
+corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T, TS> p)
 {
-    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int V = StorageV<T, TS>::V;
+    constexpr bool kBox = sizeof(TS) != sizeof(T);   // exact integer box filter
     constexpr int TX = W / V;
     constexpr int NTHREADS = TX * TY;
     using VecT = Vec<T, V>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *tile = aligned_smem<T>(smem_raw);
+    TS *tile = aligned_smem<TS>(smem_raw);
     __shared__ __align__(8) uint64_t full_bar;
 
     const int tid = threadIdx.x;
@@ -199,7 +287,7 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
     if (tid == 0) {
         mbar_init(&full_bar, 1);
         fence_barrier_init();
-        mbar_arrive_expect_tx(&full_bar, (uint32_t)(p.smem_rows * W * (int)sizeof(T)));
+        mbar_arrive_expect_tx(&full_bar, (uint32_t)(p.smem_rows * W * (int)sizeof(TS)));
         tma_load_3d(tile, &tmap, &full_bar, (int)col0, (int)(g0 + p.pad_lo), (int)o);
     }
     __syncthreads();
@@ -212,16 +300,16 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
     // mode=constant, cval=0)
     const bool low_edge = g0 < -p.pad_lo;
     const bool high_edge = g0 + p.smem_rows > p.n + p.pad_hi;
-    if ((low_edge || high_edge) && !(p.mode == B200_MODE_CONSTANT && p.cval == T(0))) {
+    if ((low_edge || high_edge) && !(p.mode == B200_MODE_CONSTANT && p.cval == TS(0))) {
         const int warp = tid >> 5, lane = tid & 31;
         for (int r = warp; r < p.smem_rows; r += NTHREADS / 32) {
             const int64_t g = g0 + r;
             if (g >= -p.pad_lo && g < p.n + p.pad_hi) continue;
             const int64_t src = ext_index_padded(g, p.n, p.mode, p.pad_lo, p.pad_hi);
-            const T *srow = (src == B200_USE_CVAL) ? nullptr : p.in + ((o * p.n + src) * p.inner + col0);
+            const TS *srow = (src == B200_USE_CVAL) ? nullptr : p.in + ((o * p.n + src) * p.inner + col0);
             for (int c = lane; c < W; c += 32) {
-                T v = p.cval;
-                if (srow) v = (col0 + c < p.inner) ? srow[c] : T(0);
+                TS v = p.cval;
+                if (srow) v = (col0 + c < p.inner) ? srow[c] : TS(0);
                 tile[r * W + c] = v;
             }
         }
@@ -230,21 +318,21 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
 
     const int Lfull = L - REM;
     const int64_t col = col0 + tx * V;
-    T *const out_col = p.out + (o * p.n * p.inner + col);
+    TS *const out_col = p.out + (o * p.n * p.inner + col);
     for (int blk = 0; blk < p.nb; ++blk) {
         const int r0 = (blk * TY + ty) * R;
-        const T *sbase = tile + r0 * W + tx * V;
+        const TS *sbase = tile + r0 * W + tx * V;
         VecT win[R];
         VecAcc<T, V> acc[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) acc[j].zero();
 #pragma unroll
-        for (int j = 0; j < R - 1; ++j) win[j] = *reinterpret_cast<const VecT *>(sbase + j * W);
-        const T *sk = sbase + (R - 1) * W;
+        for (int j = 0; j < R - 1; ++j) win[j] = load_block<T, TS, V>(sbase + j * W);
+        const TS *sk = sbase + (R - 1) * W;
         for (int k = 0; k < Lfull; k += R, sk += R * W) {
 #pragma unroll
             for (int u = 0; u < R; ++u) {
-                win[(u + R - 1) % R] = *reinterpret_cast<const VecT *>(sk + u * W);
+                win[(u + R - 1) % R] = load_block<T, TS, V>(sk + u * W);
                 const T wk = p.w[k + u];
 #pragma unroll
                 for (int j = 0; j < R; ++j) acc[j].fma(win[(u + j) % R], wk);
@@ -252,7 +340,7 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
         }
 #pragma unroll
         for (int u = 0; u < REM; ++u) {
-            win[(u + R - 1) % R] = *reinterpret_cast<const VecT *>(sk + u * W);
+            win[(u + R - 1) % R] = load_block<T, TS, V>(sk + u * W);
             const T wk = p.w[Lfull + u];
 #pragma unroll
             for (int j = 0; j < R; ++j) acc[j].fma(win[(u + j) % R], wk);
@@ -262,19 +350,27 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
             for (int j = 0; j < R; ++j) {
                 const int64_t row = row0 + r0 + j;
                 if (row < p.n) {
-                    T *dst = out_col + row * p.inner;
-                    VecT res;
-                    if (p.epilogue == B200_EPI_STORE) {
+                    TS *dst = out_col + row * p.inner;
+                    if constexpr (kBox) {
+                        T sums[V];
 #pragma unroll
-                        for (int v = 0; v < V; ++v) res.v[v] = acc[j].get(v);
+                        for (int v = 0; v < V; ++v) sums[v] = acc[j].get(v);
+                        store_box_quotients<T, TS, V>(dst, sums, p.qinv, p.qc0);
                     } else {
-                        VecT prev;
-                        if (reads_out) prev = *reinterpret_cast<const VecT *>(dst);
+                        VecT res;
+                        if (p.epilogue == B200_EPI_STORE) {
 #pragma unroll
-                        for (int v = 0; v < V; ++v)
-                            res.v[v] = apply_epilogue<T>(p.epilogue, reads_out ? prev.v[v] : T(0), acc[j].get(v));
+                            for (int v = 0; v < V; ++v) res.v[v] = acc[j].get(v);
+                        } else {
+                            VecT prev;
+                            if (reads_out) prev = *reinterpret_cast<const VecT *>(dst);
+#pragma unroll
+                            for (int v = 0; v < V; ++v)
+                                res.v[v] =
+                                    apply_epilogue<T>(p.epilogue, reads_out ? prev.v[v] : T(0), acc[j].get(v));
+                        }
+                        *reinterpret_cast<VecT *>(dst) = res;
                     }
-                    *reinterpret_cast<VecT *>(dst) = res;
                 }
             }
         }
@@ -385,10 +481,10 @@ struct ContigAcc<float, 4> {
 // 16-byte block two ahead into rotating slot (U+2)%3 and applies taps
 // [T0, T1) of the group.  U = (kb / V) % 3 is static so the register rotation
 // is free; T0/T1 are static so partial groups have no per-tap tests.
-template <typename T, int V, int U, int T0, int T1, typename ACC>
-__device__ __forceinline__ void contig_group(Vec<T, V> (&B)[3], ACC &acc, const T *srow, const T *w, int kb)
+template <typename T, typename TS, int V, int U, int T0, int T1, typename ACC>
+__device__ __forceinline__ void contig_group(Vec<T, V> (&B)[3], ACC &acc, const TS *srow, const T *w, int kb)
 {
-    B[(U + 2) % 3] = *reinterpret_cast<const Vec<T, V> *>(srow + kb + 2 * V);
+    B[(U + 2) % 3] = load_block<T, TS, V>(srow + kb + 2 * V);
     auto one = [&]<int TT>() {
         if constexpr (TT >= T0 && TT < T1) acc.template tap<U, TT>(B, w[kb + TT]);
     };
@@ -401,16 +497,17 @@ __device__ __forceinline__ void contig_group(Vec<T, V> (&B)[3], ACC &acc, const 
 }
 
 // SH = leading taps to skip (box start aligned down to 16 bytes), REM = taps % V
-template <typename T, int SH, int REM>
+template <typename T, typename TS, int SH, int REM>
 __global__ void __launch_bounds__(256, 4)
-corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T> p)
+corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T, TS> p)
 {
-    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int V = StorageV<T, TS>::V;
+    constexpr bool kBox = sizeof(TS) != sizeof(T);   // exact integer box filter
     constexpr int R = 2 * V;        // outputs per thread
     constexpr int PC = 4 * R;       // patch columns (4 lanes along x)
     using VecT = Vec<T, V>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *tile = aligned_smem<T>(smem_raw);
+    TS *tile = aligned_smem<TS>(smem_raw);
     __shared__ __align__(8) uint64_t full_bar;
 
     const int tid = threadIdx.x;
@@ -434,7 +531,7 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     if (tid == 0) {
         mbar_init(&full_bar, 1);
         fence_barrier_init();
-        mbar_arrive_expect_tx(&full_bar, (uint32_t)(TR * P * (int)sizeof(T)));
+        mbar_arrive_expect_tx(&full_bar, (uint32_t)(TR * P * (int)sizeof(TS)));
         tma_load_2d(tile, &tmap, &full_bar, (int)g0, (int)row0);
     }
     __syncthreads();
@@ -443,7 +540,7 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 
     const bool low_edge = g0 < 0;
     const bool high_edge = g0 + P > p.n;
-    if ((low_edge || high_edge) && !(p.mode == B200_MODE_CONSTANT && p.cval == T(0))) {
+    if ((low_edge || high_edge) && !(p.mode == B200_MODE_CONSTANT && p.cval == TS(0))) {
         // columns [0, -g0) and [n - g0, P) of every tile row
         const int nlow = low_edge ? (int)(-g0 < P ? -g0 : P) : 0;
         const int hstart = high_edge ? (int)((p.n - g0) > 0 ? (p.n - g0) : 0) : P;
@@ -454,8 +551,8 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             int c = idx - r * per_row;
             c = c < nlow ? c : hstart + (c - nlow);
             const int64_t src = ext_index(g0 + c, p.n, p.mode);
-            T v = p.cval;
-            if (src >= 0) v = (row0 + r < nrows) ? p.in[(row0 + r) * p.n + src] : T(0);
+            TS v = p.cval;
+            if (src >= 0) v = (row0 + r < nrows) ? p.in[(row0 + r) * p.n + src] : TS(0);
             tile[r * P + c] = v;
         }
         __syncthreads();
@@ -477,43 +574,51 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         const int xl = cg * PC + (lane & 3) * R;
         const int64_t row = row0 + r;
         const int64_t x = x0t + xl;
-        const T *srow = tile + r * P + xl;
+        const TS *srow = tile + r * P + xl;
         VecT B[3];
         ContigAcc<T, V> acc;
         acc.zero();
-        B[0] = *reinterpret_cast<const VecT *>(srow);
-        B[1] = *reinterpret_cast<const VecT *>(srow + V);
+        B[0] = load_block<T, TS, V>(srow);
+        B[1] = load_block<T, TS, V>(srow + V);
         int k = 0;
         if (Lfull >= V) {
-            contig_group<T, V, 0, SH, V>(B, acc, srow, p.w, 0);
+            contig_group<T, TS, V, 0, SH, V>(B, acc, srow, p.w, 0);
             k = V;
             for (; k + 3 * V <= Lfull; k += 3 * V) {
-                contig_group<T, V, 1, 0, V>(B, acc, srow, p.w, k);
-                contig_group<T, V, 2, 0, V>(B, acc, srow, p.w, k + V);
-                contig_group<T, V, 0, 0, V>(B, acc, srow, p.w, k + 2 * V);
+                contig_group<T, TS, V, 1, 0, V>(B, acc, srow, p.w, k);
+                contig_group<T, TS, V, 2, 0, V>(B, acc, srow, p.w, k + V);
+                contig_group<T, TS, V, 0, 0, V>(B, acc, srow, p.w, k + 2 * V);
             }
             // 0, 1 or 2 full groups left, then the partial one
             if (k + V <= Lfull) {
-                contig_group<T, V, 1, 0, V>(B, acc, srow, p.w, k);
+                contig_group<T, TS, V, 1, 0, V>(B, acc, srow, p.w, k);
                 k += V;
                 if (k + V <= Lfull) {
-                    contig_group<T, V, 2, 0, V>(B, acc, srow, p.w, k);
+                    contig_group<T, TS, V, 2, 0, V>(B, acc, srow, p.w, k);
                     k += V;
-                    if constexpr (REM > 0) contig_group<T, V, 0, 0, REM>(B, acc, srow, p.w, k);
+                    if constexpr (REM > 0) contig_group<T, TS, V, 0, 0, REM>(B, acc, srow, p.w, k);
                 } else {
-                    if constexpr (REM > 0) contig_group<T, V, 2, 0, REM>(B, acc, srow, p.w, k);
+                    if constexpr (REM > 0) contig_group<T, TS, V, 2, 0, REM>(B, acc, srow, p.w, k);
                 }
             } else {
-                if constexpr (REM > 0) contig_group<T, V, 1, 0, REM>(B, acc, srow, p.w, k);
+                if constexpr (REM > 0) contig_group<T, TS, V, 1, 0, REM>(B, acc, srow, p.w, k);
             }
         } else {
             // fewer than V taps in total: a single partial group (REM > SH here)
-            if constexpr (REM > 0) contig_group<T, V, 0, SH, REM>(B, acc, srow, p.w, 0);
+            if constexpr (REM > 0) contig_group<T, TS, V, 0, SH, REM>(B, acc, srow, p.w, 0);
         }
 
         if (patch_live && row < nrows) {
-            T *dst0 = p.out + (row * p.n + x);
-            if (p.wide_store && x + R <= p.n) {
+            TS *dst0 = p.out + (row * p.n + x);
+            if constexpr (kBox) {
+                // rows are whole multiples of 16 bytes, so x < n implies x + R <= n
+                if (x < p.n) {
+                    T sums[R];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) sums[j] = acc.get(j);
+                    store_box_quotients<T, TS, R>(dst0, sums, p.qinv, p.qc0);
+                }
+            } else if (p.wide_store && x + R <= p.n) {
                 // whole 32-byte sector(s) in one store
                 T res[R];
                 if (p.epilogue == B200_EPI_STORE) {
@@ -532,7 +637,7 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                 for (int h = 0; h < 2; ++h) {
                     const int64_t xx = x + h * V;
                     if (xx < p.n) {
-                        T *dst = dst0 + h * V;
+                        TS *dst = dst0 + h * V;
                         VecT res;
                         if (p.epilogue == B200_EPI_STORE) {
 #pragma unroll
@@ -564,14 +669,38 @@ static int env_int(const char *name, int dflt)
 
 constexpr size_t kSmemPerSm = 227 * 1024;
 
-template <typename T, int R, int MINB, int REM>
-static int launch_strided_cfg(const Corr1dArgs &a, int nb)
+// What the launchers need beyond Corr1dArgs when the storage type differs from
+// the arithmetic type (integer box filter): taps are 0/1 floats, the epilogue
+// divides by `size`.
+struct BoxInfo {
+    bool on = false;
+    float qinv = 0.f, qc0 = 0.f;
+};
+
+template <typename TS> constexpr int dtype_code();
+template <> constexpr int dtype_code<float>() { return B200_F32; }
+template <> constexpr int dtype_code<double>() { return B200_F64; }
+template <> constexpr int dtype_code<uint8_t>() { return B200_U8; }
+template <> constexpr int dtype_code<uint16_t>() { return B200_U16; }
+
+template <typename T, typename TS>
+static const char *kernel_name(bool strided)
 {
-    constexpr int V = 16 / (int)sizeof(T);
-    constexpr int W = 32 * V;   // 512-byte tile rows: one warp spans a row with 16-byte vectors
+    if (sizeof(TS) != sizeof(T))
+        return strided ? (sizeof(TS) == 2 ? "uniform1d_tma_strided_u16" : "uniform1d_tma_strided_u8")
+                       : (sizeof(TS) == 2 ? "uniform1d_tma_contig_u16" : "uniform1d_tma_contig_u8");
+    return strided ? (sizeof(T) == 4 ? "corr1d_tma_strided_f32" : "corr1d_tma_strided_f64")
+                   : (sizeof(T) == 4 ? "corr1d_tma_contig_f32" : "corr1d_tma_contig_f64");
+}
+
+template <typename T, typename TS, int R, int MINB, int REM>
+static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
+{
+    constexpr int V = StorageV<T, TS>::V;
+    constexpr int W = 32 * V;   // one warp spans a tile row (512 bytes of floats)
     constexpr int TY = 8;
     constexpr int ROWS_PER_BLK = TY * R;
-    const int es = (int)sizeof(T);
+    const int es = (int)sizeof(TS);
     const LineGeom &g = a.g;
     const int L = a.nw;
     const int64_t n_tot = a.pad_lo + g.n + a.pad_hi;
@@ -593,11 +722,11 @@ static int launch_strided_cfg(const Corr1dArgs &a, int nb)
     CUtensorMap tmap;
     uint64_t dims[3] = {(uint64_t)g.inner, (uint64_t)n_tot, (uint64_t)g.outer};
     uint64_t strides[2] = {(uint64_t)g.inner * es, (uint64_t)g.inner * es * (uint64_t)n_tot};
-    uint32_t box[3] = {(uint32_t)W, (uint32_t)smem_rows, 1u};
-    if (encode_tensor_map(&tmap, a.dtype, (void *)base, 3, dims, strides, box) != 0) return -1;
+    uint32_t bx[3] = {(uint32_t)W, (uint32_t)smem_rows, 1u};
+    if (encode_tensor_map(&tmap, dtype_code<TS>(), (void *)base, 3, dims, strides, bx) != 0) return -1;
 
-    Corr1dTmaParams<T> p;
-    p.in = (const T *)a.in; p.out = (T *)a.out;
+    Corr1dTmaParams<T, TS> p;
+    p.in = (const TS *)a.in; p.out = (TS *)a.out;
     p.outer = g.outer; p.n = g.n; p.inner = g.inner;
     p.pad_lo = a.pad_lo; p.pad_hi = a.pad_hi;
     p.num_tiles = num_tiles;
@@ -605,24 +734,27 @@ static int launch_strided_cfg(const Corr1dArgs &a, int nb)
     p.tile_rows = tile_rows; p.smem_rows = smem_rows; p.nb = nb; p.pitch = W; p.shift = 0; p.ncg = 0;
     p.stages = 1; p.stage_elems = (int)(stage_bytes / es); p.wide_store = 0;
     p.n_tiles = (int)n_tiles; p.c_tiles = c_tiles;
-    p.cval = (T)a.cval;
+    p.cval = (TS)a.cval;
+    p.qinv = (T)box.qinv; p.qc0 = (T)box.qc0;
     for (int i = 0; i < L; ++i) p.w[i] = (T)a.w[i];
 
-    auto kern = corr1d_strided_tma_kernel<T, W, TY, R, MINB, REM>;
+    auto kern = corr1d_strided_tma_kernel<T, TS, W, TY, R, MINB, REM>;
     const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
-    note_kernel(sizeof(T) == 4 ? "corr1d_tma_strided_f32" : "corr1d_tma_strided_f64");
+    note_kernel(kernel_name<T, TS>(true));
     return B200_OK;
 }
 
-template <typename T>
-static int launch_strided(const Corr1dArgs &a)
+template <typename T, typename TS>
+static int launch_strided(const Corr1dArgs &a, const BoxInfo &box)
 {
     constexpr int R = 4, MINB = 3;
-    const int es = (int)sizeof(T);
+    constexpr int V = StorageV<T, TS>::V;
+    const int es = (int)sizeof(TS);
+    const int row_bytes = 32 * V * es;
     const LineGeom &g = a.g;
     const int L = a.nw;
     if (L > kMaxTapsTma || 8 * R + L - 1 > 256) return -1;
@@ -639,33 +771,34 @@ static int launch_strided(const Corr1dArgs &a)
     int nb = env_int("B200_TMA_NB", 0);
     if (nb <= 0) {
         const int per_cta = (int)((kSmemPerSm - 3072) / MINB);
-        const int max_rows = per_cta / 512;
+        const int max_rows = per_cta / row_bytes;
         nb = (max_rows - (L - 1)) / (8 * R);
         nb = nb < 1 ? 1 : nb;
     }
     switch (L % R) {
-    case 0: return launch_strided_cfg<T, R, MINB, 0>(a, nb);
-    case 1: return launch_strided_cfg<T, R, MINB, 1>(a, nb);
-    case 2: return launch_strided_cfg<T, R, MINB, 2>(a, nb);
-    default: return launch_strided_cfg<T, R, MINB, 3>(a, nb);
+    case 0: return launch_strided_cfg<T, TS, R, MINB, 0>(a, box, nb);
+    case 1: return launch_strided_cfg<T, TS, R, MINB, 1>(a, box, nb);
+    case 2: return launch_strided_cfg<T, TS, R, MINB, 2>(a, box, nb);
+    default: return launch_strided_cfg<T, TS, R, MINB, 3>(a, box, nb);
     }
 }
 
-template <typename T, int SH, int REM>
-static int launch_contig_cfg(const Corr1dArgs &a, int lo_al, int L)
+template <typename T, typename TS, int SH, int REM>
+static int launch_contig_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al, int L)
 {
-    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int V = StorageV<T, TS>::V;
     constexpr int R = 2 * V, PC = 4 * R;
-    const int es = (int)sizeof(T);
+    constexpr int U16B = 16 / (int)sizeof(TS);   // elements per 16 bytes of storage
+    const int es = (int)sizeof(TS);
     const LineGeom &g = a.g;
     // tile width: ncg column groups of 4*R outputs; pitch = smallest odd multiple
     // of 16 bytes covering SX + L + 2V - 1 elements (the float path's odd-offset
     // pairs read one block further); TMA boxes are at most 256 elements wide.
     auto pitch_for = [&](int cand) {
         int pt = cand * PC + L + 2 * V - 1;
-        pt = (pt + V - 1) / V;   // 16-byte units
+        pt = (pt + U16B - 1) / U16B;   // 16-byte units
         if (!(pt & 1)) ++pt;
-        return pt * V;
+        return pt * U16B;
     };
     // Geometry from the B200 sweeps (profiles/): ~42 KB tiles so that 4 CTAs stay
     // resident per SM; 2 column groups for short filters (taller tiles), 4 for
@@ -692,11 +825,11 @@ static int launch_contig_cfg(const Corr1dArgs &a, int lo_al, int L)
     CUtensorMap tmap;
     uint64_t dims[2] = {(uint64_t)g.n, (uint64_t)g.outer};
     uint64_t strides[1] = {(uint64_t)g.n * es};
-    uint32_t box[2] = {(uint32_t)pitch, (uint32_t)tr};
-    if (encode_tensor_map(&tmap, a.dtype, (void *)a.in, 2, dims, strides, box) != 0) return -1;
+    uint32_t bx[2] = {(uint32_t)pitch, (uint32_t)tr};
+    if (encode_tensor_map(&tmap, dtype_code<TS>(), (void *)a.in, 2, dims, strides, bx) != 0) return -1;
 
-    Corr1dTmaParams<T> p;
-    p.in = (const T *)a.in; p.out = (T *)a.out;
+    Corr1dTmaParams<T, TS> p;
+    p.in = (const TS *)a.in; p.out = (TS *)a.out;
     p.outer = g.outer; p.n = g.n; p.inner = 1;
     p.pad_lo = 0; p.pad_hi = 0;
     p.num_tiles = num_tiles;
@@ -705,17 +838,21 @@ static int launch_contig_cfg(const Corr1dArgs &a, int lo_al, int L)
     p.stages = 1; p.stage_elems = (int)(stage_bytes / es);
     p.wide_store = (((g.n * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
     p.n_tiles = (int)r_tiles; p.c_tiles = (int)c_tiles;
-    p.cval = (T)a.cval;
-    for (int i = 0; i < SH; ++i) p.w[i] = T(0);
-    for (int i = 0; i < a.nw; ++i) p.w[SH + i] = (T)a.w[i];
+    p.cval = (TS)a.cval;
+    p.qinv = (T)box.qinv; p.qc0 = (T)box.qc0;
+    // taps: `L - a.nw` leading zeros (alignment of the TMA box start), then the
+    // caller's; the integer box filter pads to a multiple of V with zeros after
+    const int lead = lo_al - (a.nw / 2 + a.origin);
+    for (int i = 0; i < L; ++i) p.w[i] = T(0);
+    for (int i = 0; i < a.nw; ++i) p.w[lead + i] = (T)a.w[i];
 
-    auto kern = corr1d_contig_tma_kernel<T, SH, REM>;
+    auto kern = corr1d_contig_tma_kernel<T, TS, SH, REM>;
     const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
-    note_kernel(sizeof(T) == 4 ? "corr1d_tma_contig_f32" : "corr1d_tma_contig_f64");
+    note_kernel(kernel_name<T, TS>(false));
     return B200_OK;
 }
 
@@ -723,11 +860,12 @@ template <typename T, int SH>
 static int launch_contig_sh(const Corr1dArgs &a, int lo_al, int L)
 {
     constexpr int V = 16 / (int)sizeof(T);
+    const BoxInfo none;
     switch (L % V) {
-    case 0: return launch_contig_cfg<T, SH, 0>(a, lo_al, L);
-    case 1: return launch_contig_cfg<T, SH, 1>(a, lo_al, L);
-    case 2: if constexpr (V == 4) return launch_contig_cfg<T, SH, 2>(a, lo_al, L);
-    case 3: if constexpr (V == 4) return launch_contig_cfg<T, SH, 3>(a, lo_al, L);
+    case 0: return launch_contig_cfg<T, T, SH, 0>(a, none, lo_al, L);
+    case 1: return launch_contig_cfg<T, T, SH, 1>(a, none, lo_al, L);
+    case 2: if constexpr (V == 4) return launch_contig_cfg<T, T, SH, 2>(a, none, lo_al, L);
+    case 3: if constexpr (V == 4) return launch_contig_cfg<T, T, SH, 3>(a, none, lo_al, L);
     }
     return -1;
 }
@@ -759,15 +897,118 @@ static int launch_contig(const Corr1dArgs &a)
     return -1;
 }
 
+// integer box filter along the contiguous axis: the TMA box start must sit on
+// a 16-byte boundary of the STORAGE type (8 u16 / 16 u8 elements), so up to 15
+// zero taps lead; zero taps also pad the tail to a whole group (SH = REM = 0:
+// one kernel variant per storage type)
+template <typename TS>
+static int launch_contig_box(const Corr1dArgs &a, const BoxInfo &box)
+{
+    constexpr int V = 4;
+    constexpr int U16B = 16 / (int)sizeof(TS);
+    const int es = (int)sizeof(TS);
+    const LineGeom &g = a.g;
+    if (a.pad_lo || a.pad_hi) return -1;
+    if ((g.n * es) % 16 != 0) return -1;
+    if (g.n >= (1ll << 31) || g.outer >= (1ll << 31)) return -1;
+    if (((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15)) return -1;
+    const int lo = a.nw / 2 + a.origin;
+    const int lo_al = (lo + U16B - 1) / U16B * U16B;
+    int L = a.nw + (lo_al - lo);
+    L = (L + V - 1) / V * V;
+    if (L > kMaxTapsTma) return -1;
+    return launch_contig_cfg<float, TS, 0, 0>(a, box, lo_al, L);
+}
+
 int launch_corr1d_tma(const Corr1dArgs &a)
 {
     // NB the choice of kernel family must not depend on the number of planes
     // of the call: slabs of one volume (any GPU count) have to take the same
     // arithmetic path so that the whole-volume result is partition-invariant.
+    const BoxInfo none;
     if (a.dtype == B200_F32)
-        return a.g.inner == 1 ? launch_contig<float>(a) : launch_strided<float>(a);
+        return a.g.inner == 1 ? launch_contig<float>(a) : launch_strided<float, float>(a, none);
     if (a.dtype == B200_F64)
-        return a.g.inner == 1 ? launch_contig<double>(a) : launch_strided<double>(a);
+        return a.g.inner == 1 ? launch_contig<double>(a) : launch_strided<double, double>(a, none);
+    return -1;
+}
+
+// ---------------------------------------------------------------------------
+// uniform_filter1d fast paths
+// ---------------------------------------------------------------------------
+// Host proof that the float epilogue reproduces the reference's
+// trunc((double)sum / size) for EVERY window sum 0 <= s <= vmax * size: the
+// rounded value is monotone in s, so it is enough that the first and the last
+// sum of every quotient class [q*size, q*size + size - 1] land on q.
+static bool uniform_int_exact(int size, int64_t vmax)
+{
+    if (size < 2 || vmax * size >= (1ll << 23)) return false;
+    const float qinv = 1.0f / (float)size;
+    const float qc0 = 0.5f - 0.5f * (float)size;
+    auto quot = [&](int64_t s) -> int64_t {
+        const float y = fmaf((float)s + qc0, qinv, 12582912.f);
+        uint32_t bits;
+        memcpy(&bits, &y, 4);
+        return (int64_t)(bits & 0x3FFFFFu);
+    };
+    for (int64_t q = 0; q <= vmax; ++q) {
+        const int64_t s0 = q * size, s1 = q * size + size - 1;
+        const int64_t want = (int64_t)((double)s0 / (double)size);
+        if (quot(s0) != want) return false;
+        if (s1 <= vmax * size && quot(s1) != (int64_t)((double)s1 / (double)size)) return false;
+    }
+    return true;
+}
+
+template <typename TS>
+static int launch_uniform_box(const Uniform1dArgs &u, int64_t vmax)
+{
+    if (u.size > 128) return -1;
+    if (u.mode == B200_MODE_CONSTANT) {
+        // the tile holds storage-type values: cval must be one
+        if (!(u.cval >= 0.0 && u.cval <= (double)vmax) || u.cval != (double)(int64_t)u.cval) return -1;
+    }
+    // (one proof per size and type; sizes are small, the loop is ~vmax iterations)
+    static std::mutex mu;
+    static signed char proven[2][129];   // 0 unknown, 1 exact, -1 not
+    const int ti = sizeof(TS) == 2 ? 1 : 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (proven[ti][u.size] == 0) proven[ti][u.size] = uniform_int_exact(u.size, vmax) ? 1 : -1;
+        if (proven[ti][u.size] < 0) return -1;
+    }
+    double ones[128];
+    for (int i = 0; i < u.size; ++i) ones[i] = 1.0;
+    Corr1dArgs a;
+    a.in = u.in; a.out = u.out; a.dtype = u.dtype; a.g = u.g;
+    a.w = ones; a.nw = u.size; a.mode = u.mode; a.cval = u.cval; a.origin = u.origin;
+    a.pad_lo = u.pad_lo; a.pad_hi = u.pad_hi; a.epilogue = B200_EPI_STORE; a.flags = u.flags;
+    a.stream = u.stream;
+    BoxInfo box;
+    box.on = true;
+    box.qinv = 1.0f / (float)u.size;
+    box.qc0 = 0.5f - 0.5f * (float)u.size;
+    return u.g.inner == 1 ? launch_contig_box<TS>(a, box) : launch_strided<float, TS>(a, box);
+}
+
+int launch_uniform1d_fast(const Uniform1dArgs &u)
+{
+    if (u.size < 2) return -1;
+    if (u.dtype == B200_U16) return launch_uniform_box<uint16_t>(u, 65535);
+    if (u.dtype == B200_U8) return launch_uniform_box<uint8_t>(u, 255);
+    if (u.dtype == B200_F32 || u.dtype == B200_F64) {
+        // floats: the box filter is a correlation with `size` taps of 1/size
+        // (fp32 / fp64 accumulation in the array's type, like every float pass)
+        if (u.size > kMaxTapsTma) return -1;
+        double w[kMaxTapsTma];
+        for (int i = 0; i < u.size; ++i) w[i] = 1.0 / (double)u.size;
+        Corr1dArgs a;
+        a.in = u.in; a.out = u.out; a.dtype = u.dtype; a.g = u.g;
+        a.w = w; a.nw = u.size; a.mode = u.mode; a.cval = u.cval; a.origin = u.origin;
+        a.pad_lo = u.pad_lo; a.pad_hi = u.pad_hi; a.epilogue = B200_EPI_STORE; a.flags = u.flags;
+        a.stream = u.stream;
+        return launch_corr1d_tma(a);
+    }
     return -1;
 }
 

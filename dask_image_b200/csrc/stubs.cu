@@ -2,6 +2,5 @@
 // API falls through to the generic kernels.
 #include "common.cuh"
 namespace b200 {
-int launch_uniform1d_fast(const Uniform1dArgs &) { return -1; }
 int launch_corrnd_tiled(const CorrNdArgs &) { return -1; }
 }  // namespace b200

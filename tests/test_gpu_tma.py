@@ -129,3 +129,89 @@ def test_launch_counter_and_kernel_names(b200):
     _lib.launch_count(reset=True)
     b200.ndimage.gaussian_laplace(dev(b200, a), 2.0)
     assert _lib.launch_count() == 9
+
+
+# ---------------------------------------------------------------------------
+# integer box filter on the tiled kernels (exact: window sums in fp32, division
+# by the proven float epilogue) -- bit-identical to the oracle
+# ---------------------------------------------------------------------------
+U_SHAPES_AXES = [((70, 64), 0), ((70, 64), 1), ((5, 130, 48), 1), ((3, 40, 136), 2), ((200, 8, 16), 0),
+                 ((260, 512), 0), ((9, 264), 1), ((2, 3, 24, 32), 2), ((300, 16), 0), ((4, 16), 1)]
+U_SIZES = [(2, 0), (2, -1), (3, 0), (3, 1), (7, 0), (7, -3), (8, 3), (16, -8), (31, 4), (64, 0), (128, 63)]
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint8])
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("shape, axis", U_SHAPES_AXES)
+def test_tma_uniform_integer_exact(b200, dtype, mode, shape, axis):
+    from dask_image_b200 import _lib
+
+    rng = np.random.default_rng(hash((shape, axis, mode)) % (2 ** 32))
+    hi = np.iinfo(dtype).max
+    a = rng.integers(0, hi + 1, shape).astype(dtype)
+    a.flat[:: 7] = hi          # saturated runs: the largest window sums
+    a.flat[3:: 11] = 0
+    d = dev(b200, a)
+    for size, origin in U_SIZES:
+        with forced(b200, _lib.FLAG_FORCE_FAST):
+            got = b200.ndimage.uniform_filter1d(d, size, axis=axis, mode=mode, cval=float(hi // 3),
+                                                origin=origin)
+        assert _lib.last_kernel().startswith("uniform1d_tma_"), _lib.last_kernel()
+        ref = orc.uniform_filter1d(a, size, axis=axis, mode=mode, cval=float(hi // 3), origin=origin)
+        assert_parity(got.to_numpy(), ref, exact=True, what="size=%d origin=%d" % (size, origin))
+
+
+def test_tma_uniform_all_saturated_and_all_quotients(b200):
+    """Every window sum of a saturated volume, and a ramp that walks the
+    quotient classes, divide exactly."""
+    from dask_image_b200 import _lib
+
+    for dtype in (np.uint16, np.uint8):
+        hi = np.iinfo(dtype).max
+        for a in (np.full((64, 256), hi, dtype), (np.arange(64 * 256) % (hi + 1)).astype(dtype).reshape(64, 256)):
+            for size in (2, 3, 5, 7, 9, 11, 100, 127, 128):
+                for axis in (0, 1):
+                    got = b200.ndimage.uniform_filter1d(dev(b200, a), size, axis=axis, mode="nearest")
+                    assert _lib.last_kernel().startswith("uniform1d_tma_"), _lib.last_kernel()
+                    assert_parity(got.to_numpy(), ndi.uniform_filter1d(a, size, axis=axis, mode="nearest"),
+                                  exact=True, what="%s size=%d axis=%d" % (np.dtype(dtype), size, axis))
+
+
+def test_uniform_integer_falls_back_when_not_provable(b200):
+    from dask_image_b200 import _lib
+
+    a = np.random.default_rng(0).integers(0, 65536, (64, 64)).astype(np.uint16)
+    d = dev(b200, a)
+    # cval that is not a uint16 value, a window too long for exact fp32 sums, a signed dtype
+    got = b200.ndimage.uniform_filter1d(d, 5, axis=0, mode="constant", cval=0.5)
+    assert _lib.last_kernel() == "uniform1d_generic"
+    assert_parity(got.to_numpy(), ndi.uniform_filter1d(a, 5, axis=0, mode="constant", cval=0.5), exact=True)
+    got = b200.ndimage.uniform_filter1d(d, 200, axis=1)
+    assert _lib.last_kernel() == "uniform1d_generic"
+    assert_parity(got.to_numpy(), ndi.uniform_filter1d(a, 200, axis=1), exact=True)
+    s = a.astype(np.int16)
+    got = b200.ndimage.uniform_filter1d(dev(b200, s), 5, axis=1)
+    assert _lib.last_kernel() == "uniform1d_generic"
+    assert_parity(got.to_numpy(), ndi.uniform_filter1d(s, 5, axis=1), exact=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_uniform_float_uses_tiled_correlation(b200, dtype):
+    from dask_image_b200 import _lib
+
+    a = np.random.default_rng(4).random((48, 72, 96)).astype(dtype)
+    got = b200.ndimage.uniform_filter(dev(b200, a), (7, 4, 9), mode="mirror", origin=(0, -1, 2))
+    assert _lib.last_kernel().startswith("corr1d_tma_contig"), _lib.last_kernel()
+    assert_parity(got.to_numpy(), ndi.uniform_filter(a, (7, 4, 9), mode="mirror", origin=(0, -1, 2)))
+
+
+def test_config3_uniform_u16_volume(b200):
+    """BASELINE.json configs[2] at a checkable size: uniform_filter size=7 on a
+    uint16 volume, every pass on the tiled integer kernels, bit-exact."""
+    from dask_image_b200 import _lib
+
+    a = np.random.default_rng(1234).integers(0, 65536, (136, 200, 264), dtype=np.uint16)
+    _lib.launch_count(reset=True)
+    got = b200.ndfilters.uniform_filter(dev(b200, a), size=7)
+    assert _lib.launch_count() == 3 and _lib.last_kernel() == "uniform1d_tma_contig_u16"
+    assert_parity(got.to_numpy(), ndi.uniform_filter(a, 7), exact=True)
