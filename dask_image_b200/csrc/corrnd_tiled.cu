@@ -1,0 +1,298 @@
+// corrnd_tiled.cu -- shared-memory-tiled direct N-D correlate (sm_100a) for
+// non-separable weights: the float path behind convolve / correlate
+// (replaces _nd_image.correlate, scipy/ndimage/_filters.py:1305).
+//
+// The array is viewed as [Z][Y][X] (X contiguous; 2-D arrays have Z = 1).  A CTA
+// stages an input tile of (TZ + Kz - 1) x (TY + Ky - 1) rows of P elements with
+// ONE cp.async.bulk.tensor.3d (P is an odd multiple of 16 bytes: conflict-free
+// LDS.128), TMA zero-fills what lies outside the array, edge CTAs patch exactly
+// those elements through the closed-form extension maps.  A thread then owns
+// R = 2V consecutive outputs of one row and walks the Kz x Ky weight rows; each
+// row is the contiguous-axis tap engine of the 1-D kernel (tile_common.cuh:
+// three rotating 16-byte register blocks, packed FFMA2 on aligned pairs,
+// weights on the uniform datapath straight out of the parameter bank):
+// per V taps 1 LDS.128 + R*V FMAs.  The tap order per voxel is fixed
+// (kz, ky, kx), independent of tile geometry and slab partition.
+//
+// Bound: 2*taps flop / 8 bytes per voxel -- FP32 issue for anything beyond a few
+// dozen taps (9x9x9: 729 FMA per voxel), HBM for small stencils.
+// fp32 (fp64 for float64 arrays) accumulation; B200_FLAG_EXACT selects the
+// scipy-order fp64 kernel in generic.cu instead.  Weights with |w| <= DBL_EPSILON
+// are treated as zero, as the reference skips them.
+#include "tile_common.cuh"
+#include <vector>
+#include <cmath>
+
+namespace b200 {
+
+constexpr int kNdTapBytes = 24 * 1024;   // weights live in the kernel parameter bank
+
+template <typename T>
+struct CorrNdTiledParams {
+    const T *in;
+    T *out;
+    int64_t X, Y, Z;          // extents of the planes this call produces
+    int64_t pad_lo, pad_hi;   // resident planes before / after along the slowest axis
+    int pad_dim;              // which tile dimension the pads belong to: 2 = z, 1 = y (2-D arrays)
+    int Kx_al, Ky, Kz;        // taps per weight row (incl. SH alignment zeros), rows, planes
+    int lox_al, loy, loz;     // tile origin = first output - these
+    int TY, TZ, ncg;          // output tile: (ncg * 4R) x TY x TZ
+    int P, BY, BZ;            // input tile: pitch x rows x planes
+    int cx, cy;               // tiles along x and y (z = the rest of the grid)
+    int mode, wide_store;
+    T cval;
+    T w[kNdTapBytes / sizeof(T)];
+};
+
+template <typename T, int SH, int REM>
+__global__ void __launch_bounds__(256, 2)
+corrnd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CorrNdTiledParams<T> p)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int R = 2 * V;
+    constexpr int PC = 4 * R;
+    using VecT = Vec<T, V>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *tile = aligned_smem<T>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int P = p.P, BY = p.BY, BZ = p.BZ;
+    const int SX = p.ncg * PC;
+
+    int64_t t = blockIdx.x;
+    const int tcx = (int)(t % p.cx);
+    t /= p.cx;
+    const int tcy = (int)(t % p.cy);
+    const int64_t tcz = t / p.cy;
+    const int64_t x0t = (int64_t)tcx * SX, y0t = (int64_t)tcy * p.TY, z0t = tcz * p.TZ;
+    const int64_t g0x = x0t - p.lox_al, g0y = y0t - p.loy, g0z = z0t - p.loz;
+    // resident range of y and z (pads belong to the slowest axis of the array)
+    const int64_t ylo = p.pad_dim == 1 ? -p.pad_lo : 0, yhi = p.Y + (p.pad_dim == 1 ? p.pad_hi : 0);
+    const int64_t zlo = p.pad_dim == 2 ? -p.pad_lo : 0, zhi = p.Z + (p.pad_dim == 2 ? p.pad_hi : 0);
+
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        fence_barrier_init();
+        mbar_arrive_expect_tx(&full_bar, (uint32_t)((size_t)P * BY * BZ * sizeof(T)));
+        tma_load_3d(tile, &tmap, &full_bar, (int)g0x, (int)(g0y - ylo), (int)(g0z - zlo));
+    }
+    __syncthreads();
+    if (tid < 32) mbar_wait(&full_bar, 0);
+    __syncthreads();
+
+    const bool x_edge = g0x < 0 || g0x + P > p.X;
+    const bool yz_edge = g0y < ylo || g0y + BY > yhi || g0z < zlo || g0z + BZ > zhi;
+    if ((x_edge || yz_edge) && !(p.mode == B200_MODE_CONSTANT && p.cval == T(0))) {
+        for (int rr = warp; rr < BY * BZ; rr += 8) {
+            const int zz = rr / BY, r = rr - zz * BY;
+            const int64_t gy = g0y + r, gz = g0z + zz;
+            const bool row_in = gy >= ylo && gy < yhi && gz >= zlo && gz < zhi;
+            if (row_in && !x_edge) continue;
+            int64_t sy = gy, sz = gz;
+            bool row_cval = false;
+            if (!row_in) {
+                sy = p.pad_dim == 1 ? ext_index_padded(gy, p.Y, p.mode, p.pad_lo, p.pad_hi)
+                                    : ext_index_padded(gy, p.Y, p.mode, 0, 0);
+                sz = p.pad_dim == 2 ? ext_index_padded(gz, p.Z, p.mode, p.pad_lo, p.pad_hi)
+                                    : ext_index_padded(gz, p.Z, p.mode, 0, 0);
+                row_cval = sy == B200_USE_CVAL || sz == B200_USE_CVAL;
+            }
+            const T *srow = row_cval ? nullptr : p.in + (sz * p.Y + sy) * p.X;
+            T *trow = tile + (size_t)rr * P;
+            for (int c = lane; c < P; c += 32) {
+                const int64_t gx = g0x + c;
+                const bool x_in = gx >= 0 && gx < p.X;
+                if (row_in && x_in) continue;
+                T v = p.cval;
+                if (srow) {
+                    const int64_t sx = ext_index(gx, p.X, p.mode);
+                    if (sx >= 0) v = srow[sx];
+                }
+                trow[c] = v;
+            }
+        }
+        __syncthreads();
+    }
+
+    const int nrg = p.TY / 8;
+    const int per_plane = nrg * p.ncg;
+    const int npatch = per_plane * p.TZ;
+    const int patch_iters = (npatch + 7) / 8;   // uniform trip count, see corr1d_contig_tma_kernel
+    const int rows_w = p.Ky * p.Kz;
+    for (int qi = 0; qi < patch_iters; ++qi) {
+        const int q_raw = qi * 8 + warp;
+        const bool patch_live = q_raw < npatch;
+        const int q = patch_live ? q_raw : npatch - 1;
+        const int zz = q / per_plane;
+        const int qq = q - zz * per_plane;
+        const int rg = qq % nrg, cg = qq / nrg;
+        const int r = rg * 8 + (lane >> 2);
+        const int xl = cg * PC + (lane & 3) * R;
+        const T *sbase = tile + ((size_t)zz * BY + r) * P + xl;
+        ContigAcc<T, V> acc;
+        acc.zero();
+        const T *wrow = p.w;
+        int ky = 0, kz = 0;
+        for (int wr = 0; wr < rows_w; ++wr, wrow += p.Kx_al) {
+            row_taps<T, T, V, SH, REM>(acc, sbase + ((size_t)kz * BY + ky) * P, wrow, p.Kx_al);
+            if (++ky == p.Ky) { ky = 0; ++kz; }
+        }
+        const int64_t x = x0t + xl, y = y0t + r, z = z0t + zz;
+        if (patch_live && y < p.Y && z < p.Z && x < p.X) {
+            T *dst0 = p.out + ((z * p.Y + y) * p.X + x);
+            if (p.wide_store && x + R <= p.X) {
+                T res[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) res[j] = acc.get(j);
+                st_global_256(dst0, res);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (x + h * V < p.X) {
+                        VecT res;
+#pragma unroll
+                        for (int v = 0; v < V; ++v) res.v[v] = acc.get(h * V + v);
+                        *reinterpret_cast<VecT *>(dst0 + h * V) = res;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int SH, int REM>
+static int launch_cfg(const CorrNdArgs &a, int lox_al, int Kx_al)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int R = 2 * V, PC = 4 * R;
+    const int es = (int)sizeof(T);
+    const int nd = a.ndim;
+    const int64_t X = a.shape[nd - 1], Y = a.shape[nd - 2], Z = nd == 3 ? a.shape[0] : 1;
+    const int Kx = (int)a.wshape[nd - 1], Ky = (int)a.wshape[nd - 2], Kz = nd == 3 ? (int)a.wshape[0] : 1;
+    const int loy = Ky / 2 + (int)a.origins[nd - 2];
+    const int loz = nd == 3 ? Kz / 2 + (int)a.origins[0] : 0;
+    const int SH_ = lox_al - (Kx / 2 + (int)a.origins[nd - 1]);
+
+    auto pitch_for = [&](int cand) {
+        int pt = cand * PC + Kx_al + 2 * V - 1;
+        pt = (pt + V - 1) / V;
+        if (!(pt & 1)) ++pt;
+        return pt * V;
+    };
+    int ncg = 2;
+    while (ncg > 1 && pitch_for(ncg) > 256) --ncg;
+    const int P = pitch_for(ncg);
+    if (P > 256) return -1;
+    // tile depth / height: as many output planes (rows for 2-D arrays) as keep
+    // two CTAs resident per SM; geometry never changes a voxel's tap order
+    const size_t budget = (kSmemPerSm - 4096) / 2 - 256;
+    int TY = 8, TZ = 1;
+    auto bytes_for = [&](int ty, int tz) { return (size_t)P * (ty + Ky - 1) * (tz + Kz - 1) * es; };
+    if (bytes_for(TY, TZ) > budget) return -1;
+    if (nd == 3) {
+        while (TZ < 8 && bytes_for(TY, TZ * 2) <= budget) TZ *= 2;
+    } else {
+        while (TY < 64 && bytes_for(TY * 2, 1) <= budget) TY *= 2;
+    }
+    const int BY = TY + Ky - 1, BZ = TZ + Kz - 1;
+    if (BY > 256 || BZ > 256) return -1;
+    const int SX = ncg * PC;
+    const int64_t cx = (X + SX - 1) / SX, cy = (Y + TY - 1) / TY, cz = (Z + TZ - 1) / TZ;
+    const int64_t num_tiles = cx * cy * cz;
+    if (num_tiles >= (1ll << 31) || cx >= (1ll << 30) || cy >= (1ll << 30)) return -1;
+
+    const int pad_dim = nd == 3 ? 2 : 1;
+    const int64_t Ytot = pad_dim == 1 ? a.pad_lo + Y + a.pad_hi : Y;
+    const int64_t Ztot = pad_dim == 2 ? a.pad_lo + Z + a.pad_hi : Z;
+    const int64_t plane = pad_dim == 2 ? Y * X : X;
+    const char *base = (const char *)a.in - a.pad_lo * plane * es;
+    if (X >= (1ll << 31) || Ytot >= (1ll << 31) || Ztot >= (1ll << 31)) return -1;
+
+    CUtensorMap tmap;
+    uint64_t dims[3] = {(uint64_t)X, (uint64_t)Ytot, (uint64_t)Ztot};
+    uint64_t strides[2] = {(uint64_t)X * es, (uint64_t)X * es * (uint64_t)Ytot};
+    uint32_t bx[3] = {(uint32_t)P, (uint32_t)BY, (uint32_t)BZ};
+    if (encode_tensor_map(&tmap, a.dtype, (void *)base, 3, dims, strides, bx) != 0) return -1;
+
+    static_assert(sizeof(CorrNdTiledParams<T>) < 31 * 1024, "parameter bank");
+    CorrNdTiledParams<T> p;
+    p.in = (const T *)a.in; p.out = (T *)a.out;
+    p.X = X; p.Y = Y; p.Z = Z;
+    p.pad_lo = a.pad_lo; p.pad_hi = a.pad_hi; p.pad_dim = pad_dim;
+    p.Kx_al = Kx_al; p.Ky = Ky; p.Kz = Kz;
+    p.lox_al = lox_al; p.loy = loy; p.loz = loz;
+    p.TY = TY; p.TZ = TZ; p.ncg = ncg; p.P = P; p.BY = BY; p.BZ = BZ;
+    p.cx = (int)cx; p.cy = (int)cy;
+    p.mode = a.mode; p.cval = (T)a.cval;
+    p.wide_store = (((X * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
+    const int rows = Ky * Kz;
+    for (int i = 0; i < rows * Kx_al; ++i) p.w[i] = T(0);
+    for (int rw = 0; rw < rows; ++rw)
+        for (int kx = 0; kx < Kx; ++kx) {
+            const double w = a.w[(size_t)rw * Kx + kx];
+            p.w[rw * Kx_al + SH_ + kx] = std::fabs(w) > DBL_EPSILON ? (T)w : T(0);
+        }
+
+    auto kern = corrnd_tiled_kernel<T, SH, REM>;
+    const size_t smem = (size_t)P * BY * BZ * es + 128;
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
+    B200_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    note_kernel(sizeof(T) == 4 ? "corrnd_tiled_f32" : "corrnd_tiled_f64");
+    return B200_OK;
+}
+
+template <typename T, int SH>
+static int launch_sh(const CorrNdArgs &a, int lox_al, int Kx_al)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    switch (Kx_al % V) {
+    case 0: return launch_cfg<T, SH, 0>(a, lox_al, Kx_al);
+    case 1: return launch_cfg<T, SH, 1>(a, lox_al, Kx_al);
+    case 2: if constexpr (V == 4) return launch_cfg<T, SH, 2>(a, lox_al, Kx_al);
+    case 3: if constexpr (V == 4) return launch_cfg<T, SH, 3>(a, lox_al, Kx_al);
+    }
+    return -1;
+}
+
+template <typename T>
+static int launch_typed(const CorrNdArgs &a)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    const int es = (int)sizeof(T);
+    const int nd = a.ndim;
+    const int64_t X = a.shape[nd - 1];
+    if ((X * es) % 16 != 0) return -1;
+    if (((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15)) return -1;
+    const int Kx = (int)a.wshape[nd - 1];
+    const int64_t rows = a.wshape[nd - 2] * (nd == 3 ? a.wshape[0] : 1);
+    const int lox = Kx / 2 + (int)a.origins[nd - 1];
+    const int lox_al = (lox + V - 1) / V * V;
+    const int shift = lox_al - lox;
+    const int Kx_al = Kx + shift;
+    if (rows * Kx_al > (int64_t)(kNdTapBytes / sizeof(T))) return -1;
+    switch (shift) {
+    case 0: return launch_sh<T, 0>(a, lox_al, Kx_al);
+    case 1: return launch_sh<T, 1>(a, lox_al, Kx_al);
+    case 2: if constexpr (V == 4) return launch_sh<T, 2>(a, lox_al, Kx_al);
+    case 3: if constexpr (V == 4) return launch_sh<T, 3>(a, lox_al, Kx_al);
+    }
+    return -1;
+}
+
+int launch_corrnd_tiled(const CorrNdArgs &a)
+{
+    // eligibility depends on dtype, rank, the contiguous extent and the weights
+    // only (never on the number of planes): slabs of one volume agree
+    if (a.ndim != 2 && a.ndim != 3) return -1;
+    for (int d = 0; d < a.ndim; ++d)
+        if (a.wshape[d] > 128) return -1;
+    if (a.dtype == B200_F32) return launch_typed<float>(a);
+    if (a.dtype == B200_F64) return launch_typed<double>(a);
+    return -1;
+}
+
+}  // namespace b200

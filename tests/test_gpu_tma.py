@@ -135,8 +135,8 @@ def test_launch_counter_and_kernel_names(b200):
 # integer box filter on the tiled kernels (exact: window sums in fp32, division
 # by the proven float epilogue) -- bit-identical to the oracle
 # ---------------------------------------------------------------------------
-U_SHAPES_AXES = [((70, 64), 0), ((70, 64), 1), ((5, 130, 48), 1), ((3, 40, 136), 2), ((200, 8, 16), 0),
-                 ((260, 512), 0), ((9, 264), 1), ((2, 3, 24, 32), 2), ((300, 16), 0), ((4, 16), 1)]
+U_SHAPES_AXES = [((70, 64), 0), ((70, 64), 1), ((5, 130, 48), 1), ((3, 40, 144), 2), ((200, 8, 16), 0),
+                 ((260, 512), 0), ((9, 272), 1), ((2, 3, 24, 32), 2), ((300, 16), 0), ((4, 16), 1)]
 U_SIZES = [(2, 0), (2, -1), (3, 0), (3, 1), (7, 0), (7, -3), (8, 3), (16, -8), (31, 4), (64, 0), (128, 63)]
 
 
@@ -215,3 +215,49 @@ def test_config3_uniform_u16_volume(b200):
     got = b200.ndfilters.uniform_filter(dev(b200, a), size=7)
     assert _lib.launch_count() == 3 and _lib.last_kernel() == "uniform1d_tma_contig_u16"
     assert_parity(got.to_numpy(), ndi.uniform_filter(a, 7), exact=True)
+
+
+# ---------------------------------------------------------------------------
+# tiled direct N-D correlate (corrnd_tiled.cu)
+# ---------------------------------------------------------------------------
+ND_CASES = [
+    # shape, weights shape, origin
+    ((40, 64), (3, 3), 0), ((33, 72), (5, 4), (1, -2)), ((7, 16), (9, 9), (0, 3)), ((130, 260), (2, 7), (-1, 0)),
+    ((20, 24, 32), (3, 3, 3), 0), ((9, 30, 64), (4, 5, 6), (1, -2, 2)), ((25, 17, 40), (9, 9, 9), 0),
+    ((6, 5, 8), (3, 5, 7), (0, 1, -3)), ((12, 40, 132), (1, 1, 13), (0, 0, 5)), ((18, 18, 20), (7, 1, 2), (3, 0, -1)),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("shape, wshape, origin", ND_CASES)
+def test_tiled_correlate_nd(b200, dtype, mode, shape, wshape, origin):
+    from dask_image_b200 import _lib
+
+    rng = np.random.default_rng(hash((shape, wshape, mode)) % (2 ** 32))
+    a = (rng.random(shape) - 0.25).astype(dtype)
+    w = rng.random(wshape) - 0.3
+    w.flat[1] = 0.0                       # a tap the reference skips
+    d = dev(b200, a)
+    for name in ("correlate", "convolve"):
+        with forced(b200, _lib.FLAG_FORCE_FAST):
+            got = getattr(b200.ndimage, name)(d, w, mode=mode, cval=0.6, origin=origin)
+        assert _lib.last_kernel().startswith("corrnd_tiled_"), _lib.last_kernel()
+        ref = getattr(orc, name)(a, w, mode=mode, cval=0.6, origin=origin)
+        assert_parity(got.to_numpy(), ref, what=name, data=a)
+
+
+def test_config5_convolve_9cubed_wrap(b200):
+    """BASELINE.json configs[4] at a checkable size: random 9x9x9 float32 weights,
+    mode='wrap', float32 volume, through the public wrapper."""
+    from dask_image_b200 import _lib
+
+    rng = np.random.default_rng(1234)
+    a = rng.random((48, 56, 96), dtype=np.float32)
+    w = rng.random((9, 9, 9), dtype=np.float32)
+    got = b200.ndfilters.convolve(dev(b200, a), dev(b200, w), mode="wrap")
+    assert _lib.last_kernel() == "corrnd_tiled_f32"
+    assert_parity(got.to_numpy(), ndi.convolve(a, w, mode="wrap"))
+    # chunk-wise through the dispatch boundary (dask supplies periodic halos)
+    chunked = b200.ndfilters.convolve(b200.from_array(a, chunks=(24, 28, 32)), dev(b200, w), mode="wrap")
+    assert_parity(np.asarray(chunked), ndi.convolve(a, w, mode="wrap"))
