@@ -7,5 +7,6 @@ from ._array import B200Array, as_b200  # noqa: F401
 from . import ndimage, ndfilters, dispatch  # noqa: F401
 from ._overlap import HaloChunked, from_array  # noqa: F401
 from .sharded import ShardedVolume  # noqa: F401
+from .streaming import HostVolume  # noqa: F401
 
 __version__ = "0.1.0"

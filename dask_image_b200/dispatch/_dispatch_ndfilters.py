@@ -13,6 +13,7 @@ chunks to the CUDA kernels.
 """
 from .. import ndimage as _b200_ndimage
 from .. import sharded as _b200_sharded
+from .. import streaming as _b200_streaming
 from .._array import B200Array
 from ._dispatcher import Dispatcher
 
@@ -51,6 +52,8 @@ def register_b200(dispatchers):
             d.register(B200Array)(_factory(getattr(_b200_ndimage, name)))
             # a whole multi-GPU volume: the slab engine plays map_overlap's part
             d.register(_b200_sharded.ShardedVolume)(_factory(_b200_sharded.FUNCTIONS[name]))
+            # a host-resident volume streamed through the GPU (H2D | filter | D2H overlapped)
+            d.register(_b200_streaming.HostVolume)(_factory(_b200_streaming.FUNCTIONS[name]))
 
 
 _OWN = {n: globals()["dispatch_" + n] for n in _NAMES}

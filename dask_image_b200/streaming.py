@@ -1,0 +1,308 @@
+"""``HostVolume`` -- filter a volume that lives in HOST memory, streamed through
+one GPU.
+
+The reference's users hold host (numpy-backed) dask arrays; per chunk dask
+would copy a halo'd block to the device, filter it and copy the result back
+(dask_image/ndfilters/_gaussian.py:70-81 with a device chunk type).  This
+module is the B200-native form of that loop for a whole volume: the input is
+uploaded ONCE, in axis-0 chunks, and three streams overlap
+
+    H2D of chunk k+1  |  filter of chunk k  |  D2H of chunk k-1
+
+so the end-to-end time is bounded by the PCIe link (both directions busy at
+once) instead of upload + compute + download in sequence.  No halo is ever
+re-uploaded and nothing is trimmed: a chunk is filtered in place inside the
+resident input through the slab contract of the C ABI (``pad_lo`` / ``pad_hi``:
+the planes around it are simply resident), so the result is bit-identical to
+filtering the whole resident volume.
+
+Supported: every plan whose axis-0 passes read the plan's INPUT (gaussian
+filters and their derivative compositions, uniform_filter, laplace, N-D
+correlate / convolve).  Plans that filter along axis 0 after another pass
+(sobel / prewitt along a different axis) run un-pipelined on the whole volume.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import ndimage as _nd
+from ._array import _TORCH_TO_NP, torch_dtype
+
+__all__ = ["HostVolume", "FUNCTIONS"]
+
+
+def _as_host_tensor(a):
+    if isinstance(a, torch.Tensor):
+        if a.device.type != "cpu":
+            raise TypeError("HostVolume wraps host memory; use B200Array for device tensors")
+        return a if a.is_contiguous() else a.contiguous()
+    a = np.ascontiguousarray(a)
+    torch_dtype(a.dtype)
+    if a.dtype in (np.uint16, np.uint32, np.uint64):
+        signed = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32,
+                  np.dtype(np.uint64): np.int64}[a.dtype]
+        return torch.from_numpy(a.view(signed)).view(torch_dtype(a.dtype))
+    return torch.from_numpy(a)
+
+
+class HostVolume:
+    """A C-contiguous N-D volume in host memory (pinned memory gives full PCIe
+    speed and true overlap; pageable memory works, slower).
+
+    Parameters
+    ----------
+    array : numpy.ndarray or CPU torch.Tensor
+    out : optional CPU tensor / array of the same shape and dtype that receives
+        the result of the next filter (otherwise a pinned one is allocated)
+    device : CUDA device to stream through (default: current)
+    chunk_bytes : approximate size of one upload / compute / download unit
+    """
+
+    def __init__(self, array, out=None, device=None, chunk_bytes=1 << 30):
+        self.tensor = _as_host_tensor(array)
+        if self.tensor.dtype not in _TORCH_TO_NP:
+            raise RuntimeError("data type not supported")
+        self.out = None if out is None else _as_host_tensor(out)
+        if self.out is not None and (self.out.shape != self.tensor.shape or self.out.dtype != self.tensor.dtype):
+            raise RuntimeError("output shape / dtype not correct")
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("dask_image_b200 needs a CUDA device (sm_100a); none is visible "
+                                   "and there is no CPU fallback")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.chunk_bytes = int(chunk_bytes)
+
+    @classmethod
+    def pinned_empty(cls, shape, dtype, **kw):
+        return cls(torch.empty(tuple(shape), dtype=torch_dtype(dtype)).pin_memory(), **kw)
+
+    @property
+    def shape(self):
+        return tuple(int(s) for s in self.tensor.shape)
+
+    @property
+    def ndim(self):
+        return self.tensor.dim()
+
+    @property
+    def dtype(self):
+        return _TORCH_TO_NP[self.tensor.dtype]
+
+    @property
+    def size(self):
+        return int(self.tensor.numel())
+
+    def to_numpy(self):
+        t = self.tensor
+        if t.dtype in (torch.uint16, torch.uint32, torch.uint64):
+            return t.view(torch.uint8).numpy().view(self.dtype).reshape(self.shape)
+        return t.numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.to_numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __repr__(self):
+        return "HostVolume(shape=%s, dtype=%s, pinned=%s, via=%s)" % (
+            self.shape, self.dtype, self.tensor.is_pinned(), self.device)
+
+    # ------------------------------------------------------------------
+    def _run_plan(self, plan):
+        h_in = self.tensor
+        h_out = self.out if self.out is not None else torch.empty_like(h_in).pin_memory()
+        result = HostVolume(h_out, device=self.device, chunk_bytes=self.chunk_bytes)
+        if self.size == 0:
+            return result
+        if self.ndim == 0:
+            raise RuntimeError("0-d arrays are not supported")
+        dev, dt = self.device, self.dtype
+        n0 = self.shape[0]
+        tail = self.shape[1:]
+        plane_bytes = max(1, int(np.prod(tail, dtype=np.int64)) * dt.itemsize)
+
+        # reach of the plan along axis 0; plans that filter along axis 0 after
+        # another pass cannot be chunked without halos of intermediates
+        lo = hi = 0
+        streamable = True
+        ring = False
+        if plan.nd is not None:
+            w, origins, mode = plan.nd
+            lo = w.shape[0] // 2 + origins[0]
+            hi = w.shape[0] - 1 - lo
+            ring = mode in ("wrap", "grid-wrap")
+        for passes, _ in plan.chains:
+            for i, ps in enumerate(passes):
+                if ps.axis == 0:
+                    if i > 0:
+                        streamable = False
+                    L = len(ps.weights) if ps.kind == "corr" else ps.size
+                    l0 = L // 2 + ps.origin
+                    lo, hi = max(lo, l0), max(hi, L - 1 - l0)
+                    ring = ring or ps.mode in ("wrap", "grid-wrap")
+        C = max(1, min(n0, self.chunk_bytes // plane_bytes))
+        C = max(C, lo, hi, 1)
+        chunks = [(s, min(n0, s + C)) for s in range(0, n0, C)]
+        if not plan.chains and plan.nd is None:
+            h_out.copy_(h_in)
+            return result
+
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            if not streamable or len(chunks) < 3:
+                # whole volume resident, un-pipelined
+                from ._array import B200Array
+
+                d_in = B200Array(h_in.to(dev, non_blocking=True))
+                d_out = _nd._execute(plan, d_in, d_in.empty_like())
+                h_out.copy_(d_out.tensor, non_blocking=True)
+                cur.synchronize()
+                return result
+
+            d_in = torch.empty(self.shape, dtype=h_in.dtype, device=dev)
+            nslot = 3
+            d_out = [torch.empty((C,) + tail, dtype=h_in.dtype, device=dev) for _ in range(nslot)]
+            s_up, s_cmp, s_down = (torch.cuda.Stream(dev) for _ in range(3))
+            for s in (s_up, s_cmp, s_down):
+                s.wait_stream(cur)
+            ev_up = [torch.cuda.Event() for _ in chunks]
+            ev_cmp = [torch.cuda.Event() for _ in chunks]
+            ev_down = [None] * nslot
+
+            def compute(j, slot, uploaded_end, scr):
+                c0, c1 = chunks[j]
+                n = c1 - c0
+                pad = (c0, uploaded_end - c1)
+                src = d_in[c0:c1]
+                dst = d_out[slot][:n]
+                shape = (n,) + tail
+                with torch.cuda.stream(s_cmp):
+                    s_cmp.wait_event(ev_up[min(len(chunks) - 1, _chunk_of(chunks, uploaded_end - 1))])
+                    if ev_down[slot] is not None:
+                        s_cmp.wait_event(ev_down[slot])
+                    if plan.nd is not None:
+                        w, origins, mode = plan.nd
+                        _nd._launch_correlate_nd(src, dst, shape, dt, w, origins, mode, plan.cval, pad)
+                    else:
+                        if plan.zero_out:
+                            dst.zero_()
+                        for passes, op in plan.chains:
+                            if passes:
+                                _nd._run_chain(src, shape, dt, passes, plan.cval, dst, final_epilogue=op,
+                                               pad=pad, scratch=scr)
+                            else:
+                                _nd._launch_combine(dst, src, dt, op)
+                    ev_cmp[j].record(s_cmp)
+                with torch.cuda.stream(s_down):
+                    s_down.wait_event(ev_cmp[j])
+                    h_out[c0:c1].copy_(dst, non_blocking=True)
+                    ev_down[slot] = torch.cuda.Event()
+                    ev_down[slot].record(s_down)
+
+            # scratch volumes of the pass chains are chunk-sized; allocate them on
+            # the compute stream's behalf before the pipeline starts
+            need = 0
+            for passes, op in plan.chains:
+                for tgt in _nd._chain_targets(len(passes), op):
+                    if tgt != "out":
+                        need = max(need, tgt + 1)
+            scratch = [torch.empty((C,) + tail, dtype=h_in.dtype, device=dev) for _ in range(need)]
+
+            issued = 0
+            order = list(range(len(chunks)))
+            if ring:
+                # periodic volumes: chunk 0 needs the LAST planes -- filter it at the end
+                order = order[1:] + [0]
+            pending = list(order)
+            for k, (c0, c1) in enumerate(chunks):
+                with torch.cuda.stream(s_up):
+                    d_in[c0:c1].copy_(h_in[c0:c1], non_blocking=True)
+                    ev_up[k].record(s_up)
+                uploaded_end = c1
+                # every chunk whose reach is now resident can go
+                while pending:
+                    j = pending[0]
+                    j0, j1 = chunks[j]
+                    if ring and j == 0:
+                        ready = uploaded_end == n0
+                    else:
+                        ready = uploaded_end >= min(n0, j1 + hi) and (not ring or j1 + hi <= n0 or uploaded_end == n0)
+                    if not ready:
+                        break
+                    pending.pop(0)
+                    # scratch volumes are sized for whole chunks; a shorter (last)
+                    # chunk uses leading slices of them
+                    nj = chunks[j][1] - chunks[j][0]
+                    compute(j, issued % nslot, uploaded_end, scratch if nj == C else [t[:nj] for t in scratch])
+                    issued += 1
+            for s in (s_up, s_cmp, s_down):
+                cur.wait_stream(s)
+            cur.synchronize()
+        return result
+
+
+def _chunk_of(chunks, plane):
+    for k, (c0, c1) in enumerate(chunks):
+        if c0 <= plane < c1:
+            return k
+    return len(chunks) - 1
+
+
+def _check(vol):
+    if not isinstance(vol, HostVolume):
+        raise TypeError("expected a HostVolume")
+    if vol.ndim == 0:
+        raise RuntimeError("0-d arrays are not supported")
+    return vol
+
+
+def gaussian_filter(input, sigma, order=0, mode="reflect", cval=0.0, truncate=4.0, *, radius=None, axes=None):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_gaussian_filter(vol.ndim, sigma, order, mode, cval, truncate, radius, axes))
+
+
+def uniform_filter(input, size=3, mode="reflect", cval=0.0, origin=0, *, axes=None):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_uniform_filter(vol.ndim, size, mode, cval, origin, axes))
+
+
+def gaussian_gradient_magnitude(input, sigma, mode="reflect", cval=0.0, *, axes=None, **kwargs):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_gaussian_gradient_magnitude(vol.ndim, sigma, mode, cval, axes, **kwargs))
+
+
+def gaussian_laplace(input, sigma, mode="reflect", cval=0.0, *, axes=None, **kwargs):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_gaussian_laplace(vol.ndim, sigma, mode, cval, axes, **kwargs))
+
+
+def correlate(input, weights, mode="reflect", cval=0.0, origin=0):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_correlate_nd(vol.ndim, vol.dtype, weights, mode, cval, origin, False))
+
+
+def convolve(input, weights, mode="reflect", cval=0.0, origin=0):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_correlate_nd(vol.ndim, vol.dtype, weights, mode, cval, origin, True))
+
+
+def laplace(input, mode="reflect", cval=0.0, *, axes=None):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_laplace(vol.ndim, mode, cval, axes))
+
+
+def prewitt(input, axis=-1, mode="reflect", cval=0.0):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_prewitt(vol.ndim, axis, mode, cval))
+
+
+def sobel(input, axis=-1, mode="reflect", cval=0.0):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_sobel(vol.ndim, axis, mode, cval))
+
+
+FUNCTIONS = {f.__name__: f for f in (
+    convolve, correlate, laplace, prewitt, sobel, gaussian_filter, gaussian_gradient_magnitude,
+    gaussian_laplace, uniform_filter)}
+
+assert _lib is not None
