@@ -266,7 +266,6 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     const int TR = p.tile_rows;      // rows per tile (multiple of 8)
     const int SX = p.ncg * PC;       // tile columns
     const int nrg = TR / 8;
-    const int npatch = nrg * p.ncg;
     const int L = p.nw;              // taps incl. the SH alignment taps
     const int64_t nrows = p.outer;
     const bool reads_out = epilogue_reads_out(p.epilogue);
@@ -308,28 +307,33 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         __syncthreads();
     }
 
-    // group schedule (all warp-uniform): group 0 skips the SH alignment taps;
-    // full groups follow in slot order 1,2,0,...; the last group has REM taps
-    // uniform trip count (every warp runs the same number of patches, surplus
-    // ones recompute the last patch and skip the store): keeps the tap loops
-    // free of divergence so the weights stay on the uniform datapath
-    const int patch_iters = (npatch + 7) / 8;
+    // Patches: a warp keeps ONE column group (ncg is 1, 2 or 4) and walks the row
+    // groups with a fixed stride -- no div/mod, pointers advance by constants.
+    // Every warp runs the same trip count (surplus iterations recompute row
+    // group 0 and skip the store) so the tap loops stay free of divergence and
+    // the weights stay on the uniform datapath.
+    const int cg_shift = p.ncg == 4 ? 2 : (p.ncg == 2 ? 1 : 0);
+    const int cg = warp & (p.ncg - 1);
+    const int rg0 = warp >> cg_shift;
+    const int rg_step = 8 >> cg_shift;
+    const int patch_iters = (nrg + rg_step - 1) / rg_step;
+    const int xl = cg * PC + (lane & 3) * R;
+    const int r_in = lane >> 2;
+    const int64_t x = x0t + xl;
+    const TS *const tile_thr = tile + r_in * P + xl;
+    TS *const out_thr = p.out + ((row0 + r_in) * p.n + x);
     for (int qi = 0; qi < patch_iters; ++qi) {
-        const int q_raw = qi * 8 + warp;
-        const bool patch_live = q_raw < npatch;
-        const int q = patch_live ? q_raw : npatch - 1;
-        const int rg = q % nrg, cg = q / nrg;
-        const int r = rg * 8 + (lane >> 2);
-        const int xl = cg * PC + (lane & 3) * R;
-        const int64_t row = row0 + r;
-        const int64_t x = x0t + xl;
-        const TS *srow = tile + r * P + xl;
+        const int rg_raw = rg0 + qi * rg_step;
+        const bool patch_live = rg_raw < nrg;
+        const int rg = patch_live ? rg_raw : 0;
+        const int64_t row = row0 + rg * 8 + r_in;
+        const TS *srow = tile_thr + rg * 8 * P;
         ContigAcc<T, V> acc;
         acc.zero();
         row_taps<T, TS, V, SH, REM>(acc, srow, p.w, L);
 
         if (patch_live && row < nrows) {
-            TS *dst0 = p.out + (row * p.n + x);
+            TS *dst0 = out_thr + (int64_t)(rg * 8) * p.n;
             if constexpr (kBox) {
                 // rows are whole multiples of 16 bytes, so x < n implies x + R <= n
                 if (x < p.n) {
@@ -510,8 +514,8 @@ static int launch_contig_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al,
     // resident per SM; 2 column groups for short filters (taller tiles), 4 for
     // long ones (less halo re-read per output).
     int ncg = env_int("B200_TMA_NCG", L <= 24 ? 2 : 4);
-    ncg = ncg < 1 ? 1 : (ncg > 7 ? 7 : ncg);
-    while (ncg > 1 && pitch_for(ncg) > 256) --ncg;
+    ncg = ncg >= 4 ? 4 : (ncg >= 2 ? 2 : 1);   // a power of two: warps own whole column groups
+    while (ncg > 1 && pitch_for(ncg) > 256) ncg >>= 1;
     const int pitch = pitch_for(ncg);
     if (pitch > 256) return -1;
     const int SX = ncg * PC;

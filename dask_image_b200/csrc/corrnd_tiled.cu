@@ -44,42 +44,24 @@ struct CorrNdTiledParams {
     T w[kNdTapBytes / sizeof(T)];
 };
 
-template <typename T, int SH, int REM>
-__global__ void __launch_bounds__(256, 2)
-corrnd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CorrNdTiledParams<T> p)
+// Stage the CTA's input tile: one TMA 3-D box (zero fill outside the resident
+// range), then -- on CTAs that touch an edge -- patch exactly the out-of-range
+// elements through the extension maps.  Ends with the tile visible to all.
+template <typename T, typename PARAMS>
+__device__ __forceinline__ void nd_stage_tile(const PARAMS &p, const CUtensorMap &tmap, T *tile, uint64_t *full_bar,
+                                              int P, int BY, int BZ, int64_t g0x, int64_t g0y, int64_t g0z,
+                                              int64_t ylo, int64_t yhi, int64_t zlo, int64_t zhi)
 {
-    constexpr int V = 16 / (int)sizeof(T);
-    constexpr int R = 2 * V;
-    constexpr int PC = 4 * R;
-    using VecT = Vec<T, V>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *tile = aligned_smem<T>(smem_raw);
-    __shared__ __align__(8) uint64_t full_bar;
-
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int P = p.P, BY = p.BY, BZ = p.BZ;
-    const int SX = p.ncg * PC;
-
-    int64_t t = blockIdx.x;
-    const int tcx = (int)(t % p.cx);
-    t /= p.cx;
-    const int tcy = (int)(t % p.cy);
-    const int64_t tcz = t / p.cy;
-    const int64_t x0t = (int64_t)tcx * SX, y0t = (int64_t)tcy * p.TY, z0t = tcz * p.TZ;
-    const int64_t g0x = x0t - p.lox_al, g0y = y0t - p.loy, g0z = z0t - p.loz;
-    // resident range of y and z (pads belong to the slowest axis of the array)
-    const int64_t ylo = p.pad_dim == 1 ? -p.pad_lo : 0, yhi = p.Y + (p.pad_dim == 1 ? p.pad_hi : 0);
-    const int64_t zlo = p.pad_dim == 2 ? -p.pad_lo : 0, zhi = p.Z + (p.pad_dim == 2 ? p.pad_hi : 0);
-
     if (tid == 0) {
-        mbar_init(&full_bar, 1);
+        mbar_init(full_bar, 1);
         fence_barrier_init();
-        mbar_arrive_expect_tx(&full_bar, (uint32_t)((size_t)P * BY * BZ * sizeof(T)));
-        tma_load_3d(tile, &tmap, &full_bar, (int)g0x, (int)(g0y - ylo), (int)(g0z - zlo));
+        mbar_arrive_expect_tx(full_bar, (uint32_t)((size_t)P * BY * BZ * sizeof(T)));
+        tma_load_3d(tile, &tmap, full_bar, (int)g0x, (int)(g0y - ylo), (int)(g0z - zlo));
     }
     __syncthreads();
-    if (tid < 32) mbar_wait(&full_bar, 0);
+    if (tid < 32) mbar_wait(full_bar, 0);
     __syncthreads();
 
     const bool x_edge = g0x < 0 || g0x + P > p.X;
@@ -115,6 +97,38 @@ corrnd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         }
         __syncthreads();
     }
+
+}
+
+template <typename T, int SH, int REM>
+__global__ void __launch_bounds__(256, 2)
+corrnd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CorrNdTiledParams<T> p)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int R = 2 * V;
+    constexpr int PC = 4 * R;
+    using VecT = Vec<T, V>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *tile = aligned_smem<T>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int P = p.P, BY = p.BY, BZ = p.BZ;
+    const int SX = p.ncg * PC;
+
+    int64_t t = blockIdx.x;
+    const int tcx = (int)(t % p.cx);
+    t /= p.cx;
+    const int tcy = (int)(t % p.cy);
+    const int64_t tcz = t / p.cy;
+    const int64_t x0t = (int64_t)tcx * SX, y0t = (int64_t)tcy * p.TY, z0t = tcz * p.TZ;
+    const int64_t g0x = x0t - p.lox_al, g0y = y0t - p.loy, g0z = z0t - p.loz;
+    // resident range of y and z (pads belong to the slowest axis of the array)
+    const int64_t ylo = p.pad_dim == 1 ? -p.pad_lo : 0, yhi = p.Y + (p.pad_dim == 1 ? p.pad_hi : 0);
+    const int64_t zlo = p.pad_dim == 2 ? -p.pad_lo : 0, zhi = p.Z + (p.pad_dim == 2 ? p.pad_hi : 0);
+
+    nd_stage_tile<T>(p, tmap, tile, &full_bar, P, BY, BZ, g0x, g0y, g0z, ylo, yhi, zlo, zhi);
 
     const int nrg = p.TY / 8;
     const int per_plane = nrg * p.ncg;
@@ -156,6 +170,112 @@ corrnd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                         for (int v = 0; v < V; ++v) res.v[v] = acc.get(h * V + v);
                         *reinterpret_cast<VecT *>(dst0 + h * V) = res;
                     }
+                }
+            }
+        }
+    }
+}
+
+// ===========================================================================
+// float32 specialisation with the weight-row length fixed at compile time
+// (KXA = taps per row incl. alignment zeros, 1..16): the row engine is
+// straight-line code -- the thread's 16 + KXA input floats in registers, every
+// tap a run of packed FFMA2 with its weight read through the uniform datapath
+// at a static offset from the row's base -- so a row costs its FMAs, its 16-byte
+// shared loads and a handful of loop instructions.  A thread owns 16 consecutive
+// outputs (odd taps pair outputs (-1,0)...(15,16): 9 FFMA2 instead of 8); a warp
+// covers 64 x 8 outputs, lanes of a quarter warp sit on 8 different rows so the
+// odd 16-byte pitch makes every LDS.128 conflict-free.
+// ===========================================================================
+template <int KXA>
+__global__ void __launch_bounds__(256, 2)
+corrnd_static_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CorrNdTiledParams<float> p)
+{
+    constexpr int R = 16;
+    constexpr int NF = (R + KXA + 3) / 4 * 4;   // floats of a row a thread touches
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tile = aligned_smem<float>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int P = p.P, BY = p.BY, BZ = p.BZ;
+    constexpr int SX = 4 * R;
+
+    int64_t t = blockIdx.x;
+    const int tcx = (int)(t % p.cx);
+    t /= p.cx;
+    const int tcy = (int)(t % p.cy);
+    const int64_t tcz = t / p.cy;
+    const int64_t x0t = (int64_t)tcx * SX, y0t = (int64_t)tcy * p.TY, z0t = tcz * p.TZ;
+    const int64_t g0x = x0t - p.lox_al, g0y = y0t - p.loy, g0z = z0t - p.loz;
+    const int64_t ylo = p.pad_dim == 1 ? -p.pad_lo : 0, yhi = p.Y + (p.pad_dim == 1 ? p.pad_hi : 0);
+    const int64_t zlo = p.pad_dim == 2 ? -p.pad_lo : 0, zhi = p.Z + (p.pad_dim == 2 ? p.pad_hi : 0);
+
+    nd_stage_tile<float>(p, tmap, tile, &full_bar, P, BY, BZ, g0x, g0y, g0z, ylo, yhi, zlo, zhi);
+
+    // patches: (plane zz, row group yg); TY / 8 is a power of two
+    const int nyg = p.TY >> 3;
+    const int nyg_shift = 31 - __clz(nyg);
+    const int npatch = nyg * p.TZ;
+    const int patch_iters = (npatch + 7) >> 3;
+    const int r_in = lane & 7, xq = lane >> 3;
+    const int Ky = p.Ky, Kz = p.Kz;
+    for (int qi = 0; qi < patch_iters; ++qi) {
+        const int q_raw = qi * 8 + warp;
+        const bool patch_live = q_raw < npatch;
+        const int q = patch_live ? q_raw : npatch - 1;
+        const int zz = q >> nyg_shift, yg = q & (nyg - 1);
+        const int r = yg * 8 + r_in;
+        const int xl = xq * R;
+        const float *sz = tile + ((size_t)zz * BY + r) * P + xl;
+        float2 e[8], o[9];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] = make_float2(0.f, 0.f);
+        const float *wrow = p.w;
+        for (int kz = 0; kz < Kz; ++kz, sz += (size_t)BY * P) {
+            const float *srow = sz;
+            for (int ky = 0; ky < Ky; ++ky, srow += P, wrow += KXA) {
+                float f[NF];
+#pragma unroll
+                for (int b = 0; b < NF / 4; ++b) {
+                    const float4 v = *reinterpret_cast<const float4 *>(srow + 4 * b);
+                    f[4 * b] = v.x; f[4 * b + 1] = v.y; f[4 * b + 2] = v.z; f[4 * b + 3] = v.w;
+                }
+#pragma unroll
+                for (int tt = 0; tt < KXA; ++tt) {
+                    const float wk = wrow[tt];
+                    const float2 w2 = make_float2(wk, wk);
+                    if ((tt & 1) == 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            e[i] = __ffma2_rn(make_float2(f[2 * i + tt], f[2 * i + tt + 1]), w2, e[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 9; ++i)
+                            o[i] = __ffma2_rn(make_float2(f[2 * i - 1 + tt], f[2 * i + tt]), w2, o[i]);
+                    }
+                }
+            }
+        }
+        const int64_t x = x0t + xl, y = y0t + r, z = z0t + zz;
+        if (patch_live && y < p.Y && z < p.Z && x < p.X) {
+            float *dst0 = p.out + ((z * p.Y + y) * p.X + x);
+            float res[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+                res[j] = ((j & 1) ? e[j >> 1].y : e[j >> 1].x) + ((j & 1) ? o[(j + 1) >> 1].x : o[j >> 1].y);
+            if (p.wide_store && x + R <= p.X) {
+                st_global_256(dst0, reinterpret_cast<const float(&)[8]>(res[0]));
+                st_global_256(dst0 + 8, reinterpret_cast<const float(&)[8]>(res[8]));
+            } else {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    if (x + h * 4 < p.X)
+                        *reinterpret_cast<float4 *>(dst0 + h * 4) =
+                            make_float4(res[4 * h], res[4 * h + 1], res[4 * h + 2], res[4 * h + 3]);
                 }
             }
         }
@@ -245,6 +365,106 @@ static int launch_cfg(const CorrNdArgs &a, int lox_al, int Kx_al)
     return B200_OK;
 }
 
+template <int KXA>
+static int launch_static_cfg(const CorrNdArgs &a, int lox_al)
+{
+    constexpr int R = 16, SX = 4 * R;
+    constexpr int NF = (R + KXA + 3) / 4 * 4;
+    const int es = 4;
+    const int nd = a.ndim;
+    const int64_t X = a.shape[nd - 1], Y = a.shape[nd - 2], Z = nd == 3 ? a.shape[0] : 1;
+    const int Kx = (int)a.wshape[nd - 1], Ky = (int)a.wshape[nd - 2], Kz = nd == 3 ? (int)a.wshape[0] : 1;
+    const int loy = Ky / 2 + (int)a.origins[nd - 2];
+    const int loz = nd == 3 ? Kz / 2 + (int)a.origins[0] : 0;
+    const int lead = lox_al - (Kx / 2 + (int)a.origins[nd - 1]);
+    if ((int64_t)Ky * Kz * KXA > (int64_t)(kNdTapBytes / sizeof(float))) return -1;
+
+    int pu = (SX - R + NF + 3) / 4;
+    if (!(pu & 1)) ++pu;
+    const int P = pu * 4;
+    // output tile: 64 x TY x TZ with (TY / 8) * TZ patches for the 8 warps; the
+    // deepest geometry that keeps two CTAs per SM resident
+    const size_t budget = (kSmemPerSm - 4096) / 2 - 256;
+    static const int cand3[][2] = {{8, 8}, {16, 4}, {32, 2}, {8, 4}, {16, 2}, {8, 2}, {16, 1}, {8, 1}};
+    static const int cand2[][2] = {{64, 1}, {32, 1}, {16, 1}, {8, 1}};
+    int TY = 0, TZ = 0;
+    const int (*cand)[2] = nd == 3 ? cand3 : cand2;
+    const int ncand = nd == 3 ? 8 : 4;
+    for (int i = 0; i < ncand; ++i) {
+        const size_t bytes = (size_t)P * (cand[i][0] + Ky - 1) * (cand[i][1] + Kz - 1) * es;
+        if (bytes <= budget && cand[i][0] + Ky - 1 <= 256 && cand[i][1] + Kz - 1 <= 256) {
+            TY = cand[i][0]; TZ = cand[i][1];
+            break;
+        }
+    }
+    if (!TY) return -1;
+    const int BY = TY + Ky - 1, BZ = TZ + Kz - 1;
+    const int64_t cx = (X + SX - 1) / SX, cy = (Y + TY - 1) / TY, cz = (Z + TZ - 1) / TZ;
+    const int64_t num_tiles = cx * cy * cz;
+    if (num_tiles >= (1ll << 31) || cx >= (1ll << 30) || cy >= (1ll << 30)) return -1;
+
+    const int pad_dim = nd == 3 ? 2 : 1;
+    const int64_t Ytot = pad_dim == 1 ? a.pad_lo + Y + a.pad_hi : Y;
+    const int64_t Ztot = pad_dim == 2 ? a.pad_lo + Z + a.pad_hi : Z;
+    const int64_t plane = pad_dim == 2 ? Y * X : X;
+    const char *base = (const char *)a.in - a.pad_lo * plane * es;
+    if (X >= (1ll << 31) || Ytot >= (1ll << 31) || Ztot >= (1ll << 31)) return -1;
+
+    CUtensorMap tmap;
+    uint64_t dims[3] = {(uint64_t)X, (uint64_t)Ytot, (uint64_t)Ztot};
+    uint64_t strides[2] = {(uint64_t)X * es, (uint64_t)X * es * (uint64_t)Ytot};
+    uint32_t bx[3] = {(uint32_t)P, (uint32_t)BY, (uint32_t)BZ};
+    if (encode_tensor_map(&tmap, a.dtype, (void *)base, 3, dims, strides, bx) != 0) return -1;
+
+    CorrNdTiledParams<float> p;
+    p.in = (const float *)a.in; p.out = (float *)a.out;
+    p.X = X; p.Y = Y; p.Z = Z;
+    p.pad_lo = a.pad_lo; p.pad_hi = a.pad_hi; p.pad_dim = pad_dim;
+    p.Kx_al = KXA; p.Ky = Ky; p.Kz = Kz;
+    p.lox_al = lox_al; p.loy = loy; p.loz = loz;
+    p.TY = TY; p.TZ = TZ; p.ncg = 1; p.P = P; p.BY = BY; p.BZ = BZ;
+    p.cx = (int)cx; p.cy = (int)cy;
+    p.mode = a.mode; p.cval = (float)a.cval;
+    p.wide_store = (((X * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
+    const int rows = Ky * Kz;
+    for (int i = 0; i < rows * KXA; ++i) p.w[i] = 0.f;
+    for (int rw = 0; rw < rows; ++rw)
+        for (int kx = 0; kx < Kx; ++kx) {
+            const double w = a.w[(size_t)rw * Kx + kx];
+            p.w[rw * KXA + lead + kx] = std::fabs(w) > DBL_EPSILON ? (float)w : 0.f;
+        }
+
+    auto kern = corrnd_static_kernel<KXA>;
+    const size_t smem = (size_t)P * BY * BZ * es + 128;
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
+    B200_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    note_kernel("corrnd_tiled_f32");
+    return B200_OK;
+}
+
+// float32 with at most 16 taps per weight row (alignment zeros included)
+static int launch_static(const CorrNdArgs &a)
+{
+    const int nd = a.ndim;
+    const int64_t X = a.shape[nd - 1];
+    if ((X * 4) % 16 != 0) return -1;
+    if (((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15)) return -1;
+    const int Kx = (int)a.wshape[nd - 1];
+    const int lox = Kx / 2 + (int)a.origins[nd - 1];
+    const int lox_al = (lox + 3) / 4 * 4;
+    const int kxa = Kx + (lox_al - lox);
+    switch (kxa) {
+#define B200_ND_CASE(K) case K: return launch_static_cfg<K>(a, lox_al);
+    B200_ND_CASE(1) B200_ND_CASE(2) B200_ND_CASE(3) B200_ND_CASE(4) B200_ND_CASE(5) B200_ND_CASE(6)
+    B200_ND_CASE(7) B200_ND_CASE(8) B200_ND_CASE(9) B200_ND_CASE(10) B200_ND_CASE(11) B200_ND_CASE(12)
+    B200_ND_CASE(13) B200_ND_CASE(14) B200_ND_CASE(15) B200_ND_CASE(16)
+#undef B200_ND_CASE
+    default: return -2;   // longer rows: the run-time row engine
+    }
+}
+
 template <typename T, int SH>
 static int launch_sh(const CorrNdArgs &a, int lox_al, int Kx_al)
 {
@@ -290,7 +510,11 @@ int launch_corrnd_tiled(const CorrNdArgs &a)
     if (a.ndim != 2 && a.ndim != 3) return -1;
     for (int d = 0; d < a.ndim; ++d)
         if (a.wshape[d] > 128) return -1;
-    if (a.dtype == B200_F32) return launch_typed<float>(a);
+    if (a.dtype == B200_F32) {
+        // (which engine runs depends on the weights' row length only)
+        const int rc = env_int("B200_ND_STATIC", 1) ? launch_static(a) : -2;
+        return rc == -2 ? launch_typed<float>(a) : rc;
+    }
     if (a.dtype == B200_F64) return launch_typed<double>(a);
     return -1;
 }

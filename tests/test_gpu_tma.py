@@ -224,7 +224,7 @@ ND_CASES = [
     # shape, weights shape, origin
     ((40, 64), (3, 3), 0), ((33, 72), (5, 4), (1, -2)), ((7, 16), (9, 9), (0, 3)), ((130, 260), (2, 7), (-1, 0)),
     ((20, 24, 32), (3, 3, 3), 0), ((9, 30, 64), (4, 5, 6), (1, -2, 2)), ((25, 17, 40), (9, 9, 9), 0),
-    ((6, 5, 8), (3, 5, 7), (0, 1, -3)), ((12, 40, 132), (1, 1, 13), (0, 0, 5)), ((18, 18, 20), (7, 1, 2), (3, 0, -1)),
+    ((6, 5, 8), (3, 5, 7), (0, 1, -3)), ((10, 12, 64), (2, 3, 21), (0, 1, 4)), ((9, 72), (3, 30), (1, -7)), ((12, 40, 132), (1, 1, 13), (0, 0, 5)), ((18, 18, 20), (7, 1, 2), (3, 0, -1)),
 ]
 
 
