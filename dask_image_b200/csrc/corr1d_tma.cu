@@ -395,14 +395,17 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 // ~14 instructions per output instead of ~38 for the run-time loop.  A thread
 // owns 16 outputs, a warp 64 x 8; the lanes of a quarter warp sit on 8
 // different rows, which the odd 16-byte pitch spreads over all bank groups.
-template <int NG, bool PLAIN>
+template <typename TS, int NG, bool PLAIN>
 __global__ void __launch_bounds__(256, 3)
 corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
-                            const __grid_constant__ Corr1dTmaParams<float, float> p)
+                            const __grid_constant__ Corr1dTmaParams<float, TS> p)
 {
     constexpr int R = 16, PC = 4 * R, LA = 4 * NG, NF = R + LA;
+    constexpr bool kBox = sizeof(TS) != sizeof(float);   // exact integer box filter
+    constexpr int EB = 16 / (int)sizeof(TS);             // elements per 16-byte shared load
+    static_assert(NF % EB == 0, "row window must be whole 16-byte blocks of the storage type");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *tile = aligned_smem<float>(smem_raw);
+    TS *tile = aligned_smem<TS>(smem_raw);
     __shared__ __align__(8) uint64_t full_bar;
 
     const int tid = threadIdx.x;
@@ -423,7 +426,7 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
     if (tid == 0) {
         mbar_init(&full_bar, 1);
         fence_barrier_init();
-        mbar_arrive_expect_tx(&full_bar, (uint32_t)(TR * P * (int)sizeof(float)));
+        mbar_arrive_expect_tx(&full_bar, (uint32_t)(TR * P * (int)sizeof(TS)));
         tma_load_2d(tile, &tmap, &full_bar, (int)g0, (int)row0);
     }
     __syncthreads();
@@ -432,7 +435,7 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
 
     const bool low_edge = g0 < 0;
     const bool high_edge = g0 + P > p.n;
-    if ((low_edge || high_edge) && !(p.mode == B200_MODE_CONSTANT && p.cval == 0.f)) {
+    if ((low_edge || high_edge) && !(p.mode == B200_MODE_CONSTANT && p.cval == TS(0))) {
         const int nlow = low_edge ? (int)(-g0 < P ? -g0 : P) : 0;
         const int hstart = high_edge ? (int)((p.n - g0) > 0 ? (p.n - g0) : 0) : P;
         const int per_row = nlow + (P - hstart);
@@ -441,8 +444,8 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
             int c = idx - r * per_row;
             c = c < nlow ? c : hstart + (c - nlow);
             const int64_t src = ext_index(g0 + c, p.n, p.mode);
-            float v = p.cval;
-            if (src >= 0) v = (row0 + r < nrows) ? p.in[(row0 + r) * p.n + src] : 0.f;
+            TS v = p.cval;
+            if (src >= 0) v = (row0 + r < nrows) ? p.in[(row0 + r) * p.n + src] : TS(0);
             tile[r * P + c] = v;
         }
         __syncthreads();
@@ -457,18 +460,27 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
     const int r_in = lane & 7;
     const int xl = cg * PC + (lane >> 3) * R;
     const int64_t x = x0t + xl;
-    const float *const tile_thr = tile + r_in * P + xl;
-    float *const out_thr = p.out + ((row0 + r_in) * p.n + x);
+    const TS *const tile_thr = tile + r_in * P + xl;
+    TS *const out_thr = p.out + ((row0 + r_in) * p.n + x);
     for (int qi = 0; qi < patch_iters; ++qi) {
         const int rg_raw = rg0 + qi * rg_step;
         const bool patch_live = rg_raw < nrg;
         const int rg = patch_live ? rg_raw : 0;
-        const float *srow = tile_thr + rg * 8 * P;
+        const TS *srow = tile_thr + rg * 8 * P;
         float f[NF];
+        if constexpr (!kBox) {
 #pragma unroll
-        for (int b = 0; b < NF / 4; ++b) {
-            const float4 v = *reinterpret_cast<const float4 *>(srow + 4 * b);
-            f[4 * b] = v.x; f[4 * b + 1] = v.y; f[4 * b + 2] = v.z; f[4 * b + 3] = v.w;
+            for (int b = 0; b < NF / 4; ++b) {
+                const float4 v = *reinterpret_cast<const float4 *>(srow + 4 * b);
+                f[4 * b] = v.x; f[4 * b + 1] = v.y; f[4 * b + 2] = v.z; f[4 * b + 3] = v.w;
+            }
+        } else {
+            // one LDS.128 = 8 uint16 / 16 uint8; widen 4 at a time (PRMT + packed unbias)
+#pragma unroll
+            for (int b = 0; b < NF / 4; ++b) {
+                const Vec<float, 4> v = load_block<float, TS, 4>(srow + 4 * b);
+                f[4 * b] = v.v[0]; f[4 * b + 1] = v.v[1]; f[4 * b + 2] = v.v[2]; f[4 * b + 3] = v.v[3];
+            }
         }
         float2 e[8], o[9];
 #pragma unroll
@@ -491,12 +503,18 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
         }
         const int64_t row = row0 + rg * 8 + r_in;
         if (patch_live && row < nrows && x < p.n) {
-            float *dst0 = out_thr + (int64_t)(rg * 8) * p.n;
+            TS *dst0 = out_thr + (int64_t)(rg * 8) * p.n;
             float res[R];
 #pragma unroll
             for (int j = 0; j < R; ++j)
                 res[j] = ((j & 1) ? e[j >> 1].y : e[j >> 1].x) + ((j & 1) ? o[(j + 1) >> 1].x : o[j >> 1].y);
-            if (p.wide_store && x + R <= p.n) {
+            if constexpr (kBox) {
+                // rows are whole multiples of 16 bytes and x is a multiple of 16 elements
+                store_box_quotients<float, TS, 8>(dst0, reinterpret_cast<const float(&)[8]>(res[0]), p.qinv, p.qc0);
+                if (x + 8 < p.n)
+                    store_box_quotients<float, TS, 8>(dst0 + 8, reinterpret_cast<const float(&)[8]>(res[8]), p.qinv,
+                                                      p.qc0);
+            } else if (p.wide_store && x + R <= p.n) {
                 if constexpr (!PLAIN) {
                     const bool reads_out = epilogue_reads_out(p.epilogue);
                     float prev[R];
@@ -717,16 +735,17 @@ static int launch_contig_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al,
     return B200_OK;
 }
 
-template <int NG, bool PLAIN>
-static int launch_contig_static_cfg(const Corr1dArgs &a, int lo_al, int lead)
+template <typename TS, int NG, bool PLAIN>
+static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al, int lead)
 {
     constexpr int R = 16, PC = 4 * R, LA = 4 * NG;
-    const int es = 4;
+    constexpr int EB = 16 / (int)sizeof(TS);   // elements per 16 bytes of storage
+    const int es = (int)sizeof(TS);
     const LineGeom &g = a.g;
     auto pitch_for = [&](int cand) {
-        int pu = (cand * PC + LA) / 4;
+        int pu = (cand * PC + LA + EB - 1) / EB;
         if (!(pu & 1)) ++pu;
-        return pu * 4;
+        return pu * EB;
     };
     int ncg = env_int("B200_TMA_SNCG", 2);
     ncg = ncg >= 2 ? 2 : 1;
@@ -751,10 +770,10 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, int lo_al, int lead)
     uint64_t dims[2] = {(uint64_t)g.n, (uint64_t)g.outer};
     uint64_t strides[1] = {(uint64_t)g.n * es};
     uint32_t bx[2] = {(uint32_t)pitch, (uint32_t)tr};
-    if (encode_tensor_map(&tmap, B200_F32, (void *)a.in, 2, dims, strides, bx) != 0) return -1;
+    if (encode_tensor_map(&tmap, dtype_code<TS>(), (void *)a.in, 2, dims, strides, bx) != 0) return -1;
 
-    Corr1dTmaParams<float, float> p;
-    p.in = (const float *)a.in; p.out = (float *)a.out;
+    Corr1dTmaParams<float, TS> p;
+    p.in = (const TS *)a.in; p.out = (TS *)a.out;
     p.outer = g.outer; p.n = g.n; p.inner = 1;
     p.pad_lo = 0; p.pad_hi = 0;
     p.num_tiles = num_tiles;
@@ -763,18 +782,18 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, int lo_al, int lead)
     p.stages = 1; p.stage_elems = (int)(stage_bytes / es);
     p.wide_store = (((g.n * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
     p.n_tiles = (int)r_tiles; p.c_tiles = (int)c_tiles;
-    p.cval = (float)a.cval;
-    p.qinv = 0.f; p.qc0 = 0.f;
+    p.cval = (TS)a.cval;
+    p.qinv = box.qinv; p.qc0 = box.qc0;
     for (int i = 0; i < LA; ++i) p.w[i] = 0.f;
     for (int i = 0; i < a.nw; ++i) p.w[lead + i] = (float)a.w[i];
 
-    auto kern = corr1d_contig_static_kernel<NG, PLAIN>;
+    auto kern = corr1d_contig_static_kernel<TS, NG, PLAIN>;
     const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
-    note_kernel("corr1d_tma_contig_f32");
+    note_kernel(kernel_name<float, TS>(false));
     return B200_OK;
 }
 
@@ -794,10 +813,11 @@ static int launch_contig_static(const Corr1dArgs &a)
     const int ng = (lead + a.nw + 3) / 4;
     if (ng > kStaticNG) return -2;
     const bool plain = a.epilogue == B200_EPI_STORE;
+    const BoxInfo none;
     switch (ng) {
 #define B200_C1_CASE(K) \
-    case K: return plain ? launch_contig_static_cfg<K, true>(a, lo_al, lead) \
-                         : launch_contig_static_cfg<K, false>(a, lo_al, lead);
+    case K: return plain ? launch_contig_static_cfg<float, K, true>(a, none, lo_al, lead) \
+                         : launch_contig_static_cfg<float, K, false>(a, none, lo_al, lead);
     B200_C1_CASE(1) B200_C1_CASE(2) B200_C1_CASE(3) B200_C1_CASE(4) B200_C1_CASE(5) B200_C1_CASE(6)
     B200_C1_CASE(7) B200_C1_CASE(8) B200_C1_CASE(9) B200_C1_CASE(10) B200_C1_CASE(11) B200_C1_CASE(12)
 #undef B200_C1_CASE
@@ -863,7 +883,23 @@ static int launch_contig_box(const Corr1dArgs &a, const BoxInfo &box)
     if (((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15)) return -1;
     const int lo = a.nw / 2 + a.origin;
     const int lo_al = (lo + U16B - 1) / U16B * U16B;
-    int L = a.nw + (lo_al - lo);
+    const int lead = lo_al - lo;
+    if (env_int("B200_TMA_STATIC", 1)) {
+        // compile-time tap engine: taps padded to whole 16-byte blocks of storage
+        const int la = (lead + a.nw + U16B - 1) / U16B * U16B;
+        switch (la / 4) {
+#define B200_BOX_CASE(K) case K: return launch_contig_static_cfg<TS, K, true>(a, box, lo_al, lead);
+        case 2: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 2, true>(a, box, lo_al, lead); break;
+        B200_BOX_CASE(4)
+        case 6: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 6, true>(a, box, lo_al, lead); break;
+        B200_BOX_CASE(8)
+        case 10: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 10, true>(a, box, lo_al, lead); break;
+        B200_BOX_CASE(12)
+#undef B200_BOX_CASE
+        default: break;
+        }
+    }
+    int L = a.nw + lead;
     L = (L + V - 1) / V * V;
     if (L > kMaxTapsTma) return -1;
     return launch_contig_cfg<float, TS, 0, 0>(a, box, lo_al, L);
