@@ -55,6 +55,12 @@ class HaloChunked:
         dropped = self.ndim - sub.ndim
         return HaloChunked(sub, self.chunksize[dropped:]) if sub.ndim else sub
 
+    def astype(self, dtype):
+        return HaloChunked(self._array.astype(dtype), self.chunksize)
+
+    def __sub__(self, other):
+        return HaloChunked(self._array - other, self.chunksize)
+
     def map_overlap(self, func, depth, boundary, dtype=None, meta=None, **kwargs):
         nd = self.ndim
         # dask accepts a scalar or a per-axis mapping for both arguments

@@ -123,10 +123,10 @@ struct Corr1dTmaParams {
 // code; nothing in the tap loops is divergent, which lets ptxas keep the
 // weights on the uniform datapath (LDCU -> FFMA2 with a UR operand).
 template <typename T, typename TS, int W, int TY, int R, int MINB, int REM>
-__global__ void __launch_bounds__((W / StorageV<T, TS>::V) * TY, MINB)
+__global__ void __launch_bounds__((W / StridedV<T, TS>::V) * TY, MINB)
 corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T, TS> p)
 {
-    constexpr int V = StorageV<T, TS>::V;
+    constexpr int V = StridedV<T, TS>::V;
     constexpr bool kBox = sizeof(TS) != sizeof(T);   // exact integer box filter
     constexpr int TX = W / V;
     constexpr int NTHREADS = TX * TY;
@@ -575,7 +575,7 @@ static const char *kernel_name(bool strided)
 template <typename T, typename TS, int R, int MINB, int REM>
 static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
 {
-    constexpr int V = StorageV<T, TS>::V;
+    constexpr int V = StridedV<T, TS>::V;
     constexpr int W = 32 * V;   // one warp spans a tile row (512 bytes of floats)
     constexpr int TY = 8;
     constexpr int ROWS_PER_BLK = TY * R;
@@ -631,7 +631,7 @@ template <typename T, typename TS>
 static int launch_strided(const Corr1dArgs &a, const BoxInfo &box)
 {
     constexpr int R = 4, MINB = 3;
-    constexpr int V = StorageV<T, TS>::V;
+    constexpr int V = StridedV<T, TS>::V;
     const int es = (int)sizeof(TS);
     const int row_bytes = 32 * V * es;
     const LineGeom &g = a.g;

@@ -50,20 +50,22 @@ struct VecAcc {
     __device__ __forceinline__ T get(int i) const { return a[i]; }
 };
 
-template <>
-struct VecAcc<float, 4> {
-    float2 a[2];
-    __device__ __forceinline__ void zero() { a[0] = a[1] = make_float2(0.f, 0.f); }
-    __device__ __forceinline__ void fma(const Vec<float, 4> &x, float w)
+template <int V>
+struct VecAcc<float, V> {
+    static_assert(V % 2 == 0, "packed pairs");
+    float2 a[V / 2];
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) a[i] = make_float2(0.f, 0.f);
+    }
+    __device__ __forceinline__ void fma(const Vec<float, V> &x, float w)
     {
         const float2 w2 = make_float2(w, w);
-        a[0] = __ffma2_rn(make_float2(x.v[0], x.v[1]), w2, a[0]);
-        a[1] = __ffma2_rn(make_float2(x.v[2], x.v[3]), w2, a[1]);
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) a[i] = __ffma2_rn(make_float2(x.v[2 * i], x.v[2 * i + 1]), w2, a[i]);
     }
-    __device__ __forceinline__ float get(int i) const
-    {
-        return i == 0 ? a[0].x : i == 1 ? a[0].y : i == 2 ? a[1].x : a[1].y;
-    }
+    __device__ __forceinline__ float get(int i) const { return (i & 1) ? a[i >> 1].y : a[i >> 1].x; }
 };
 
 // 16-byte aligned base of the dynamic shared memory (TMA destinations need
@@ -87,11 +89,48 @@ struct StorageV {
     static constexpr int V = sizeof(TS) == sizeof(T) ? 16 / (int)sizeof(T) : 4;
 };
 
+// strided-axis passes: a thread's column vector is 16 bytes of floats, or 8
+// integer elements (16 bytes of uint16, 8 bytes of uint8) widened to 8 floats
+template <typename T, typename TS>
+struct StridedV {
+    static constexpr int V = sizeof(TS) == sizeof(T) ? 16 / (int)sizeof(T) : 8;
+};
+
 template <typename T, typename TS, int V>
 __device__ __forceinline__ Vec<T, V> load_block(const TS *ptr)
 {
     if constexpr (sizeof(TS) == sizeof(T)) {
         return *reinterpret_cast<const Vec<T, V> *>(ptr);
+    } else if constexpr (V == 8) {
+        static_assert(sizeof(T) == 4, "integer storage widens to floats");
+        uint32_t f[8];
+        if constexpr (sizeof(TS) == 2) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(ptr);
+            const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                f[2 * i] = __byte_perm(wds[i], 0x4B000000u, 0x7410);
+                f[2 * i + 1] = __byte_perm(wds[i], 0x4B000000u, 0x7432);
+            }
+        } else {
+            const uint2 raw = *reinterpret_cast<const uint2 *>(ptr);
+            const uint32_t wds[2] = {raw.x, raw.y};
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                f[4 * i] = __byte_perm(wds[i], 0x4B000000u, 0x7440);
+                f[4 * i + 1] = __byte_perm(wds[i], 0x4B000000u, 0x7441);
+                f[4 * i + 2] = __byte_perm(wds[i], 0x4B000000u, 0x7442);
+                f[4 * i + 3] = __byte_perm(wds[i], 0x4B000000u, 0x7443);
+            }
+        }
+        const float2 bias = make_float2(-8388608.f, -8388608.f);
+        Vec<T, V> r;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 a = __fadd2_rn(make_float2(__uint_as_float(f[2 * i]), __uint_as_float(f[2 * i + 1])), bias);
+            r.v[2 * i] = a.x; r.v[2 * i + 1] = a.y;
+        }
+        return r;
     } else {
         static_assert(V == 4 && sizeof(T) == 4, "integer storage widens to 4 floats");
         uint32_t f[4];

@@ -6,13 +6,14 @@ from ._edge import prewitt, sobel
 from ._gaussian import (gaussian, gaussian_filter, gaussian_gradient_magnitude,
                         gaussian_laplace)
 from ._smooth import uniform_filter
+from ._threshold import threshold_local
 
 __all__ = [
     "convolve", "correlate", "laplace", "prewitt", "sobel", "gaussian", "gaussian_filter",
-    "gaussian_gradient_magnitude", "gaussian_laplace", "uniform_filter",
+    "gaussian_gradient_magnitude", "gaussian_laplace", "uniform_filter", "threshold_local",
 ]
 
 for _f in (convolve, correlate, laplace, prewitt, sobel, gaussian, gaussian_filter,
-           gaussian_gradient_magnitude, gaussian_laplace, uniform_filter):
+           gaussian_gradient_magnitude, gaussian_laplace, uniform_filter, threshold_local):
     _f.__module__ = __name__
 del _f

@@ -201,6 +201,17 @@ class ShardedVolume:
         """This rank's planes (a view; no pads)."""
         return self._buf.interior
 
+    def astype(self, dtype):
+        """A copy of the volume in another dtype (same partition)."""
+        out = ShardedVolume.empty(self.shape, dtype, self.device, self.group, self.backend, self._buf.cap)
+        out.local.copy_(self.local.to(torch_dtype(dtype)))
+        return out
+
+    def __sub__(self, other):
+        out = ShardedVolume.empty(self.shape, self.dtype, self.device, self.group, self.backend, self._buf.cap)
+        torch.sub(self.local, other, out=out.local)
+        return out
+
     def gather(self):
         """The whole volume as a host array on every rank (tests / small data)."""
         loc = self.local.contiguous()

@@ -281,3 +281,43 @@ def test_three_tap_compositions(b200, name, dt):
     if name != "laplace":
         got = getattr(b200.ndfilters, name)(d, axis=0, mode="mirror")
         assert_parity(np.asarray(got), getattr(ndi, name)(a, axis=0, mode="mirror"))
+
+
+# ---------------------------------------------------------------------------
+# threshold_local: the reference's stored known-answer
+# masks (tests/test_dask_image/test_ndfilters/test__threshold.py:24-64)
+# ---------------------------------------------------------------------------
+_THRESH_IMAGE = np.array([[0, 0, 1, 3, 5], [0, 1, 4, 3, 4], [1, 2, 5, 4, 1], [2, 4, 5, 2, 1], [4, 5, 1, 0, 0]],
+                         dtype=np.int64)
+_THRESH_MASK = np.array([[False, False, False, False, True], [False, False, True, False, True],
+                         [False, False, True, True, False], [False, True, True, False, False],
+                         [True, True, False, False, False]])
+
+
+@pytest.mark.parametrize("block_size", [3, [3, 3], np.array([3, 3])])
+@pytest.mark.parametrize("chunked", [False, True])
+def test_threshold_local_known_answers(b200, block_size, chunked):
+    img = dev(b200, _THRESH_IMAGE)
+    if chunked:
+        img = b200.from_array(img, chunks=(3, 2))
+    for kw in (dict(method="gaussian"), dict(method="gaussian", param=1. / 3.), dict(method="mean")):
+        out = b200.ndfilters.threshold_local(img, block_size, **kw)
+        assert np.asarray(out).dtype == np.float64
+        assert np.array_equal(_THRESH_IMAGE > np.asarray(out), _THRESH_MASK), kw
+
+
+def test_threshold_local_values_and_errors(b200):
+    rng = np.random.default_rng(8)
+    a = rng.integers(0, 255, (40, 48)).astype(np.uint8)
+    got = b200.ndfilters.threshold_local(dev(b200, a), 7, offset=2.5, mode="mirror")
+    ref = ndi.gaussian_filter(a.astype(np.float64), (7 - 1) / 6.0, mode="mirror") - 2.5
+    assert_parity(np.asarray(got), ref)
+    got = b200.ndfilters.threshold_local(dev(b200, a), (5, 3), method="mean", offset=-1.0)
+    ref = ndi.uniform_filter(a.astype(np.float64), (5, 3)) + 1.0
+    assert_parity(np.asarray(got), ref)
+    with pytest.raises(ValueError):
+        b200.ndfilters.threshold_local(dev(b200, a), 3, method="generic", param=None)
+    with pytest.raises(ValueError):
+        b200.ndfilters.threshold_local(dev(b200, a), 3, method="otsu")
+    with pytest.raises(NotImplementedError):
+        b200.ndfilters.threshold_local(dev(b200, a), 3, method="median")
