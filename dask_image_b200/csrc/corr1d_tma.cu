@@ -491,6 +491,9 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
         for (int tt = 0; tt < LA; ++tt) {
             const float wk = p.w[tt];
             const float2 w2 = make_float2(wk, wk);
+            // box filter: taps are 0 or 1 and up to 15 of them are alignment
+            // padding -- a warp-uniform skip is cheaper than 8 dead FFMA2
+            if (kBox && wk == 0.f) continue;
             if ((tt & 1) == 0) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
