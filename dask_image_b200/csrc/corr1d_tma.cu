@@ -122,7 +122,9 @@ struct Corr1dTmaParams {
 // REM = taps % R is a template parameter so that the tap tail is straight-line
 // code; nothing in the tap loops is divergent, which lets ptxas keep the
 // weights on the uniform datapath (LDCU -> FFMA2 with a UR operand).
-template <typename T, typename TS, int W, int TY, int R, int MINB, int REM>
+// LS > 0: the tap count is a compile-time constant and the tap loop is fully
+// unrolled -- no loop control, weights at static parameter offsets.
+template <typename T, typename TS, int W, int TY, int R, int MINB, int REM, int LS = 0>
 __global__ void __launch_bounds__((W / StridedV<T, TS>::V) * TY, MINB)
 corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T, TS> p)
 {
@@ -194,21 +196,32 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
 #pragma unroll
         for (int j = 0; j < R - 1; ++j) win[j] = load_block<T, TS, V>(sbase + j * W);
         const TS *sk = sbase + (R - 1) * W;
-        for (int k = 0; k < Lfull; k += R, sk += R * W) {
+        if constexpr (LS > 0) {
+            static_assert(REM == 0, "the static engine has no tap tail");
 #pragma unroll
-            for (int u = 0; u < R; ++u) {
+            for (int k = 0; k < LS; ++k) {
+                win[(k + R - 1) % R] = load_block<T, TS, V>(sk + k * W);
+                const T wk = p.w[k];
+#pragma unroll
+                for (int j = 0; j < R; ++j) acc[j].fma(win[(k + j) % R], wk);
+            }
+        } else {
+            for (int k = 0; k < Lfull; k += R, sk += R * W) {
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    win[(u + R - 1) % R] = load_block<T, TS, V>(sk + u * W);
+                    const T wk = p.w[k + u];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) acc[j].fma(win[(u + j) % R], wk);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < REM; ++u) {
                 win[(u + R - 1) % R] = load_block<T, TS, V>(sk + u * W);
-                const T wk = p.w[k + u];
+                const T wk = p.w[Lfull + u];
 #pragma unroll
                 for (int j = 0; j < R; ++j) acc[j].fma(win[(u + j) % R], wk);
             }
-        }
-#pragma unroll
-        for (int u = 0; u < REM; ++u) {
-            win[(u + R - 1) % R] = load_block<T, TS, V>(sk + u * W);
-            const T wk = p.w[Lfull + u];
-#pragma unroll
-            for (int j = 0; j < R; ++j) acc[j].fma(win[(u + j) % R], wk);
         }
         if (col < p.inner) {
 #pragma unroll
@@ -475,11 +488,13 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
                 f[4 * b] = v.x; f[4 * b + 1] = v.y; f[4 * b + 2] = v.z; f[4 * b + 3] = v.w;
             }
         } else {
-            // one LDS.128 = 8 uint16 / 16 uint8; widen 4 at a time (PRMT + packed unbias)
+            // 8 elements per load (one LDS.128 of uint16: the quarter warp's 8 rows
+            // hit 8 different bank groups), widened with PRMT + a packed unbias
 #pragma unroll
-            for (int b = 0; b < NF / 4; ++b) {
-                const Vec<float, 4> v = load_block<float, TS, 4>(srow + 4 * b);
-                f[4 * b] = v.v[0]; f[4 * b + 1] = v.v[1]; f[4 * b + 2] = v.v[2]; f[4 * b + 3] = v.v[3];
+            for (int b = 0; b < NF / 8; ++b) {
+                const Vec<float, 8> v = load_block<float, TS, 8>(srow + 8 * b);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[8 * b + i] = v.v[i];
             }
         }
         float2 e[8], o[9];
@@ -491,9 +506,11 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
         for (int tt = 0; tt < LA; ++tt) {
             const float wk = p.w[tt];
             const float2 w2 = make_float2(wk, wk);
-            // box filter: taps are 0 or 1 and up to 15 of them are alignment
-            // padding -- a warp-uniform skip is cheaper than 8 dead FFMA2
-            if (kBox && wk == 0.f) continue;
+            // Alignment padding (up to 3 taps at either end; up to 15 for the box
+            // filter, whose taps are 0 or 1): a warp-uniform skip.  It keeps
+            // non-finite neighbours outside the real window from leaking in as
+            // 0 * inf, and is cheaper than 8 dead FFMA2.
+            if ((kBox || tt < 3 || tt >= LA - 3) && wk == 0.f) continue;
             if ((tt & 1) == 0) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -575,7 +592,7 @@ static const char *kernel_name(bool strided)
                    : (sizeof(T) == 4 ? "corr1d_tma_contig_f32" : "corr1d_tma_contig_f64");
 }
 
-template <typename T, typename TS, int R, int MINB, int REM>
+template <typename T, typename TS, int R, int MINB, int REM, int LS = 0>
 static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
 {
     constexpr int V = StridedV<T, TS>::V;
@@ -612,7 +629,7 @@ static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     p.outer = g.outer; p.n = g.n; p.inner = g.inner;
     p.pad_lo = a.pad_lo; p.pad_hi = a.pad_hi;
     p.num_tiles = num_tiles;
-    p.nw = L; p.lo = L / 2 + a.origin; p.mode = a.mode; p.epilogue = a.epilogue;
+    p.nw = L; p.lo = a.nw / 2 + a.origin; p.mode = a.mode; p.epilogue = a.epilogue;
     p.tile_rows = tile_rows; p.smem_rows = smem_rows; p.nb = nb; p.pitch = W; p.shift = 0; p.ncg = 0;
     p.stages = 1; p.stage_elems = (int)(stage_bytes / es); p.wide_store = 0;
     p.n_tiles = (int)n_tiles; p.c_tiles = c_tiles;
@@ -620,7 +637,7 @@ static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     p.qinv = (T)box.qinv; p.qc0 = (T)box.qc0;
     for (int i = 0; i < L; ++i) p.w[i] = (T)a.w[i];
 
-    auto kern = corr1d_strided_tma_kernel<T, TS, W, TY, R, MINB, REM>;
+    auto kern = corr1d_strided_tma_kernel<T, TS, W, TY, R, MINB, REM, LS>;
     const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, p);
@@ -656,6 +673,21 @@ static int launch_strided(const Corr1dArgs &a, const BoxInfo &box)
         const int max_rows = per_cta / row_bytes;
         nb = (max_rows - (L - 1)) / (8 * R);
         nb = nb < 1 ? 1 : nb;
+    }
+    // float32 filters of up to 48 taps: the fully unrolled tap engine (the tap
+    // count decides, so every slab of a volume takes the same path)
+    if constexpr (sizeof(T) == 4 && sizeof(TS) == 4) {
+        if (L <= 48 && env_int("B200_TMA_STATIC", 1)) {
+            switch (L) {
+#define B200_S_CASE(K) case K: return launch_strided_cfg<T, TS, R, MINB, 0, K>(a, box, nb);
+#define B200_S_CASE4(K) B200_S_CASE(K) B200_S_CASE(K + 1) B200_S_CASE(K + 2) B200_S_CASE(K + 3)
+            B200_S_CASE4(1) B200_S_CASE4(5) B200_S_CASE4(9) B200_S_CASE4(13) B200_S_CASE4(17) B200_S_CASE4(21)
+            B200_S_CASE4(25) B200_S_CASE4(29) B200_S_CASE4(33) B200_S_CASE4(37) B200_S_CASE4(41) B200_S_CASE4(45)
+#undef B200_S_CASE4
+#undef B200_S_CASE
+            default: break;
+            }
+        }
     }
     switch (L % R) {
     case 0: return launch_strided_cfg<T, TS, R, MINB, 0>(a, box, nb);

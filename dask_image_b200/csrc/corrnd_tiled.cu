@@ -248,6 +248,9 @@ corrnd_static_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                 for (int tt = 0; tt < KXA; ++tt) {
                     const float wk = wrow[tt];
                     const float2 w2 = make_float2(wk, wk);
+                    // alignment padding in front of the row: a warp-uniform skip, so
+                    // non-finite neighbours outside the footprint cannot leak in
+                    if (tt < 3 && wk == 0.f) continue;
                     if ((tt & 1) == 0) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)

@@ -237,17 +237,31 @@ def _chain_targets(n_passes, epilogue):
     return [i % 2 for i in range(n_passes - 1)] + ["out"]
 
 
+def _pass_signature(ps):
+    return (ps.kind, ps.axis, ps.mode, ps.origin, ps.size,
+            None if ps.weights is None else np.asarray(ps.weights, dtype=np.float64).tobytes())
+
+
 def _run_chain(x_tensor, shape, np_dtype, passes, cval, out_tensor, final_epilogue=_lib.EPI_STORE,
-               pad=(0, 0), scratch=None, flags=None):
+               pad=(0, 0), scratch=None, flags=None, prov=None):
     """Run 1-D passes in order (input -> ... -> out), never writing the input;
     the last pass applies ``final_epilogue`` into ``out_tensor``.  ``pad``
     describes axis-0 halo planes around ``x_tensor`` and only the first pass
-    may consume it -- later passes read buffers that hold the interior only."""
+    may consume it -- later passes read buffers that hold the interior only.
+
+    ``prov`` (a dict shared by the chains of one plan) records which pass prefix
+    of the INPUT each scratch volume currently holds; a chain whose leading
+    passes equal what is already there skips them.  The chains of
+    gaussian_gradient_magnitude / gaussian_laplace along the last two axes both
+    start with the same smoothing pass along axis 0, so 8 launches do the work
+    of scipy's 9 passes -- same arithmetic, computed once."""
     scratch = scratch if scratch is not None else []
     src, src_pad = x_tensor, pad
     targets = _chain_targets(len(passes), final_epilogue)
+    sig = ()
     for i, ps in enumerate(passes):
         last = i == len(passes) - 1
+        sig = sig + (_pass_signature(ps),)
         if targets[i] == "out":
             dst = out_tensor
         else:
@@ -256,6 +270,9 @@ def _run_chain(x_tensor, shape, np_dtype, passes, cval, out_tensor, final_epilog
                 scratch.append(torch.empty(tuple(shape), dtype=out_tensor.dtype,
                                            device=out_tensor.device))
             dst = scratch[k]
+            if prov is not None and prov.get(k) == sig:
+                src, src_pad = dst, (0, 0)      # this prefix of the input is already there
+                continue
         use_pad = src_pad if ps.axis == 0 else (0, 0)
         epi = final_epilogue if last else _lib.EPI_STORE
         if ps.kind == "corr":
@@ -266,6 +283,8 @@ def _run_chain(x_tensor, shape, np_dtype, passes, cval, out_tensor, final_epilog
                 raise RuntimeError("uniform passes have no fused epilogue")
             _launch_uniform1d(src, dst, shape, np_dtype, ps.axis, ps.size, ps.mode, cval,
                               ps.origin, use_pad, flags)
+        if prov is not None and targets[i] != "out":
+            prov[targets[i]] = sig
         src, src_pad = dst, (0, 0)
     return scratch
 
@@ -334,11 +353,11 @@ def _execute(plan, x, out):
         return out
     if plan.zero_out:
         out.tensor.zero_()
-    scratch = []
+    scratch, prov = [], {}
     for passes, op in plan.chains:
         if passes:
             scratch = _run_chain(x.tensor, x.shape, x.dtype, passes, plan.cval, out.tensor,
-                                 final_epilogue=op, scratch=scratch)
+                                 final_epilogue=op, scratch=scratch, prov=prov)
         else:
             # all sigmas ~ 0: the "derivative" is the input itself
             _launch_combine(out.tensor, x.tensor, x.dtype, op)

@@ -349,15 +349,17 @@ class ShardedVolume:
             return result
         if plan.zero_out:
             out.interior.zero_()
-        scratch = []
+        scratch, prov = [], {}
         for passes, op in plan.chains:
             if not passes:
                 be.combine(out.interior, src0.interior, dt, op)
                 continue
             src = src0
             targets = _nd._chain_targets(len(passes), op)
+            sig = ()
             for i, ps in enumerate(passes):
                 last = i == len(passes) - 1
+                sig = sig + (_nd._pass_signature(ps),)
                 if targets[i] == "out":
                     dst = out
                 else:
@@ -365,6 +367,10 @@ class ShardedVolume:
                     while len(scratch) <= k:
                         scratch.append(self._like(depth))
                     dst = scratch[k]
+                    if prov.get(k) == sig:
+                        src = dst                   # shared chain prefix, computed once
+                        continue
+                    prov[k] = sig
                 epi = op if last else _lib.EPI_STORE
                 if ps.kind != "corr" and epi != _lib.EPI_STORE:
                     raise RuntimeError("uniform passes have no fused epilogue")

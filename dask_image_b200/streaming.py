@@ -186,10 +186,11 @@ class HostVolume:
                     else:
                         if plan.zero_out:
                             dst.zero_()
+                        prov = {}
                         for passes, op in plan.chains:
                             if passes:
                                 _nd._run_chain(src, shape, dt, passes, plan.cval, dst, final_epilogue=op,
-                                               pad=pad, scratch=scr)
+                                               pad=pad, scratch=scr, prov=prov)
                             else:
                                 _nd._launch_combine(dst, src, dt, op)
                     ev_cmp[j].record(s_cmp)

@@ -128,7 +128,7 @@ def test_launch_counter_and_kernel_names(b200):
     assert _lib.launch_count() == 3
     _lib.launch_count(reset=True)
     b200.ndimage.gaussian_laplace(dev(b200, a), 2.0)
-    assert _lib.launch_count() == 9
+    assert _lib.launch_count() == 8      # scipy's 9 passes; the shared axis-0 smoothing runs once
 
 
 # ---------------------------------------------------------------------------
