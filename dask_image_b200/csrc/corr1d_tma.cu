@@ -122,9 +122,7 @@ struct Corr1dTmaParams {
 // REM = taps % R is a template parameter so that the tap tail is straight-line
 // code; nothing in the tap loops is divergent, which lets ptxas keep the
 // weights on the uniform datapath (LDCU -> FFMA2 with a UR operand).
-// LS > 0: the tap count is a compile-time constant and the tap loop is fully
-// unrolled -- no loop control, weights at static parameter offsets.
-template <typename T, typename TS, int W, int TY, int R, int MINB, int REM, int LS = 0>
+template <typename T, typename TS, int W, int TY, int R, int MINB, int REM>
 __global__ void __launch_bounds__((W / StridedV<T, TS>::V) * TY, MINB)
 corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T, TS> p)
 {
@@ -196,32 +194,21 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
 #pragma unroll
         for (int j = 0; j < R - 1; ++j) win[j] = load_block<T, TS, V>(sbase + j * W);
         const TS *sk = sbase + (R - 1) * W;
-        if constexpr (LS > 0) {
-            static_assert(REM == 0, "the static engine has no tap tail");
+        for (int k = 0; k < Lfull; k += R, sk += R * W) {
 #pragma unroll
-            for (int k = 0; k < LS; ++k) {
-                win[(k + R - 1) % R] = load_block<T, TS, V>(sk + k * W);
-                const T wk = p.w[k];
-#pragma unroll
-                for (int j = 0; j < R; ++j) acc[j].fma(win[(k + j) % R], wk);
-            }
-        } else {
-            for (int k = 0; k < Lfull; k += R, sk += R * W) {
-#pragma unroll
-                for (int u = 0; u < R; ++u) {
-                    win[(u + R - 1) % R] = load_block<T, TS, V>(sk + u * W);
-                    const T wk = p.w[k + u];
-#pragma unroll
-                    for (int j = 0; j < R; ++j) acc[j].fma(win[(u + j) % R], wk);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < REM; ++u) {
+            for (int u = 0; u < R; ++u) {
                 win[(u + R - 1) % R] = load_block<T, TS, V>(sk + u * W);
-                const T wk = p.w[Lfull + u];
+                const T wk = p.w[k + u];
 #pragma unroll
                 for (int j = 0; j < R; ++j) acc[j].fma(win[(u + j) % R], wk);
             }
+        }
+#pragma unroll
+        for (int u = 0; u < REM; ++u) {
+            win[(u + R - 1) % R] = load_block<T, TS, V>(sk + u * W);
+            const T wk = p.w[Lfull + u];
+#pragma unroll
+            for (int j = 0; j < R; ++j) acc[j].fma(win[(u + j) % R], wk);
         }
         if (col < p.inner) {
 #pragma unroll
@@ -398,25 +385,26 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 // ===========================================================================
 // contiguous-axis pass, float32, tap count fixed at compile time
 // ===========================================================================
-// The launcher pads the taps with zeros to LA = 4 * NG (alignment zeros in
-// front, as above, and up to 3 behind), so the whole tap loop is straight-line
-// code: the thread's 16 + LA input floats of the row come in as LDS.128, every
-// tap is a run of packed FFMA2 (8 for an even data offset, 9 for an odd one: the
-// odd set pairs outputs (-1,0)...(15,16) so operand pairs stay register
-// aligned) with its weight read through the uniform datapath at a static
-// parameter offset.  No loop-carried register rotation, no per-group branches:
-// ~14 instructions per output instead of ~38 for the run-time loop.  A thread
-// owns 16 outputs, a warp 64 x 8; the lanes of a quarter warp sit on 8
-// different rows, which the odd 16-byte pitch spreads over all bank groups.
-template <typename TS, int NG, bool PLAIN>
+// NT = taps including the alignment zeros in front (the TMA box starts on a
+// 16-byte boundary).  The whole tap loop is straight-line code: the thread's
+// 16 + NT input floats of the row come in as LDS.128, every tap is a run of
+// packed FFMA2 (8 for an even data offset, 9 for an odd one: the odd set pairs
+// outputs (-1,0)...(15,16) so operand pairs stay register aligned) with its
+// weight read through the uniform datapath at a static parameter offset.  No
+// loop-carried register rotation, no per-group branches: ~14 instructions per
+// output instead of ~38 for the run-time loop.  A thread owns 16 outputs, a
+// warp 64 x 8; the lanes of a quarter warp sit on 8 different rows, which the
+// odd 16-byte pitch spreads over all bank groups.  TS = uint16_t / uint8_t is
+// the exact integer box filter (taps 0/1, quotient epilogue).
+template <typename TS, int NT>
 __global__ void __launch_bounds__(256, 3)
 corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
                             const __grid_constant__ Corr1dTmaParams<float, TS> p)
 {
-    constexpr int R = 16, PC = 4 * R, LA = 4 * NG, NF = R + LA;
     constexpr bool kBox = sizeof(TS) != sizeof(float);   // exact integer box filter
     constexpr int EB = 16 / (int)sizeof(TS);             // elements per 16-byte shared load
-    static_assert(NF % EB == 0, "row window must be whole 16-byte blocks of the storage type");
+    constexpr int R = 16, PC = 4 * R, LA = NT;
+    constexpr int NF = (R + NT + EB - 1) / EB * EB;       // row window: whole 16-byte blocks
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TS *tile = aligned_smem<TS>(smem_raw);
     __shared__ __align__(8) uint64_t full_bar;
@@ -506,11 +494,11 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
         for (int tt = 0; tt < LA; ++tt) {
             const float wk = p.w[tt];
             const float2 w2 = make_float2(wk, wk);
-            // Alignment padding (up to 3 taps at either end; up to 15 for the box
-            // filter, whose taps are 0 or 1): a warp-uniform skip.  It keeps
-            // non-finite neighbours outside the real window from leaking in as
-            // 0 * inf, and is cheaper than 8 dead FFMA2.
-            if ((kBox || tt < 3 || tt >= LA - 3) && wk == 0.f) continue;
+            // Alignment padding in front of the taps (up to 3; for the box filter,
+            // whose taps are 0 or 1, up to 15 and some behind): a warp-uniform
+            // skip.  It keeps non-finite neighbours outside the real window from
+            // leaking in as 0 * inf, and is cheaper than 8 dead FFMA2.
+            if ((kBox || tt < 3) && wk == 0.f) continue;
             if ((tt & 1) == 0) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -535,7 +523,7 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
                     store_box_quotients<float, TS, 8>(dst0 + 8, reinterpret_cast<const float(&)[8]>(res[8]), p.qinv,
                                                       p.qc0);
             } else if (p.wide_store && x + R <= p.n) {
-                if constexpr (!PLAIN) {
+                if (p.epilogue != B200_EPI_STORE) {
                     const bool reads_out = epilogue_reads_out(p.epilogue);
                     float prev[R];
                     if (reads_out) {
@@ -554,7 +542,7 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
                     if (x + h * 4 < p.n) {   // rows are whole multiples of 16 bytes
                         float4 *dst = reinterpret_cast<float4 *>(dst0 + h * 4);
                         float4 r4 = make_float4(res[4 * h], res[4 * h + 1], res[4 * h + 2], res[4 * h + 3]);
-                        if constexpr (!PLAIN) {
+                        if (p.epilogue != B200_EPI_STORE) {
                             const bool reads_out = epilogue_reads_out(p.epilogue);
                             float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (reads_out) pv = *dst;
@@ -592,7 +580,7 @@ static const char *kernel_name(bool strided)
                    : (sizeof(T) == 4 ? "corr1d_tma_contig_f32" : "corr1d_tma_contig_f64");
 }
 
-template <typename T, typename TS, int R, int MINB, int REM, int LS = 0>
+template <typename T, typename TS, int R, int MINB, int REM>
 static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
 {
     constexpr int V = StridedV<T, TS>::V;
@@ -637,7 +625,7 @@ static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     p.qinv = (T)box.qinv; p.qc0 = (T)box.qc0;
     for (int i = 0; i < L; ++i) p.w[i] = (T)a.w[i];
 
-    auto kern = corr1d_strided_tma_kernel<T, TS, W, TY, R, MINB, REM, LS>;
+    auto kern = corr1d_strided_tma_kernel<T, TS, W, TY, R, MINB, REM>;
     const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, p);
@@ -667,27 +655,15 @@ static int launch_strided(const Corr1dArgs &a, const BoxInfo &box)
     // nb = row blocks (of 8*R rows) per CTA tile: the tallest tile that still
     // leaves MINB CTAs resident per SM (B200 sweeps in profiles/: more, smaller
     // CTAs beat a deeper per-CTA pipeline for this streaming kernel)
+    // Long filters are FP32-issue bound rather than HBM bound: a fourth resident
+    // CTA hides more of each CTA's load phase (B200 sweep, profiles/).
     int nb = env_int("B200_TMA_NB", 0);
     if (nb <= 0) {
-        const int per_cta = (int)((kSmemPerSm - 3072) / MINB);
+        const int ctas = L >= 24 ? MINB + 1 : MINB;
+        const int per_cta = (int)((kSmemPerSm - 3072) / ctas);
         const int max_rows = per_cta / row_bytes;
         nb = (max_rows - (L - 1)) / (8 * R);
         nb = nb < 1 ? 1 : nb;
-    }
-    // float32 filters of up to 48 taps: the fully unrolled tap engine (the tap
-    // count decides, so every slab of a volume takes the same path)
-    if constexpr (sizeof(T) == 4 && sizeof(TS) == 4) {
-        if (L <= 48 && env_int("B200_TMA_STATIC", 1)) {
-            switch (L) {
-#define B200_S_CASE(K) case K: return launch_strided_cfg<T, TS, R, MINB, 0, K>(a, box, nb);
-#define B200_S_CASE4(K) B200_S_CASE(K) B200_S_CASE(K + 1) B200_S_CASE(K + 2) B200_S_CASE(K + 3)
-            B200_S_CASE4(1) B200_S_CASE4(5) B200_S_CASE4(9) B200_S_CASE4(13) B200_S_CASE4(17) B200_S_CASE4(21)
-            B200_S_CASE4(25) B200_S_CASE4(29) B200_S_CASE4(33) B200_S_CASE4(37) B200_S_CASE4(41) B200_S_CASE4(45)
-#undef B200_S_CASE4
-#undef B200_S_CASE
-            default: break;
-            }
-        }
     }
     switch (L % R) {
     case 0: return launch_strided_cfg<T, TS, R, MINB, 0>(a, box, nb);
@@ -770,11 +746,12 @@ static int launch_contig_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al,
     return B200_OK;
 }
 
-template <typename TS, int NG, bool PLAIN>
+template <typename TS, int NT>
 static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al, int lead)
 {
-    constexpr int R = 16, PC = 4 * R, LA = 4 * NG;
     constexpr int EB = 16 / (int)sizeof(TS);   // elements per 16 bytes of storage
+    constexpr int R = 16, PC = 4 * R;
+    constexpr int LA = (R + NT + EB - 1) / EB * EB - R;   // window beyond the 16 outputs
     const int es = (int)sizeof(TS);
     const LineGeom &g = a.g;
     auto pitch_for = [&](int cand) {
@@ -812,17 +789,17 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int
     p.outer = g.outer; p.n = g.n; p.inner = 1;
     p.pad_lo = 0; p.pad_hi = 0;
     p.num_tiles = num_tiles;
-    p.nw = LA; p.lo = lo_al; p.mode = a.mode; p.epilogue = a.epilogue;
+    p.nw = NT; p.lo = lo_al; p.mode = a.mode; p.epilogue = a.epilogue;
     p.tile_rows = tr; p.smem_rows = tr; p.nb = 1; p.pitch = pitch; p.shift = 0; p.ncg = ncg;
     p.stages = 1; p.stage_elems = (int)(stage_bytes / es);
     p.wide_store = (((g.n * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
     p.n_tiles = (int)r_tiles; p.c_tiles = (int)c_tiles;
     p.cval = (TS)a.cval;
     p.qinv = box.qinv; p.qc0 = box.qc0;
-    for (int i = 0; i < LA; ++i) p.w[i] = 0.f;
+    for (int i = 0; i < NT; ++i) p.w[i] = 0.f;
     for (int i = 0; i < a.nw; ++i) p.w[lead + i] = (float)a.w[i];
 
-    auto kern = corr1d_contig_static_kernel<TS, NG, PLAIN>;
+    auto kern = corr1d_contig_static_kernel<TS, NT>;
     const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
@@ -832,9 +809,9 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int
     return B200_OK;
 }
 
-// float32 rows with at most kStaticNG * 4 taps (alignment zeros included): the
-// compile-time tap engine.  Returns -2 when the filter is longer.
-constexpr int kStaticNG = 12;
+// float32 rows with at most kStaticTaps taps (alignment zeros in front
+// included): the compile-time tap engine.  Returns -2 when the filter is longer.
+constexpr int kStaticTaps = 48;
 static int launch_contig_static(const Corr1dArgs &a)
 {
     const LineGeom &g = a.g;
@@ -845,16 +822,15 @@ static int launch_contig_static(const Corr1dArgs &a)
     const int lo = a.nw / 2 + a.origin;
     const int lo_al = (lo + 3) / 4 * 4;
     const int lead = lo_al - lo;
-    const int ng = (lead + a.nw + 3) / 4;
-    if (ng > kStaticNG) return -2;
-    const bool plain = a.epilogue == B200_EPI_STORE;
+    const int nt = lead + a.nw;
+    if (nt > kStaticTaps) return -2;
     const BoxInfo none;
-    switch (ng) {
-#define B200_C1_CASE(K) \
-    case K: return plain ? launch_contig_static_cfg<float, K, true>(a, none, lo_al, lead) \
-                         : launch_contig_static_cfg<float, K, false>(a, none, lo_al, lead);
-    B200_C1_CASE(1) B200_C1_CASE(2) B200_C1_CASE(3) B200_C1_CASE(4) B200_C1_CASE(5) B200_C1_CASE(6)
-    B200_C1_CASE(7) B200_C1_CASE(8) B200_C1_CASE(9) B200_C1_CASE(10) B200_C1_CASE(11) B200_C1_CASE(12)
+    switch (nt) {
+#define B200_C1_CASE(K) case K: return launch_contig_static_cfg<float, K>(a, none, lo_al, lead);
+#define B200_C1_CASE4(K) B200_C1_CASE(K) B200_C1_CASE(K + 1) B200_C1_CASE(K + 2) B200_C1_CASE(K + 3)
+    B200_C1_CASE4(1) B200_C1_CASE4(5) B200_C1_CASE4(9) B200_C1_CASE4(13) B200_C1_CASE4(17) B200_C1_CASE4(21)
+    B200_C1_CASE4(25) B200_C1_CASE4(29) B200_C1_CASE4(33) B200_C1_CASE4(37) B200_C1_CASE4(41) B200_C1_CASE4(45)
+#undef B200_C1_CASE4
 #undef B200_C1_CASE
     default: return -2;
     }
@@ -922,15 +898,13 @@ static int launch_contig_box(const Corr1dArgs &a, const BoxInfo &box)
     if (env_int("B200_TMA_STATIC", 1)) {
         // compile-time tap engine: taps padded to whole 16-byte blocks of storage
         const int la = (lead + a.nw + U16B - 1) / U16B * U16B;
-        switch (la / 4) {
-#define B200_BOX_CASE(K) case K: return launch_contig_static_cfg<TS, K, true>(a, box, lo_al, lead);
-        case 2: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 2, true>(a, box, lo_al, lead); break;
-        B200_BOX_CASE(4)
-        case 6: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 6, true>(a, box, lo_al, lead); break;
-        B200_BOX_CASE(8)
-        case 10: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 10, true>(a, box, lo_al, lead); break;
-        B200_BOX_CASE(12)
-#undef B200_BOX_CASE
+        switch (la) {
+        case 8: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 8>(a, box, lo_al, lead); break;
+        case 16: return launch_contig_static_cfg<TS, 16>(a, box, lo_al, lead);
+        case 24: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 24>(a, box, lo_al, lead); break;
+        case 32: return launch_contig_static_cfg<TS, 32>(a, box, lo_al, lead);
+        case 40: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 40>(a, box, lo_al, lead); break;
+        case 48: return launch_contig_static_cfg<TS, 48>(a, box, lo_al, lead);
         default: break;
         }
     }
