@@ -155,29 +155,45 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
         mbar_arrive_expect_tx(&full_bar, (uint32_t)(p.smem_rows * W * (int)sizeof(TS)));
         tma_load_3d(tile, &tmap, &full_bar, (int)col0, (int)(g0 + p.pad_lo), (int)o);
     }
+
+    // Rows of the tile that lie outside the resident range (TMA zero-fills
+    // them): edge CTAs fetch their images under the extension map WHILE the
+    // tile is in flight -- the first kPre elements per thread into registers --
+    // and drop them into the tile once the TMA has landed, so the patch costs no
+    // extra round trip to memory.  (Zeros are already right for constant/0.)
+    constexpr int kPre = 8;
+    const int64_t res_lo = -p.pad_lo, res_hi = p.n + p.pad_hi;        // resident rows
+    const int nlo = (int)(g0 < res_lo ? (res_lo - g0 < p.smem_rows ? res_lo - g0 : p.smem_rows) : 0);
+    const int rhi = (int)(g0 + p.smem_rows > res_hi ? (res_hi - g0 > nlo ? res_hi - g0 : nlo) : p.smem_rows);
+    const int npatch_el = (nlo + (p.smem_rows - rhi)) * W;
+    const bool patch = npatch_el > 0 && !(p.mode == B200_MODE_CONSTANT && p.cval == TS(0));
+    auto patch_row = [&](int j) { return j < nlo ? j : rhi + (j - nlo); };
+    auto patch_value = [&](int idx) -> TS {
+        const int j = idx / W, c = idx - j * W;
+        const int64_t src = ext_index_padded(g0 + patch_row(j), p.n, p.mode, p.pad_lo, p.pad_hi);
+        if (src == B200_USE_CVAL) return p.cval;
+        return (col0 + c < p.inner) ? p.in[(o * p.n + src) * p.inner + col0 + c] : TS(0);
+    };
+    TS pre[kPre];
+    if (patch) {
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+            const int idx = tid + i * NTHREADS;
+            pre[i] = idx < npatch_el ? patch_value(idx) : TS(0);
+        }
+    }
     __syncthreads();
     // one warp polls the mbarrier; the others sleep at the CTA barrier
     if (tid < 32) mbar_wait(&full_bar, 0);
     __syncthreads();
-
-    // rows of the tile that lie outside the resident range: patch through the
-    // extension map (TMA left zeros there, which is already right for
-    // mode=constant, cval=0)
-    const bool low_edge = g0 < -p.pad_lo;
-    const bool high_edge = g0 + p.smem_rows > p.n + p.pad_hi;
-    if ((low_edge || high_edge) && !(p.mode == B200_MODE_CONSTANT && p.cval == TS(0))) {
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int r = warp; r < p.smem_rows; r += NTHREADS / 32) {
-            const int64_t g = g0 + r;
-            if (g >= -p.pad_lo && g < p.n + p.pad_hi) continue;
-            const int64_t src = ext_index_padded(g, p.n, p.mode, p.pad_lo, p.pad_hi);
-            const TS *srow = (src == B200_USE_CVAL) ? nullptr : p.in + ((o * p.n + src) * p.inner + col0);
-            for (int c = lane; c < W; c += 32) {
-                TS v = p.cval;
-                if (srow) v = (col0 + c < p.inner) ? srow[c] : TS(0);
-                tile[r * W + c] = v;
-            }
+    if (patch) {
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+            const int idx = tid + i * NTHREADS;
+            if (idx < npatch_el) tile[patch_row(idx / W) * W + (idx % W)] = pre[i];
         }
+        for (int idx = tid + kPre * NTHREADS; idx < npatch_el; idx += NTHREADS)
+            tile[patch_row(idx / W) * W + (idx % W)] = patch_value(idx);
         __syncthreads();
     }
 
@@ -243,6 +259,84 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
 }
 
 
+// ---------------------------------------------------------------------------
+// Contiguous-axis tiles: the columns of a tile that fall outside [0, n) (TMA
+// zero-fills them).  Edge CTAs fetch their images under the extension map while
+// the tile is still in flight (kPre elements per thread into registers) and
+// store them into the tile after the TMA has landed.
+// ---------------------------------------------------------------------------
+template <typename TS>
+struct ContigEdge {
+    int nlow, hstart, per_row, total;
+    __device__ __forceinline__ void init(int64_t g0, int P, int64_t n, int TR)
+    {
+        nlow = g0 < 0 ? (int)(-g0 < P ? -g0 : P) : 0;
+        hstart = g0 + P > n ? (int)((n - g0) > nlow ? (n - g0) : nlow) : P;
+        per_row = nlow + (P - hstart);
+        total = per_row * TR;
+    }
+    __device__ __forceinline__ void locate(int idx, int &r, int &c) const
+    {
+        r = idx / per_row;
+        c = idx - r * per_row;
+        c = c < nlow ? c : hstart + (c - nlow);
+    }
+    __device__ __forceinline__ TS value(int idx, const TS *in, int64_t g0, int64_t n, int64_t row0, int64_t nrows,
+                                        int mode, TS cval) const
+    {
+        int r, c;
+        locate(idx, r, c);
+        const int64_t src = ext_index(g0 + c, n, mode);
+        if (src < 0) return cval;
+        return (row0 + r < nrows) ? in[(row0 + r) * n + src] : TS(0);
+    }
+};
+
+template <typename TS, int KPRE>
+__device__ __forceinline__ void contig_stage_tile(const CUtensorMap &tmap, TS *tile, uint64_t *full_bar, const TS *in,
+                                                  int64_t g0, int64_t row0, int64_t n, int64_t nrows, int P, int TR,
+                                                  int mode, TS cval)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(full_bar, 1);
+        fence_barrier_init();
+        mbar_arrive_expect_tx(full_bar, (uint32_t)(TR * P * (int)sizeof(TS)));
+        tma_load_2d(tile, &tmap, full_bar, (int)g0, (int)row0);
+    }
+    ContigEdge<TS> edge;
+    edge.init(g0, P, n, TR);
+    const bool patch = edge.total > 0 && !(mode == B200_MODE_CONSTANT && cval == TS(0));
+    TS pre[KPRE];
+    if (patch) {
+#pragma unroll
+        for (int i = 0; i < KPRE; ++i) {
+            const int idx = tid + i * 256;
+            pre[i] = idx < edge.total ? edge.value(idx, in, g0, n, row0, nrows, mode, cval) : TS(0);
+        }
+    }
+    __syncthreads();
+    if (tid < 32) mbar_wait(full_bar, 0);
+    __syncthreads();
+    if (patch) {
+#pragma unroll
+        for (int i = 0; i < KPRE; ++i) {
+            const int idx = tid + i * 256;
+            if (idx < edge.total) {
+                int r, c;
+                edge.locate(idx, r, c);
+                tile[r * P + c] = pre[i];
+            }
+        }
+        for (int idx = tid + KPRE * 256; idx < edge.total; idx += 256) {
+            int r, c;
+            edge.locate(idx, r, c);
+            tile[r * P + c] = edge.value(idx, in, g0, n, row0, nrows, mode, cval);
+        }
+        __syncthreads();
+    }
+}
+
 // ===========================================================================
 // contiguous-axis pass: one tile per CTA
 // ===========================================================================
@@ -277,35 +371,7 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     const int64_t row0 = trow * TR;
     const int64_t g0 = x0t - p.lo;             // array column held by smem column 0 (16-byte aligned)
 
-    if (tid == 0) {
-        mbar_init(&full_bar, 1);
-        fence_barrier_init();
-        mbar_arrive_expect_tx(&full_bar, (uint32_t)(TR * P * (int)sizeof(TS)));
-        tma_load_2d(tile, &tmap, &full_bar, (int)g0, (int)row0);
-    }
-    __syncthreads();
-    if (tid < 32) mbar_wait(&full_bar, 0);
-    __syncthreads();
-
-    const bool low_edge = g0 < 0;
-    const bool high_edge = g0 + P > p.n;
-    if ((low_edge || high_edge) && !(p.mode == B200_MODE_CONSTANT && p.cval == TS(0))) {
-        // columns [0, -g0) and [n - g0, P) of every tile row
-        const int nlow = low_edge ? (int)(-g0 < P ? -g0 : P) : 0;
-        const int hstart = high_edge ? (int)((p.n - g0) > 0 ? (p.n - g0) : 0) : P;
-        const int nhigh = P - hstart;
-        const int per_row = nlow + nhigh;
-        for (int idx = tid; idx < per_row * TR; idx += 256) {
-            const int r = idx / per_row;
-            int c = idx - r * per_row;
-            c = c < nlow ? c : hstart + (c - nlow);
-            const int64_t src = ext_index(g0 + c, p.n, p.mode);
-            TS v = p.cval;
-            if (src >= 0) v = (row0 + r < nrows) ? p.in[(row0 + r) * p.n + src] : TS(0);
-            tile[r * P + c] = v;
-        }
-        __syncthreads();
-    }
+    contig_stage_tile<TS, 8>(tmap, tile, &full_bar, p.in, g0, row0, p.n, nrows, P, TR, p.mode, p.cval);
 
     // Patches: a warp keeps ONE column group (ncg is 1, 2 or 4) and walks the row
     // groups with a fixed stride -- no div/mod, pointers advance by constants.
@@ -424,33 +490,7 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
     const int64_t row0 = trow * TR;
     const int64_t g0 = x0t - p.lo;
 
-    if (tid == 0) {
-        mbar_init(&full_bar, 1);
-        fence_barrier_init();
-        mbar_arrive_expect_tx(&full_bar, (uint32_t)(TR * P * (int)sizeof(TS)));
-        tma_load_2d(tile, &tmap, &full_bar, (int)g0, (int)row0);
-    }
-    __syncthreads();
-    if (tid < 32) mbar_wait(&full_bar, 0);
-    __syncthreads();
-
-    const bool low_edge = g0 < 0;
-    const bool high_edge = g0 + P > p.n;
-    if ((low_edge || high_edge) && !(p.mode == B200_MODE_CONSTANT && p.cval == TS(0))) {
-        const int nlow = low_edge ? (int)(-g0 < P ? -g0 : P) : 0;
-        const int hstart = high_edge ? (int)((p.n - g0) > 0 ? (p.n - g0) : 0) : P;
-        const int per_row = nlow + (P - hstart);
-        for (int idx = tid; idx < per_row * TR; idx += 256) {
-            const int r = idx / per_row;
-            int c = idx - r * per_row;
-            c = c < nlow ? c : hstart + (c - nlow);
-            const int64_t src = ext_index(g0 + c, p.n, p.mode);
-            TS v = p.cval;
-            if (src >= 0) v = (row0 + r < nrows) ? p.in[(row0 + r) * p.n + src] : TS(0);
-            tile[r * P + c] = v;
-        }
-        __syncthreads();
-    }
+    contig_stage_tile<TS, 8>(tmap, tile, &full_bar, p.in, g0, row0, p.n, nrows, P, TR, p.mode, p.cval);
 
     // a warp keeps one 64-column group and walks the 8-row groups (uniform trip count)
     const int cg_shift = p.ncg == 4 ? 2 : (p.ncg == 2 ? 1 : 0);
@@ -635,10 +675,10 @@ static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     return B200_OK;
 }
 
-template <typename T, typename TS>
-static int launch_strided(const Corr1dArgs &a, const BoxInfo &box)
+template <typename T, typename TS, int R>
+static int launch_strided_r(const Corr1dArgs &a, const BoxInfo &box)
 {
-    constexpr int R = 4, MINB = 3;
+    constexpr int MINB = 3;
     constexpr int V = StridedV<T, TS>::V;
     const int es = (int)sizeof(TS);
     const int row_bytes = 32 * V * es;
@@ -665,13 +705,35 @@ static int launch_strided(const Corr1dArgs &a, const BoxInfo &box)
         nb = (max_rows - (L - 1)) / (8 * R);
         nb = nb < 1 ? 1 : nb;
     }
-    switch (L % R) {
-    case 0: return launch_strided_cfg<T, TS, R, MINB, 0>(a, box, nb);
-    case 1: return launch_strided_cfg<T, TS, R, MINB, 1>(a, box, nb);
-    case 2: return launch_strided_cfg<T, TS, R, MINB, 2>(a, box, nb);
-    default: return launch_strided_cfg<T, TS, R, MINB, 3>(a, box, nb);
+    if constexpr (R == 1) {
+        return launch_strided_cfg<T, TS, R, MINB, 0>(a, box, nb);
+    } else if constexpr (R == 2) {
+        return (L & 1) ? launch_strided_cfg<T, TS, R, MINB, 1>(a, box, nb)
+                       : launch_strided_cfg<T, TS, R, MINB, 0>(a, box, nb);
+    } else {
+        switch (L % R) {
+        case 0: return launch_strided_cfg<T, TS, R, MINB, 0>(a, box, nb);
+        case 1: return launch_strided_cfg<T, TS, R, MINB, 1>(a, box, nb);
+        case 2: return launch_strided_cfg<T, TS, R, MINB, 2>(a, box, nb);
+        default: return launch_strided_cfg<T, TS, R, MINB, 3>(a, box, nb);
+        }
     }
 }
+
+// R = output rows per thread; a tile is a multiple of 8 * R rows.  Thin calls
+// (the edge planes of a slab, filtered after the halo exchange) take fewer rows
+// per thread so that tiles are not mostly padding.  Every output still sums its
+// taps in the same order, so the choice does not change a single bit.
+template <typename T, typename TS>
+static int launch_strided(const Corr1dArgs &a, const BoxInfo &box)
+{
+    if constexpr (sizeof(T) == sizeof(TS)) {
+        if (a.g.n <= 8) return launch_strided_r<T, TS, 1>(a, box);
+        if (a.g.n <= 16) return launch_strided_r<T, TS, 2>(a, box);
+    }
+    return launch_strided_r<T, TS, 4>(a, box);
+}
+
 
 template <typename T, typename TS, int SH, int REM>
 static int launch_contig_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al, int L)

@@ -124,8 +124,9 @@ def _nccl_worker(rank, world, port, q):
         import dask_image_b200 as b200
 
         rng = np.random.default_rng(21)
-        f32 = rng.random((50, 20, 64), dtype=np.float32)
-        u16 = rng.integers(0, 65536, (45, 16, 24), dtype=np.uint16)
+        # at least 12 planes per rank: the deepest filter below reaches 8
+        f32 = rng.random((max(50, 12 * world + 5), 20, 64), dtype=np.float32)
+        u16 = rng.integers(0, 65536, (max(45, 12 * world + 1), 16, 24), dtype=np.uint16)
         w3 = rng.random((3, 5, 4)) - 0.3
         failures = []
         cases = []
