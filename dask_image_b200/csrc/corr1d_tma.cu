@@ -107,7 +107,7 @@ struct Corr1dTmaParams {
     int pitch;       // contig: smem row pitch in elements (V * odd)
     int shift;       // contig: leading taps to skip (box start aligned down to 16 bytes)
     int ncg;         // contig: 4*R-column groups per tile
-    int stages;      // strided: > 1 = column-tile group width of the page-friendly tile order
+    int stages;      // (unused: one tile per CTA)
     int wide_store;  // contig: rows and base are 32-byte aligned -> 256-bit stores
     int stage_elems; // elements per stage
     int n_tiles, c_tiles;
@@ -140,34 +140,11 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
     const int L = p.nw;
     const bool reads_out = epilogue_reads_out(p.epilogue);
 
-    // Tile order.  Default: tiles along the filtered axis are consecutive, so
-    // vertically adjacent tiles run together and share their halo rows in L2.
-    // When the rows of a tile are megabytes apart (axis-0 pass of a volume: every
-    // row sits in its own 2 MB page) that order makes the ~450 resident CTAs
-    // touch thousands of pages at once; there the grid is walked in groups of
-    // `swz` column tiles instead -- column tiles fastest, then down the axis --
-    // so concurrent CTAs share a few hundred pages and the halo rows of the
-    // previous wave are still in L2.
     const int64_t t = blockIdx.x;
-    int tn, tc;
-    int64_t o;
-    if (p.stages > 1) {
-        const int64_t per_o = (int64_t)p.n_tiles * p.c_tiles;
-        o = t / per_o;
-        const int64_t rem = t - o * per_o;
-        const int64_t tpg = (int64_t)p.stages * p.n_tiles;
-        const int grp = (int)(rem / tpg);
-        const int r2 = (int)(rem - grp * tpg);
-        const int left = p.c_tiles - grp * p.stages;
-        const int gw = left < p.stages ? left : p.stages;
-        tn = r2 / gw;
-        tc = grp * p.stages + (r2 - tn * gw);
-    } else {
-        tn = (int)(t % p.n_tiles);
-        const int64_t q = t / p.n_tiles;
-        tc = (int)(q % p.c_tiles);
-        o = q / p.c_tiles;
-    }
+    const int tn = (int)(t % p.n_tiles);
+    const int64_t q = t / p.n_tiles;
+    const int tc = (int)(q % p.c_tiles);
+    const int64_t o = q / p.c_tiles;
     const int64_t row0 = (int64_t)tn * p.tile_rows;  // first output row of this tile
     const int64_t col0 = (int64_t)tc * W;
     const int64_t g0 = row0 - p.lo;                  // array row held by smem row 0
@@ -682,10 +659,7 @@ static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     p.num_tiles = num_tiles;
     p.nw = L; p.lo = a.nw / 2 + a.origin; p.mode = a.mode; p.epilogue = a.epilogue;
     p.tile_rows = tile_rows; p.smem_rows = smem_rows; p.nb = nb; p.pitch = W; p.shift = 0; p.ncg = 0;
-    // page-friendly tile order when a tile's rows are >= 1 MB apart (see kernel)
-    const int swz = env_int("B200_TMA_SWZ", 256);
-    p.stages = ((size_t)g.inner * es >= (1u << 20) && n_tiles > 1 && swz > 1) ? swz : 1;
-    p.stage_elems = (int)(stage_bytes / es); p.wide_store = 0;
+    p.stages = 1; p.stage_elems = (int)(stage_bytes / es); p.wide_store = 0;
     p.n_tiles = (int)n_tiles; p.c_tiles = c_tiles;
     p.cval = (TS)a.cval;
     p.qinv = (T)box.qinv; p.qc0 = (T)box.qc0;
