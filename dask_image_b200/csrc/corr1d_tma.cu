@@ -168,11 +168,23 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
     const int npatch_el = (nlo + (p.smem_rows - rhi)) * W;
     const bool patch = npatch_el > 0 && !(p.mode == B200_MODE_CONSTANT && p.cval == TS(0));
     auto patch_row = [&](int j) { return j < nlo ? j : rhi + (j - nlo); };
+    // source row of every patch row, computed once (the extension map costs a
+    // 64-bit modulo): -1 = cval
+    __shared__ int patch_src[256];
+    if (patch) {
+        const int npr = nlo + (p.smem_rows - rhi);
+        if (tid < npr) {
+            const int64_t src = ext_index_padded(g0 + patch_row(tid), p.n, p.mode, p.pad_lo, p.pad_hi);
+            // resident rows relative to the first resident one, so the value fits an int
+            patch_src[tid] = src == B200_USE_CVAL ? -1 : (int)(src + p.pad_lo);
+        }
+        __syncthreads();
+    }
     auto patch_value = [&](int idx) -> TS {
         const int j = idx / W, c = idx - j * W;
-        const int64_t src = ext_index_padded(g0 + patch_row(j), p.n, p.mode, p.pad_lo, p.pad_hi);
-        if (src == B200_USE_CVAL) return p.cval;
-        return (col0 + c < p.inner) ? p.in[(o * p.n + src) * p.inner + col0 + c] : TS(0);
+        const int sr = patch_src[j];
+        if (sr < 0) return p.cval;
+        return (col0 + c < p.inner) ? p.in[(o * p.n + (sr - p.pad_lo)) * p.inner + col0 + c] : TS(0);
     };
     TS pre[kPre];
     if (patch) {
@@ -275,21 +287,7 @@ struct ContigEdge {
         per_row = nlow + (P - hstart);
         total = per_row * TR;
     }
-    __device__ __forceinline__ void locate(int idx, int &r, int &c) const
-    {
-        r = idx / per_row;
-        c = idx - r * per_row;
-        c = c < nlow ? c : hstart + (c - nlow);
-    }
-    __device__ __forceinline__ TS value(int idx, const TS *in, int64_t g0, int64_t n, int64_t row0, int64_t nrows,
-                                        int mode, TS cval) const
-    {
-        int r, c;
-        locate(idx, r, c);
-        const int64_t src = ext_index(g0 + c, n, mode);
-        if (src < 0) return cval;
-        return (row0 + r < nrows) ? in[(row0 + r) * n + src] : TS(0);
-    }
+    __device__ __forceinline__ int column(int k) const { return k < nlow ? k : hstart + (k - nlow); }
 };
 
 template <typename TS, int KPRE>
@@ -307,12 +305,25 @@ __device__ __forceinline__ void contig_stage_tile(const CUtensorMap &tmap, TS *t
     ContigEdge<TS> edge;
     edge.init(g0, P, n, TR);
     const bool patch = edge.total > 0 && !(mode == B200_MODE_CONSTANT && cval == TS(0));
+    // source column of every patch column, computed once (the extension map
+    // costs a 64-bit modulo): -1 = cval.  Rows are < 2^31 elements long.
+    __shared__ int patch_src[256];
+    if (patch) {
+        if (tid < edge.per_row) patch_src[tid] = (int)ext_index(g0 + edge.column(tid), n, mode);
+        __syncthreads();
+    }
+    auto value = [&](int idx) -> TS {
+        const int r = idx / edge.per_row, k = idx - r * edge.per_row;
+        const int sc = patch_src[k];
+        if (sc < 0) return cval;
+        return (row0 + r < nrows) ? in[(row0 + r) * n + sc] : TS(0);
+    };
     TS pre[KPRE];
     if (patch) {
 #pragma unroll
         for (int i = 0; i < KPRE; ++i) {
             const int idx = tid + i * 256;
-            pre[i] = idx < edge.total ? edge.value(idx, in, g0, n, row0, nrows, mode, cval) : TS(0);
+            pre[i] = idx < edge.total ? value(idx) : TS(0);
         }
     }
     __syncthreads();
@@ -323,15 +334,13 @@ __device__ __forceinline__ void contig_stage_tile(const CUtensorMap &tmap, TS *t
         for (int i = 0; i < KPRE; ++i) {
             const int idx = tid + i * 256;
             if (idx < edge.total) {
-                int r, c;
-                edge.locate(idx, r, c);
-                tile[r * P + c] = pre[i];
+                const int r = idx / edge.per_row, k = idx - r * edge.per_row;
+                tile[r * P + edge.column(k)] = pre[i];
             }
         }
         for (int idx = tid + KPRE * 256; idx < edge.total; idx += 256) {
-            int r, c;
-            edge.locate(idx, r, c);
-            tile[r * P + c] = edge.value(idx, in, g0, n, row0, nrows, mode, cval);
+            const int r = idx / edge.per_row, k = idx - r * edge.per_row;
+            tile[r * P + edge.column(k)] = value(idx);
         }
         __syncthreads();
     }
