@@ -192,6 +192,8 @@ def run_b200(args, wl, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
 
+        # keep stdout for the one JSON line: NCCL's banner / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     shape = tuple(wl["shape"])
     sigma, mode = wl["sigma"], wl["mode"]
@@ -291,24 +293,17 @@ def run_b200(args, wl, rank, world, local_rank):
             x_t = out_t = None
             torch.cuda.empty_cache()
 
-            if world == 1:
-                # host volume streamed through the GPU: H2D | filter | D2H overlapped
-                hv = b200.HostVolume(h_in, out=h_out, device=dev)
+            # host volume (this rank's slab) streamed through the GPU: H2D | filter | D2H
+            # overlapped on three streams, neighbour faces over NCCL for N > 1
+            hv = b200.HostVolume(h_in, out=h_out, device=dev,
+                                 global_shape=shape if world > 1 else None)
 
-                def e2e_step():
-                    b200.ndfilters.gaussian_filter(hv, sigma, mode=mode)
+            def e2e_step():
+                b200.ndfilters.gaussian_filter(hv, sigma, mode=mode)
 
-                how = ("pinned host volume -> ndfilters.gaussian_filter(HostVolume) -> pinned host result: "
-                       "chunked H2D | filter | D2H pipeline on three streams; wall clock with device sync")
-            else:
-                def e2e_step():
-                    d = ShardedVolume.empty(shape, np.float32, device=dev, halo=halo)
-                    d.local.copy_(h_in, non_blocking=True)
-                    r = b200.ndfilters.gaussian_filter(d, sigma, mode=mode)
-                    h_out.copy_(r.local, non_blocking=True)
-
-                how = ("pinned host slab -> H2D -> ndfilters.gaussian_filter(ShardedVolume) -> D2H into pinned "
-                       "host; wall clock with device sync, max over ranks")
+            how = ("pinned host volume (one axis-0 slab per rank) -> ndfilters.gaussian_filter(HostVolume) -> "
+                   "pinned host result: chunked H2D | filter | D2H pipeline on three streams%s; wall clock "
+                   "with device sync, max over ranks" % (", NCCL halo faces" if world > 1 else ""))
 
             e2e_step()
             torch.cuda.synchronize()

@@ -23,10 +23,12 @@ correlate / convolve).  Plans that filter along axis 0 after another pass
 """
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import _lib
 from . import ndimage as _nd
 from ._array import _TORCH_TO_NP, torch_dtype
+from .sharded import ShardedVolume, slab_bounds
 
 __all__ = ["HostVolume", "FUNCTIONS"]
 
@@ -52,13 +54,16 @@ class HostVolume:
     Parameters
     ----------
     array : numpy.ndarray or CPU torch.Tensor
+        The whole volume -- or, with ``global_shape``, this rank's axis-0 slab
+        of a volume spread over the ranks of ``group`` (one process per GPU;
+        slabs as :func:`dask_image_b200.sharded.slab_bounds` cuts them).
     out : optional CPU tensor / array of the same shape and dtype that receives
         the result of the next filter (otherwise a pinned one is allocated)
     device : CUDA device to stream through (default: current)
     chunk_bytes : approximate size of one upload / compute / download unit
     """
 
-    def __init__(self, array, out=None, device=None, chunk_bytes=1 << 30):
+    def __init__(self, array, out=None, device=None, chunk_bytes=1 << 30, global_shape=None, group=None):
         self.tensor = _as_host_tensor(array)
         if self.tensor.dtype not in _TORCH_TO_NP:
             raise RuntimeError("data type not supported")
@@ -72,6 +77,17 @@ class HostVolume:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
         self.chunk_bytes = int(chunk_bytes)
+        self.group = group
+        self.world = self.rank = None
+        self.global_shape = None
+        if global_shape is not None:
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("a sharded HostVolume needs torch.distributed to be initialised")
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            self.global_shape = tuple(int(v) for v in global_shape)
+            s0, s1 = slab_bounds(self.global_shape[0], self.world)[self.rank]
+            if tuple(self.tensor.shape) != (s1 - s0,) + self.global_shape[1:]:
+                raise ValueError("rank %d must hold planes [%d, %d) of %s" % (self.rank, s0, s1, self.global_shape))
 
     @classmethod
     def pinned_empty(cls, shape, dtype, **kw):
@@ -79,7 +95,8 @@ class HostVolume:
 
     @property
     def shape(self):
-        return tuple(int(s) for s in self.tensor.shape)
+        """Global shape of the volume."""
+        return self.global_shape if self.global_shape is not None else tuple(int(s) for s in self.tensor.shape)
 
     @property
     def ndim(self):
@@ -91,12 +108,13 @@ class HostVolume:
 
     @property
     def size(self):
-        return int(self.tensor.numel())
+        return int(np.prod(self.shape, dtype=np.int64))
 
     def to_numpy(self):
+        """This process's planes as a numpy array (the whole volume unless sharded)."""
         t = self.tensor
         if t.dtype in (torch.uint16, torch.uint32, torch.uint64):
-            return t.view(torch.uint8).numpy().view(self.dtype).reshape(self.shape)
+            return t.view(torch.uint8).numpy().view(self.dtype).reshape(tuple(t.shape))
         return t.numpy()
 
     def __array__(self, dtype=None, copy=None):
@@ -104,22 +122,28 @@ class HostVolume:
         return a if dtype is None else a.astype(dtype, copy=False)
 
     def __repr__(self):
-        return "HostVolume(shape=%s, dtype=%s, pinned=%s, via=%s)" % (
-            self.shape, self.dtype, self.tensor.is_pinned(), self.device)
+        return "HostVolume(shape=%s, dtype=%s, pinned=%s, via=%s%s)" % (
+            self.shape, self.dtype, self.tensor.is_pinned(), self.device,
+            "" if self.world is None else ", rank %d/%d" % (self.rank, self.world))
+
+    def _result(self, h_out):
+        return HostVolume(h_out, device=self.device, chunk_bytes=self.chunk_bytes,
+                          global_shape=self.global_shape, group=self.group)
 
     # ------------------------------------------------------------------
     def _run_plan(self, plan):
         h_in = self.tensor
         h_out = self.out if self.out is not None else torch.empty_like(h_in).pin_memory()
-        result = HostVolume(h_out, device=self.device, chunk_bytes=self.chunk_bytes)
-        if self.size == 0:
-            return result
+        result = self._result(h_out)
         if self.ndim == 0:
             raise RuntimeError("0-d arrays are not supported")
+        if self.size == 0:
+            return result
         dev, dt = self.device, self.dtype
-        n0 = self.shape[0]
-        tail = self.shape[1:]
+        n0 = int(h_in.shape[0])                 # planes held by this process
+        tail = tuple(int(v) for v in h_in.shape[1:])
         plane_bytes = max(1, int(np.prod(tail, dtype=np.int64)) * dt.itemsize)
+        sharded = self.world is not None and self.world > 1
 
         # reach of the plan along axis 0; plans that filter along axis 0 after
         # another pass cannot be chunked without halos of intermediates
@@ -140,44 +164,111 @@ class HostVolume:
                     l0 = L // 2 + ps.origin
                     lo, hi = max(lo, l0), max(hi, L - 1 - l0)
                     ring = ring or ps.mode in ("wrap", "grid-wrap")
-        C = max(1, min(n0, self.chunk_bytes // plane_bytes))
-        C = max(C, lo, hi, 1)
-        chunks = [(s, min(n0, s + C)) for s in range(0, n0, C)]
         if not plan.chains and plan.nd is None:
             h_out.copy_(h_in)
             return result
+        # chunking decisions must agree on every rank: derive them from the thinnest slab
+        nmin = n0
+        if sharded:
+            nmin = min(e - s for s, e in slab_bounds(self.global_shape[0], self.world))
+        C = max(1, min(nmin, self.chunk_bytes // plane_bytes))
+        C = max(C, lo, hi, 1)
+        chunks = [(s, min(n0, s + C)) for s in range(0, n0, C)]
+        pipelined = streamable and -(-nmin // C) >= 3
+
+        # neighbours along axis 0 (other ranks; the ring closes for mode='wrap')
+        has_prev = has_next = False
+        prev = nxt = None
+        if sharded:
+            if max(lo, hi) > nmin:
+                raise ValueError("halo depth %d exceeds the thinnest slab (%d planes on %d ranks)"
+                                 % (max(lo, hi), nmin, self.world))
+            has_prev = (ring or self.rank > 0) and lo > 0
+            has_next = (ring or self.rank < self.world - 1) and hi > 0
+            prev, nxt = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+            if self.group is not None:
+                prev, nxt = dist.get_global_rank(self.group, prev), dist.get_global_rank(self.group, nxt)
 
         with torch.cuda.device(dev):
             cur = torch.cuda.current_stream(dev)
-            if not streamable or len(chunks) < 3:
-                # whole volume resident, un-pipelined
-                from ._array import B200Array
+            if not pipelined:
+                # un-pipelined: upload, filter the resident volume, download
+                if sharded:
+                    vol = ShardedVolume.from_local(h_in.to(dev, non_blocking=True), self.global_shape, self.group,
+                                                   halo=max(lo, hi))
+                    h_out.copy_(vol._run_plan(plan).local, non_blocking=True)
+                else:
+                    from ._array import B200Array
 
-                d_in = B200Array(h_in.to(dev, non_blocking=True))
-                d_out = _nd._execute(plan, d_in, d_in.empty_like())
-                h_out.copy_(d_out.tensor, non_blocking=True)
+                    d_in = B200Array(h_in.to(dev, non_blocking=True))
+                    d_out = _nd._execute(plan, d_in, d_in.empty_like())
+                    h_out.copy_(d_out.tensor, non_blocking=True)
                 cur.synchronize()
                 return result
 
-            d_in = torch.empty(self.shape, dtype=h_in.dtype, device=dev)
+            cap_lo, cap_hi = (lo if has_prev else 0), (hi if has_next else 0)
+            d_full = torch.empty((cap_lo + n0 + cap_hi,) + tail, dtype=h_in.dtype, device=dev)
+            d_in = d_full[cap_lo:cap_lo + n0]
             nslot = 3
             d_out = [torch.empty((C,) + tail, dtype=h_in.dtype, device=dev) for _ in range(nslot)]
+            need = 0
+            for passes, op in plan.chains:
+                for tgt in _nd._chain_targets(len(passes), op):
+                    if tgt != "out":
+                        need = max(need, tgt + 1)
+            scratch = [torch.empty((C,) + tail, dtype=h_in.dtype, device=dev) for _ in range(need)]
             s_up, s_cmp, s_down = (torch.cuda.Stream(dev) for _ in range(3))
             for s in (s_up, s_cmp, s_down):
                 s.wait_stream(cur)
             ev_up = [torch.cuda.Event() for _ in chunks]
             ev_cmp = [torch.cuda.Event() for _ in chunks]
             ev_down = [None] * nslot
+            halo_reqs = {"down": None, "up": None}
+
+            def face(t):
+                return t.view(torch.uint8)
+
+            def post_exchange(which):
+                """'down': my first planes -> prev's upper pad, next's first planes ->
+                my upper pad (posted once chunk 0 is uploaded).  'up': my last
+                planes -> next's lower pad, prev's last planes -> my lower pad
+                (posted once the last chunk is uploaded).  Same order on every
+                rank; the NCCL stream picks the uploads up from ``s_up``."""
+                ops = []
+                if which == "down":
+                    if (ring or self.rank > 0) and hi > 0:
+                        ops.append(dist.P2POp(dist.isend, face(d_in[0:hi]), prev, self.group, tag=0))
+                    if has_next:
+                        ops.append(dist.P2POp(dist.irecv, face(d_full[cap_lo + n0:cap_lo + n0 + hi]), nxt, self.group,
+                                              tag=0))
+                else:
+                    if (ring or self.rank < self.world - 1) and lo > 0:
+                        ops.append(dist.P2POp(dist.isend, face(d_in[n0 - lo:n0]), nxt, self.group, tag=1))
+                    if has_prev:
+                        ops.append(dist.P2POp(dist.irecv, face(d_full[0:lo]), prev, self.group, tag=1))
+                if ops:
+                    with torch.cuda.stream(s_up):
+                        halo_reqs[which] = dist.batch_isend_irecv(ops)
 
             def compute(j, slot, uploaded_end, scr):
                 c0, c1 = chunks[j]
                 n = c1 - c0
-                pad = (c0, uploaded_end - c1)
+                # planes resident around the chunk: the uploaded part of the slab,
+                # the previous rank's face below chunk 0, the next rank's face above
+                # the slab once all of it is up
+                top = uploaded_end == n0
+                pad = (cap_lo if j == 0 else c0, (uploaded_end - c1) + (cap_hi if top else 0))
                 src = d_in[c0:c1]
                 dst = d_out[slot][:n]
                 shape = (n,) + tail
                 with torch.cuda.stream(s_cmp):
                     s_cmp.wait_event(ev_up[min(len(chunks) - 1, _chunk_of(chunks, uploaded_end - 1))])
+                    if j == 0 and halo_reqs["up"] is not None:
+                        for rq in halo_reqs["up"]:
+                            rq.wait()
+                    if top and cap_hi and halo_reqs["down"] is not None:
+                        for rq in halo_reqs["down"]:
+                            rq.wait()
                     if ev_down[slot] is not None:
                         s_cmp.wait_event(ev_down[slot])
                     if plan.nd is not None:
@@ -200,40 +291,37 @@ class HostVolume:
                     ev_down[slot] = torch.cuda.Event()
                     ev_down[slot].record(s_down)
 
-            # scratch volumes of the pass chains are chunk-sized; allocate them on
-            # the compute stream's behalf before the pipeline starts
-            need = 0
-            for passes, op in plan.chains:
-                for tgt in _nd._chain_targets(len(passes), op):
-                    if tgt != "out":
-                        need = max(need, tgt + 1)
-            scratch = [torch.empty((C,) + tail, dtype=h_in.dtype, device=dev) for _ in range(need)]
-
-            issued = 0
+            # chunk 0 reaches below the slab: the last planes of the volume for a
+            # periodic one, the previous rank's last planes for a sharded one --
+            # either way it is filtered at the end
+            defer0 = ring or has_prev
             order = list(range(len(chunks)))
-            if ring:
-                # periodic volumes: chunk 0 needs the LAST planes -- filter it at the end
+            if defer0:
                 order = order[1:] + [0]
             pending = list(order)
+            issued = 0
             for k, (c0, c1) in enumerate(chunks):
                 with torch.cuda.stream(s_up):
                     d_in[c0:c1].copy_(h_in[c0:c1], non_blocking=True)
                     ev_up[k].record(s_up)
                 uploaded_end = c1
-                # every chunk whose reach is now resident can go
+                if sharded and k == 0:
+                    post_exchange("down")
+                if sharded and k == len(chunks) - 1:
+                    post_exchange("up")
                 while pending:
                     j = pending[0]
                     j0, j1 = chunks[j]
-                    if ring and j == 0:
+                    if j == 0 and defer0:
                         ready = uploaded_end == n0
+                    elif j1 + hi <= n0:
+                        ready = uploaded_end >= j1 + hi
                     else:
-                        ready = uploaded_end >= min(n0, j1 + hi) and (not ring or j1 + hi <= n0 or uploaded_end == n0)
+                        ready = uploaded_end == n0     # reaches the slab's upper face
                     if not ready:
                         break
                     pending.pop(0)
-                    # scratch volumes are sized for whole chunks; a shorter (last)
-                    # chunk uses leading slices of them
-                    nj = chunks[j][1] - chunks[j][0]
+                    nj = j1 - j0
                     compute(j, issued % nslot, uploaded_end, scratch if nj == C else [t[:nj] for t in scratch])
                     issued += 1
             for s in (s_up, s_cmp, s_down):
