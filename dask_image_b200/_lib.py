@@ -31,6 +31,7 @@ MODE_CODES = {
 
 EXPORTS = (
     "b200_correlate1d", "b200_uniform_filter1d", "b200_correlate_nd", "b200_combine",
+    "b200_minmax_filter1d", "b200_minmax_filter_nd",
     "b200_last_kernel", "b200_last_error", "b200_version", "b200_launch_count",
 )
 
@@ -72,6 +73,11 @@ def load():
     lib.b200_correlate_nd.argtypes = [vp, vp, ci, ci, i64p, dblp, i64p, i64p, ci, dbl, i64, i64,
                                       cu, vp]
     lib.b200_correlate_nd.restype = ci
+    u8p = ctypes.POINTER(ctypes.c_uint8)
+    lib.b200_minmax_filter1d.argtypes = [vp, vp, ci, ci, i64p, ci, i64, ci, ci, dbl, i64, i64, i64, cu, vp]
+    lib.b200_minmax_filter1d.restype = ci
+    lib.b200_minmax_filter_nd.argtypes = [vp, vp, ci, ci, i64p, u8p, i64p, i64p, ci, ci, dbl, i64, i64, cu, vp]
+    lib.b200_minmax_filter_nd.restype = ci
     lib.b200_combine.argtypes = [vp, vp, ci, i64, ci, vp]
     lib.b200_combine.restype = ci
     for name in ("b200_last_kernel", "b200_last_error", "b200_version"):

@@ -172,6 +172,57 @@ int b200_correlate_nd(const void *in, void *out, int dtype, int ndim, const int6
     return launch_corrnd_generic(a);
 }
 
+int b200_minmax_filter1d(const void *in, void *out, int dtype, int ndim, const int64_t *shape, int axis,
+                         int64_t size, int is_max, int mode, double cval, int64_t origin, int64_t pad_lo,
+                         int64_t pad_hi, unsigned flags, void *stream)
+{
+    int64_t total;
+    if (int rc = check_common(in, out, dtype, ndim, shape, mode, &total)) return rc;
+    if (axis < 0 || axis >= ndim) return set_error(B200_EINVAL, "axis out of range");
+    if (size < 1 || size > (1 << 20)) return set_error(B200_EINVAL, "incorrect filter size");
+    if (size / 2 + origin < 0 || size / 2 + origin >= size) return set_error(B200_EORIGIN, "invalid origin");
+    if (pad_lo < 0 || pad_hi < 0 || ((pad_lo || pad_hi) && axis != 0))
+        return set_error(B200_EINVAL, "halo pads are only defined for axis 0");
+    if (total == 0) return B200_OK;
+    MinMax1dArgs a;
+    a.in = in; a.out = out; a.dtype = dtype;
+    a.g = line_geometry(ndim, shape, axis);
+    a.size = (int)size; a.is_max = is_max ? 1 : 0; a.mode = mode; a.cval = cval; a.origin = (int)origin;
+    a.pad_lo = pad_lo; a.pad_hi = pad_hi; a.flags = flags; a.stream = (cudaStream_t)stream;
+    if (flags & B200_FLAG_FORCE_FAST)
+        return set_error(B200_EINVAL, "no tiled kernel is eligible for this call");
+    return launch_minmax1d_generic(a);
+}
+
+int b200_minmax_filter_nd(const void *in, void *out, int dtype, int ndim, const int64_t *shape,
+                          const uint8_t *footprint, const int64_t *fshape, const int64_t *origins, int is_max,
+                          int mode, double cval, int64_t pad_lo, int64_t pad_hi, unsigned flags, void *stream)
+{
+    int64_t total;
+    if (int rc = check_common(in, out, dtype, ndim, shape, mode, &total)) return rc;
+    if (!footprint || !fshape || !origins) return set_error(B200_EINVAL, "no footprint provided");
+    int64_t ftotal = 1;
+    for (int d = 0; d < ndim; ++d) {
+        if (fshape[d] < 1) return set_error(B200_EINVAL, "footprint must have non-zero extents");
+        ftotal *= fshape[d];
+        if (ftotal > (1 << 24)) return set_error(B200_EINVAL, "footprint too large");
+        if (origins[d] < -(fshape[d] / 2) || origins[d] > (fshape[d] - 1) / 2)
+            return set_error(B200_EORIGIN, "invalid origin");
+    }
+    if (pad_lo < 0 || pad_hi < 0) return set_error(B200_EINVAL, "negative halo pad");
+    if (total == 0) return B200_OK;
+    MinMaxNdArgs a;
+    a.in = in; a.out = out; a.dtype = dtype; a.ndim = ndim;
+    for (int d = 0; d < ndim; ++d) {
+        a.shape[d] = shape[d]; a.fshape[d] = fshape[d]; a.origins[d] = origins[d];
+    }
+    a.footprint = footprint; a.is_max = is_max ? 1 : 0; a.mode = mode; a.cval = cval;
+    a.pad_lo = pad_lo; a.pad_hi = pad_hi; a.flags = flags; a.stream = (cudaStream_t)stream;
+    if (flags & B200_FLAG_FORCE_FAST)
+        return set_error(B200_EINVAL, "no tiled kernel is eligible for this call");
+    return launch_minmaxnd_generic(a);
+}
+
 int b200_combine(void *acc, const void *src, int dtype, int64_t n, int op, void *stream)
 {
     if (dtype < B200_U8 || dtype > B200_F64) return set_error(B200_EDTYPE, "data type not supported");

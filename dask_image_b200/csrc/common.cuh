@@ -270,6 +270,40 @@ int launch_corrnd_tiled(const CorrNdArgs &a);
 
 int launch_combine(void *acc, const void *src, int dtype, int64_t n, int op, cudaStream_t stream);
 
+struct MinMax1dArgs {
+    const void *in;
+    void *out;
+    int dtype;
+    LineGeom g;
+    int size;
+    int is_max;
+    int mode;
+    double cval;
+    int origin;
+    int64_t pad_lo, pad_hi;
+    unsigned flags;
+    cudaStream_t stream;
+};
+int launch_minmax1d_generic(const MinMax1dArgs &a);
+
+struct MinMaxNdArgs {
+    const void *in;
+    void *out;
+    int dtype;
+    int ndim;
+    int64_t shape[B200_MAXDIM];
+    const uint8_t *footprint;  // host, C order, shape fshape
+    int64_t fshape[B200_MAXDIM];
+    int64_t origins[B200_MAXDIM];
+    int is_max;
+    int mode;
+    double cval;
+    int64_t pad_lo, pad_hi;
+    unsigned flags;
+    cudaStream_t stream;
+};
+int launch_minmaxnd_generic(const MinMaxNdArgs &a);
+
 int device_sm_count();
 
 }  // namespace b200

@@ -347,6 +347,209 @@ int launch_corrnd_generic(const CorrNdArgs &a)
 }
 
 // ===========================================================================
+// minimum / maximum filters
+//   1-D: replaces _nd_image.min_or_max_filter1d (scipy/ndimage/_filters.py:1660-1666,
+//        1720-1726): values and cval go through double, the extreme of the
+//        `size` window samples is cast back with the reference's cast rules.
+//   N-D: replaces _nd_image.min_or_max_filter (scipy/ndimage/_filters.py:1771):
+//        extreme over the true positions of a boolean footprint; here cval is
+//        first cast to the ARRAY type (as the reference's C loop does).
+// Min / max select, they do not round: results are bit-identical for every
+// dtype (NaN ordering of the reference's ring-buffer scan is not reproduced).
+// ===========================================================================
+struct MinMax1dParams {
+    const void *in;
+    void *out;
+    int64_t outer, n, inner, total;
+    int64_t pad_lo, pad_hi;
+    int size, lo, mode, is_max;
+    double cval;
+};
+
+template <typename T, typename IDX>
+__global__ void __launch_bounds__(256)
+minmax1d_generic_kernel(const __grid_constant__ MinMax1dParams p)
+{
+    const T *__restrict__ in = (const T *)p.in;
+    T *__restrict__ out = (T *)p.out;
+    const IDX total = (IDX)p.total, inner = (IDX)p.inner, n = (IDX)p.n;
+    const IDX step = (IDX)gridDim.x * blockDim.x;
+    for (IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+        IDX c = e % inner;
+        IDX t = e / inner;
+        IDX i = t % n;
+        IDX o = t / n;
+        const T *line = in + ((int64_t)o * p.n * p.inner + (int64_t)c);
+        const int64_t first = (int64_t)i - p.lo;
+        const bool interior = (first >= -p.pad_lo) && (first + p.size - 1 < p.n + p.pad_hi);
+        double m = 0.0;
+        for (int k = 0; k < p.size; ++k) {
+            double v;
+            if (interior) {
+                v = (double)line[(first + k) * p.inner];
+            } else {
+                const int64_t pos = ext_index_padded(first + k, p.n, p.mode, p.pad_lo, p.pad_hi);
+                v = (pos == B200_USE_CVAL) ? p.cval : (double)line[pos * p.inner];
+            }
+            if (k == 0) m = v;
+            else if (p.is_max ? (v > m) : (v < m)) m = v;
+        }
+        out[e] = cast_out<T>(m);
+    }
+}
+
+int launch_minmax1d_generic(const MinMax1dArgs &a)
+{
+    MinMax1dParams p;
+    p.in = a.in; p.out = a.out;
+    p.outer = a.g.outer; p.n = a.g.n; p.inner = a.g.inner;
+    p.total = a.g.outer * a.g.n * a.g.inner;
+    p.pad_lo = a.pad_lo; p.pad_hi = a.pad_hi;
+    p.size = a.size; p.lo = a.size / 2 + a.origin; p.mode = a.mode; p.is_max = a.is_max; p.cval = a.cval;
+    const int threads = 256;
+    const int blocks = grid_for(p.total, threads);
+    const bool idx32 = p.total < (int64_t)0x7fffffff - (int64_t)blocks * threads;
+    int rc = dispatch_dtype(a.dtype, [&]<typename T>() -> int {
+        if (idx32)
+            minmax1d_generic_kernel<T, uint32_t><<<blocks, threads, 0, a.stream>>>(p);
+        else
+            minmax1d_generic_kernel<T, int64_t><<<blocks, threads, 0, a.stream>>>(p);
+        return check_cuda(cudaGetLastError(), "minmax1d_generic launch");
+    });
+    if (rc) return rc;
+    count_launch();
+    note_kernel(a.is_max ? "max1d_generic" : "min1d_generic");
+    return B200_OK;
+}
+
+struct MinMaxNdParams {
+    const void *in;
+    void *out;
+    int ndim;
+    int64_t shape[B200_MAXDIM];
+    int64_t stride[B200_MAXDIM];
+    int64_t total;
+    int64_t pad_lo, pad_hi;
+    int lo[B200_MAXDIM], hi[B200_MAXDIM];
+    int nnz;
+    const int32_t *tk;     // [nnz][ndim] relative tap coordinates
+    const int64_t *tlin;   // [nnz] linear element offsets (interior fast path)
+    int mode, is_max;
+    double cval;
+};
+
+template <typename T, typename IDX>
+__global__ void __launch_bounds__(256)
+minmaxnd_generic_kernel(const __grid_constant__ MinMaxNdParams p)
+{
+    const T *__restrict__ in = (const T *)p.in;
+    T *__restrict__ out = (T *)p.out;
+    const IDX total = (IDX)p.total;
+    const IDX step = (IDX)gridDim.x * blockDim.x;
+    const int nd = p.ndim;
+    const double cv = (double)cast_out<T>(p.cval);   // the reference casts cval to the array type first
+    for (IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+        int64_t idx[B200_MAXDIM];
+        IDX r = e;
+        bool interior = true;
+#pragma unroll
+        for (int d = B200_MAXDIM - 1; d >= 0; --d) {
+            if (d < nd) {
+                IDX s = (IDX)p.shape[d];
+                IDX q = r / s;
+                idx[d] = (int64_t)(r - q * s);
+                r = q;
+                int64_t plo = d == 0 ? p.pad_lo : 0, phi = d == 0 ? p.pad_hi : 0;
+                interior = interior && (idx[d] - p.lo[d] >= -plo) && (idx[d] + p.hi[d] < p.shape[d] + phi);
+            }
+        }
+        double m = 0.0;
+        for (int t = 0; t < p.nnz; ++t) {
+            double v;
+            if (interior) {
+                v = (double)in[(int64_t)e + p.tlin[t]];
+            } else {
+                int64_t off = 0;
+                bool outside = false;
+#pragma unroll
+                for (int d = 0; d < B200_MAXDIM; ++d) {
+                    if (d < nd) {
+                        int64_t plo = d == 0 ? p.pad_lo : 0, phi = d == 0 ? p.pad_hi : 0;
+                        int64_t s = ext_index_padded(idx[d] + p.tk[t * nd + d], p.shape[d], p.mode, plo, phi);
+                        if (s == B200_USE_CVAL) outside = true;
+                        else off += s * p.stride[d];
+                    }
+                }
+                v = outside ? cv : (double)in[off];
+            }
+            if (t == 0) m = v;
+            else if (p.is_max ? (v > m) : (v < m)) m = v;
+        }
+        out[e] = cast_out<T>(m);
+    }
+}
+
+int launch_minmaxnd_generic(const MinMaxNdArgs &a)
+{
+    MinMaxNdParams p;
+    p.in = a.in; p.out = a.out; p.ndim = a.ndim;
+    p.total = 1;
+    int64_t ftotal = 1;
+    for (int d = 0; d < a.ndim; ++d) {
+        p.shape[d] = a.shape[d];
+        p.total *= a.shape[d];
+        ftotal *= a.fshape[d];
+        p.lo[d] = (int)(a.fshape[d] / 2 + a.origins[d]);
+        p.hi[d] = (int)(a.fshape[d] - 1 - a.fshape[d] / 2 - a.origins[d]);
+    }
+    p.stride[a.ndim - 1] = 1;
+    for (int d = a.ndim - 2; d >= 0; --d) p.stride[d] = p.stride[d + 1] * a.shape[d + 1];
+    p.pad_lo = a.pad_lo; p.pad_hi = a.pad_hi; p.mode = a.mode; p.is_max = a.is_max; p.cval = a.cval;
+
+    std::vector<int32_t> tk;
+    std::vector<int64_t> tlin;
+    for (int64_t f = 0; f < ftotal; ++f) {
+        if (a.footprint[f]) {
+            int64_t r = f, lin = 0;
+            int32_t k[B200_MAXDIM];
+            for (int d = a.ndim - 1; d >= 0; --d) {
+                k[d] = (int32_t)(r % a.fshape[d] - a.fshape[d] / 2 - a.origins[d]);
+                r /= a.fshape[d];
+                lin += (int64_t)k[d] * p.stride[d];
+            }
+            for (int d = 0; d < a.ndim; ++d) tk.push_back(k[d]);
+            tlin.push_back(lin);
+        }
+    }
+    p.nnz = (int)tlin.size();
+    if (p.nnz == 0) return set_error(B200_EINVAL, "All-zero footprint is not supported.");
+    char *dev = nullptr;
+    const size_t b_lin = sizeof(int64_t) * tlin.size(), b_tk = sizeof(int32_t) * tk.size();
+    B200_CUDA_TRY(cudaMallocAsync((void **)&dev, b_lin + b_tk, a.stream));
+    B200_CUDA_TRY(cudaMemcpyAsync(dev, tlin.data(), b_lin, cudaMemcpyHostToDevice, a.stream));
+    B200_CUDA_TRY(cudaMemcpyAsync(dev + b_lin, tk.data(), b_tk, cudaMemcpyHostToDevice, a.stream));
+    // (pageable sources: cudaMemcpyAsync returns once they are staged, so the vectors may die)
+    p.tlin = (const int64_t *)dev;
+    p.tk = (const int32_t *)(dev + b_lin);
+
+    const int threads = 256;
+    const int blocks = grid_for(p.total, threads);
+    const bool idx32 = p.total < (int64_t)0x7fffffff - (int64_t)blocks * threads;
+    int rc = dispatch_dtype(a.dtype, [&]<typename T>() -> int {
+        if (idx32)
+            minmaxnd_generic_kernel<T, uint32_t><<<blocks, threads, 0, a.stream>>>(p);
+        else
+            minmaxnd_generic_kernel<T, int64_t><<<blocks, threads, 0, a.stream>>>(p);
+        return check_cuda(cudaGetLastError(), "minmaxnd_generic launch");
+    });
+    cudaFreeAsync(dev, a.stream);
+    if (rc) return rc;
+    count_launch();
+    note_kernel(a.is_max ? "maxnd_generic" : "minnd_generic");
+    return B200_OK;
+}
+
+// ===========================================================================
 // elementwise combine (numpy ufuncs of scipy/ndimage/_filters.py:1025-1030,
 // 1184-1193), in the array dtype
 // ===========================================================================

@@ -20,6 +20,7 @@ from ._dispatcher import Dispatcher
 _NAMES = (
     "convolve", "correlate", "laplace", "prewitt", "sobel", "gaussian_filter",
     "gaussian_gradient_magnitude", "gaussian_laplace", "uniform_filter",
+    "minimum_filter", "maximum_filter",
 )
 
 __all__ = ["dispatch_" + n for n in _NAMES] + ["register_b200"]
@@ -33,6 +34,8 @@ dispatch_gaussian_filter = Dispatcher(name="dispatch_gaussian_filter")
 dispatch_gaussian_gradient_magnitude = Dispatcher(name="dispatch_gaussian_gradient_magnitude")
 dispatch_gaussian_laplace = Dispatcher(name="dispatch_gaussian_laplace")
 dispatch_uniform_filter = Dispatcher(name="dispatch_uniform_filter")
+dispatch_minimum_filter = Dispatcher(name="dispatch_minimum_filter")
+dispatch_maximum_filter = Dispatcher(name="dispatch_maximum_filter")
 
 
 def _factory(func):

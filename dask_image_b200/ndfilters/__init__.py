@@ -5,15 +5,18 @@ from ._diff import laplace
 from ._edge import prewitt, sobel
 from ._gaussian import (gaussian, gaussian_filter, gaussian_gradient_magnitude,
                         gaussian_laplace)
+from ._order import maximum_filter, minimum_filter
 from ._smooth import uniform_filter
 from ._threshold import threshold_local
 
 __all__ = [
     "convolve", "correlate", "laplace", "prewitt", "sobel", "gaussian", "gaussian_filter",
     "gaussian_gradient_magnitude", "gaussian_laplace", "uniform_filter", "threshold_local",
+    "minimum_filter", "maximum_filter",
 ]
 
 for _f in (convolve, correlate, laplace, prewitt, sobel, gaussian, gaussian_filter,
-           gaussian_gradient_magnitude, gaussian_laplace, uniform_filter, threshold_local):
+           gaussian_gradient_magnitude, gaussian_laplace, uniform_filter, threshold_local,
+           minimum_filter, maximum_filter):
     _f.__module__ = __name__
 del _f

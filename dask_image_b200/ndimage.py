@@ -22,6 +22,7 @@ __all__ = [
     "correlate1d", "convolve1d", "gaussian_filter1d", "gaussian_filter",
     "uniform_filter1d", "uniform_filter", "correlate", "convolve",
     "gaussian_gradient_magnitude", "gaussian_laplace", "laplace", "prewitt", "sobel",
+    "minimum_filter1d", "maximum_filter1d", "minimum_filter", "maximum_filter",
 ]
 
 _default_flags = _lib.FLAG_EXACT if os.environ.get("B200_NDFILTERS_EXACT", "") not in ("", "0") else 0
@@ -113,6 +114,31 @@ def _launch_correlate_nd(src, dst, shape, np_dtype, weights, origins, mode, cval
             _lib.i64_array(shape), _lib.f64_pointer(w), _lib.i64_array(w.shape),
             _lib.i64_array(origins), _lib.mode_code(mode), float(cval), int(pad[0]), int(pad[1]),
             int(_default_flags if flags is None else flags), _stream_ptr(src))
+    _lib.check(rc)
+
+
+def _launch_minmax1d(src, dst, shape, np_dtype, axis, size, is_max, mode, cval, origin, pad=(0, 0), flags=None):
+    lib = _lib.load()
+    with torch.cuda.device(src.device):
+        rc = lib.b200_minmax_filter1d(
+            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape),
+            _lib.i64_array(shape), int(axis), int(size), int(bool(is_max)), _lib.mode_code(mode), float(cval),
+            int(origin), int(pad[0]), int(pad[1]),
+            int(_default_flags if flags is None else flags) & ~_lib.FLAG_FORCE_FAST, _stream_ptr(src))
+    _lib.check(rc)
+
+
+def _launch_minmax_nd(src, dst, shape, np_dtype, footprint, origins, is_max, mode, cval, pad=(0, 0), flags=None):
+    import ctypes
+
+    lib = _lib.load()
+    fp = np.ascontiguousarray(footprint, dtype=np.uint8)
+    with torch.cuda.device(src.device):
+        rc = lib.b200_minmax_filter_nd(
+            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape),
+            _lib.i64_array(shape), fp.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _lib.i64_array(fp.shape),
+            _lib.i64_array(origins), int(bool(is_max)), _lib.mode_code(mode), float(cval), int(pad[0]), int(pad[1]),
+            int(_default_flags if flags is None else flags) & ~_lib.FLAG_FORCE_FAST, _stream_ptr(src))
     _lib.check(rc)
 
 
@@ -280,9 +306,13 @@ def _run_chain(x_tensor, shape, np_dtype, passes, cval, out_tensor, final_epilog
                                 ps.origin, use_pad, epi, flags)
         else:
             if epi != _lib.EPI_STORE:
-                raise RuntimeError("uniform passes have no fused epilogue")
-            _launch_uniform1d(src, dst, shape, np_dtype, ps.axis, ps.size, ps.mode, cval,
-                              ps.origin, use_pad, flags)
+                raise RuntimeError("only correlation passes have a fused epilogue")
+            if ps.kind == "uniform":
+                _launch_uniform1d(src, dst, shape, np_dtype, ps.axis, ps.size, ps.mode, cval,
+                                  ps.origin, use_pad, flags)
+            else:
+                _launch_minmax1d(src, dst, shape, np_dtype, ps.axis, ps.size, ps.kind == "max", ps.mode, cval,
+                                 ps.origin, use_pad, flags)
         if prov is not None and targets[i] != "out":
             prov[targets[i]] = sig
         src, src_pad = dst, (0, 0)
@@ -334,15 +364,23 @@ class _Plan:
     * ``nd``: ``(weights, origins, mode)`` of a direct N-D correlate instead.
     * ``zero_out``: clear the output first (1-axis gradient magnitude).
     """
-    __slots__ = ("chains", "nd", "cval", "zero_out")
+    __slots__ = ("chains", "nd", "cval", "zero_out", "extreme")
 
-    def __init__(self, chains=(), nd=None, cval=0.0, zero_out=False):
+    def __init__(self, chains=(), nd=None, cval=0.0, zero_out=False, extreme=None):
         self.chains, self.nd, self.cval, self.zero_out = list(chains), nd, cval, zero_out
+        # extreme = (footprint, origins, mode, is_max): a direct N-D minimum / maximum
+        # filter over a boolean footprint; `nd` then holds (footprint, origins, mode)
+        # as well so that the engines size their axis-0 halos the same way
+        self.extreme = extreme
 
 
 def _execute(plan, x, out):
     """Run ``plan`` on one resident array: x (B200Array) -> out (B200Array)."""
     if x.size == 0:
+        return out
+    if plan.extreme is not None:
+        fp, origins, mode, is_max = plan.extreme
+        _launch_minmax_nd(x.tensor, out.tensor, x.shape, x.dtype, fp, origins, is_max, mode, plan.cval)
         return out
     if plan.nd is not None:
         w, origins, mode = plan.nd
@@ -465,6 +503,60 @@ def _plan_correlate_nd(ndim, np_dtype, weights, mode="reflect", cval=0.0, origin
     return _Plan(nd=(w, origins, mode), cval=cval)
 
 
+def _plan_minmax(ndim, is_max, size=None, footprint=None, mode="reflect", cval=0.0, origin=0, axes=None):
+    """scipy/ndimage/_filters.py:1669-1773 (_min_or_max_filter): a box (``size``,
+    or an all-true footprint) is separable -> one 1-D pass per axis with size > 1;
+    any other footprint is a direct N-D scan of its true positions."""
+    axes = _check_axes(axes, ndim)
+    if len(axes) != ndim:
+        raise NotImplementedError("axes subsets are not supported (the reference never passes them)")
+    if footprint is None:
+        if size is None:
+            raise RuntimeError("no footprint provided")
+        separable = True
+    else:
+        footprint = np.asarray(_weights_to_host(footprint), dtype=bool)
+        if footprint.ndim != ndim:
+            raise RuntimeError("footprint.ndim (%d) must match len(axes) (%d)" % (footprint.ndim, ndim))
+        if not footprint.any():
+            raise ValueError("All-zero footprint is not supported.")
+        if footprint.all():
+            size, footprint, separable = footprint.shape, None, True
+        else:
+            separable = False
+    kind = "max" if is_max else "min"
+    if separable:
+        sizes, origins, modes = _per_axis(size, ndim), _per_axis(origin, ndim), _per_axis(mode, ndim)
+        passes = []
+        for ax in range(ndim):
+            sz, og = int(sizes[ax]), int(origins[ax])
+            if sz < 1:
+                raise RuntimeError("incorrect filter size")
+            if sz > 1:
+                if (sz // 2 + og < 0) or (sz // 2 + og >= sz):
+                    raise ValueError("invalid origin")
+                _lib.mode_code(modes[ax])
+                passes.append(_Pass(kind, ax, modes[ax], size=sz, origin=og))
+        return _Plan([(passes, _lib.EPI_STORE)] if passes else [], cval=cval)
+    if not isinstance(mode, str) and np.iterable(mode):
+        raise RuntimeError("A sequence of modes is not supported for non-separable footprints")
+    origins = [int(o) for o in _per_axis(origin, ndim)]
+    for og, lenf in zip(origins, footprint.shape):
+        if (og < -(lenf // 2)) or (og > (lenf - 1) // 2):
+            raise ValueError("invalid origin")
+    _lib.mode_code(mode)
+    fp = np.ascontiguousarray(footprint)
+    return _Plan(nd=(fp, origins, mode), cval=cval, extreme=(fp, origins, mode, bool(is_max)))
+
+
+def _plan_minimum_filter(ndim, size=None, footprint=None, mode="reflect", cval=0.0, origin=0, axes=None):
+    return _plan_minmax(ndim, False, size, footprint, mode, cval, origin, axes)
+
+
+def _plan_maximum_filter(ndim, size=None, footprint=None, mode="reflect", cval=0.0, origin=0, axes=None):
+    return _plan_minmax(ndim, True, size, footprint, mode, cval, origin, axes)
+
+
 def _run(plan_fn, input, output, *args, **kwargs):
     x = as_b200(input)
     _zero_dim_guard(x)
@@ -573,3 +665,42 @@ def sobel(input, axis=-1, output=None, mode="reflect", cval=0.0):
     """scipy.ndimage.sobel (scipy/ndimage/_filters.py:924-982): as prewitt with
     [1,2,1] smoothing."""
     return _run(_plan_sobel, input, output, axis, mode, cval)
+
+
+# --------------------------------------------------------------------------
+# SURVEY.md 8(f) rank 4: minimum / maximum filters
+# --------------------------------------------------------------------------
+def _minmax1d(input, size, axis, output, mode, cval, origin, is_max):
+    x = as_b200(input)
+    _zero_dim_guard(x)
+    axis = _axis_index(axis, x.ndim)
+    if size < 1:
+        raise RuntimeError("incorrect filter size")
+    if (size // 2 + origin < 0) or (size // 2 + origin >= size):
+        raise ValueError("invalid origin")
+    out = _check_output(output, x) or x.empty_like()
+    if x.size:
+        _launch_minmax1d(x.tensor, out.tensor, x.shape, x.dtype, axis, size, is_max, mode, cval, origin)
+    return out
+
+
+def minimum_filter1d(input, size, axis=-1, output=None, mode="reflect", cval=0.0, origin=0):
+    """scipy.ndimage.minimum_filter1d (scipy/ndimage/_filters.py:1625-1666)."""
+    return _minmax1d(input, size, axis, output, mode, cval, origin, False)
+
+
+def maximum_filter1d(input, size, axis=-1, output=None, mode="reflect", cval=0.0, origin=0):
+    """scipy.ndimage.maximum_filter1d (scipy/ndimage/_filters.py:1669-1726)."""
+    return _minmax1d(input, size, axis, output, mode, cval, origin, True)
+
+
+def minimum_filter(input, size=None, footprint=None, output=None, mode="reflect", cval=0.0, origin=0, *,
+                   axes=None):
+    """scipy.ndimage.minimum_filter (scipy/ndimage/_filters.py:1776-1830)."""
+    return _run(_plan_minimum_filter, input, output, size, footprint, mode, cval, origin, axes)
+
+
+def maximum_filter(input, size=None, footprint=None, output=None, mode="reflect", cval=0.0, origin=0, *,
+                   axes=None):
+    """scipy.ndimage.maximum_filter (scipy/ndimage/_filters.py:1833-1887)."""
+    return _run(_plan_maximum_filter, input, output, size, footprint, mode, cval, origin, axes)

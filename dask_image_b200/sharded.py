@@ -79,6 +79,17 @@ class CudaBackend:
                                  np_dtype, w, origins, mode, cval, pad, flags)
 
     @staticmethod
+    def minmax1d(src_full, s0, dst_full, d0, n, pad, shape, np_dtype, ps, cval, flags=None):
+        _nd._launch_minmax1d(src_full[s0:s0 + n], dst_full[d0:d0 + n], (n,) + tuple(shape[1:]),
+                             np_dtype, ps.axis, ps.size, ps.kind == "max", ps.mode, cval, ps.origin, pad, flags)
+
+    @staticmethod
+    def minmax_nd(src_full, s0, dst_full, d0, n, pad, shape, np_dtype, fp, origins, is_max, mode, cval,
+                  flags=None):
+        _nd._launch_minmax_nd(src_full[s0:s0 + n], dst_full[d0:d0 + n], (n,) + tuple(shape[1:]),
+                              np_dtype, fp, origins, is_max, mode, cval, pad, flags)
+
+    @staticmethod
     def combine(dst, src, np_dtype, op):
         _nd._launch_combine(dst, src, np_dtype, op)
 
@@ -339,6 +350,13 @@ class ShardedVolume:
             w, origins, mode = plan.nd
             lo = w.shape[0] // 2 + origins[0]
             hi = w.shape[0] - 1 - w.shape[0] // 2 - origins[0]
+            if plan.extreme is not None:
+                is_max = plan.extreme[3]
+                self._axis0_call(src0, lo, hi, mode in ("wrap", "grid-wrap"),
+                                 lambda p0, p1, pad: be.minmax_nd(
+                                     src0.full, src0.cap + p0, out.full, out.cap + p0, p1 - p0, pad,
+                                     shape, dt, w, origins, is_max, mode, plan.cval, flags))
+                return result
             self._axis0_call(src0, lo, hi, mode in ("wrap", "grid-wrap"),
                              lambda p0, p1, pad: be.correlate_nd(
                                  src0.full, src0.cap + p0, out.full, out.cap + p0, p1 - p0, pad,
@@ -373,15 +391,18 @@ class ShardedVolume:
                     prov[k] = sig
                 epi = op if last else _lib.EPI_STORE
                 if ps.kind != "corr" and epi != _lib.EPI_STORE:
-                    raise RuntimeError("uniform passes have no fused epilogue")
+                    raise RuntimeError("only correlation passes have a fused epilogue")
 
                 def call(p0, p1, pad, src=src, dst=dst, ps=ps, epi=epi):
                     if ps.kind == "corr":
                         be.correlate1d(src.full, src.cap + p0, dst.full, dst.cap + p0, p1 - p0, pad,
                                        shape, dt, ps, plan.cval, epi, flags)
-                    else:
+                    elif ps.kind == "uniform":
                         be.uniform1d(src.full, src.cap + p0, dst.full, dst.cap + p0, p1 - p0, pad,
                                      shape, dt, ps, plan.cval, flags)
+                    else:
+                        be.minmax1d(src.full, src.cap + p0, dst.full, dst.cap + p0, p1 - p0, pad,
+                                    shape, dt, ps, plan.cval, flags)
 
                 if ps.axis == 0:
                     lo, hi = _reach(ps)
@@ -488,8 +509,18 @@ def sobel(input, axis=-1, mode="reflect", cval=0.0):
     return vol._run_plan(_nd._plan_sobel(vol.ndim, axis, mode, cval))
 
 
+def minimum_filter(input, size=None, footprint=None, mode="reflect", cval=0.0, origin=0, *, axes=None):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_minimum_filter(vol.ndim, size, footprint, mode, cval, origin, axes))
+
+
+def maximum_filter(input, size=None, footprint=None, mode="reflect", cval=0.0, origin=0, *, axes=None):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_maximum_filter(vol.ndim, size, footprint, mode, cval, origin, axes))
+
+
 FUNCTIONS = {f.__name__: f for f in (
     convolve, correlate, laplace, prewitt, sobel, gaussian_filter, gaussian_gradient_magnitude,
-    gaussian_laplace, uniform_filter)}
+    gaussian_laplace, uniform_filter, minimum_filter, maximum_filter)}
 
 assert set(_NP_TO_TORCH)  # dtype tables shared with B200Array

@@ -271,7 +271,10 @@ class HostVolume:
                             rq.wait()
                     if ev_down[slot] is not None:
                         s_cmp.wait_event(ev_down[slot])
-                    if plan.nd is not None:
+                    if plan.extreme is not None:
+                        fp, origins, mode, is_max = plan.extreme
+                        _nd._launch_minmax_nd(src, dst, shape, dt, fp, origins, is_max, mode, plan.cval, pad)
+                    elif plan.nd is not None:
                         w, origins, mode = plan.nd
                         _nd._launch_correlate_nd(src, dst, shape, dt, w, origins, mode, plan.cval, pad)
                     else:
@@ -390,8 +393,18 @@ def sobel(input, axis=-1, mode="reflect", cval=0.0):
     return vol._run_plan(_nd._plan_sobel(vol.ndim, axis, mode, cval))
 
 
+def minimum_filter(input, size=None, footprint=None, mode="reflect", cval=0.0, origin=0, *, axes=None):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_minimum_filter(vol.ndim, size, footprint, mode, cval, origin, axes))
+
+
+def maximum_filter(input, size=None, footprint=None, mode="reflect", cval=0.0, origin=0, *, axes=None):
+    vol = _check(input)
+    return vol._run_plan(_nd._plan_maximum_filter(vol.ndim, size, footprint, mode, cval, origin, axes))
+
+
 FUNCTIONS = {f.__name__: f for f in (
     convolve, correlate, laplace, prewitt, sobel, gaussian_filter, gaussian_gradient_magnitude,
-    gaussian_laplace, uniform_filter)}
+    gaussian_laplace, uniform_filter, minimum_filter, maximum_filter)}
 
 assert _lib is not None

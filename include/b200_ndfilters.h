@@ -118,6 +118,23 @@ int b200_correlate_nd(const void *in, void *out, int dtype, int ndim,
 int b200_combine(void *acc, const void *src, int dtype, int64_t n, int op,
                  void *stream);
 
+/* replaces _nd_image.min_or_max_filter1d (scipy/ndimage/_filters.py:1660-1666,
+ * 1720-1726; reached via dask_image/dispatch/_dispatch_ndfilters.py:193,209):
+ * minimum (is_max = 0) or maximum (is_max != 0) of the `size` window samples */
+int b200_minmax_filter1d(const void *in, void *out, int dtype, int ndim,
+                         const int64_t *shape, int axis, int64_t size,
+                         int is_max, int mode, double cval, int64_t origin,
+                         int64_t pad_lo, int64_t pad_hi, unsigned flags,
+                         void *stream);
+
+/* replaces _nd_image.min_or_max_filter (scipy/ndimage/_filters.py:1771) for a
+ * boolean `footprint` of shape `fshape` (host, one byte per element, C order) */
+int b200_minmax_filter_nd(const void *in, void *out, int dtype, int ndim,
+                          const int64_t *shape, const uint8_t *footprint,
+                          const int64_t *fshape, const int64_t *origins,
+                          int is_max, int mode, double cval, int64_t pad_lo,
+                          int64_t pad_hi, unsigned flags, void *stream);
+
 /* name of the kernel family the last successful call on this thread chose
  * ("corr1d_tma_strided_f32", "corr1d_generic", ...); for tests and profiling */
 const char *b200_last_kernel(void);

@@ -68,6 +68,27 @@ class OracleBackend:
         r = orc.correlate(blk, w, mode, cval, origins)
         _np(dst_full)[d0:d0 + n] = r[pad[0]:pad[0] + n]
 
+    @classmethod
+    def minmax1d(cls, src_full, s0, dst_full, d0, n, pad, shape, np_dtype, ps, cval, flags=None):
+        import scipy.ndimage as ndi
+
+        blk = cls._block(src_full, s0, n, pad if ps.axis == 0 else (0, 0))
+        f = ndi.maximum_filter1d if ps.kind == "max" else ndi.minimum_filter1d
+        r = f(blk, ps.size, axis=ps.axis, mode=ps.mode, cval=cval, origin=ps.origin)
+        if ps.axis == 0:
+            r = r[pad[0]:pad[0] + n]
+        _np(dst_full)[d0:d0 + n] = r
+
+    @classmethod
+    def minmax_nd(cls, src_full, s0, dst_full, d0, n, pad, shape, np_dtype, fp, origins, is_max, mode, cval,
+                  flags=None):
+        import scipy.ndimage as ndi
+
+        blk = cls._block(src_full, s0, n, pad)
+        f = ndi.maximum_filter if is_max else ndi.minimum_filter
+        r = f(blk, footprint=fp, mode=mode, cval=cval, origin=origins)
+        _np(dst_full)[d0:d0 + n] = r[pad[0]:pad[0] + n]
+
     @staticmethod
     def combine(dst, src, np_dtype, op):
         _fold(_np(dst), _np(src).copy(), op)

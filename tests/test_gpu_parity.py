@@ -321,3 +321,59 @@ def test_threshold_local_values_and_errors(b200):
         b200.ndfilters.threshold_local(dev(b200, a), 3, method="otsu")
     with pytest.raises(NotImplementedError):
         b200.ndfilters.threshold_local(dev(b200, a), 3, method="median")
+
+
+# ---------------------------------------------------------------------------
+# minimum / maximum filters: bit-identical to scipy for
+# every dtype, separable boxes and general footprints, chunked or whole
+# ---------------------------------------------------------------------------
+EXT_DTYPES = [np.uint8, np.int16, np.uint16, np.int32, np.int64, np.uint64, np.float32, np.float64]
+
+
+@pytest.mark.parametrize("dtype", EXT_DTYPES)
+@pytest.mark.parametrize("mode", ["reflect", "mirror", "nearest", "constant", "wrap"])
+def test_min_max_filters_bitwise(b200, dtype, mode):
+    rng = np.random.default_rng(17)
+    shape = (19, 14, 23)
+    if np.dtype(dtype).kind == "f":
+        a = (rng.random(shape) - 0.5).astype(dtype)
+    elif np.dtype(dtype).itemsize == 8:
+        a = rng.integers(0, 2 ** 62, shape).astype(dtype)       # beyond 2^53: the reference rounds through double
+    else:
+        info = np.iinfo(dtype)
+        a = rng.integers(info.min, info.max, shape, endpoint=True).astype(dtype)
+    d = dev(b200, a)
+    fp = rng.random((3, 4, 5)) > 0.45
+    fp[1, 2, 2] = True
+    for name in ("minimum_filter", "maximum_filter"):
+        f, sp = getattr(b200.ndimage, name), getattr(ndi, name)
+        for kw in (dict(size=3), dict(size=(5, 1, 4), origin=(2, 0, -2)), dict(footprint=fp, origin=(0, 1, -1)),
+                   dict(footprint=np.ones((2, 3, 2), bool))):
+            got = f(d, mode=mode, cval=-7.5, **kw)
+            assert_parity(got.to_numpy(), sp(a, mode=mode, cval=-7.5, **kw), exact=True, what="%s %s" % (name, kw))
+        f1, sp1 = getattr(b200.ndimage, name + "1d"), getattr(ndi, name + "1d")
+        for axis, size, origin in ((0, 4, -2), (1, 7, 3), (2, 2, 0), (-1, 30, 5)):
+            got = f1(d, size, axis=axis, mode=mode, cval=300.7, origin=origin)
+            assert_parity(got.to_numpy(), sp1(a, size, axis=axis, mode=mode, cval=300.7, origin=origin), exact=True)
+
+
+def test_min_max_public_wrappers_and_errors(b200):
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 65536, (40, 36), dtype=np.uint16)
+    d = dev(b200, a)
+    fp = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], bool)
+    for name in ("minimum_filter", "maximum_filter"):
+        f, sp = getattr(b200.ndfilters, name), getattr(ndi, name)
+        assert_parity(np.asarray(f(d, size=5)), sp(a, size=5), exact=True)
+        assert_parity(np.asarray(f(d, footprint=fp, mode="wrap")), sp(a, footprint=fp, mode="wrap"), exact=True)
+        chunked = f(b200.from_array(a, chunks=(16, 12)), size=(3, 7), origin=(1, -2))
+        assert_parity(np.asarray(chunked), sp(a, size=(3, 7), origin=(1, -2)), exact=True)
+        with pytest.raises(RuntimeError):
+            f(d)                                    # neither size nor footprint
+        with pytest.raises(RuntimeError):
+            f(d, size=3, footprint=fp)              # both
+        with pytest.raises(ValueError):
+            f(d, size=3, origin=2)                  # origin outside the footprint
+    with pytest.raises(ValueError):
+        b200.ndimage.minimum_filter(d, footprint=np.zeros((3, 3), bool))
+    assert b200.ndfilters.minimum_filter.__name__ == "minimum_filter"

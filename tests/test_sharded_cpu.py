@@ -50,6 +50,9 @@ def _cases():
             ("sobel", f32, dict(axis=-1, mode=mode)),
             ("prewitt", u16, dict(axis=0, mode=mode)),
             ("laplace", f64, dict(mode=mode)),
+            ("minimum_filter", u16, dict(size=(5, 1, 3), mode=mode, origin=(1, 0, -1), cval=9.0)),
+            ("maximum_filter", f32, dict(footprint=np.array([[[1, 0, 1]], [[0, 1, 0]], [[1, 1, 0]]], bool),
+                                         mode=mode, cval=0.4)),
         ]
     return cases
 
