@@ -296,6 +296,7 @@ __device__ __forceinline__ void contig_stage_tile(const CUtensorMap &tmap, TS *t
                                                   int mode, TS cval)
 {
     const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
     if (tid == 0) {
         mbar_init(full_bar, 1);
         fence_barrier_init();
@@ -309,7 +310,7 @@ __device__ __forceinline__ void contig_stage_tile(const CUtensorMap &tmap, TS *t
     // costs a 64-bit modulo): -1 = cval.  Rows are < 2^31 elements long.
     __shared__ int patch_src[256];
     if (patch) {
-        if (tid < edge.per_row) patch_src[tid] = (int)ext_index(g0 + edge.column(tid), n, mode);
+        for (int k = tid; k < edge.per_row; k += nthr) patch_src[k] = (int)ext_index(g0 + edge.column(k), n, mode);
         __syncthreads();
     }
     auto value = [&](int idx) -> TS {
@@ -322,7 +323,7 @@ __device__ __forceinline__ void contig_stage_tile(const CUtensorMap &tmap, TS *t
     if (patch) {
 #pragma unroll
         for (int i = 0; i < KPRE; ++i) {
-            const int idx = tid + i * 256;
+            const int idx = tid + i * nthr;
             pre[i] = idx < edge.total ? value(idx) : TS(0);
         }
     }
@@ -332,13 +333,13 @@ __device__ __forceinline__ void contig_stage_tile(const CUtensorMap &tmap, TS *t
     if (patch) {
 #pragma unroll
         for (int i = 0; i < KPRE; ++i) {
-            const int idx = tid + i * 256;
+            const int idx = tid + i * nthr;
             if (idx < edge.total) {
                 const int r = idx / edge.per_row, k = idx - r * edge.per_row;
                 tile[r * P + edge.column(k)] = pre[i];
             }
         }
-        for (int idx = tid + KPRE * 256; idx < edge.total; idx += 256) {
+        for (int idx = tid + KPRE * nthr; idx < edge.total; idx += nthr) {
             const int r = idx / edge.per_row, k = idx - r * edge.per_row;
             tile[r * P + edge.column(k)] = value(idx);
         }
@@ -501,11 +502,12 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
 
     contig_stage_tile<TS, 8>(tmap, tile, &full_bar, p.in, g0, row0, p.n, nrows, P, TR, p.mode, p.cval);
 
-    // a warp keeps one 64-column group and walks the 8-row groups (uniform trip count)
+    // a warp keeps one 64-column group and walks the 8-row groups (uniform trip
+    // count); CTAs have 8 or 4 warps
     const int cg_shift = p.ncg == 4 ? 2 : (p.ncg == 2 ? 1 : 0);
     const int cg = warp & (p.ncg - 1);
     const int rg0 = warp >> cg_shift;
-    const int rg_step = 8 >> cg_shift;
+    const int rg_step = (int)(blockDim.x >> 5) >> cg_shift;
     const int patch_iters = (nrg + rg_step - 1) / rg_step;
     const int r_in = lane & 7;
     const int xl = cg * PC + (lane >> 3) * R;
@@ -836,9 +838,12 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int
     const int pitch = pitch_for(ncg);
     if (pitch > 256) return -1;
     const int SX = ncg * PC;
-    // ~3 CTAs per SM
+    // CTAs per SM: 3 CTAs of 8 warps; long filters (FP32-issue bound) overlap their
+    // load and compute phases better as 6 CTAs of 4 warps
+    const int threads = env_int("B200_TMA_STHREADS", NT >= 24 ? 128 : 256);
+    const int ctas = env_int("B200_TMA_SCTAS", threads == 128 ? 6 : 3);
     int tr = env_int("B200_TMA_STR", 0);
-    if (tr <= 0) tr = (int)(((kSmemPerSm - 3072) / 3 - 256) / ((size_t)pitch * es));
+    if (tr <= 0) tr = (int)(((kSmemPerSm - 3072) / ctas - 256) / ((size_t)pitch * es));
     tr = tr / 8 * 8;
     tr = tr < 8 ? 8 : (tr > 256 ? 256 : tr);
     const int64_t rows8 = (g.outer + 7) / 8 * 8;
@@ -873,7 +878,7 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int
     auto kern = corr1d_contig_static_kernel<TS, NT>;
     const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
+    kern<<<(unsigned)num_tiles, threads == 128 ? 128 : 256, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
     note_kernel(kernel_name<float, TS>(false));
