@@ -173,10 +173,10 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
     __shared__ int patch_src[256];
     if (patch) {
         const int npr = nlo + (p.smem_rows - rhi);
-        if (tid < npr) {
-            const int64_t src = ext_index_padded(g0 + patch_row(tid), p.n, p.mode, p.pad_lo, p.pad_hi);
+        for (int k = tid; k < npr; k += NTHREADS) {
+            const int64_t src = ext_index_padded(g0 + patch_row(k), p.n, p.mode, p.pad_lo, p.pad_hi);
             // resident rows relative to the first resident one, so the value fits an int
-            patch_src[tid] = src == B200_USE_CVAL ? -1 : (int)(src + p.pad_lo);
+            patch_src[k] = src == B200_USE_CVAL ? -1 : (int)(src + p.pad_lo);
         }
         __syncthreads();
     }
@@ -631,12 +631,11 @@ static const char *kernel_name(bool strided)
                    : (sizeof(T) == 4 ? "corr1d_tma_contig_f32" : "corr1d_tma_contig_f64");
 }
 
-template <typename T, typename TS, int R, int MINB, int REM>
+template <typename T, typename TS, int R, int MINB, int REM, int TY = 8>
 static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
 {
     constexpr int V = StridedV<T, TS>::V;
     constexpr int W = 32 * V;   // one warp spans a tile row (512 bytes of floats)
-    constexpr int TY = 8;
     constexpr int ROWS_PER_BLK = TY * R;
     const int es = (int)sizeof(TS);
     const LineGeom &g = a.g;
@@ -708,12 +707,16 @@ static int launch_strided_r(const Corr1dArgs &a, const BoxInfo &box)
     // CTAs beat a deeper per-CTA pipeline for this streaming kernel)
     // Long filters are FP32-issue bound rather than HBM bound: a fourth resident
     // CTA hides more of each CTA's load phase (B200 sweep, profiles/).
+    // CTA shape: 8 warps (8*R rows per row block) or, for R = 4, 4 warps with
+    // twice the CTAs resident (env B200_TMA_TY / B200_TMA_CTAS for sweeps)
+    const int ty = (R == 4) ? env_int("B200_TMA_TY", 8) : 8;
     int nb = env_int("B200_TMA_NB", 0);
     if (nb <= 0) {
-        const int ctas = L >= 24 ? MINB + 1 : MINB;
+        int ctas = env_int("B200_TMA_CTAS", 0);
+        if (ctas <= 0) ctas = (L >= 24 ? MINB + 1 : MINB) * (ty == 4 ? 2 : 1);
         const int per_cta = (int)((kSmemPerSm - 3072) / ctas);
         const int max_rows = per_cta / row_bytes;
-        nb = (max_rows - (L - 1)) / (8 * R);
+        nb = (max_rows - (L - 1)) / (ty * R);
         nb = nb < 1 ? 1 : nb;
     }
     if constexpr (R == 1) {
@@ -722,6 +725,14 @@ static int launch_strided_r(const Corr1dArgs &a, const BoxInfo &box)
         return (L & 1) ? launch_strided_cfg<T, TS, R, MINB, 1>(a, box, nb)
                        : launch_strided_cfg<T, TS, R, MINB, 0>(a, box, nb);
     } else {
+        if (ty == 4) {
+            switch (L % R) {
+            case 0: return launch_strided_cfg<T, TS, R, MINB, 0, 4>(a, box, nb);
+            case 1: return launch_strided_cfg<T, TS, R, MINB, 1, 4>(a, box, nb);
+            case 2: return launch_strided_cfg<T, TS, R, MINB, 2, 4>(a, box, nb);
+            default: return launch_strided_cfg<T, TS, R, MINB, 3, 4>(a, box, nb);
+            }
+        }
         switch (L % R) {
         case 0: return launch_strided_cfg<T, TS, R, MINB, 0>(a, box, nb);
         case 1: return launch_strided_cfg<T, TS, R, MINB, 1>(a, box, nb);
@@ -832,16 +843,18 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int
         if (!(pu & 1)) ++pu;
         return pu * EB;
     };
-    int ncg = env_int("B200_TMA_SNCG", 2);
+    // Geometry from the B200 sweep (tools/sweep_static2.py, profiles/): 4-warp
+    // CTAs, many of them resident, so that one CTA's load phase hides behind the
+    // others' FMA phases; two 64-column groups for short filters (less halo per
+    // output), one for long ones (smaller tiles).
+    const int threads = env_int("B200_TMA_STHREADS", 128);
+    const int ctas = env_int("B200_TMA_SCTAS", NT < 24 ? 8 : (NT < 32 ? 6 : 4));
+    int ncg = env_int("B200_TMA_SNCG", (NT < 24 || (NT >= 32 && NT < 40)) ? 2 : 1);
     ncg = ncg >= 2 ? 2 : 1;
     if (pitch_for(ncg) > 256) ncg = 1;
     const int pitch = pitch_for(ncg);
     if (pitch > 256) return -1;
     const int SX = ncg * PC;
-    // CTAs per SM: 3 CTAs of 8 warps; long filters (FP32-issue bound) overlap their
-    // load and compute phases better as 6 CTAs of 4 warps
-    const int threads = env_int("B200_TMA_STHREADS", NT >= 24 ? 128 : 256);
-    const int ctas = env_int("B200_TMA_SCTAS", threads == 128 ? 6 : 3);
     int tr = env_int("B200_TMA_STR", 0);
     if (tr <= 0) tr = (int)(((kSmemPerSm - 3072) / ctas - 256) / ((size_t)pitch * es));
     tr = tr / 8 * 8;
