@@ -709,11 +709,14 @@ static int launch_strided_r(const Corr1dArgs &a, const BoxInfo &box)
     // CTA hides more of each CTA's load phase (B200 sweep, profiles/).
     // CTA shape: 8 warps (8*R rows per row block) or, for R = 4, 4 warps with
     // twice the CTAs resident (env B200_TMA_TY / B200_TMA_CTAS for sweeps)
-    const int ty = (R == 4) ? env_int("B200_TMA_TY", 8) : 8;
+    // B200 sweep (tools/sweep_strided2.py): short filters are HBM bound and like
+    // 3 big CTAs; from ~24 taps on the pass is FP32-issue bound and 6-8 small
+    // CTAs overlap their load and FMA phases better.
+    const int ty = (R == 4) ? env_int("B200_TMA_TY", (L >= 24 && sizeof(T) == sizeof(TS)) ? 4 : 8) : 8;
     int nb = env_int("B200_TMA_NB", 0);
     if (nb <= 0) {
         int ctas = env_int("B200_TMA_CTAS", 0);
-        if (ctas <= 0) ctas = (L >= 24 ? MINB + 1 : MINB) * (ty == 4 ? 2 : 1);
+        if (ctas <= 0) ctas = ty == 4 ? (L < 32 ? 8 : 6) : MINB;
         const int per_cta = (int)((kSmemPerSm - 3072) / ctas);
         const int max_rows = per_cta / row_bytes;
         nb = (max_rows - (L - 1)) / (ty * R);
