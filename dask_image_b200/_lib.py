@@ -31,7 +31,7 @@ MODE_CODES = {
 
 EXPORTS = (
     "b200_correlate1d", "b200_uniform_filter1d", "b200_correlate_nd", "b200_combine",
-    "b200_minmax_filter1d", "b200_minmax_filter_nd",
+    "b200_minmax_filter1d", "b200_minmax_filter_nd", "b200_correlate1d_halo", "b200_correlate1d_halo_eligible",
     "b200_last_kernel", "b200_last_error", "b200_version", "b200_launch_count",
 )
 
@@ -73,6 +73,10 @@ def load():
     lib.b200_correlate_nd.argtypes = [vp, vp, ci, ci, i64p, dblp, i64p, i64p, ci, dbl, i64, i64,
                                       cu, vp]
     lib.b200_correlate_nd.restype = ci
+    lib.b200_correlate1d_halo.argtypes = [vp, vp, ci, ci, i64p, dblp, i64, ci, dbl, i64, vp, i64, vp, i64, ci, cu, vp]
+    lib.b200_correlate1d_halo.restype = ci
+    lib.b200_correlate1d_halo_eligible.argtypes = [ci, i64, i64, i64, i64]
+    lib.b200_correlate1d_halo_eligible.restype = ci
     u8p = ctypes.POINTER(ctypes.c_uint8)
     lib.b200_minmax_filter1d.argtypes = [vp, vp, ci, ci, i64p, ci, i64, ci, ci, dbl, i64, i64, i64, cu, vp]
     lib.b200_minmax_filter1d.restype = ci

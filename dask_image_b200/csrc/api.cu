@@ -109,6 +109,44 @@ int b200_correlate1d(const void *in, void *out, int dtype, int ndim, const int64
     return launch_corr1d_generic(a);
 }
 
+int b200_correlate1d_halo(const void *in, void *out, int dtype, int ndim, const int64_t *shape,
+                          const double *weights, int64_t nw, int mode, double cval, int64_t origin,
+                          const void *halo_lo, int64_t n_lo, const void *halo_hi, int64_t n_hi, int epilogue,
+                          unsigned flags, void *stream)
+{
+    int64_t total;
+    if (int rc = check_common(in, out, dtype, ndim, shape, mode, &total)) return rc;
+    if (!weights || nw < 1) return set_error(B200_EINVAL, "no filter weights given");
+    if (nw > (1 << 20)) return set_error(B200_EINVAL, "too many filter weights");
+    if (origin < -(nw / 2) || origin > (nw - 1) / 2)
+        return set_error(B200_EORIGIN, "Invalid origin; origin must satisfy "
+                                       "-(len(weights) // 2) <= origin <= (len(weights)-1) // 2");
+    if (epilogue < B200_EPI_STORE || epilogue > B200_EPI_SQ_ACC_SQRT)
+        return set_error(B200_EINVAL, "unknown epilogue");
+    if (n_lo < 0 || n_hi < 0 || (n_lo > 0 && !halo_lo) || (n_hi > 0 && !halo_hi))
+        return set_error(B200_EINVAL, "halo planes and their counts do not agree");
+    if (total == 0) return B200_OK;
+    if (dtype != B200_F32 && dtype != B200_F64)
+        return set_error(B200_EINVAL, "not eligible: in-place halo reads are implemented for float32 / float64");
+    Corr1dArgs a;
+    a.in = in; a.out = out; a.dtype = dtype;
+    a.g = line_geometry(ndim, shape, 0);
+    a.w = weights; a.nw = (int)nw; a.mode = mode; a.cval = cval; a.origin = (int)origin;
+    a.pad_lo = 0; a.pad_hi = 0; a.epilogue = epilogue; a.flags = flags;
+    a.stream = (cudaStream_t)stream;
+    a.peer_lo = n_lo > 0 ? halo_lo : nullptr; a.peer_hi = n_hi > 0 ? halo_hi : nullptr;
+    a.n_peer_lo = (int)n_lo; a.n_peer_hi = (int)n_hi;
+    int rc = launch_corr1d_peer(a);
+    if (rc < 0) return set_error(B200_EINVAL, "not eligible: tile geometry cannot place the neighbour rows");
+    return rc;
+}
+
+int b200_correlate1d_halo_eligible(int dtype, int64_t n, int64_t inner, int64_t nw, int64_t origin)
+{
+    if (nw < 1 || nw > 4096) return 0;
+    return corr1d_peer_eligible(dtype, n, inner, (int)nw, (int)origin);
+}
+
 int b200_uniform_filter1d(const void *in, void *out, int dtype, int ndim, const int64_t *shape, int axis,
                           int64_t size, int mode, double cval, int64_t origin, int64_t pad_lo,
                           int64_t pad_hi, unsigned flags, void *stream)

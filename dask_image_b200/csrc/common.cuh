@@ -229,8 +229,14 @@ struct Corr1dArgs {
     int epilogue;
     unsigned flags;
     cudaStream_t stream;
+    // neighbour planes read in place (b200_correlate1d_halo); null = none
+    const void *peer_lo = nullptr, *peer_hi = nullptr;
+    int n_peer_lo = 0, n_peer_hi = 0;
 };
 int launch_corr1d_generic(const Corr1dArgs &a);
+// axis-0 pass with the halo planes read where they live; -1 = geometry not eligible
+int launch_corr1d_peer(const Corr1dArgs &a);
+int corr1d_peer_eligible(int dtype, int64_t n, int64_t inner, int nw, int origin);
 // returns B200_OK when it ran, -1 when the shape/alignment is not eligible
 int launch_corr1d_tma(const Corr1dArgs &a);
 

@@ -122,9 +122,26 @@ struct Corr1dTmaParams {
 // REM = taps % R is a template parameter so that the tap tail is straight-line
 // code; nothing in the tap loops is divergent, which lets ptxas keep the
 // weights on the uniform datapath (LDCU -> FFMA2 with a UR operand).
-template <typename T, typename TS, int W, int TY, int R, int MINB, int REM>
-__global__ void __launch_bounds__((W / StridedV<T, TS>::V) * TY, MINB)
-corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T, TS> p)
+// Peer halos (multi-GPU axis-0 pass, sharded.py): the planes below / above the
+// slab are NOT copied next to it first -- the kernel reads them where they
+// live, in the neighbour GPU's memory, with its own TMA loads over NVLink, so
+// the "exchange" is part of the tile pipeline of the pass itself: no NCCL
+// kernel competing for SMs, no staging planes, no separate edge launches.
+// The first tile of the axis takes its top `lo` rows from `lo` (the previous
+// rank's last planes) and the rest from a shorter local box; the last tile takes
+// the `hi` rows behind the slab from `hi`.  Every other tile is unchanged.
+struct PeerMaps {
+    CUtensorMap first;   // local slab, box rows = smem_rows - lo (first tile, below its peer rows)
+    CUtensorMap last;    // local slab, box rows = k_last         (last tile, above which peer rows follow)
+    CUtensorMap lo;      // the lo planes that precede the slab (in a peer's memory)
+    CUtensorMap hi;      // the hi planes that follow it
+    int has_lo, has_hi;
+    int lo_rows, hi_rows, k_last;
+};
+
+template <typename T, typename TS, int W, int TY, int R, int REM, bool PEER>
+__device__ __forceinline__ void strided_tile_body(const CUtensorMap &tmap, const Corr1dTmaParams<T, TS> &p,
+                                                  const PeerMaps *hm)
 {
     constexpr int V = StridedV<T, TS>::V;
     constexpr bool kBox = sizeof(TS) != sizeof(T);   // exact integer box filter
@@ -152,8 +169,24 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
     if (tid == 0) {
         mbar_init(&full_bar, 1);
         fence_barrier_init();
-        mbar_arrive_expect_tx(&full_bar, (uint32_t)(p.smem_rows * W * (int)sizeof(TS)));
-        tma_load_3d(tile, &tmap, &full_bar, (int)col0, (int)(g0 + p.pad_lo), (int)o);
+        if constexpr (PEER) {
+            // (the slab's tensor map has no pad rows in front: coordinates are slab rows)
+            if (tn == 0 && hm->has_lo) {
+                mbar_arrive_expect_tx(&full_bar, (uint32_t)(p.smem_rows * W * (int)sizeof(TS)));
+                tma_load_3d(tile, &hm->lo, &full_bar, (int)col0, 0, 0);
+                tma_load_3d(tile + hm->lo_rows * W, &hm->first, &full_bar, (int)col0, 0, 0);
+            } else if (tn == p.n_tiles - 1 && hm->has_hi) {
+                mbar_arrive_expect_tx(&full_bar, (uint32_t)((hm->k_last + hm->hi_rows) * W * (int)sizeof(TS)));
+                tma_load_3d(tile, &hm->last, &full_bar, (int)col0, (int)g0, 0);
+                tma_load_3d(tile + hm->k_last * W, &hm->hi, &full_bar, (int)col0, 0, 0);
+            } else {
+                mbar_arrive_expect_tx(&full_bar, (uint32_t)(p.smem_rows * W * (int)sizeof(TS)));
+                tma_load_3d(tile, &tmap, &full_bar, (int)col0, (int)g0, (int)o);
+            }
+        } else {
+            mbar_arrive_expect_tx(&full_bar, (uint32_t)(p.smem_rows * W * (int)sizeof(TS)));
+            tma_load_3d(tile, &tmap, &full_bar, (int)col0, (int)(g0 + p.pad_lo), (int)o);
+        }
     }
 
     // Rows of the tile that lie outside the resident range (TMA zero-fills
@@ -270,6 +303,21 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
     }
 }
 
+
+template <typename T, typename TS, int W, int TY, int R, int MINB, int REM>
+__global__ void __launch_bounds__((W / StridedV<T, TS>::V) * TY, MINB)
+corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T, TS> p)
+{
+    strided_tile_body<T, TS, W, TY, R, REM, false>(tmap, p, nullptr);
+}
+
+template <typename T, int W, int TY, int R, int MINB, int REM>
+__global__ void __launch_bounds__((W / StridedV<T, T>::V) * TY, MINB)
+corr1d_strided_peer_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PeerMaps hm,
+                           const __grid_constant__ Corr1dTmaParams<T, T> p)
+{
+    strided_tile_body<T, T, W, TY, R, REM, true>(tmap, p, &hm);
+}
 
 // ---------------------------------------------------------------------------
 // Contiguous-axis tiles: the columns of a tile that fall outside [0, n) (TMA
@@ -743,6 +791,151 @@ static int launch_strided_r(const Corr1dArgs &a, const BoxInfo &box)
         default: return launch_strided_cfg<T, TS, R, MINB, 3>(a, box, nb);
         }
     }
+}
+
+// Tile height (in row blocks of 32) for the peer-halo pass: the tallest tile
+// <= nb_max blocks for which neighbour rows enter only the first and the last
+// tile of the axis.  0 = no such geometry.
+static int peer_row_blocks(int64_t n, int L, int lo, int hi, int nb_max)
+{
+    for (int nb = nb_max; nb >= 1; --nb) {
+        const int tile_rows = nb * 32;
+        if (tile_rows + L - 1 > 256) continue;
+        const int64_t n_tiles = (n + tile_rows - 1) / tile_rows;
+        const int64_t last_rows = n - (n_tiles - 1) * tile_rows;
+        if (n_tiles >= 2 && tile_rows >= lo && last_rows >= hi && n >= tile_rows + hi) return nb;
+    }
+    return 0;
+}
+
+// Axis-0 pass of a slab whose neighbour planes are read in place (PeerMaps).
+// float32 / float64, R = 4, 8-warp CTAs.  Returns -1 when the geometry does not
+// fit (the caller then exchanges the planes and uses the padded form).
+template <typename T, int REM>
+static int launch_peer_cfg(const Corr1dArgs &a, int nb)
+{
+    constexpr int R = 4, MINB = 3, TY = 8;
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int W = 32 * V;
+    constexpr int ROWS_PER_BLK = TY * R;
+    const int es = (int)sizeof(T);
+    const LineGeom &g = a.g;
+    const int L = a.nw;
+    const int lo = L / 2 + a.origin, hi = L - 1 - lo;
+    const bool has_lo = a.peer_lo != nullptr && lo > 0, has_hi = a.peer_hi != nullptr && hi > 0;
+    if ((has_lo && a.n_peer_lo != lo) || (has_hi && a.n_peer_hi != hi)) return -1;
+
+    const int c_tiles = (int)((g.inner + W - 1) / W);
+    nb = peer_row_blocks(g.n, L, lo, hi, nb);
+    if (nb < 1) return -1;
+    const int tile_rows = nb * ROWS_PER_BLK;
+    const int smem_rows = tile_rows + L - 1;
+    const size_t stage_bytes = (size_t)smem_rows * W * es;
+    if (stage_bytes + 256 > kSmemPerSm - 1024) return -1;
+    const int64_t n_tiles = (g.n + tile_rows - 1) / tile_rows;
+    const int64_t last_rows = g.n - (n_tiles - 1) * tile_rows;
+    const int k_last = (int)(last_rows + lo);
+    const int64_t num_tiles = n_tiles * c_tiles;
+    if (num_tiles >= (1ll << 31)) return -1;
+
+    CUtensorMap tmap;
+    PeerMaps hm;
+    memset(&hm, 0, sizeof(hm));
+    uint64_t dims[3] = {(uint64_t)g.inner, (uint64_t)g.n, 1u};
+    uint64_t strides[2] = {(uint64_t)g.inner * es, (uint64_t)g.inner * es * (uint64_t)g.n};
+    uint32_t bx[3] = {(uint32_t)W, (uint32_t)smem_rows, 1u};
+    if (encode_tensor_map(&tmap, a.dtype, (void *)a.in, 3, dims, strides, bx) != 0) return -1;
+    hm.has_lo = has_lo; hm.has_hi = has_hi; hm.lo_rows = lo; hm.hi_rows = hi; hm.k_last = k_last;
+    if (has_lo) {
+        uint32_t b1[3] = {(uint32_t)W, (uint32_t)(smem_rows - lo), 1u};
+        if (encode_tensor_map(&hm.first, a.dtype, (void *)a.in, 3, dims, strides, b1) != 0) return -1;
+        uint64_t d2[3] = {(uint64_t)g.inner, (uint64_t)lo, 1u};
+        uint64_t s2[2] = {(uint64_t)g.inner * es, (uint64_t)g.inner * es * (uint64_t)lo};
+        uint32_t b2[3] = {(uint32_t)W, (uint32_t)lo, 1u};
+        if (encode_tensor_map(&hm.lo, a.dtype, (void *)a.peer_lo, 3, d2, s2, b2) != 0) return -1;
+    }
+    if (has_hi) {
+        uint32_t b1[3] = {(uint32_t)W, (uint32_t)k_last, 1u};
+        if (encode_tensor_map(&hm.last, a.dtype, (void *)a.in, 3, dims, strides, b1) != 0) return -1;
+        uint64_t d2[3] = {(uint64_t)g.inner, (uint64_t)hi, 1u};
+        uint64_t s2[2] = {(uint64_t)g.inner * es, (uint64_t)g.inner * es * (uint64_t)hi};
+        uint32_t b2[3] = {(uint32_t)W, (uint32_t)hi, 1u};
+        if (encode_tensor_map(&hm.hi, a.dtype, (void *)a.peer_hi, 3, d2, s2, b2) != 0) return -1;
+    }
+
+    Corr1dTmaParams<T, T> p;
+    p.in = (const T *)a.in; p.out = (T *)a.out;
+    p.outer = 1; p.n = g.n; p.inner = g.inner;
+    p.pad_lo = has_lo ? lo : 0; p.pad_hi = has_hi ? hi : 0;   // rows the neighbours supply: never patched
+    p.num_tiles = num_tiles;
+    p.nw = L; p.lo = lo; p.mode = a.mode; p.epilogue = a.epilogue;
+    p.tile_rows = tile_rows; p.smem_rows = smem_rows; p.nb = nb; p.pitch = W; p.shift = 0; p.ncg = 0;
+    p.stages = 1; p.stage_elems = (int)(stage_bytes / es); p.wide_store = 0;
+    p.n_tiles = (int)n_tiles; p.c_tiles = c_tiles;
+    p.cval = (T)a.cval;
+    p.qinv = T(0); p.qc0 = T(0);
+    for (int i = 0; i < L; ++i) p.w[i] = (T)a.w[i];
+
+    auto kern = corr1d_strided_peer_kernel<T, W, TY, R, MINB, REM>;
+    const size_t smem = stage_bytes + 128;
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, hm, p);
+    B200_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    note_kernel(sizeof(T) == 4 ? "corr1d_tma_strided_peer_f32" : "corr1d_tma_strided_peer_f64");
+    return B200_OK;
+}
+
+// geometry test of launch_peer_cfg, without launching (all ranks of a slab
+// decomposition must agree on the path: they evaluate it for every slab size)
+int corr1d_peer_eligible(int dtype, int64_t n, int64_t inner, int nw, int origin)
+{
+    if (dtype != B200_F32 && dtype != B200_F64) return 0;
+    constexpr int R = 4, MINB = 3, ROWS_PER_BLK = 8 * R;
+    const int es = dtype == B200_F32 ? 4 : 8;
+    const int L = nw;
+    if (L < 1 || origin < -(L / 2) || origin > (L - 1) / 2) return 0;
+    const int lo = L / 2 + origin, hi = L - 1 - lo;
+    if (inner == 1 || (inner * es) % 16 != 0 || inner >= (1ll << 31) || n >= (1ll << 31)) return 0;
+    if (L > kMaxTapsTma || 8 * R + L - 1 > 256) return 0;
+    int nb = ((int)((kSmemPerSm - 3072) / MINB) / 512 - (L - 1)) / ROWS_PER_BLK;
+    nb = peer_row_blocks(n, L, lo, hi, nb < 1 ? 1 : nb);
+    if (nb < 1) return 0;
+    const int tile_rows = nb * ROWS_PER_BLK;
+    const int64_t n_tiles = (n + tile_rows - 1) / tile_rows;
+    const int64_t c_tiles = (inner + 32 * (16 / es) - 1) / (32 * (16 / es));
+    return n_tiles * c_tiles < (1ll << 31) ? 1 : 0;
+}
+
+template <typename T>
+static int launch_peer_typed(const Corr1dArgs &a)
+{
+    constexpr int R = 4, MINB = 3;
+    const int es = (int)sizeof(T);
+    const LineGeom &g = a.g;
+    const int L = a.nw;
+    if (g.outer != 1 || g.inner == 1) return -1;
+    if (L > kMaxTapsTma || 8 * R + L - 1 > 256) return -1;
+    if ((g.inner * es) % 16 != 0) return -1;
+    if (g.inner >= (1ll << 31) || g.n >= (1ll << 31)) return -1;
+    if (((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15) || ((uintptr_t)a.peer_lo & 15) || ((uintptr_t)a.peer_hi & 15))
+        return -1;
+    const int per_cta = (int)((kSmemPerSm - 3072) / MINB);
+    int nb = (per_cta / (32 * 16) - (L - 1)) / (8 * R);
+    nb = nb < 1 ? 1 : nb;
+    switch (L % R) {
+    case 0: return launch_peer_cfg<T, 0>(a, nb);
+    case 1: return launch_peer_cfg<T, 1>(a, nb);
+    case 2: return launch_peer_cfg<T, 2>(a, nb);
+    default: return launch_peer_cfg<T, 3>(a, nb);
+    }
+}
+
+int launch_corr1d_peer(const Corr1dArgs &a)
+{
+    if (a.dtype == B200_F32) return launch_peer_typed<float>(a);
+    if (a.dtype == B200_F64) return launch_peer_typed<double>(a);
+    return -1;
 }
 
 // R = output rows per thread; a tile is a multiple of 8 * R rows.  Thin calls

@@ -92,6 +92,28 @@ def _launch_correlate1d(src, dst, shape, np_dtype, axis, weights, mode, cval, or
     _lib.check(rc)
 
 
+def _launch_correlate1d_halo(src, dst, shape, np_dtype, weights, mode, cval, origin, halo_lo, halo_hi,
+                             epilogue=_lib.EPI_STORE, flags=None):
+    """Axis-0 pass of a slab whose neighbour planes are read in place:
+    ``halo_lo`` / ``halo_hi`` are tensors (any device-accessible memory, e.g. a
+    peer GPU's planes mapped through CUDA IPC) or None for a volume boundary."""
+    lib = _lib.load()
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    with torch.cuda.device(src.device):
+        rc = lib.b200_correlate1d_halo(
+            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape), _lib.i64_array(shape),
+            _lib.f64_pointer(w), int(w.shape[0]), _lib.mode_code(mode), float(cval), int(origin),
+            halo_lo.data_ptr() if halo_lo is not None else None, int(halo_lo.shape[0]) if halo_lo is not None else 0,
+            halo_hi.data_ptr() if halo_hi is not None else None, int(halo_hi.shape[0]) if halo_hi is not None else 0,
+            int(epilogue), int(_default_flags if flags is None else flags), _stream_ptr(src))
+    _lib.check(rc)
+
+
+def _halo_eligible(np_dtype, n, inner, nw, origin):
+    return bool(_lib.load().b200_correlate1d_halo_eligible(_lib.DTYPE_CODES[np_dtype.name], int(n), int(inner),
+                                                           int(nw), int(origin)))
+
+
 def _launch_uniform1d(src, dst, shape, np_dtype, axis, size, mode, cval, origin, pad=(0, 0),
                       flags=None):
     lib = _lib.load()

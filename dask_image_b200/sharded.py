@@ -28,6 +28,8 @@ The arithmetic backend is pluggable (``backend=``): the product one launches
 the CUDA kernels through the C ABI; the CPU test-suite injects the oracle to
 check partitioning, exchange and boundary handling on ``gloo``.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -257,6 +259,58 @@ class ShardedVolume:
             new.interior.copy_(self._buf.interior)
             self._buf = new
 
+    # ---- neighbour slabs mapped through CUDA IPC ------------------------------
+    def _peer_views(self, buf):
+        """Map the slab buffers of the two axis-0 neighbours into this process
+        (CUDA IPC, once per buffer; collective).  Returns ``{"prev": (full, cap,
+        n), "next": (...)}`` or None when any rank could not share / open."""
+        cache = self.__dict__.setdefault("_peer_cache", {})
+        key = id(buf)
+        if key in cache and cache[key][0] is buf:
+            return cache[key][1]
+        G, r = self.world, self.rank
+        info, ok = None, True
+        try:
+            from torch.multiprocessing.reductions import reduce_tensor
+
+            fn, args = reduce_tensor(buf.full)
+            info = (args, buf.cap, buf.n)
+        except Exception:
+            ok = False
+        gathered = [None] * G
+        dist.all_gather_object(gathered, (ok, info), group=self.group)
+        views = None
+        if all(g[0] for g in gathered):
+            try:
+                from torch.multiprocessing.reductions import rebuild_cuda_tensor
+
+                opened, views = {}, {}
+                for name, peer in (("prev", (r - 1) % G), ("next", (r + 1) % G)):
+                    if peer == r:
+                        continue
+                    if peer not in opened:
+                        args, cap, n = gathered[peer][1]
+                        opened[peer] = (rebuild_cuda_tensor(*args), cap, n)
+                    views[name] = opened[peer]
+            except Exception:
+                views = None
+        # every rank must take the same path
+        flag = torch.tensor([1 if views is not None else 0], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            views = None
+        cache[key] = (buf, views)
+        return views
+
+    def _peer_sync(self):
+        """Stream-ordered rendezvous of all ranks (a one-element all-reduce):
+        before it, nobody reads a neighbour's planes; after it, everybody's
+        producers have finished / everybody's reads have finished."""
+        t = self.__dict__.get("_peer_flag")
+        if t is None:
+            t = self.__dict__["_peer_flag"] = torch.zeros(1, device=self.device, dtype=torch.float32)
+        dist.all_reduce(t, group=self.group)
+
     def _exchange(self, buf, lo, hi, ring):
         """Start the face exchange for a pass that reaches ``lo`` planes below
         and ``hi`` planes above.  Returns ``(pad_lo, pad_hi, requests)``."""
@@ -367,6 +421,22 @@ class ShardedVolume:
             return result
         if plan.zero_out:
             out.interior.zero_()
+        # Fused halo path: axis-0 passes that read the plan's INPUT take the
+        # neighbour planes straight out of the neighbours' memory (CUDA IPC
+        # mappings, TMA loads over NVLink inside the pass) instead of an NCCL
+        # exchange + separate edge launches.  All ranks decide alike: the test is
+        # evaluated for every slab size.
+        peers = None
+        if (self.world > 1 and be is CudaBackend and dt.kind == "f" and self.ndim >= 2
+                and os.environ.get("B200_PEER_HALO", "1") != "0"):
+            inner = int(np.prod(self.shape[1:], dtype=np.int64))
+            sizes = sorted({e - s for s, e in self.bounds})
+            firsts = [passes[0] for passes, _ in plan.chains
+                      if passes and passes[0].axis == 0 and passes[0].kind == "corr"]
+            if firsts and all(_nd._halo_eligible(dt, n, inner, len(ps.weights), ps.origin)
+                              for ps in firsts for n in sizes):
+                peers = self._peer_views(src0)
+        peer_synced = False
         scratch, prov = [], {}
         for passes, op in plan.chains:
             if not passes:
@@ -404,13 +474,30 @@ class ShardedVolume:
                         be.minmax1d(src.full, src.cap + p0, dst.full, dst.cap + p0, p1 - p0, pad,
                                     shape, dt, ps, plan.cval, flags)
 
-                if ps.axis == 0:
+                if ps.axis == 0 and i == 0 and peers is not None and ps.kind == "corr":
+                    lo, hi = _reach(ps)
+                    ring = ps.mode in ("wrap", "grid-wrap")
+                    if not peer_synced:
+                        self._peer_sync()               # the neighbours' inputs are complete
+                        peer_synced = True
+                    halo_lo = halo_hi = None
+                    if lo > 0 and (ring or self.rank > 0):
+                        full, cap, n_p = peers["prev"]
+                        halo_lo = full[cap + n_p - lo:cap + n_p]
+                    if hi > 0 and (ring or self.rank < self.world - 1):
+                        full, cap, n_p = peers["next"]
+                        halo_hi = full[cap:cap + hi]
+                    _nd._launch_correlate1d_halo(src.interior, dst.interior, shape, dt, ps.weights, ps.mode,
+                                                 plan.cval, ps.origin, halo_lo, halo_hi, epi, flags)
+                elif ps.axis == 0:
                     lo, hi = _reach(ps)
                     self._axis0_call(src, lo, hi, ps.mode in ("wrap", "grid-wrap"), call,
                                      cache0 if src is src0 else None)
                 else:
                     call(0, self.n_local, (0, 0))
                 src = dst
+        if peer_synced:
+            self._peer_sync()       # nobody still reads this rank's input planes
         return result
 
 

@@ -96,6 +96,32 @@ int b200_correlate1d(const void *in, void *out, int dtype, int ndim,
                      int64_t pad_lo, int64_t pad_hi, int epilogue,
                      unsigned flags, void *stream);
 
+/* The same pass along axis 0 of a slab whose neighbour planes are NOT resident
+ * next to it: `halo_lo` points at the `n_lo` planes that precede plane 0 of the
+ * slab in the global volume, `halo_hi` at the `n_hi` planes that follow its last
+ * plane -- anywhere in device-accessible memory, typically a peer GPU's slab
+ * mapped through CUDA IPC, read over NVLink by the kernel's own TMA loads
+ * (multi-GPU slab engine, replaces dask's map_overlap halo assembly without an
+ * exchange step).  n_lo / n_hi must equal the filter's reach below / above
+ * (nw/2 + origin, nw - 1 - nw/2 - origin) or be 0 with a NULL pointer, which
+ * makes that end of the slab a boundary of the volume (`mode` applies).
+ * float32 / float64 only; returns B200_EINVAL ("not eligible") when the tile
+ * geometry cannot place the neighbour rows -- callers then copy the planes next
+ * to the slab and use b200_correlate1d with pad_lo / pad_hi. */
+int b200_correlate1d_halo(const void *in, void *out, int dtype, int ndim,
+                          const int64_t *shape, const double *weights,
+                          int64_t nw, int mode, double cval, int64_t origin,
+                          const void *halo_lo, int64_t n_lo,
+                          const void *halo_hi, int64_t n_hi, int epilogue,
+                          unsigned flags, void *stream);
+
+/* 1 if b200_correlate1d_halo can take an axis-0 pass over `n` planes of `inner`
+ * elements each with these taps, else 0 (host-only query, no CUDA call: every
+ * rank of a slab decomposition evaluates it for every slab size so that all of
+ * them choose the same path) */
+int b200_correlate1d_halo_eligible(int dtype, int64_t n, int64_t inner,
+                                   int64_t nw, int64_t origin);
+
 /* replaces _nd_image.uniform_filter1d (scipy/ndimage/_filters.py:1542) */
 int b200_uniform_filter1d(const void *in, void *out, int dtype, int ndim,
                           const int64_t *shape, int axis, int64_t size,

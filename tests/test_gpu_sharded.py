@@ -248,3 +248,49 @@ def test_host_volume_pinned_output_reuse(b200):
     res = b200.ndfilters.gaussian_filter(b200.HostVolume(h_in, out=h_out, chunk_bytes=8 * 32 * 32 * 4), 2.0)
     assert res.tensor.data_ptr() == h_out.data_ptr()
     assert_parity(res.to_numpy(), orc.gaussian_filter(a, 2.0))
+
+
+# ---------------------------------------------------------------------------
+# b200_correlate1d_halo: neighbour planes read in place (the fused multi-GPU path)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", MODES)
+def test_halo_in_place_equals_whole_call(b200, dtype, mode):
+    """Slabs of one resident volume, their halos passed as pointers to the
+    neighbouring planes (here: of the same volume; on several GPUs: a peer's
+    memory) -- bit-identical to the whole-volume pass, volume boundaries included."""
+    import torch
+    from dask_image_b200 import _lib, ndimage as nd
+
+    rng = np.random.default_rng(23)
+    N, tail = 330, (6, 64)
+    a = (rng.random((N,) + tail) - 0.4).astype(dtype)
+    x = torch.from_numpy(a).cuda()
+    dt = np.dtype(dtype)
+    for nw, origin in ((17, 0), (9, 2), (33, -5), (4, 1), (1, 0)):
+        w = rng.random(nw) - 0.3
+        lo = nw // 2 + origin
+        hi = nw - 1 - lo
+        whole = torch.empty_like(x)
+        nd._launch_correlate1d(x, whole, a.shape, dt, 0, w, mode, 0.3, origin)
+        for bounds in ([(0, 160), (160, 330)], [(0, 100), (100, 215), (215, 330)]):
+            if not all(nd._halo_eligible(dt, e - s, int(np.prod(tail)), nw, origin) for s, e in bounds):
+                continue
+            out = torch.zeros_like(x)
+            for k, (s, e) in enumerate(bounds):
+                ring = mode == "wrap"
+                first, last = k == 0, k == len(bounds) - 1
+                halo_lo = halo_hi = None
+                if lo > 0 and (not first or ring):
+                    halo_lo = x[s - lo:s] if not first else x[N - lo:N]
+                if hi > 0 and (not last or ring):
+                    halo_hi = x[e:e + hi] if not last else x[0:hi]
+                nd._launch_correlate1d_halo(x[s:e], out[s:e], (e - s,) + tail, dt, w, mode, 0.3, origin,
+                                            halo_lo, halo_hi)
+                assert _lib.last_kernel().startswith("corr1d_tma_strided_peer"), _lib.last_kernel()
+            assert torch.equal(out.view(torch.uint8), whole.view(torch.uint8)), (nw, origin, mode, bounds)
+    # a slab too thin for the tile geometry is refused, not mis-computed
+    assert not nd._halo_eligible(dt, 20, int(np.prod(tail)), 17, 0)
+    with pytest.raises(RuntimeError, match="not eligible"):
+        nd._launch_correlate1d_halo(x[:20], torch.empty_like(x[:20]), (20,) + tail, dt, np.ones(17), mode, 0.0, 0,
+                                    None, x[20:28])
