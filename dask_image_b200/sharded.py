@@ -290,7 +290,17 @@ class ShardedVolume:
                         continue
                     if peer not in opened:
                         args, cap, n = gathered[peer][1]
-                        opened[peer] = (rebuild_cuda_tensor(*args), cap, n)
+                        full = rebuild_cuda_tensor(*args)
+                        if full.device != self.device:
+                            if not torch.cuda.can_device_access_peer(self.device.index, full.device.index):
+                                raise RuntimeError("no peer access")
+                            # the mapping is opened in the owner device's context; a
+                            # cross-device copy makes torch enable peer access for
+                            # this pair, after which kernels here may read it
+                            probe = torch.empty(4, dtype=full.dtype, device=self.device)
+                            probe.copy_(full.reshape(-1)[:4])
+                            torch.cuda.synchronize(self.device)
+                        opened[peer] = (full, cap, n)
                     views[name] = opened[peer]
             except Exception:
                 views = None
