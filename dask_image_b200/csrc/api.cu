@@ -141,6 +141,22 @@ int b200_correlate1d_halo(const void *in, void *out, int dtype, int ndim, const 
     return rc;
 }
 
+int b200_enable_peer_access(int peer_device)
+{
+    int dev = -1;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev == peer_device) return B200_OK;
+    int can = 0;
+    B200_CUDA_TRY(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) return set_error(B200_ENODEVICE, "device %d cannot access device %d", dev, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();   // clear the sticky-less error state
+        return B200_OK;
+    }
+    return check_cuda(e, "cudaDeviceEnablePeerAccess");
+}
+
 int b200_correlate1d_halo_eligible(int dtype, int64_t n, int64_t inner, int64_t nw, int64_t origin)
 {
     if (nw < 1 || nw > 4096) return 0;

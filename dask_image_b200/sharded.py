@@ -292,14 +292,10 @@ class ShardedVolume:
                         args, cap, n = gathered[peer][1]
                         full = rebuild_cuda_tensor(*args)
                         if full.device != self.device:
-                            if not torch.cuda.can_device_access_peer(self.device.index, full.device.index):
-                                raise RuntimeError("no peer access")
-                            # the mapping is opened in the owner device's context; a
-                            # cross-device copy makes torch enable peer access for
-                            # this pair, after which kernels here may read it
-                            probe = torch.empty(4, dtype=full.dtype, device=self.device)
-                            probe.copy_(full.reshape(-1)[:4])
-                            torch.cuda.synchronize(self.device)
+                            # the mapping lives in the owner device's context: kernels
+                            # on this device need peer access to it
+                            with torch.cuda.device(self.device):
+                                _lib.check(_lib.load().b200_enable_peer_access(int(full.device.index)))
                         opened[peer] = (full, cap, n)
                     views[name] = opened[peer]
             except Exception:

@@ -115,6 +115,11 @@ int b200_correlate1d_halo(const void *in, void *out, int dtype, int ndim,
                           const void *halo_hi, int64_t n_hi, int epilogue,
                           unsigned flags, void *stream);
 
+/* Let kernels on the current device read memory of `peer_device` (needed once
+ * per device pair before b200_correlate1d_halo is given a peer GPU's planes;
+ * cudaDeviceEnablePeerAccess, "already enabled" is success). */
+int b200_enable_peer_access(int peer_device);
+
 /* 1 if b200_correlate1d_halo can take an axis-0 pass over `n` planes of `inner`
  * elements each with these taps, else 0 (host-only query, no CUDA call: every
  * rank of a slab decomposition evaluates it for every slab size so that all of
