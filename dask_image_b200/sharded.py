@@ -290,12 +290,17 @@ class ShardedVolume:
                         continue
                     if peer not in opened:
                         args, cap, n = gathered[peer][1]
-                        full = rebuild_cuda_tensor(*args)
-                        if full.device != self.device:
-                            # the mapping lives in the owner device's context: kernels
-                            # on this device need peer access to it
-                            with torch.cuda.device(self.device):
-                                _lib.check(_lib.load().b200_enable_peer_access(int(full.device.index)))
+                        owner = int(args[6])
+                        with torch.cuda.device(self.device):
+                            if owner != self.device.index:
+                                _lib.check(_lib.load().b200_enable_peer_access(owner))
+                            # Open the handle in THIS device's context (args[6] is the
+                            # storage device): cudaIpcOpenMemHandle then maps the
+                            # neighbour's allocation for kernels running here; opened
+                            # under the owner's context it is visible to that device only.
+                            args = list(args)
+                            args[6] = self.device.index
+                            full = rebuild_cuda_tensor(*args)
                         opened[peer] = (full, cap, n)
                     views[name] = opened[peer]
             except Exception:
