@@ -194,6 +194,8 @@ def run_b200(args, wl, rank, world, local_rank):
 
         # keep stdout for the one JSON line: NCCL's banner / debug lines go to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     shape = tuple(wl["shape"])
     sigma, mode = wl["sigma"], wl["mode"]

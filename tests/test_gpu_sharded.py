@@ -150,6 +150,27 @@ def _nccl_worker(rank, world, port, q):
             if not np.array_equal(got, one):
                 failures.append("%s %s %s: %d voxels differ from the 1-GPU result" % (
                     name, a.dtype, kw["mode"], int((got != one).sum())))
+        # fused halo path: slabs thick enough for the peer-TMA kernel read their
+        # neighbours' planes in place (CUDA IPC); with it on or off the result is
+        # the 1-GPU result, bit for bit
+        from dask_image_b200 import ndimage as nd
+
+        thick = rng.random((80 * world + 3, 8, 64), dtype=np.float32)
+        sizes = {e - s for s, e in b200.sharded.slab_bounds(thick.shape[0], world)}
+        assert all(nd._halo_eligible(np.dtype(np.float32), n, 8 * 64, 17, 0) for n in sizes)
+        for mode in MODES:
+            for name, kw in [("gaussian_filter", dict(sigma=2.0, mode=mode, cval=0.1)),
+                             ("gaussian_gradient_magnitude", dict(sigma=(2.0, 1.0, 1.5), mode=mode)),
+                             ("gaussian_laplace", dict(sigma=1.0, mode=mode))]:
+                f = getattr(b200.ndfilters, name)
+                one = f(b200.B200Array.from_numpy(thick), **kw).to_numpy()
+                for flag in ("1", "0"):
+                    os.environ["B200_PEER_HALO"] = flag
+                    got = f(b200.ShardedVolume.from_global(thick, halo=8), **kw).gather()
+                    if not np.array_equal(got, one):
+                        failures.append("peer=%s %s %s: %d voxels differ from the 1-GPU result" % (
+                            flag, name, mode, int((got != one).sum())))
+        os.environ["B200_PEER_HALO"] = "1"
         # host-resident slabs streamed through each GPU (H2D | filter | D2H pipeline,
         # faces from the neighbours over NCCL): still bit-identical to one GPU
         from dask_image_b200.sharded import slab_bounds
