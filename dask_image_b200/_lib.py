@@ -32,7 +32,7 @@ MODE_CODES = {
 EXPORTS = (
     "b200_correlate1d", "b200_uniform_filter1d", "b200_correlate_nd", "b200_combine",
     "b200_minmax_filter1d", "b200_minmax_filter_nd", "b200_correlate1d_halo", "b200_correlate1d_halo_eligible",
-    "b200_enable_peer_access",
+    "b200_enable_peer_access", "b200_uniform_filter1d_halo", "b200_uniform_filter1d_halo_eligible",
     "b200_last_kernel", "b200_last_error", "b200_version", "b200_launch_count",
 )
 
@@ -76,6 +76,10 @@ def load():
     lib.b200_correlate_nd.restype = ci
     lib.b200_correlate1d_halo.argtypes = [vp, vp, ci, ci, i64p, dblp, i64, ci, dbl, i64, vp, i64, vp, i64, ci, cu, vp]
     lib.b200_correlate1d_halo.restype = ci
+    lib.b200_uniform_filter1d_halo.argtypes = [vp, vp, ci, ci, i64p, i64, ci, dbl, i64, vp, i64, vp, i64, cu, vp]
+    lib.b200_uniform_filter1d_halo.restype = ci
+    lib.b200_uniform_filter1d_halo_eligible.argtypes = [ci, i64, i64, i64, i64, ci, dbl]
+    lib.b200_uniform_filter1d_halo_eligible.restype = ci
     lib.b200_enable_peer_access.argtypes = [ci]
     lib.b200_enable_peer_access.restype = ci
     lib.b200_correlate1d_halo_eligible.argtypes = [ci, i64, i64, i64, i64]

@@ -190,6 +190,34 @@ int b200_uniform_filter1d(const void *in, void *out, int dtype, int ndim, const 
     return launch_uniform1d_generic(a);
 }
 
+int b200_uniform_filter1d_halo(const void *in, void *out, int dtype, int ndim, const int64_t *shape, int64_t size,
+                               int mode, double cval, int64_t origin, const void *halo_lo, int64_t n_lo,
+                               const void *halo_hi, int64_t n_hi, unsigned flags, void *stream)
+{
+    int64_t total;
+    if (int rc = check_common(in, out, dtype, ndim, shape, mode, &total)) return rc;
+    if (size < 1 || size > (1 << 20)) return set_error(B200_EINVAL, "incorrect filter size");
+    if (size / 2 + origin < 0 || size / 2 + origin >= size) return set_error(B200_EORIGIN, "invalid origin");
+    if (n_lo < 0 || n_hi < 0 || (n_lo > 0 && !halo_lo) || (n_hi > 0 && !halo_hi))
+        return set_error(B200_EINVAL, "halo planes and their counts do not agree");
+    if (total == 0) return B200_OK;
+    Uniform1dArgs a;
+    a.in = in; a.out = out; a.dtype = dtype;
+    a.g = line_geometry(ndim, shape, 0);
+    a.size = (int)size; a.mode = mode; a.cval = cval; a.origin = (int)origin;
+    a.pad_lo = 0; a.pad_hi = 0; a.flags = flags; a.stream = (cudaStream_t)stream;
+    int rc = launch_uniform1d_peer(a, n_lo > 0 ? halo_lo : nullptr, (int)n_lo, n_hi > 0 ? halo_hi : nullptr, (int)n_hi);
+    if (rc < 0) return set_error(B200_EINVAL, "not eligible: no in-place halo kernel for this box filter");
+    return rc;
+}
+
+int b200_uniform_filter1d_halo_eligible(int dtype, int64_t n, int64_t inner, int64_t size, int64_t origin, int mode,
+                                        double cval)
+{
+    if (size < 1 || size > 4096) return 0;
+    return uniform1d_peer_eligible(dtype, n, inner, (int)size, (int)origin, mode, cval);
+}
+
 int b200_correlate_nd(const void *in, void *out, int dtype, int ndim, const int64_t *shape,
                       const double *weights, const int64_t *wshape, const int64_t *origins, int mode,
                       double cval, int64_t pad_lo, int64_t pad_hi, unsigned flags, void *stream)

@@ -254,6 +254,8 @@ struct Uniform1dArgs {
     cudaStream_t stream;
 };
 int launch_uniform1d_generic(const Uniform1dArgs &a);
+int launch_uniform1d_peer(const Uniform1dArgs &u, const void *peer_lo, int n_lo, const void *peer_hi, int n_hi);
+int uniform1d_peer_eligible(int dtype, int64_t n, int64_t inner, int size, int origin, int mode, double cval);
 int launch_uniform1d_fast(const Uniform1dArgs &a);
 
 struct CorrNdArgs {

@@ -311,12 +311,12 @@ corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid
     strided_tile_body<T, TS, W, TY, R, REM, false>(tmap, p, nullptr);
 }
 
-template <typename T, int W, int TY, int R, int MINB, int REM>
-__global__ void __launch_bounds__((W / StridedV<T, T>::V) * TY, MINB)
+template <typename T, typename TS, int W, int TY, int R, int MINB, int REM>
+__global__ void __launch_bounds__((W / StridedV<T, TS>::V) * TY, MINB)
 corr1d_strided_peer_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PeerMaps hm,
-                           const __grid_constant__ Corr1dTmaParams<T, T> p)
+                           const __grid_constant__ Corr1dTmaParams<T, TS> p)
 {
-    strided_tile_body<T, T, W, TY, R, REM, true>(tmap, p, &hm);
+    strided_tile_body<T, TS, W, TY, R, REM, true>(tmap, p, &hm);
 }
 
 // ---------------------------------------------------------------------------
@@ -811,14 +811,14 @@ static int peer_row_blocks(int64_t n, int L, int lo, int hi, int nb_max)
 // Axis-0 pass of a slab whose neighbour planes are read in place (PeerMaps).
 // float32 / float64, R = 4, 8-warp CTAs.  Returns -1 when the geometry does not
 // fit (the caller then exchanges the planes and uses the padded form).
-template <typename T, int REM>
-static int launch_peer_cfg(const Corr1dArgs &a, int nb)
+template <typename T, typename TS, int REM>
+static int launch_peer_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
 {
     constexpr int R = 4, MINB = 3, TY = 8;
-    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int V = StridedV<T, TS>::V;
     constexpr int W = 32 * V;
     constexpr int ROWS_PER_BLK = TY * R;
-    const int es = (int)sizeof(T);
+    const int es = (int)sizeof(TS);
     const LineGeom &g = a.g;
     const int L = a.nw;
     const int lo = L / 2 + a.origin, hi = L - 1 - lo;
@@ -863,8 +863,8 @@ static int launch_peer_cfg(const Corr1dArgs &a, int nb)
         if (encode_tensor_map(&hm.hi, a.dtype, (void *)a.peer_hi, 3, d2, s2, b2) != 0) return -1;
     }
 
-    Corr1dTmaParams<T, T> p;
-    p.in = (const T *)a.in; p.out = (T *)a.out;
+    Corr1dTmaParams<T, TS> p;
+    p.in = (const TS *)a.in; p.out = (TS *)a.out;
     p.outer = 1; p.n = g.n; p.inner = g.inner;
     p.pad_lo = has_lo ? lo : 0; p.pad_hi = has_hi ? hi : 0;   // rows the neighbours supply: never patched
     p.num_tiles = num_tiles;
@@ -872,17 +872,20 @@ static int launch_peer_cfg(const Corr1dArgs &a, int nb)
     p.tile_rows = tile_rows; p.smem_rows = smem_rows; p.nb = nb; p.pitch = W; p.shift = 0; p.ncg = 0;
     p.stages = 1; p.stage_elems = (int)(stage_bytes / es); p.wide_store = 0;
     p.n_tiles = (int)n_tiles; p.c_tiles = c_tiles;
-    p.cval = (T)a.cval;
-    p.qinv = T(0); p.qc0 = T(0);
+    p.cval = (TS)a.cval;
+    p.qinv = (T)box.qinv; p.qc0 = (T)box.qc0;
     for (int i = 0; i < L; ++i) p.w[i] = (T)a.w[i];
 
-    auto kern = corr1d_strided_peer_kernel<T, W, TY, R, MINB, REM>;
+    auto kern = corr1d_strided_peer_kernel<T, TS, W, TY, R, MINB, REM>;
     const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, hm, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
-    note_kernel(sizeof(T) == 4 ? "corr1d_tma_strided_peer_f32" : "corr1d_tma_strided_peer_f64");
+    note_kernel(sizeof(TS) != sizeof(T) ? (sizeof(TS) == 2 ? "uniform1d_tma_strided_peer_u16"
+                                                           : "uniform1d_tma_strided_peer_u8")
+                                        : (sizeof(T) == 4 ? "corr1d_tma_strided_peer_f32"
+                                                          : "corr1d_tma_strided_peer_f64"));
     return B200_OK;
 }
 
@@ -890,28 +893,29 @@ static int launch_peer_cfg(const Corr1dArgs &a, int nb)
 // decomposition must agree on the path: they evaluate it for every slab size)
 int corr1d_peer_eligible(int dtype, int64_t n, int64_t inner, int nw, int origin)
 {
-    if (dtype != B200_F32 && dtype != B200_F64) return 0;
+    if (dtype != B200_F32 && dtype != B200_F64 && dtype != B200_U16 && dtype != B200_U8) return 0;
     constexpr int R = 4, MINB = 3, ROWS_PER_BLK = 8 * R;
-    const int es = dtype == B200_F32 ? 4 : 8;
+    const int es = dtype_size(dtype);
     const int L = nw;
     if (L < 1 || origin < -(L / 2) || origin > (L - 1) / 2) return 0;
     const int lo = L / 2 + origin, hi = L - 1 - lo;
     if (inner == 1 || (inner * es) % 16 != 0 || inner >= (1ll << 31) || n >= (1ll << 31)) return 0;
     if (L > kMaxTapsTma || 8 * R + L - 1 > 256) return 0;
-    int nb = ((int)((kSmemPerSm - 3072) / MINB) / 512 - (L - 1)) / ROWS_PER_BLK;
+    int nb = ((int)((kSmemPerSm - 3072) / MINB) / (es == 1 ? 256 : 512) - (L - 1)) / ROWS_PER_BLK;
     nb = peer_row_blocks(n, L, lo, hi, nb < 1 ? 1 : nb);
     if (nb < 1) return 0;
     const int tile_rows = nb * ROWS_PER_BLK;
     const int64_t n_tiles = (n + tile_rows - 1) / tile_rows;
-    const int64_t c_tiles = (inner + 32 * (16 / es) - 1) / (32 * (16 / es));
+    const int wtile = 32 * (es >= 4 ? 16 / es : 8);   // tile width in elements
+    const int64_t c_tiles = (inner + wtile - 1) / wtile;
     return n_tiles * c_tiles < (1ll << 31) ? 1 : 0;
 }
 
-template <typename T>
-static int launch_peer_typed(const Corr1dArgs &a)
+template <typename T, typename TS>
+static int launch_peer_typed(const Corr1dArgs &a, const BoxInfo &box)
 {
     constexpr int R = 4, MINB = 3;
-    const int es = (int)sizeof(T);
+    const int es = (int)sizeof(TS);
     const LineGeom &g = a.g;
     const int L = a.nw;
     if (g.outer != 1 || g.inner == 1) return -1;
@@ -921,20 +925,21 @@ static int launch_peer_typed(const Corr1dArgs &a)
     if (((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15) || ((uintptr_t)a.peer_lo & 15) || ((uintptr_t)a.peer_hi & 15))
         return -1;
     const int per_cta = (int)((kSmemPerSm - 3072) / MINB);
-    int nb = (per_cta / (32 * 16) - (L - 1)) / (8 * R);
+    int nb = (per_cta / (32 * StridedV<T, TS>::V * es) - (L - 1)) / (8 * R);
     nb = nb < 1 ? 1 : nb;
     switch (L % R) {
-    case 0: return launch_peer_cfg<T, 0>(a, nb);
-    case 1: return launch_peer_cfg<T, 1>(a, nb);
-    case 2: return launch_peer_cfg<T, 2>(a, nb);
-    default: return launch_peer_cfg<T, 3>(a, nb);
+    case 0: return launch_peer_cfg<T, TS, 0>(a, box, nb);
+    case 1: return launch_peer_cfg<T, TS, 1>(a, box, nb);
+    case 2: return launch_peer_cfg<T, TS, 2>(a, box, nb);
+    default: return launch_peer_cfg<T, TS, 3>(a, box, nb);
     }
 }
 
 int launch_corr1d_peer(const Corr1dArgs &a)
 {
-    if (a.dtype == B200_F32) return launch_peer_typed<float>(a);
-    if (a.dtype == B200_F64) return launch_peer_typed<double>(a);
+    const BoxInfo none;
+    if (a.dtype == B200_F32) return launch_peer_typed<float, float>(a, none);
+    if (a.dtype == B200_F64) return launch_peer_typed<double, double>(a, none);
     return -1;
 }
 
@@ -1243,23 +1248,30 @@ static bool uniform_int_exact(int size, int64_t vmax)
     return true;
 }
 
-template <typename TS>
-static int launch_uniform_box(const Uniform1dArgs &u, int64_t vmax)
+// can the exact float epilogue serve this integer box filter?
+static bool uniform_box_ok(int dtype, int size, int mode, double cval)
 {
-    if (u.size > 128) return -1;
-    if (u.mode == B200_MODE_CONSTANT) {
+    if (dtype != B200_U16 && dtype != B200_U8) return false;
+    const int64_t vmax = dtype == B200_U16 ? 65535 : 255;
+    if (size < 2 || size > 128) return false;
+    if (mode == B200_MODE_CONSTANT) {
         // the tile holds storage-type values: cval must be one
-        if (!(u.cval >= 0.0 && u.cval <= (double)vmax) || u.cval != (double)(int64_t)u.cval) return -1;
+        if (!(cval >= 0.0 && cval <= (double)vmax) || cval != (double)(int64_t)cval) return false;
     }
     // (one proof per size and type; sizes are small, the loop is ~vmax iterations)
     static std::mutex mu;
     static signed char proven[2][129];   // 0 unknown, 1 exact, -1 not
-    const int ti = sizeof(TS) == 2 ? 1 : 0;
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        if (proven[ti][u.size] == 0) proven[ti][u.size] = uniform_int_exact(u.size, vmax) ? 1 : -1;
-        if (proven[ti][u.size] < 0) return -1;
-    }
+    const int ti = dtype == B200_U16 ? 1 : 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if (proven[ti][size] == 0) proven[ti][size] = uniform_int_exact(size, vmax) ? 1 : -1;
+    return proven[ti][size] > 0;
+}
+
+template <typename TS>
+static int launch_uniform_box(const Uniform1dArgs &u, int64_t vmax)
+{
+    (void)vmax;
+    if (!uniform_box_ok(u.dtype, u.size, u.mode, u.cval)) return -1;
     double ones[128];
     for (int i = 0; i < u.size; ++i) ones[i] = 1.0;
     Corr1dArgs a;
@@ -1293,6 +1305,35 @@ int launch_uniform1d_fast(const Uniform1dArgs &u)
         return launch_corr1d_tma(a);
     }
     return -1;
+}
+
+// box filter along axis 0 of a slab, neighbour planes read in place
+int uniform1d_peer_eligible(int dtype, int64_t n, int64_t inner, int size, int origin, int mode, double cval)
+{
+    if (size < 2 || size / 2 + origin < 0 || size / 2 + origin >= size) return 0;
+    if (dtype == B200_F32 || dtype == B200_F64) return corr1d_peer_eligible(dtype, n, inner, size, origin);
+    if (!uniform_box_ok(dtype, size, mode, cval)) return 0;
+    return corr1d_peer_eligible(dtype, n, inner, size, origin);
+}
+
+int launch_uniform1d_peer(const Uniform1dArgs &u, const void *peer_lo, int n_lo, const void *peer_hi, int n_hi)
+{
+    if (u.size < 2 || u.size > kMaxTapsTma) return -1;
+    double w[kMaxTapsTma];
+    const bool is_float = u.dtype == B200_F32 || u.dtype == B200_F64;
+    if (!is_float && !uniform_box_ok(u.dtype, u.size, u.mode, u.cval)) return -1;
+    for (int i = 0; i < u.size; ++i) w[i] = is_float ? 1.0 / (double)u.size : 1.0;
+    Corr1dArgs a;
+    a.in = u.in; a.out = u.out; a.dtype = u.dtype; a.g = u.g;
+    a.w = w; a.nw = u.size; a.mode = u.mode; a.cval = u.cval; a.origin = u.origin;
+    a.pad_lo = 0; a.pad_hi = 0; a.epilogue = B200_EPI_STORE; a.flags = u.flags; a.stream = u.stream;
+    a.peer_lo = peer_lo; a.peer_hi = peer_hi; a.n_peer_lo = n_lo; a.n_peer_hi = n_hi;
+    if (is_float) return launch_corr1d_peer(a);
+    BoxInfo box;
+    box.on = true;
+    box.qinv = 1.0f / (float)u.size;
+    box.qc0 = 0.5f - 0.5f * (float)u.size;
+    return u.dtype == B200_U16 ? launch_peer_typed<float, uint16_t>(a, box) : launch_peer_typed<float, uint8_t>(a, box);
 }
 
 }  // namespace b200

@@ -109,6 +109,25 @@ def _launch_correlate1d_halo(src, dst, shape, np_dtype, weights, mode, cval, ori
     _lib.check(rc)
 
 
+def _launch_uniform1d_halo(src, dst, shape, np_dtype, size, mode, cval, origin, halo_lo, halo_hi, flags=None):
+    """Box filter along axis 0 of a slab, neighbour planes read in place."""
+    lib = _lib.load()
+    with torch.cuda.device(src.device):
+        rc = lib.b200_uniform_filter1d_halo(
+            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape), _lib.i64_array(shape),
+            int(size), _lib.mode_code(mode), float(cval), int(origin),
+            halo_lo.data_ptr() if halo_lo is not None else None, int(halo_lo.shape[0]) if halo_lo is not None else 0,
+            halo_hi.data_ptr() if halo_hi is not None else None, int(halo_hi.shape[0]) if halo_hi is not None else 0,
+            int(_default_flags if flags is None else flags), _stream_ptr(src))
+    _lib.check(rc)
+
+
+def _uniform_halo_eligible(np_dtype, n, inner, size, origin, mode, cval):
+    return bool(_lib.load().b200_uniform_filter1d_halo_eligible(
+        _lib.DTYPE_CODES[np_dtype.name], int(n), int(inner), int(size), int(origin), _lib.mode_code(mode),
+        float(cval)))
+
+
 def _halo_eligible(np_dtype, n, inner, nw, origin):
     return bool(_lib.load().b200_correlate1d_halo_eligible(_lib.DTYPE_CODES[np_dtype.name], int(n), int(inner),
                                                            int(nw), int(origin)))

@@ -438,14 +438,22 @@ class ShardedVolume:
         # exchange + separate edge launches.  All ranks decide alike: the test is
         # evaluated for every slab size.
         peers = None
-        if (self.world > 1 and be is CudaBackend and dt.kind == "f" and self.ndim >= 2
+        if (self.world > 1 and be is CudaBackend and self.ndim >= 2
                 and os.environ.get("B200_PEER_HALO", "1") != "0"):
             inner = int(np.prod(self.shape[1:], dtype=np.int64))
             sizes = sorted({e - s for s, e in self.bounds})
-            firsts = [passes[0] for passes, _ in plan.chains
-                      if passes and passes[0].axis == 0 and passes[0].kind == "corr"]
-            if firsts and all(_nd._halo_eligible(dt, n, inner, len(ps.weights), ps.origin)
-                              for ps in firsts for n in sizes):
+
+            def fits(ps):
+                if ps.kind == "corr":
+                    return dt.kind == "f" and all(_nd._halo_eligible(dt, n, inner, len(ps.weights), ps.origin)
+                                                  for n in sizes)
+                if ps.kind == "uniform":
+                    return all(_nd._uniform_halo_eligible(dt, n, inner, ps.size, ps.origin, ps.mode, plan.cval)
+                               for n in sizes)
+                return False
+
+            firsts = [passes[0] for passes, _ in plan.chains if passes and passes[0].axis == 0]
+            if firsts and all(fits(ps) for ps in firsts):
                 peers = self._peer_views(src0)
         peer_synced = False
         scratch, prov = [], {}
@@ -485,7 +493,7 @@ class ShardedVolume:
                         be.minmax1d(src.full, src.cap + p0, dst.full, dst.cap + p0, p1 - p0, pad,
                                     shape, dt, ps, plan.cval, flags)
 
-                if ps.axis == 0 and i == 0 and peers is not None and ps.kind == "corr":
+                if ps.axis == 0 and i == 0 and peers is not None:
                     lo, hi = _reach(ps)
                     ring = ps.mode in ("wrap", "grid-wrap")
                     if not peer_synced:
@@ -498,8 +506,12 @@ class ShardedVolume:
                     if hi > 0 and (ring or self.rank < self.world - 1):
                         full, cap, n_p = peers["next"]
                         halo_hi = full[cap:cap + hi]
-                    _nd._launch_correlate1d_halo(src.interior, dst.interior, shape, dt, ps.weights, ps.mode,
-                                                 plan.cval, ps.origin, halo_lo, halo_hi, epi, flags)
+                    if ps.kind == "corr":
+                        _nd._launch_correlate1d_halo(src.interior, dst.interior, shape, dt, ps.weights, ps.mode,
+                                                     plan.cval, ps.origin, halo_lo, halo_hi, epi, flags)
+                    else:
+                        _nd._launch_uniform1d_halo(src.interior, dst.interior, shape, dt, ps.size, ps.mode,
+                                                   plan.cval, ps.origin, halo_lo, halo_hi, flags)
                 elif ps.axis == 0:
                     lo, hi = _reach(ps)
                     self._axis0_call(src, lo, hi, ps.mode in ("wrap", "grid-wrap"), call,

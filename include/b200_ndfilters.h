@@ -134,6 +134,18 @@ int b200_uniform_filter1d(const void *in, void *out, int dtype, int ndim,
                           int64_t pad_lo, int64_t pad_hi, unsigned flags,
                           void *stream);
 
+/* b200_uniform_filter1d along axis 0 of a slab with the neighbour planes read in
+ * place (see b200_correlate1d_halo): float32 / float64, and the exact uint8 /
+ * uint16 box filter.  The _eligible query is host-only. */
+int b200_uniform_filter1d_halo(const void *in, void *out, int dtype, int ndim,
+                               const int64_t *shape, int64_t size, int mode,
+                               double cval, int64_t origin, const void *halo_lo,
+                               int64_t n_lo, const void *halo_hi, int64_t n_hi,
+                               unsigned flags, void *stream);
+int b200_uniform_filter1d_halo_eligible(int dtype, int64_t n, int64_t inner,
+                                        int64_t size, int64_t origin, int mode,
+                                        double cval);
+
 /* replaces _nd_image.correlate (scipy/ndimage/_filters.py:1305); `weights` has
  * shape `wshape` (ndim entries, C order), taps with |w| <= DBL_EPSILON are
  * skipped as scipy does; convolve = flipped weights + adjusted origins,

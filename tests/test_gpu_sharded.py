@@ -170,6 +170,17 @@ def _nccl_worker(rank, world, port, q):
                     if not np.array_equal(got, one):
                         failures.append("peer=%s %s %s: %d voxels differ from the 1-GPU result" % (
                             flag, name, mode, int((got != one).sum())))
+        thick16 = rng.integers(0, 65536, (80 * world + 3, 8, 64), dtype=np.uint16)
+        for mode in MODES:
+            for arr in (thick16, thick):
+                kw = dict(size=(7, 3, 5), mode=mode, origin=(1, 0, -1), cval=11.0)
+                one = b200.ndfilters.uniform_filter(b200.B200Array.from_numpy(arr), **kw).to_numpy()
+                for flag in ("1", "0"):
+                    os.environ["B200_PEER_HALO"] = flag
+                    got = b200.ndfilters.uniform_filter(b200.ShardedVolume.from_global(arr, halo=8), **kw).gather()
+                    if not np.array_equal(got, one):
+                        failures.append("peer=%s uniform_filter %s %s: %d voxels differ from the 1-GPU result" % (
+                            flag, arr.dtype, mode, int((got != one).sum())))
         os.environ["B200_PEER_HALO"] = "1"
         # host-resident slabs streamed through each GPU (H2D | filter | D2H pipeline,
         # faces from the neighbours over NCCL): still bit-identical to one GPU
@@ -315,3 +326,38 @@ def test_halo_in_place_equals_whole_call(b200, dtype, mode):
     with pytest.raises(RuntimeError, match="not eligible"):
         nd._launch_correlate1d_halo(x[:20], torch.empty_like(x[:20]), (20,) + tail, dt, np.ones(17), mode, 0.0, 0,
                                     None, x[20:28])
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint8, np.float32])
+@pytest.mark.parametrize("mode", MODES)
+def test_uniform_halo_in_place_equals_whole_call(b200, dtype, mode):
+    import torch
+    from dask_image_b200 import _lib, ndimage as nd
+
+    rng = np.random.default_rng(29)
+    N, tail = 300, (4, 256)
+    if np.dtype(dtype).kind == "f":
+        a = rng.random((N,) + tail).astype(dtype)
+    else:
+        a = rng.integers(0, np.iinfo(dtype).max, (N,) + tail, endpoint=True).astype(dtype)
+    x = b200.B200Array.from_numpy(a).tensor
+    dt = np.dtype(dtype)
+    for size, origin in ((7, 0), (4, 1), (15, -7)):
+        lo = size // 2 + origin
+        hi = size - 1 - lo
+        whole = torch.empty_like(x)
+        nd._launch_uniform1d(x, whole, a.shape, dt, 0, size, mode, 5.0, origin)
+        bounds = [(0, 140), (140, 300)]
+        assert all(nd._uniform_halo_eligible(dt, e - s, int(np.prod(tail)), size, origin, mode, 5.0) for s, e in bounds)
+        out = torch.zeros_like(x)
+        for k, (s, e) in enumerate(bounds):
+            ring = mode == "wrap"
+            first, last = k == 0, k == len(bounds) - 1
+            halo_lo = halo_hi = None
+            if lo > 0 and (not first or ring):
+                halo_lo = x[s - lo:s] if not first else x[N - lo:N]
+            if hi > 0 and (not last or ring):
+                halo_hi = x[e:e + hi] if not last else x[0:hi]
+            nd._launch_uniform1d_halo(x[s:e], out[s:e], (e - s,) + tail, dt, size, mode, 5.0, origin, halo_lo, halo_hi)
+            assert "_peer_" in _lib.last_kernel(), _lib.last_kernel()
+        assert torch.equal(out.view(torch.uint8), whole.view(torch.uint8)), (size, origin, mode)
