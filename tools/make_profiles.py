@@ -92,9 +92,9 @@ def main():
     sass_dir = os.path.join(PROF, "sass")
     os.makedirs(sass_dir, exist_ok=True)
     wanted = {
-        "corr1d_tma.o": [r"corr1d_strided_tma_kernelIffLi128ELi8ELi4ELi3ELi1E", r"corr1d_contig_static_kernelIfLi5ELb1E",
-                         r"corr1d_strided_tma_kernelIftLi256ELi8ELi4ELi3ELi3E", r"corr1d_contig_static_kernelItLi4ELb1E",
-                         r"corr1d_contig_tma_kernelIffLi0ELi1E"],
+        "corr1d_tma.o": [r"corr1d_strided_tma_kernelIffLi128ELi8ELi4ELi3ELi1E", r"corr1d_contig_static_kernelIfLi17E",
+                         r"corr1d_strided_tma_kernelIftLi256ELi8ELi4ELi3ELi3E", r"corr1d_contig_static_kernelItLi16E",
+                         r"corr1d_strided_peer_kernelIffLi128ELi8ELi4ELi3ELi1E", r"corr1d_contig_tma_kernelIffLi0ELi1E"],
         "corrnd_tiled.o": [r"corrnd_static_kernelILi9E"],
     }
     for obj, pats in wanted.items():
