@@ -1,29 +1,34 @@
-// corr1d_tma.cu -- TMA-staged shared-memory 1-D correlation passes (sm_100a).
+// corr1d_tma.cu -- TMA-staged shared-memory 1-D passes (sm_100a): the float hot
+// path behind gaussian_filter and its derivative / gradient-magnitude / laplace
+// variants (one launch per 1-D pass of scipy's chain,
+// scipy/ndimage/_filters.py:852-858), the float box filter, and the exact
+// uint8 / uint16 box filter.
 //
-// The two kernels here are the float hot path behind gaussian_filter and its
-// derivative / gradient-magnitude / laplace variants (one launch per 1-D pass
-// of scipy's chain, scipy/ndimage/_filters.py:852-858):
+//  * strided_tile_body / corr1d_strided_tma_kernel -- the filtered axis is NOT
+//    the contiguous one.  The array is viewed as [outer][n][inner]; one CTA
+//    stages a (tile_rows + taps - 1) x W box (rows along the filtered axis, W
+//    contiguous elements) with ONE cp.async.bulk.tensor.3d, then every thread
+//    owns a 16-byte column vector and R consecutive output rows, sliding a
+//    register window of R rows down the tile: per tap 1 LDS.128 + R*V FMAs.
+//    corr1d_strided_peer_kernel is the same body for the axis-0 pass of a
+//    multi-GPU slab: the halo rows of the first / last tile come straight out
+//    of the neighbour GPUs' memory with extra TMA loads (PeerMaps).
 //
-//  * corr1d_strided_tma_kernel  -- filtered axis is NOT the contiguous one.
-//    The array is viewed as [outer][n][inner]; one CTA stages a
-//    (tile_rows + taps - 1) x W box (rows along the filtered axis, W contiguous
-//    elements) with ONE cp.async.bulk.tensor.3d, then every thread owns a 16-byte
-//    column vector and R consecutive output rows, sliding a register window of
-//    R rows down the tile: per tap 1 LDS.128 + R*V FMAs, nothing else.
+//  * corr1d_contig_static_kernel -- the filtered axis IS the contiguous one,
+//    float32 (or uint8/uint16 storage) and at most 48 taps: the tap count is a
+//    template parameter and the tap loop is straight-line packed FFMA2.
+//    corr1d_contig_tma_kernel is the run-time-loop form (float64, longer
+//    filters).  View [rows][n]; a CTA stages a TR x P box with one
+//    cp.async.bulk.tensor.2d whose pitch P is an odd multiple of 16 bytes, so
+//    the lanes of a quarter warp hit 8 distinct 16-byte bank groups.
 //
-//  * corr1d_contig_tma_kernel   -- filtered axis IS the contiguous one.  View
-//    [rows][n]; a CTA stages a TR x P box with one cp.async.bulk.tensor.2d where
-//    the pitch P is an odd multiple of 16 bytes, so that the 8 lanes of a
-//    quarter warp (4 lanes x 32 bytes along x, 2 rows) hit 8 distinct 16-byte
-//    bank groups: conflict-free LDS.128 straight out of the dense TMA layout.
-//    Every thread produces R = 2V consecutive outputs of one row from three
-//    rotating 16-byte register blocks: per V taps 1 LDS.128 + R*V FMAs.
-//
-// Out-of-range rows/columns are zero-filled by TMA; CTAs on an array edge then
-// patch exactly those smem rows/columns through the closed-form extension map
-// (reflect / mirror / nearest / wrap / constant), so interior CTAs carry no
-// boundary logic at all.  Accumulation is in the array's own float type
-// (fp32 for f32, fp64 for f64) with FMA; B200_FLAG_EXACT selects generic.cu.
+// Out-of-range rows/columns are zero-filled by TMA; CTAs on an array edge
+// fetch exactly those elements through the closed-form extension map (reflect /
+// mirror / nearest / wrap / constant) while the tile is in flight, so interior
+// CTAs carry no boundary logic at all.  Accumulation is in the array's own
+// float type (fp32 for f32, fp64 for f64) with FMA; B200_FLAG_EXACT selects
+// generic.cu.  The integer box filter sums in fp32 (exact below 2^23) and
+// divides with one proven-exact fused rounding (box_quotient_bits).
 #include "tile_common.cuh"
 #include <mutex>
 #include <cstdlib>
@@ -88,7 +93,6 @@ int encode_tensor_map(CUtensorMap *map, int dtype, void *base, int rank, const u
 
 // ---------------------------------------------------------------------------
 constexpr int kMaxTapsTma = 208;
-constexpr int kMaxStages = 6;
 
 // T = arithmetic type (float / double), TS = storage type of the array: TS == T
 // for the float passes; TS = uint8_t / uint16_t with T = float for the exact
@@ -99,7 +103,6 @@ struct Corr1dTmaParams {
     TS *out;
     int64_t outer, n, inner;
     int64_t pad_lo, pad_hi;
-    int64_t num_tiles;
     int nw, lo, mode, epilogue;
     int tile_rows;   // strided: outputs per CTA tile along the filtered axis
     int smem_rows;   // strided: tile_rows + nw - 1
@@ -107,9 +110,7 @@ struct Corr1dTmaParams {
     int pitch;       // contig: smem row pitch in elements (V * odd)
     int shift;       // contig: leading taps to skip (box start aligned down to 16 bytes)
     int ncg;         // contig: 4*R-column groups per tile
-    int stages;      // (unused: one tile per CTA)
     int wide_store;  // contig: rows and base are 32-byte aligned -> 256-bit stores
-    int stage_elems; // elements per stage
     int n_tiles, c_tiles;
     TS cval;
     T qinv, qc0;     // integer box filter: 1/size and the (0.5 - size/2) offset
@@ -714,10 +715,9 @@ static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     p.in = (const TS *)a.in; p.out = (TS *)a.out;
     p.outer = g.outer; p.n = g.n; p.inner = g.inner;
     p.pad_lo = a.pad_lo; p.pad_hi = a.pad_hi;
-    p.num_tiles = num_tiles;
     p.nw = L; p.lo = a.nw / 2 + a.origin; p.mode = a.mode; p.epilogue = a.epilogue;
     p.tile_rows = tile_rows; p.smem_rows = smem_rows; p.nb = nb; p.pitch = W; p.shift = 0; p.ncg = 0;
-    p.stages = 1; p.stage_elems = (int)(stage_bytes / es); p.wide_store = 0;
+    p.wide_store = 0;
     p.n_tiles = (int)n_tiles; p.c_tiles = c_tiles;
     p.cval = (TS)a.cval;
     p.qinv = (T)box.qinv; p.qc0 = (T)box.qc0;
@@ -867,10 +867,9 @@ static int launch_peer_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     p.in = (const TS *)a.in; p.out = (TS *)a.out;
     p.outer = 1; p.n = g.n; p.inner = g.inner;
     p.pad_lo = has_lo ? lo : 0; p.pad_hi = has_hi ? hi : 0;   // rows the neighbours supply: never patched
-    p.num_tiles = num_tiles;
     p.nw = L; p.lo = lo; p.mode = a.mode; p.epilogue = a.epilogue;
     p.tile_rows = tile_rows; p.smem_rows = smem_rows; p.nb = nb; p.pitch = W; p.shift = 0; p.ncg = 0;
-    p.stages = 1; p.stage_elems = (int)(stage_bytes / es); p.wide_store = 0;
+    p.wide_store = 0;
     p.n_tiles = (int)n_tiles; p.c_tiles = c_tiles;
     p.cval = (TS)a.cval;
     p.qinv = (T)box.qinv; p.qc0 = (T)box.qc0;
@@ -1007,10 +1006,8 @@ static int launch_contig_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al,
     p.in = (const TS *)a.in; p.out = (TS *)a.out;
     p.outer = g.outer; p.n = g.n; p.inner = 1;
     p.pad_lo = 0; p.pad_hi = 0;
-    p.num_tiles = num_tiles;
     p.nw = L; p.lo = lo_al; p.mode = a.mode; p.epilogue = a.epilogue;
     p.tile_rows = tr; p.smem_rows = tr; p.nb = 1; p.pitch = pitch; p.shift = SH; p.ncg = ncg;
-    p.stages = 1; p.stage_elems = (int)(stage_bytes / es);
     p.wide_store = (((g.n * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
     p.n_tiles = (int)r_tiles; p.c_tiles = (int)c_tiles;
     p.cval = (TS)a.cval;
@@ -1078,10 +1075,8 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int
     p.in = (const TS *)a.in; p.out = (TS *)a.out;
     p.outer = g.outer; p.n = g.n; p.inner = 1;
     p.pad_lo = 0; p.pad_hi = 0;
-    p.num_tiles = num_tiles;
     p.nw = NT; p.lo = lo_al; p.mode = a.mode; p.epilogue = a.epilogue;
     p.tile_rows = tr; p.smem_rows = tr; p.nb = 1; p.pitch = pitch; p.shift = 0; p.ncg = ncg;
-    p.stages = 1; p.stage_elems = (int)(stage_bytes / es);
     p.wide_store = (((g.n * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
     p.n_tiles = (int)r_tiles; p.c_tiles = (int)c_tiles;
     p.cval = (TS)a.cval;

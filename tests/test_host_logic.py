@@ -291,3 +291,73 @@ def test_conv_params_host_side():
     for f in (nf.convolve, nf.correlate):
         with pytest.raises(ValueError):   # array types differ
             f(img, np.ones((1, 1)))
+
+
+# ---------------------------------------------------------------------------
+# planning layer (pure host logic shared by the array, slab and streaming engines)
+# ---------------------------------------------------------------------------
+def test_plans_follow_scipy_pass_structure():
+    from dask_image_b200 import _lib, ndimage as nd
+
+    p = nd._plan_gaussian_filter(3, (2.0, 0.0, 1.0), order=(0, 0, 1), mode=("reflect", "wrap", "mirror"))
+    (passes, op), = p.chains
+    assert [ps.axis for ps in passes] == [0, 2] and op == _lib.EPI_STORE      # sigma 0 axis skipped
+    assert [ps.mode for ps in passes] == ["reflect", "mirror"]
+    assert len(passes[0].weights) == 2 * int(4 * 2.0 + 0.5) + 1
+    assert nd._plan_gaussian_filter(2, 0.0).chains == []                       # identity
+    g = nd._plan_gaussian_gradient_magnitude(3, 1.5)
+    assert [op for _, op in g.chains] == [_lib.EPI_SQ_STORE, _lib.EPI_SQ_ACC, _lib.EPI_SQ_ACC_SQRT]
+    assert all([ps.axis for ps in ch] == [0, 1, 2] for ch, _ in g.chains)
+    g1 = nd._plan_gaussian_gradient_magnitude(1, 1.5)
+    assert g1.zero_out and g1.chains[0][1] == _lib.EPI_SQ_ACC_SQRT
+    lap = nd._plan_gaussian_laplace(2, (1.0, 2.0))
+    assert [op for _, op in lap.chains] == [_lib.EPI_STORE, _lib.EPI_ACC]
+    u = nd._plan_uniform_filter(3, (5, 1, 4), origin=(1, 0, -2))
+    assert [(ps.kind, ps.axis, ps.size, ps.origin) for ps in u.chains[0][0]] == [("uniform", 0, 5, 1), ("uniform", 2, 4, -2)]
+    with pytest.raises(ValueError):
+        nd._plan_uniform_filter(2, 4, origin=2)
+    s = nd._plan_sobel(3, axis=-1)
+    assert [ps.axis for ps in s.chains[0][0]] == [2, 0, 1]                     # derivative axis first
+    c = nd._plan_correlate_nd(2, np.dtype("f4"), np.arange(6.0).reshape(2, 3), origin=(0, 1), convolution=True)
+    w, origins, mode = c.nd
+    assert np.array_equal(w, np.arange(6.0).reshape(2, 3)[::-1, ::-1]) and origins == [-1, -1]
+    m = nd._plan_minimum_filter(2, footprint=np.ones((3, 3), bool))
+    assert [ps.kind for ps in m.chains[0][0]] == ["min", "min"] and m.extreme is None   # all-true footprint: separable
+    m = nd._plan_maximum_filter(2, footprint=np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], bool))
+    assert m.extreme is not None and m.extreme[3] is True and m.chains == []
+    with pytest.raises(RuntimeError):
+        nd._plan_minimum_filter(2)
+
+
+def test_chain_targets_and_prefix_signatures():
+    from dask_image_b200 import _lib, ndimage as nd
+
+    # store epilogues ping-pong between the output and ONE scratch volume
+    assert nd._chain_targets(3, _lib.EPI_STORE) == ["out", 0, "out"]
+    assert nd._chain_targets(2, _lib.EPI_SQ_STORE) == [0, "out"]
+    assert nd._chain_targets(1, _lib.EPI_STORE) == ["out"]
+    # accumulating epilogues must leave the output alone until the last pass
+    assert nd._chain_targets(3, _lib.EPI_ACC) == [0, 1, "out"]
+    assert nd._chain_targets(3, _lib.EPI_SQ_ACC_SQRT) == [0, 1, "out"]
+    # the chains of ggm / laplace along axes 1 and 2 start with the same pass
+    g = nd._plan_gaussian_gradient_magnitude(3, 2.0)
+    sig = [tuple(nd._pass_signature(ps) for ps in ch) for ch, _ in g.chains]
+    assert sig[1][0] == sig[2][0] and sig[0][0] != sig[1][0] and sig[1][1] != sig[2][1]
+
+
+def test_slab_halo_eligibility_is_a_pure_host_query():
+    """b200_correlate1d_halo_eligible needs no GPU and depends on the geometry
+    only, so every rank can evaluate it for every slab size."""
+    from dask_image_b200 import ndimage as nd
+
+    f4 = np.dtype("f4")
+    assert nd._halo_eligible(f4, 256, 2048 * 2048, 17, 0)
+    assert nd._halo_eligible(np.dtype("f8"), 300, 512, 9, 2)
+    assert not nd._halo_eligible(f4, 20, 2048 * 2048, 17, 0)          # thinner than one tile + halo
+    assert not nd._halo_eligible(f4, 256, 2047, 17, 0)                # rows not 16-byte multiples
+    assert not nd._halo_eligible(np.dtype("i4"), 256, 2048, 17, 0)
+    u2 = np.dtype("u2")
+    assert nd._uniform_halo_eligible(u2, 256, 4096, 7, 0, "reflect", 0.0)
+    assert not nd._uniform_halo_eligible(u2, 256, 4096, 7, 0, "constant", 0.5)    # cval is not a uint16
+    assert not nd._uniform_halo_eligible(u2, 256, 4096, 200, 0, "reflect", 0.0)   # window too long for exact fp32 sums
+    assert nd._uniform_halo_eligible(f4, 256, 4096, 7, 0, "constant", 0.5)
