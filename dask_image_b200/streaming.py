@@ -60,10 +60,11 @@ class HostVolume:
     out : optional CPU tensor / array of the same shape and dtype that receives
         the result of the next filter (otherwise a pinned one is allocated)
     device : CUDA device to stream through (default: current)
-    chunk_bytes : approximate size of one upload / compute / download unit
+    chunk_bytes : approximate size of one upload / compute / download unit (B200 / PCIe 5 scan,
+        tools/e2e_scan.py: 128-512 MiB is the plateau)
     """
 
-    def __init__(self, array, out=None, device=None, chunk_bytes=1 << 30, global_shape=None, group=None):
+    def __init__(self, array, out=None, device=None, chunk_bytes=256 << 20, global_shape=None, group=None):
         self.tensor = _as_host_tensor(array)
         if self.tensor.dtype not in _TORCH_TO_NP:
             raise RuntimeError("data type not supported")
