@@ -18,6 +18,9 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++20", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
     "-cudart", "static",
+    # the tiled translation units hold dozens of kernel instantiations:
+    # optimise / assemble them on all host cores
+    "--split-compile=0",
 ]
 
 

@@ -271,6 +271,10 @@ int b200_minmax_filter1d(const void *in, void *out, int dtype, int ndim, const i
     a.g = line_geometry(ndim, shape, axis);
     a.size = (int)size; a.is_max = is_max ? 1 : 0; a.mode = mode; a.cval = cval; a.origin = (int)origin;
     a.pad_lo = pad_lo; a.pad_hi = pad_hi; a.flags = flags; a.stream = (cudaStream_t)stream;
+    if (!(flags & (B200_FLAG_EXACT | B200_FLAG_NO_TMA))) {
+        int rc = launch_minmax1d_fast(a);
+        if (rc >= 0) return rc;
+    }
     if (flags & B200_FLAG_FORCE_FAST)
         return set_error(B200_EINVAL, "no tiled kernel is eligible for this call");
     return launch_minmax1d_generic(a);

@@ -293,6 +293,7 @@ struct MinMax1dArgs {
     cudaStream_t stream;
 };
 int launch_minmax1d_generic(const MinMax1dArgs &a);
+int launch_minmax1d_fast(const MinMax1dArgs &a);   // -1 = not eligible
 
 struct MinMaxNdArgs {
     const void *in;

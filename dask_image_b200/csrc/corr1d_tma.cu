@@ -140,7 +140,7 @@ struct PeerMaps {
     int lo_rows, hi_rows, k_last;
 };
 
-template <typename T, typename TS, int W, int TY, int R, int REM, bool PEER>
+template <typename T, typename TS, int W, int TY, int R, int REM, bool PEER, int OP = 0>
 __device__ __forceinline__ void strided_tile_body(const CUtensorMap &tmap, const Corr1dTmaParams<T, TS> &p,
                                                   const PeerMaps *hm)
 {
@@ -250,7 +250,7 @@ __device__ __forceinline__ void strided_tile_body(const CUtensorMap &tmap, const
         const int r0 = (blk * TY + ty) * R;
         const TS *sbase = tile + r0 * W + tx * V;
         VecT win[R];
-        VecAcc<T, V> acc[R];
+        typename TapAcc<T, V, OP>::type acc[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) acc[j].zero();
 #pragma unroll
@@ -310,6 +310,16 @@ __global__ void __launch_bounds__((W / StridedV<T, TS>::V) * TY, MINB)
 corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T, TS> p)
 {
     strided_tile_body<T, TS, W, TY, R, REM, false>(tmap, p, nullptr);
+}
+
+// minimum (OP = 1) / maximum (OP = 2) filter along a non-contiguous axis: the
+// same tile, window walk and stores, the taps select instead of accumulating
+template <typename TS, int W, int TY, int R, int MINB, int REM, int OP>
+__global__ void __launch_bounds__((W / StridedV<float, TS>::V) * TY, MINB)
+minmax_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                          const __grid_constant__ Corr1dTmaParams<float, TS> p)
+{
+    strided_tile_body<float, TS, W, TY, R, REM, false, OP>(tmap, p, nullptr);
 }
 
 template <typename T, typename TS, int W, int TY, int R, int MINB, int REM>
@@ -680,7 +690,7 @@ static const char *kernel_name(bool strided)
                    : (sizeof(T) == 4 ? "corr1d_tma_contig_f32" : "corr1d_tma_contig_f64");
 }
 
-template <typename T, typename TS, int R, int MINB, int REM, int TY = 8>
+template <typename T, typename TS, int R, int MINB, int REM, int TY = 8, int OP = 0>
 static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
 {
     constexpr int V = StridedV<T, TS>::V;
@@ -723,17 +733,23 @@ static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     p.qinv = (T)box.qinv; p.qc0 = (T)box.qc0;
     for (int i = 0; i < L; ++i) p.w[i] = (T)a.w[i];
 
-    auto kern = corr1d_strided_tma_kernel<T, TS, W, TY, R, MINB, REM>;
     const size_t smem = stage_bytes + 128;
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, p);
+    if constexpr (OP == 0) {
+        auto kern = corr1d_strided_tma_kernel<T, TS, W, TY, R, MINB, REM>;
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, p);
+    } else {
+        auto kern = minmax_strided_tma_kernel<TS, W, TY, R, MINB, REM, OP>;
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, p);
+    }
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
-    note_kernel(kernel_name<T, TS>(true));
+    note_kernel(OP == 0 ? kernel_name<T, TS>(true) : (OP == 1 ? "min1d_tma_strided" : "max1d_tma_strided"));
     return B200_OK;
 }
 
-template <typename T, typename TS, int R>
+template <typename T, typename TS, int R, int OP = 0>
 static int launch_strided_r(const Corr1dArgs &a, const BoxInfo &box)
 {
     constexpr int MINB = 3;
@@ -760,7 +776,7 @@ static int launch_strided_r(const Corr1dArgs &a, const BoxInfo &box)
     // B200 sweep (tools/sweep_strided2.py): short filters are HBM bound and like
     // 3 big CTAs; from ~24 taps on the pass is FP32-issue bound and 6-8 small
     // CTAs overlap their load and FMA phases better.
-    const int ty = (R == 4) ? env_int("B200_TMA_TY", (L >= 24 && sizeof(T) == sizeof(TS)) ? 4 : 8) : 8;
+    const int ty = (R == 4 && OP == 0) ? env_int("B200_TMA_TY", (L >= 24 && sizeof(T) == sizeof(TS)) ? 4 : 8) : 8;
     int nb = env_int("B200_TMA_NB", 0);
     if (nb <= 0) {
         int ctas = env_int("B200_TMA_CTAS", 0);
@@ -775,6 +791,13 @@ static int launch_strided_r(const Corr1dArgs &a, const BoxInfo &box)
     } else if constexpr (R == 2) {
         return (L & 1) ? launch_strided_cfg<T, TS, R, MINB, 1>(a, box, nb)
                        : launch_strided_cfg<T, TS, R, MINB, 0>(a, box, nb);
+    } else if constexpr (OP != 0) {
+        switch (L % R) {
+        case 0: return launch_strided_cfg<T, TS, R, MINB, 0, 8, OP>(a, box, nb);
+        case 1: return launch_strided_cfg<T, TS, R, MINB, 1, 8, OP>(a, box, nb);
+        case 2: return launch_strided_cfg<T, TS, R, MINB, 2, 8, OP>(a, box, nb);
+        default: return launch_strided_cfg<T, TS, R, MINB, 3, 8, OP>(a, box, nb);
+        }
     } else {
         if (ty == 4) {
             switch (L % R) {
@@ -1329,6 +1352,220 @@ int launch_uniform1d_peer(const Uniform1dArgs &u, const void *peer_lo, int n_lo,
     box.qinv = 1.0f / (float)u.size;
     box.qc0 = 0.5f - 0.5f * (float)u.size;
     return u.dtype == B200_U16 ? launch_peer_typed<float, uint16_t>(a, box) : launch_peer_typed<float, uint8_t>(a, box);
+}
+
+
+// ===========================================================================
+// minimum / maximum filter along the contiguous axis (float32, uint8/uint16
+// storage): the tile, the lane mapping and the stores of the static
+// contiguous-axis engine; NT = window taps incl. alignment padding (flagged 0 in
+// p.w and skipped), every real tap is 16 FMNMX.
+// ===========================================================================
+template <typename TS, int NT, bool IS_MAX>
+__global__ void __launch_bounds__(256, 3)
+minmax_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
+                            const __grid_constant__ Corr1dTmaParams<float, TS> p)
+{
+    constexpr bool kInt = sizeof(TS) != sizeof(float);
+    constexpr int EB = 16 / (int)sizeof(TS);
+    constexpr int R = 16, PC = 4 * R;
+    constexpr int NF = (R + NT + EB - 1) / EB * EB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TS *tile = aligned_smem<TS>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int P = p.pitch;
+    const int TR = p.tile_rows;
+    const int SX = p.ncg * PC;
+    const int nrg = TR >> 3;
+    const int64_t nrows = p.outer;
+    const int64_t t = blockIdx.x;
+    const int tcx = (int)(t % p.c_tiles);
+    const int64_t trow = t / p.c_tiles;
+    const int64_t x0t = (int64_t)tcx * SX;
+    const int64_t row0 = trow * TR;
+    const int64_t g0 = x0t - p.lo;
+
+    contig_stage_tile<TS, 8>(tmap, tile, &full_bar, p.in, g0, row0, p.n, nrows, P, TR, p.mode, p.cval);
+
+    const int cg_shift = p.ncg == 4 ? 2 : (p.ncg == 2 ? 1 : 0);
+    const int cg = warp & (p.ncg - 1);
+    const int rg0 = warp >> cg_shift;
+    const int rg_step = (int)(blockDim.x >> 5) >> cg_shift;
+    const int patch_iters = (nrg + rg_step - 1) / rg_step;
+    const int r_in = lane & 7;
+    const int xl = cg * PC + (lane >> 3) * R;
+    const int64_t x = x0t + xl;
+    const TS *const tile_thr = tile + r_in * P + xl;
+    TS *const out_thr = p.out + ((row0 + r_in) * p.n + x);
+    for (int qi = 0; qi < patch_iters; ++qi) {
+        const int rg_raw = rg0 + qi * rg_step;
+        const bool patch_live = rg_raw < nrg;
+        const int rg = patch_live ? rg_raw : 0;
+        const TS *srow = tile_thr + rg * 8 * P;
+        float f[NF];
+        if constexpr (!kInt) {
+#pragma unroll
+            for (int b = 0; b < NF / 4; ++b) {
+                const float4 v = *reinterpret_cast<const float4 *>(srow + 4 * b);
+                f[4 * b] = v.x; f[4 * b + 1] = v.y; f[4 * b + 2] = v.z; f[4 * b + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < NF / 8; ++b) {
+                const Vec<float, 8> v = load_block<float, TS, 8>(srow + 8 * b);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[8 * b + i] = v.v[i];
+            }
+        }
+        float m[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) m[j] = IS_MAX ? -INFINITY : INFINITY;
+#pragma unroll
+        for (int tt = 0; tt < NT; ++tt) {
+            if (p.w[tt] == 0.f) continue;     // alignment padding: warp-uniform skip
+#pragma unroll
+            for (int j = 0; j < R; ++j) m[j] = IS_MAX ? fmaxf(m[j], f[j + tt]) : fminf(m[j], f[j + tt]);
+        }
+        const int64_t row = row0 + rg * 8 + r_in;
+        if (patch_live && row < nrows && x < p.n) {
+            TS *dst0 = out_thr + (int64_t)(rg * 8) * p.n;
+            if constexpr (kInt) {
+                // exact small integers in floats: v + 1.5 * 2^23 has v in its low mantissa bits
+                store_box_quotients<float, TS, 8>(dst0, reinterpret_cast<const float(&)[8]>(m[0]), 1.f, 0.f);
+                if (x + 8 < p.n)
+                    store_box_quotients<float, TS, 8>(dst0 + 8, reinterpret_cast<const float(&)[8]>(m[8]), 1.f, 0.f);
+            } else if (p.wide_store && x + R <= p.n) {
+                st_global_256(dst0, reinterpret_cast<const float(&)[8]>(m[0]));
+                st_global_256(dst0 + 8, reinterpret_cast<const float(&)[8]>(m[8]));
+            } else {
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                    if (x + h * 4 < p.n)
+                        *reinterpret_cast<float4 *>(dst0 + h * 4) =
+                            make_float4(m[4 * h], m[4 * h + 1], m[4 * h + 2], m[4 * h + 3]);
+            }
+        }
+    }
+}
+
+template <typename TS, int NT, bool IS_MAX>
+static int launch_minmax_contig_cfg(const Corr1dArgs &a, int lo_al, int lead)
+{
+    constexpr int EB = 16 / (int)sizeof(TS);
+    constexpr int R = 16, PC = 4 * R;
+    constexpr int LA = (R + NT + EB - 1) / EB * EB - R;
+    const int es = (int)sizeof(TS);
+    const LineGeom &g = a.g;
+    auto pitch_for = [&](int cand) {
+        int pu = (cand * PC + LA + EB - 1) / EB;
+        if (!(pu & 1)) ++pu;
+        return pu * EB;
+    };
+    int ncg = 2;
+    if (pitch_for(ncg) > 256) ncg = 1;
+    const int pitch = pitch_for(ncg);
+    if (pitch > 256) return -1;
+    const int SX = ncg * PC;
+    int tr = (int)(((kSmemPerSm - 3072) / 6 - 256) / ((size_t)pitch * es));
+    tr = tr / 8 * 8;
+    tr = tr < 8 ? 8 : (tr > 256 ? 256 : tr);
+    const int64_t rows8 = (g.outer + 7) / 8 * 8;
+    if (tr > rows8) tr = (int)rows8;
+    const int64_t c_tiles = (g.n + SX - 1) / SX;
+    const int64_t r_tiles = (g.outer + tr - 1) / tr;
+    const int64_t num_tiles = c_tiles * r_tiles;
+    if (num_tiles >= (1ll << 31)) return -1;
+    const size_t stage_bytes = (size_t)tr * pitch * es;
+
+    CUtensorMap tmap;
+    uint64_t dims[2] = {(uint64_t)g.n, (uint64_t)g.outer};
+    uint64_t strides[1] = {(uint64_t)g.n * es};
+    uint32_t bx[2] = {(uint32_t)pitch, (uint32_t)tr};
+    if (encode_tensor_map(&tmap, dtype_code<TS>(), (void *)a.in, 2, dims, strides, bx) != 0) return -1;
+
+    Corr1dTmaParams<float, TS> p;
+    p.in = (const TS *)a.in; p.out = (TS *)a.out;
+    p.outer = g.outer; p.n = g.n; p.inner = 1;
+    p.pad_lo = 0; p.pad_hi = 0;
+    p.nw = NT; p.lo = lo_al; p.mode = a.mode; p.epilogue = B200_EPI_STORE;
+    p.tile_rows = tr; p.smem_rows = tr; p.nb = 1; p.pitch = pitch; p.shift = 0; p.ncg = ncg;
+    p.wide_store = (((g.n * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
+    p.n_tiles = (int)r_tiles; p.c_tiles = (int)c_tiles;
+    p.cval = (TS)a.cval;
+    p.qinv = 1.f; p.qc0 = 0.f;
+    for (int i = 0; i < NT; ++i) p.w[i] = (i >= lead && i < lead + a.nw) ? 1.f : 0.f;
+
+    auto kern = minmax_contig_static_kernel<TS, NT, IS_MAX>;
+    const size_t smem = stage_bytes + 128;
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)num_tiles, 128, smem, a.stream>>>(tmap, p);
+    B200_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    note_kernel(IS_MAX ? "max1d_tma_contig" : "min1d_tma_contig");
+    return B200_OK;
+}
+
+template <typename TS, bool IS_MAX>
+static int launch_minmax_contig(const Corr1dArgs &a)
+{
+    constexpr int EB = 16 / (int)sizeof(TS);
+    const int es = (int)sizeof(TS);
+    const LineGeom &g = a.g;
+    if (a.pad_lo || a.pad_hi) return -1;
+    if ((g.n * es) % 16 != 0) return -1;
+    if (g.n >= (1ll << 31) || g.outer >= (1ll << 31)) return -1;
+    if (((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15)) return -1;
+    const int lo = a.nw / 2 + a.origin;
+    const int lo_al = (lo + EB - 1) / EB * EB;
+    const int lead = lo_al - lo;
+    const int nt = lead + a.nw;
+    // window lengths are rounded up to the instantiated tap counts (padding taps are skipped)
+    if (nt <= 8) return launch_minmax_contig_cfg<TS, 8, IS_MAX>(a, lo_al, lead);
+    if (nt <= 16) return launch_minmax_contig_cfg<TS, 16, IS_MAX>(a, lo_al, lead);
+    if (nt <= 32) return launch_minmax_contig_cfg<TS, 32, IS_MAX>(a, lo_al, lead);
+    if (nt <= 48) return launch_minmax_contig_cfg<TS, 48, IS_MAX>(a, lo_al, lead);
+    return -1;
+}
+
+template <typename TS>
+static int launch_minmax_typed(const MinMax1dArgs &u)
+{
+    double ones[kMaxTapsTma];
+    if (u.size > 64) return -1;
+    for (int i = 0; i < u.size; ++i) ones[i] = 1.0;
+    Corr1dArgs a;
+    a.in = u.in; a.out = u.out; a.dtype = u.dtype; a.g = u.g;
+    a.w = ones; a.nw = u.size; a.mode = u.mode; a.cval = u.cval; a.origin = u.origin;
+    a.pad_lo = u.pad_lo; a.pad_hi = u.pad_hi; a.epilogue = B200_EPI_STORE; a.flags = u.flags;
+    a.stream = u.stream;
+    BoxInfo box;
+    box.on = true; box.qinv = 1.f; box.qc0 = 0.f;
+    if (u.g.inner == 1)
+        return u.is_max ? launch_minmax_contig<TS, true>(a) : launch_minmax_contig<TS, false>(a);
+    return u.is_max ? launch_strided_r<float, TS, 4, 2>(a, box) : launch_strided_r<float, TS, 4, 1>(a, box);
+}
+
+// minimum / maximum filter on the tiled kernels: float32 and uint8 / uint16
+// (exact in fp32).  The tile holds storage-type values, so a constant-mode cval
+// must be one; -1 = not eligible (the generic exact kernel takes the call).
+int launch_minmax1d_fast(const MinMax1dArgs &u)
+{
+    if (u.size < 2) return -1;
+    if (u.dtype == B200_F32) {
+        if (u.mode == B200_MODE_CONSTANT && (double)(float)u.cval != u.cval) return -1;
+        return launch_minmax_typed<float>(u);
+    }
+    if (u.dtype == B200_U16 || u.dtype == B200_U8) {
+        const double vmax = u.dtype == B200_U16 ? 65535.0 : 255.0;
+        if (u.mode == B200_MODE_CONSTANT &&
+            (!(u.cval >= 0.0 && u.cval <= vmax) || u.cval != (double)(int64_t)u.cval))
+            return -1;
+        return u.dtype == B200_U16 ? launch_minmax_typed<uint16_t>(u) : launch_minmax_typed<uint8_t>(u);
+    }
+    return -1;
 }
 
 }  // namespace b200

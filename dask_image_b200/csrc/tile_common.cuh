@@ -68,6 +68,30 @@ struct VecAcc<float, V> {
     __device__ __forceinline__ float get(int i) const { return (i & 1) ? a[i >> 1].y : a[i >> 1].x; }
 };
 
+// Running extreme of the taps instead of a weighted sum (minimum / maximum
+// filters): same interface as VecAcc, the weight is ignored.  Selection does not
+// round, so the result is exact for floats and for integers widened to float.
+template <typename T, int V, bool IS_MAX>
+struct VecExt {
+    T a[V];
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[i] = IS_MAX ? -INFINITY : INFINITY;
+    }
+    __device__ __forceinline__ void fma(const Vec<T, V> &x, T)
+    {
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[i] = IS_MAX ? fmaxf(a[i], x.v[i]) : fminf(a[i], x.v[i]);
+    }
+    __device__ __forceinline__ T get(int i) const { return a[i]; }
+};
+
+// OP: 0 = correlation (FMA), 1 = minimum, 2 = maximum
+template <typename T, int V, int OP> struct TapAcc { using type = VecAcc<T, V>; };
+template <int V> struct TapAcc<float, V, 1> { using type = VecExt<float, V, false>; };
+template <int V> struct TapAcc<float, V, 2> { using type = VecExt<float, V, true>; };
+
 // 16-byte aligned base of the dynamic shared memory (TMA destinations need
 // 128-byte alignment; the launcher over-allocates by 128).  Pointer arithmetic
 // on the __shared__ array keeps the shared address space (LDS, not LD).

@@ -165,7 +165,7 @@ def _launch_minmax1d(src, dst, shape, np_dtype, axis, size, is_max, mode, cval, 
             src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape),
             _lib.i64_array(shape), int(axis), int(size), int(bool(is_max)), _lib.mode_code(mode), float(cval),
             int(origin), int(pad[0]), int(pad[1]),
-            int(_default_flags if flags is None else flags) & ~_lib.FLAG_FORCE_FAST, _stream_ptr(src))
+            int(_default_flags if flags is None else flags), _stream_ptr(src))
     _lib.check(rc)
 
 
