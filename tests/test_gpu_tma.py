@@ -283,9 +283,17 @@ def test_tma_min_max_filter1d(b200, dtype, mode, shape, axis):
     d = dev(b200, a)
     for size, origin in [(2, 0), (3, 1), (7, 0), (7, -3), (8, 3), (16, -8), (31, 4), (40, 0)]:
         for name in ("minimum_filter1d", "maximum_filter1d"):
-            with forced(b200, _lib.FLAG_FORCE_FAST):
+            # uint8 rows align to 16 elements: up to 15 padding taps, so long windows
+            # along the contiguous axis exceed the 48 instantiated taps and fall back
+            lead = (-(size // 2 + origin)) % (16 // a.dtype.itemsize)
+            tiled = not (axis == a.ndim - 1 and lead + size > 48)
+            if tiled:
+                with forced(b200, _lib.FLAG_FORCE_FAST):
+                    got = getattr(b200.ndimage, name)(d, size, axis=axis, mode=mode, cval=cval, origin=origin)
+                assert _lib.last_kernel().startswith(name[:3] + "1d_tma_"), _lib.last_kernel()
+            else:
                 got = getattr(b200.ndimage, name)(d, size, axis=axis, mode=mode, cval=cval, origin=origin)
-            assert _lib.last_kernel().startswith(name[:3] + "1d_tma_"), _lib.last_kernel()
+                assert _lib.last_kernel() == name[:3] + "1d_generic", _lib.last_kernel()
             ref = getattr(ndi, name)(a, size, axis=axis, mode=mode, cval=cval, origin=origin)
             assert_parity(got.to_numpy(), ref, exact=True, what="%s size=%d origin=%d" % (name, size, origin))
 
