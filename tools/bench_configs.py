@@ -45,6 +45,8 @@ def main():
          lambda v: f.gaussian_laplace(v, 3.0)),
         ("C5 convolve 9^3 wrap 1536^3 f32", (1536 // scale,) * 3, np.float32, 8,
          lambda v: f.convolve(v, w9, mode="wrap")),
+        ("M maximum 7 2048^3 u16", (2048 // scale,) * 3, np.uint16, 12,
+         lambda v: f.maximum_filter(v, size=7)),
         ("H gaussian s=2 2048^3 f32", (2048 // scale,) * 3, np.float32, 24,
          lambda v: f.gaussian_filter(v, 2.0)),
         ("H4 gaussian s=4 2048^3 f32", (2048 // scale,) * 3, np.float32, 24,
