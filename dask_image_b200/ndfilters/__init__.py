@@ -1,5 +1,11 @@
 """Drop-in for the correlation family of ``dask_image.ndfilters``: same names,
-signatures, validation and exception classes (dask_image/ndfilters/__init__.py)."""
+signatures, validation and exception classes (dask_image/ndfilters/__init__.py).
+
+The wrapper modules import ``scipy.ndimage`` for ONE purpose, the one the
+reference has (dask_image/ndfilters/_utils.py:10-48): every public function
+takes its ``__name__`` and docstring from the scipy function it mirrors.  No
+scipy function is ever called on this path -- all arithmetic runs in the CUDA
+library, and there is no CPU fallback."""
 from ._conv import convolve, correlate
 from ._diff import laplace
 from ._edge import prewitt, sobel
