@@ -84,3 +84,68 @@ def test_map_overlap_emulation_periodic_wrap():
     whole = ndi.convolve(a, w, mode="wrap")
     chunked = orc.map_overlap_emulated(ndi.convolve, a, (20, 22), (2, 2), "periodic", weights=w, mode="constant")
     assert np.array_equal(whole, chunked)
+
+
+# ---------------------------------------------------------------------------
+# randomised pinning against live scipy (bounded hypothesis run)
+# ---------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_DT = ["uint8", "int8", "uint16", "int16", "uint32", "int32", "int64", "float32", "float64"]
+_MODES = ["nearest", "wrap", "reflect", "mirror", "constant"]
+
+
+@settings(max_examples=120, deadline=None)
+@given(st.data())
+def test_oracle_fuzz_against_scipy(data):
+    nd = data.draw(st.integers(1, 3))
+    shape = tuple(data.draw(st.integers(1, 9)) for _ in range(nd))
+    dt = np.dtype(data.draw(st.sampled_from(_DT)))
+    mode = data.draw(st.sampled_from(_MODES))
+    cval = data.draw(st.sampled_from([0.0, -3.5, 2.25, 300.0]))
+    seed = data.draw(st.integers(0, 2 ** 16))
+    rng = np.random.default_rng(seed)
+    a = (rng.random(shape) * 200 - (60 if dt.kind != "u" else 0)).astype(dt)
+    axis = data.draw(st.integers(0, nd - 1))
+    nw = data.draw(st.integers(1, 12))
+    origin = data.draw(st.integers(-(nw // 2), (nw - 1) // 2))
+    w = rng.random(nw) - 0.4
+    if data.draw(st.booleans()) and nw % 2:
+        w = (w + w[::-1]) / 2 if data.draw(st.booleans()) else (w - w[::-1]) / 2     # the folded branches
+    assert np.array_equal(ndi.correlate1d(a, w, axis=axis, mode=mode, cval=cval, origin=origin),
+                          orc.correlate1d(a, w, axis, mode, cval, origin), equal_nan=True)
+    assert np.array_equal(ndi.uniform_filter1d(a, nw, axis=axis, mode=mode, cval=cval, origin=origin),
+                          orc.uniform_filter1d(a, nw, axis, mode, cval, origin), equal_nan=True)
+    wshape = tuple(data.draw(st.integers(1, 4)) for _ in range(nd))
+    wn = rng.random(wshape) - 0.4
+    origins = tuple(data.draw(st.integers(-(s // 2), (s - 1) // 2)) for s in wshape)
+    assert np.array_equal(ndi.correlate(a, wn, mode=mode, cval=cval, origin=origins),
+                          orc.correlate(a, wn, mode, cval, origins), equal_nan=True)
+    conv_origins = tuple(data.draw(st.integers(-(s // 2), (s - 1) // 2)) for s in wshape)
+    assert np.array_equal(ndi.convolve(a, wn, mode=mode, cval=cval, origin=conv_origins),
+                          orc.convolve(a, wn, mode, cval, conv_origins), equal_nan=True)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.data())
+def test_oracle_driver_fuzz_against_scipy(data):
+    nd = data.draw(st.integers(1, 3))
+    shape = tuple(data.draw(st.integers(1, 8)) for _ in range(nd))
+    dt = np.dtype(data.draw(st.sampled_from(_DT)))
+    mode = data.draw(st.sampled_from(_MODES))
+    rng = np.random.default_rng(data.draw(st.integers(0, 2 ** 16)))
+    a = (rng.random(shape) * 100).astype(dt)
+    sigma = tuple(data.draw(st.sampled_from([0.0, 0.6, 1.0, 1.7])) for _ in range(nd))
+    order = tuple(data.draw(st.integers(0, 2)) for _ in range(nd))
+    truncate = data.draw(st.sampled_from([1.0, 2.5, 4.0]))
+    with np.errstate(all="ignore"):
+        assert np.array_equal(ndi.gaussian_filter(a, sigma, order=order, mode=mode, cval=1.5, truncate=truncate),
+                              orc.gaussian_filter(a, sigma, order, mode, 1.5, truncate), equal_nan=True)
+        assert np.array_equal(ndi.gaussian_gradient_magnitude(a, sigma, mode=mode, cval=1.5, truncate=truncate),
+                              orc.gaussian_gradient_magnitude(a, sigma, mode, 1.5, truncate), equal_nan=True)
+        assert np.array_equal(ndi.gaussian_laplace(a, sigma, mode=mode, cval=1.5, truncate=truncate),
+                              orc.gaussian_laplace(a, sigma, mode, 1.5, truncate), equal_nan=True)
+    size = tuple(data.draw(st.integers(1, 5)) for _ in range(nd))
+    origin = tuple(data.draw(st.integers(-(s // 2), (s - 1) // 2)) for s in size)
+    assert np.array_equal(ndi.uniform_filter(a, size, mode=mode, cval=1.5, origin=origin),
+                          orc.uniform_filter(a, size, mode, 1.5, origin), equal_nan=True)
