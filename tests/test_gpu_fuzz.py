@@ -10,6 +10,9 @@ from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
 
+import os
+
+_N = int(os.environ.get("B200_FUZZ_EXAMPLES", "0"))      # raise for a longer hunt
 _DT = ["uint8", "uint16", "int16", "int32", "float32", "float64"]
 _MODES = ["nearest", "wrap", "reflect", "mirror", "constant"]
 
@@ -31,7 +34,7 @@ def _array(data, dt, max_nd=3):
     return a, rng
 
 
-@settings(max_examples=80, deadline=None, derandomize=True)
+@settings(max_examples=_N or 80, deadline=None, derandomize=True)
 @given(st.data())
 def test_fuzz_1d_primitives(b200, data):
     dt = np.dtype(data.draw(st.sampled_from(_DT)))
@@ -55,7 +58,7 @@ def test_fuzz_1d_primitives(b200, data):
         assert_parity(got.to_numpy(), ref, exact=True, what=name)
 
 
-@settings(max_examples=50, deadline=None, derandomize=True)
+@settings(max_examples=_N or 50, deadline=None, derandomize=True)
 @given(st.data())
 def test_fuzz_drivers(b200, data):
     dt = np.dtype(data.draw(st.sampled_from(_DT)))
