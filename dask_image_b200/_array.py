@@ -34,6 +34,22 @@ def default_device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+# numpy functions that work on B200Array without leaving the device (the
+# __array_function__ protocol, NEP 18): what dask needs to assemble halo'd blocks
+# from B200Array chunks (concatenate / stack / *_like / slicing) -- SURVEY.md
+# 8(f) rank 3.  Anything else raises TypeError instead of silently copying to
+# the host.
+_HANDLED = {}
+
+
+def _implements(np_function):
+    def deco(fn):
+        _HANDLED[np_function] = fn
+        return fn
+
+    return deco
+
+
 class B200Array:
     """N-D array resident in B200 HBM.
 
@@ -141,6 +157,19 @@ class B200Array:
             return B200Array(self.tensor - other.tensor)
         return B200Array(self.tensor - other)
 
+    def __array_function__(self, func, types, args, kwargs):
+        handler = _HANDLED.get(func)
+        if handler is None or not all(issubclass(t, B200Array) for t in types):
+            return NotImplemented
+        return handler(*args, **kwargs)
+
+    def transpose(self, *axes):
+        if len(axes) == 1 and not np.isscalar(axes[0]):
+            axes = tuple(axes[0])
+        if not axes:
+            axes = tuple(range(self.ndim))[::-1]
+        return B200Array(self.tensor.permute(*axes))
+
     def __repr__(self):
         return "B200Array(shape=%s, dtype=%s, device=%s)" % (self.shape, self.dtype, self.device)
 
@@ -153,3 +182,51 @@ def as_b200(x, like=None):
         return B200Array(x)
     dev = like.device if like is not None else None
     return B200Array.from_numpy(np.asarray(x), device=dev)
+
+
+@_implements(np.concatenate)
+def _concatenate(arrays, axis=0, out=None, **kwargs):
+    if out is not None:
+        raise TypeError("concatenate(out=...) is not supported for B200Array")
+    return B200Array(torch.cat([as_b200(a).tensor for a in arrays], dim=0 if axis is None else int(axis)))
+
+
+@_implements(np.stack)
+def _stack(arrays, axis=0, out=None, **kwargs):
+    if out is not None:
+        raise TypeError("stack(out=...) is not supported for B200Array")
+    return B200Array(torch.stack([as_b200(a).tensor for a in arrays], dim=int(axis)))
+
+
+def _like(prototype, dtype, shape):
+    dt = prototype.tensor.dtype if dtype is None else torch_dtype(dtype)
+    shp = prototype.shape if shape is None else tuple(np.atleast_1d(shape).tolist())
+    return dt, shp
+
+
+@_implements(np.empty_like)
+def _empty_like(prototype, dtype=None, order="K", subok=True, shape=None, **kwargs):
+    dt, shp = _like(prototype, dtype, shape)
+    return B200Array(torch.empty(shp, dtype=dt, device=prototype.device))
+
+
+@_implements(np.zeros_like)
+def _zeros_like(a, dtype=None, order="K", subok=True, shape=None, **kwargs):
+    dt, shp = _like(a, dtype, shape)
+    return B200Array(torch.zeros(shp, dtype=dt, device=a.device))
+
+
+@_implements(np.shape)
+def _shape(a):
+    return a.shape
+
+
+@_implements(np.ndim)
+def _ndim(a):
+    return a.ndim
+
+
+@_implements(np.transpose)
+def _transpose(a, axes=None):
+    return a.transpose() if axes is None else a.transpose(axes)
+

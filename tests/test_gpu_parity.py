@@ -377,3 +377,27 @@ def test_min_max_public_wrappers_and_errors(b200):
     with pytest.raises(ValueError):
         b200.ndimage.minimum_filter(d, footprint=np.zeros((3, 3), bool))
     assert b200.ndfilters.minimum_filter.__name__ == "minimum_filter"
+
+
+def test_b200array_numpy_protocol_stays_on_device(b200):
+    """NEP-18 surface dask needs to assemble halo'd blocks from B200Array chunks."""
+    a = np.arange(24, dtype=np.float32).reshape(4, 6)
+    d = dev(b200, a)
+    c = np.concatenate([d[:, :2], d[:, 2:]], axis=1)
+    assert type(c) is b200.B200Array and np.array_equal(np.asarray(c), a)
+    s = np.stack([d, d], axis=0)
+    assert type(s) is b200.B200Array and s.shape == (2, 4, 6)
+    e = np.empty_like(d, shape=(3, 3))
+    z = np.zeros_like(d)
+    assert type(e) is b200.B200Array and e.shape == (3, 3) and e.dtype == np.float32
+    assert type(z) is b200.B200Array and not np.asarray(z).any()
+    assert np.shape(d) == (4, 6) and np.ndim(d) == 2
+    assert np.array_equal(np.asarray(np.transpose(d)), a.T)
+    with pytest.raises(TypeError):
+        np.fft.fft(d)                 # not on the path: refused, not silently computed on the host
+    # halo assembly the way map_overlap does it: neighbours' planes concatenated, filtered, trimmed
+    top, bottom = d[:2], d[2:]
+    block = np.concatenate([top, bottom[:1]], axis=0)
+    got = b200.ndimage.uniform_filter(block, size=(3, 1), mode="nearest")[:2]
+    ref = ndi.uniform_filter(a, size=(3, 1), mode="nearest")[:2]
+    assert_parity(np.asarray(got)[:1], ref[:1])
