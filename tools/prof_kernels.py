@@ -34,6 +34,15 @@ if what == "f32":
     for axis in (0, 1, 2):
         timed(lambda: ndimage._launch_correlate1d(x, out, tuple(x.shape), np.dtype(np.float32), axis, w,
                                                   "reflect", 0.0, 0), "gauss sigma %g axis %d" % (sigma, axis))
+elif what == "f64":
+    m = 768
+    x = torch.rand((m, m, m), dtype=torch.float64, device="cuda")
+    out = torch.empty_like(x)
+    w = ndimage._gaussian_weights(sigma, 0, 4.0)
+    gb = 2 * 8 * x.numel() / 1e9
+    for axis in (0, 1, 2):
+        timed(lambda: ndimage._launch_correlate1d(x, out, tuple(x.shape), np.dtype(np.float64), axis, w,
+                                                  "reflect", 0.0, 0), "f64 %d^3 (%.1f GB/pass) gauss sigma %g axis %d" % (m, gb, sigma, axis))
 elif what == "u16":
     x = torch.randint(0, 65536, (n, n, n), dtype=torch.int32, device="cuda").to(torch.uint16)
     out = torch.empty_like(x)
