@@ -361,3 +361,26 @@ def test_slab_halo_eligibility_is_a_pure_host_query():
     assert not nd._uniform_halo_eligible(u2, 256, 4096, 7, 0, "constant", 0.5)    # cval is not a uint16
     assert not nd._uniform_halo_eligible(u2, 256, 4096, 200, 0, "reflect", 0.0)   # window too long for exact fp32 sums
     assert nd._uniform_halo_eligible(f4, 256, 4096, 7, 0, "constant", 0.5)
+
+
+# ---- remaining parameter tables of the reference's tests ------------------------
+@pytest.mark.parametrize("err_type, axis", [(ValueError, 0.0), (ValueError, 2), (ValueError, -3)])
+@pytest.mark.parametrize("name", ["prewitt", "sobel"])
+def test_edge_func_params(name, err_type, axis):
+    # reference: test__edge.py:15-37
+    with pytest.raises(err_type):
+        getattr(dask_image_b200.ndfilters, name)(_Shape2D(), axis)
+
+
+@pytest.mark.parametrize("err_type, size, footprint, origin", [
+    (RuntimeError, None, None, 0), (TypeError, 1.0, None, 0), (RuntimeError, (1,), None, 0),
+    (RuntimeError, [(1,)], None, 0), (RuntimeError, 1, np.ones((1,)), 0), (RuntimeError, None, np.ones((1,)), 0),
+    (RuntimeError, None, np.ones((1, 0)), 0), (RuntimeError, 1, None, (0,)), (RuntimeError, 1, None, [(0,)]),
+    (ValueError, 1, None, 1), (TypeError, 1, None, 0.0), (TypeError, 1, None, (0.0, 0.0)),
+    (TypeError, 1, None, 1 + 0j), (TypeError, 1, None, (0 + 0j, 1 + 0j)),
+])
+@pytest.mark.parametrize("name", ["minimum_filter", "maximum_filter"])
+def test_order_filter_params(name, err_type, size, footprint, origin):
+    # reference: test__order.py:20-66 -- all raised before any dispatch / compute
+    with pytest.raises(err_type):
+        getattr(dask_image_b200.ndfilters, name)(_Shape2D(), size=size, footprint=footprint, origin=origin)
