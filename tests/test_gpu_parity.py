@@ -401,3 +401,43 @@ def test_b200array_numpy_protocol_stays_on_device(b200):
     got = b200.ndimage.uniform_filter(block, size=(3, 1), mode="nearest")[:2]
     ref = ndi.uniform_filter(a, size=(3, 1), mode="nearest")[:2]
     assert_parity(np.asarray(got)[:1], ref[:1])
+
+
+def test_concurrent_calls_from_a_thread_pool(b200):
+    """dask's threaded scheduler calls chunk functions concurrently (SURVEY.md 8b,
+    'Threading'): the C ABI keeps only thread-local state, every call takes the
+    calling thread's stream."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+
+    import torch
+
+    rng = np.random.default_rng(99)
+    jobs = []
+    for k in range(24):
+        dt = [np.float32, np.uint16, np.float64][k % 3]
+        a = (rng.random((20 + k, 24, 32)) * 1000).astype(dt)
+        jobs.append((k, a))
+    errors = []
+    lock = threading.Lock()
+
+    def work(job):
+        k, a = job
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                d = b200.B200Array.from_numpy(a)
+                g = b200.ndfilters.gaussian_filter(d, sigma=1.0 + (k % 4) * 0.5)
+                u = b200.ndfilters.uniform_filter(d, size=3 + (k % 3) * 2)
+                m = b200.ndfilters.maximum_filter(d, size=3)
+                stream.synchronize()
+            assert_parity(np.asarray(g), ndi.gaussian_filter(a, 1.0 + (k % 4) * 0.5), data=a)
+            assert_parity(np.asarray(u), ndi.uniform_filter(a, 3 + (k % 3) * 2), data=a)
+            assert_parity(np.asarray(m), ndi.maximum_filter(a, size=3), exact=True)
+        except Exception as exc:       # collected, not raised inside the pool
+            with lock:
+                errors.append("job %d: %r" % (k, exc))
+
+    with ThreadPoolExecutor(8) as ex:
+        list(ex.map(work, jobs))
+    assert not errors, "\n".join(errors)
