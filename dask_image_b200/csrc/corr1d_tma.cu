@@ -112,7 +112,6 @@ struct Corr1dTmaParams {
     int ncg;         // contig: 4*R-column groups per tile
     int wide_store;  // contig: rows and base are 32-byte aligned -> 256-bit stores
     int n_tiles, c_tiles;
-    int64_t nb_tiles;  // ring kernel: total number of tiles
     TS cval;
     T qinv, qc0;     // integer box filter: 1/size and the (0.5 - size/2) offset
     T w[kMaxTapsTma];
@@ -532,15 +531,19 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 // warp 64 x 8; the lanes of a quarter warp sit on 8 different rows, which the
 // odd 16-byte pitch spreads over all bank groups.  TS = uint16_t / uint8_t is
 // the exact integer box filter (taps 0/1, quotient epilogue).
-// the outputs of one staged tile (tile column tcx, tile row trow)
 template <typename TS, int NT>
-__device__ __forceinline__ void contig_static_compute(const Corr1dTmaParams<float, TS> &p, const TS *tile, int tcx,
-                                                      int64_t trow)
+__global__ void __launch_bounds__(256, 3)
+corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
+                            const __grid_constant__ Corr1dTmaParams<float, TS> p)
 {
     constexpr bool kBox = sizeof(TS) != sizeof(float);   // exact integer box filter
     constexpr int EB = 16 / (int)sizeof(TS);             // elements per 16-byte shared load
     constexpr int R = 16, PC = 4 * R, LA = NT;
     constexpr int NF = (R + NT + EB - 1) / EB * EB;       // row window: whole 16-byte blocks
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TS *tile = aligned_smem<TS>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar;
+
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int P = p.pitch;
@@ -548,8 +551,16 @@ __device__ __forceinline__ void contig_static_compute(const Corr1dTmaParams<floa
     const int SX = p.ncg * PC;
     const int nrg = TR >> 3;
     const int64_t nrows = p.outer;
+
+    const int64_t t = blockIdx.x;
+    const int tcx = (int)(t % p.c_tiles);
+    const int64_t trow = t / p.c_tiles;
     const int64_t x0t = (int64_t)tcx * SX;
     const int64_t row0 = trow * TR;
+    const int64_t g0 = x0t - p.lo;
+
+    contig_stage_tile<TS, 8>(tmap, tile, &full_bar, p.in, g0, row0, p.n, nrows, P, TR, p.mode, p.cval);
+
     // a warp keeps one 64-column group and walks the 8-row groups (uniform trip
     // count); CTAs have 8 or 4 warps
     const int cg_shift = p.ncg == 4 ? 2 : (p.ncg == 2 ? 1 : 0);
@@ -1041,89 +1052,6 @@ static int launch_contig_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al,
 }
 
 template <typename TS, int NT>
-__global__ void __launch_bounds__(256, 3)
-corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
-                            const __grid_constant__ Corr1dTmaParams<float, TS> p)
-{
-    constexpr int PC = 64;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TS *tile = aligned_smem<TS>(smem_raw);
-    __shared__ __align__(8) uint64_t full_bar;
-    const int64_t t = blockIdx.x;
-    const int tcx = (int)(t % p.c_tiles);
-    const int64_t trow = t / p.c_tiles;
-    const int64_t g0 = (int64_t)tcx * (p.ncg * PC) - p.lo;
-    contig_stage_tile<TS, 8>(tmap, tile, &full_bar, p.in, g0, trow * p.tile_rows, p.n, p.outer, p.pitch, p.tile_rows,
-                             p.mode, p.cval);
-    contig_static_compute<TS, NT>(p, tile, tcx, trow);
-}
-
-// Persistent form for long (FP32-issue bound) filters: a CTA walks tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ... through a two-stage shared-memory
-// ring; the TMA load of tile k+2 is issued as soon as tile k has been consumed,
-// so the load of the next tile always overlaps the FFMA2 run of the current one
-// inside the same CTA (p.nb = total tiles, p.shift = elements per stage).
-template <int NT>
-__global__ void __launch_bounds__(256, 3)
-corr1d_contig_static_ring_kernel(const __grid_constant__ CUtensorMap tmap,
-                                 const __grid_constant__ Corr1dTmaParams<float, float> p)
-{
-    constexpr int PC = 64;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *ring = aligned_smem<float>(smem_raw);
-    __shared__ __align__(8) uint64_t full_bar[2];
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int P = p.pitch, TR = p.tile_rows;
-    const int64_t T = p.nb_tiles;
-    const uint32_t tile_bytes = (uint32_t)(TR * P * (int)sizeof(float));
-    auto issue = [&](int64_t t, int s) {
-        const int tcx = (int)(t % p.c_tiles);
-        const int64_t trow = t / p.c_tiles;
-        mbar_arrive_expect_tx(&full_bar[s], tile_bytes);
-        tma_load_2d(ring + (size_t)s * p.shift, &tmap, &full_bar[s], (int)((int64_t)tcx * (p.ncg * PC) - p.lo),
-                    (int)(trow * TR));
-    };
-    if (tid == 0) {
-        mbar_init(&full_bar[0], 1);
-        mbar_init(&full_bar[1], 1);
-        fence_barrier_init();
-        for (int s = 0; s < 2; ++s) {
-            const int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-            if (t < T) issue(t, s);
-        }
-    }
-    __syncthreads();
-    int k = 0;
-    for (int64_t t = blockIdx.x; t < T; t += gridDim.x, ++k) {
-        const int s = k & 1;
-        float *tile = ring + (size_t)s * p.shift;
-        mbar_wait(&full_bar[s], (uint32_t)((k >> 1) & 1));
-        const int tcx = (int)(t % p.c_tiles);
-        const int64_t trow = t / p.c_tiles;
-        const int64_t g0 = (int64_t)tcx * (p.ncg * PC) - p.lo, row0 = trow * TR;
-        // columns outside [0, n): this tile's images under the extension map
-        ContigEdge<float> edge;
-        edge.init(g0, P, p.n, TR);
-        if (edge.total > 0 && !(p.mode == B200_MODE_CONSTANT && p.cval == 0.f)) {
-            for (int idx = tid; idx < edge.total; idx += nthr) {
-                const int r = idx / edge.per_row, kk = idx - r * edge.per_row;
-                const int c = edge.column(kk);
-                const int64_t src = ext_index(g0 + c, p.n, p.mode);
-                float v = p.cval;
-                if (src >= 0) v = (row0 + r < p.outer) ? p.in[(row0 + r) * p.n + src] : 0.f;
-                tile[r * P + c] = v;
-            }
-            __syncthreads();
-        }
-        contig_static_compute<float, NT>(p, tile, tcx, trow);
-        fence_proxy_async();          // generic-proxy accesses to this stage precede its next TMA fill
-        __syncthreads();
-        const int64_t t2 = t + 2 * (int64_t)gridDim.x;
-        if (tid == 0 && t2 < T) issue(t2, s);
-    }
-}
-
-template <typename TS, int NT>
 static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al, int lead)
 {
     constexpr int EB = 16 / (int)sizeof(TS);   // elements per 16 bytes of storage
@@ -1175,37 +1103,10 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int
     p.wide_store = (((g.n * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
     p.n_tiles = (int)r_tiles; p.c_tiles = (int)c_tiles;
     p.cval = (TS)a.cval;
-    p.nb_tiles = num_tiles;
     p.qinv = box.qinv; p.qc0 = box.qc0;
     for (int i = 0; i < NT; ++i) p.w[i] = 0.f;
     for (int i = 0; i < a.nw; ++i) p.w[lead + i] = (float)a.w[i];
 
-    if constexpr (sizeof(TS) == sizeof(float) && NT >= 24) {
-        // long filters: persistent CTAs with a two-stage tile ring (see kernel)
-        if (env_int("B200_TMA_RING", 0)) {
-            const int rctas = env_int("B200_TMA_RING_CTAS", 3);
-            int rtr = (int)((((kSmemPerSm - 3072) / rctas - 512) / 2) / ((size_t)pitch * es));
-            rtr = rtr / 8 * 8;
-            rtr = rtr < 8 ? 8 : (rtr > 256 ? 256 : rtr);
-            if (rtr > rows8) rtr = (int)rows8;
-            const int64_t rr_tiles = (g.outer + rtr - 1) / rtr;
-            const int64_t T = c_tiles * rr_tiles;
-            uint32_t rbx[2] = {(uint32_t)pitch, (uint32_t)rtr};
-            if (encode_tensor_map(&tmap, dtype_code<TS>(), (void *)a.in, 2, dims, strides, rbx) != 0) return -1;
-            p.tile_rows = rtr; p.smem_rows = rtr; p.n_tiles = (int)rr_tiles; p.nb_tiles = T;
-            p.shift = rtr * pitch;
-            auto rk = corr1d_contig_static_ring_kernel<NT>;
-            const size_t rsmem = 2 * (size_t)rtr * pitch * es + 128;
-            B200_CUDA_TRY(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-            int64_t grid = (int64_t)device_sm_count() * rctas;
-            if (grid > T) grid = T;
-            rk<<<(unsigned)grid, threads == 128 ? 128 : 256, rsmem, a.stream>>>(tmap, p);
-            B200_CUDA_TRY(cudaGetLastError());
-            count_launch();
-            note_kernel(kernel_name<float, TS>(false));
-            return B200_OK;
-        }
-    }
     auto kern = corr1d_contig_static_kernel<TS, NT>;
     const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
