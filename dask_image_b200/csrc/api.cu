@@ -104,6 +104,10 @@ int b200_correlate1d(const void *in, void *out, int dtype, int ndim, const int64
         int rc = launch_corr1d_tma(a);
         if (rc >= 0) return rc;
     }
+    if (!is_float && !(flags & B200_FLAG_EXACT)) {
+        int rc = launch_corr1d_int(a);
+        if (rc >= 0) return rc;
+    }
     if (flags & B200_FLAG_FORCE_FAST)
         return set_error(B200_EINVAL, "no tiled kernel is eligible for this call");
     return launch_corr1d_generic(a);

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <float.h>
+#include <cmath>
 #include "../../include/b200_ndfilters.h"
 
 namespace b200 {
@@ -111,30 +112,30 @@ __host__ __device__ __forceinline__ int64_t ext_index_padded(int64_t i, int64_t 
 // low bits are kept); uint32 / int64 through the 64-bit form; uint64 through
 // gcc's two-range sequence.  SURVEY.md A4: u16 -1.5 -> 65535, 120000 -> 54464.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int32_t x86_cvtt32(double v)
+__host__ __device__ __forceinline__ int32_t x86_cvtt32(double v)
 {
     return (v > -2147483649.0 && v < 2147483648.0) ? (int32_t)v : INT32_MIN;
 }
-__device__ __forceinline__ int64_t x86_cvtt64(double v)
+__host__ __device__ __forceinline__ int64_t x86_cvtt64(double v)
 {
     return (v >= -9223372036854775808.0 && v < 9223372036854775808.0) ? (int64_t)v : INT64_MIN;
 }
 
-template <typename T> __device__ __forceinline__ T cast_out(double v);
-template <> __device__ __forceinline__ uint8_t cast_out<uint8_t>(double v) { return (uint8_t)x86_cvtt32(v); }
-template <> __device__ __forceinline__ int8_t cast_out<int8_t>(double v) { return (int8_t)x86_cvtt32(v); }
-template <> __device__ __forceinline__ uint16_t cast_out<uint16_t>(double v) { return (uint16_t)x86_cvtt32(v); }
-template <> __device__ __forceinline__ int16_t cast_out<int16_t>(double v) { return (int16_t)x86_cvtt32(v); }
-template <> __device__ __forceinline__ int32_t cast_out<int32_t>(double v) { return x86_cvtt32(v); }
-template <> __device__ __forceinline__ uint32_t cast_out<uint32_t>(double v) { return (uint32_t)x86_cvtt64(v); }
-template <> __device__ __forceinline__ int64_t cast_out<int64_t>(double v) { return x86_cvtt64(v); }
-template <> __device__ __forceinline__ uint64_t cast_out<uint64_t>(double v)
+template <typename T> __host__ __device__ __forceinline__ T cast_out(double v);
+template <> __host__ __device__ __forceinline__ uint8_t cast_out<uint8_t>(double v) { return (uint8_t)x86_cvtt32(v); }
+template <> __host__ __device__ __forceinline__ int8_t cast_out<int8_t>(double v) { return (int8_t)x86_cvtt32(v); }
+template <> __host__ __device__ __forceinline__ uint16_t cast_out<uint16_t>(double v) { return (uint16_t)x86_cvtt32(v); }
+template <> __host__ __device__ __forceinline__ int16_t cast_out<int16_t>(double v) { return (int16_t)x86_cvtt32(v); }
+template <> __host__ __device__ __forceinline__ int32_t cast_out<int32_t>(double v) { return x86_cvtt32(v); }
+template <> __host__ __device__ __forceinline__ uint32_t cast_out<uint32_t>(double v) { return (uint32_t)x86_cvtt64(v); }
+template <> __host__ __device__ __forceinline__ int64_t cast_out<int64_t>(double v) { return x86_cvtt64(v); }
+template <> __host__ __device__ __forceinline__ uint64_t cast_out<uint64_t>(double v)
 {
     if (v < 9223372036854775808.0) return (uint64_t)x86_cvtt64(v);
     return (uint64_t)x86_cvtt64(v - 9223372036854775808.0) ^ 0x8000000000000000ull;
 }
-template <> __device__ __forceinline__ float cast_out<float>(double v) { return (float)v; }
-template <> __device__ __forceinline__ double cast_out<double>(double v) { return v; }
+template <> __host__ __device__ __forceinline__ float cast_out<float>(double v) { return (float)v; }
+template <> __host__ __device__ __forceinline__ double cast_out<double>(double v) { return v; }
 
 template <typename T> struct is_float_type { static constexpr bool value = false; };
 template <> struct is_float_type<float> { static constexpr bool value = true; };
@@ -152,22 +153,30 @@ template <> struct wrap_type<int16_t> { using type = uint16_t; };
 template <> struct wrap_type<int32_t> { using type = uint32_t; };
 template <> struct wrap_type<int64_t> { using type = uint64_t; };
 
-template <typename T> __device__ __forceinline__ T t_add(T a, T b)
+template <typename T> __host__ __device__ __forceinline__ T t_add(T a, T b)
 {
     using U = typename wrap_type<T>::type;
     return (T)(U)((U)a + (U)b);
 }
-template <typename T> __device__ __forceinline__ T t_mul(T a, T b)
+template <typename T> __host__ __device__ __forceinline__ T t_mul(T a, T b)
 {
     using U = typename wrap_type<T>::type;
     return (T)(U)((U)a * (U)b);
 }
-template <> __device__ __forceinline__ float t_add<float>(float a, float b) { return __fadd_rn(a, b); }
-template <> __device__ __forceinline__ float t_mul<float>(float a, float b) { return __fmul_rn(a, b); }
-template <> __device__ __forceinline__ double t_add<double>(double a, double b) { return __dadd_rn(a, b); }
-template <> __device__ __forceinline__ double t_mul<double>(double a, double b) { return __dmul_rn(a, b); }
+// (no contraction on the device: the intrinsics keep ptxas from fusing the pair)
+#ifdef __CUDA_ARCH__
+template <> __host__ __device__ __forceinline__ float t_add<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __host__ __device__ __forceinline__ float t_mul<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __host__ __device__ __forceinline__ double t_add<double>(double a, double b) { return __dadd_rn(a, b); }
+template <> __host__ __device__ __forceinline__ double t_mul<double>(double a, double b) { return __dmul_rn(a, b); }
+#else
+template <> __host__ __device__ __forceinline__ float t_add<float>(float a, float b) { return a + b; }
+template <> __host__ __device__ __forceinline__ float t_mul<float>(float a, float b) { return a * b; }
+template <> __host__ __device__ __forceinline__ double t_add<double>(double a, double b) { return a + b; }
+template <> __host__ __device__ __forceinline__ double t_mul<double>(double a, double b) { return a * b; }
+#endif
 
-template <typename T> __device__ __forceinline__ T t_sqrt(T a)
+template <typename T> __host__ __device__ __forceinline__ T t_sqrt(T a)
 {
     if constexpr (sizeof(T) == 1) {
         // float16 loop: value -> half, sqrt evaluated in float, rounded to half
@@ -180,10 +189,10 @@ template <typename T> __device__ __forceinline__ T t_sqrt(T a)
         return cast_out<T>(sqrt((double)a));
     }
 }
-template <> __device__ __forceinline__ float t_sqrt<float>(float a) { return sqrtf(a); }
-template <> __device__ __forceinline__ double t_sqrt<double>(double a) { return sqrt(a); }
+template <> __host__ __device__ __forceinline__ float t_sqrt<float>(float a) { return sqrtf(a); }
+template <> __host__ __device__ __forceinline__ double t_sqrt<double>(double a) { return sqrt(a); }
 
-template <typename T> __device__ __forceinline__ T apply_epilogue(int epi, T prev, T r)
+template <typename T> __host__ __device__ __forceinline__ T apply_epilogue(int epi, T prev, T r)
 {
     switch (epi) {
     case B200_EPI_ACC: return t_add<T>(prev, r);
@@ -214,6 +223,23 @@ inline LineGeom line_geometry(int ndim, const int64_t *shape, int axis)
 
 constexpr int kMaxTaps1D = 1024;  // taps carried in kernel parameters
 
+// symmetry classification of the reference's compiled 1-D loop:
+// +1 symmetric, -1 antisymmetric, 0 neither (or an even tap count)
+inline int classify_symmetry(const double *w, int nw)
+{
+    if (!(nw & 1)) return 0;
+    const int size1 = nw / 2;
+    int sym = 1;
+    for (int k = 1; k <= size1; ++k)
+        if (std::fabs(w[size1 + k] - w[size1 - k]) > DBL_EPSILON) { sym = 0; break; }
+    if (!sym) {
+        sym = -1;
+        for (int k = 1; k <= size1; ++k)
+            if (std::fabs(w[size1 + k] + w[size1 - k]) > DBL_EPSILON) { sym = 0; break; }
+    }
+    return sym;
+}
+
 // host-side launch entry points implemented by the kernel translation units --
 struct Corr1dArgs {
     const void *in;
@@ -239,6 +265,8 @@ int launch_corr1d_peer(const Corr1dArgs &a);
 int corr1d_peer_eligible(int dtype, int64_t n, int64_t inner, int nw, int origin);
 // returns B200_OK when it ran, -1 when the shape/alignment is not eligible
 int launch_corr1d_tma(const Corr1dArgs &a);
+// exact tiled path of the 8/16-bit integer dtypes (corr1d_int.cu); -1 = not eligible
+int launch_corr1d_int(const Corr1dArgs &a);
 
 struct Uniform1dArgs {
     const void *in;

@@ -77,22 +77,6 @@ corr1d_generic_kernel(const __grid_constant__ Corr1dGenericParams p)
     }
 }
 
-// symmetry classification of the reference's compiled loop
-static int classify_symmetry(const double *w, int nw)
-{
-    if (!(nw & 1)) return 0;
-    int size1 = nw / 2;
-    int sym = 1;
-    for (int k = 1; k <= size1; ++k)
-        if (std::fabs(w[size1 + k] - w[size1 - k]) > DBL_EPSILON) { sym = 0; break; }
-    if (!sym) {
-        sym = -1;
-        for (int k = 1; k <= size1; ++k)
-            if (std::fabs(w[size1 + k] + w[size1 - k]) > DBL_EPSILON) { sym = 0; break; }
-    }
-    return sym;
-}
-
 static int grid_for(int64_t total, int threads)
 {
     int64_t blocks = (total + threads - 1) / threads;
