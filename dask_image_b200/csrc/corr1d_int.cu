@@ -14,10 +14,12 @@ __global__ void __launch_bounds__(kIntThreads, 8)
 corr1d_int_strided_kernel(const __grid_constant__ IntParams p)
 {
     extern __shared__ __align__(16) unsigned char int_smem[];
-    TS *tile = reinterpret_cast<TS *>(int_smem);
+    IntTap *wc = reinterpret_cast<IntTap *>(int_smem);
+    TS *tile = reinterpret_cast<TS *>(int_smem + kIntTapBytes);
+    int_stage_taps(p, wc, threadIdx.x);
     int_strided_stage<TS>(p, tile, threadIdx.x, blockIdx.x);
     __syncthreads();
-    int_strided_compute<TS, KIND>(p, tile, threadIdx.x, blockIdx.x);
+    int_strided_compute<TS, KIND>(p, tile, wc, threadIdx.x, blockIdx.x);
 }
 
 template <typename TS, int KIND>
@@ -25,11 +27,13 @@ __global__ void __launch_bounds__(kIntThreads, 8)
 corr1d_int_contig_kernel(const __grid_constant__ IntParams p)
 {
     extern __shared__ __align__(16) unsigned char int_smem[];
-    TS *tile = reinterpret_cast<TS *>(int_smem);
+    IntTap *wc = reinterpret_cast<IntTap *>(int_smem);
+    TS *tile = reinterpret_cast<TS *>(int_smem + kIntTapBytes);
     TS *otile = tile + kIntContigRows * p.pitch;
+    int_stage_taps(p, wc, threadIdx.x);
     int_contig_stage<TS>(p, tile, threadIdx.x, blockIdx.x);
     __syncthreads();
-    int_contig_compute<TS, KIND>(p, tile, otile, threadIdx.x, blockIdx.x);
+    int_contig_compute<TS, KIND>(p, tile, otile, wc, threadIdx.x, blockIdx.x);
     __syncthreads();
     int_contig_writeout<TS>(p, otile, threadIdx.x, blockIdx.x);
 }

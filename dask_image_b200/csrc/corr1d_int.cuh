@@ -41,6 +41,7 @@ constexpr int kMaxTapsInt = 129;
 constexpr int kIntThreads = 128;
 constexpr int kIntStridedW = 128;   // strided tiles: columns per tile, one per thread
 constexpr int kIntContigRows = 32;  // contiguous tiles: lines per tile, one per lane
+constexpr int kIntTapBytes = ((kMaxTapsInt * 16 + 127) / 128) * 128;   // shared {w, c} table in front of the tile
 
 struct IntParams {
     const void *in;
@@ -151,19 +152,33 @@ __host__ __device__ __forceinline__ double int_pattern_product(uint64_t sq, doub
 #endif
 }
 
+// One tap: the weight and c = -(2^52 * w).  The tap loop reads the pair from a
+// shared-memory table with one broadcast LDS.128 (an indexed read of the kernel
+// parameters is two LDC.64).
+struct alignas(16) IntTap {
+    double w, c;
+};
+
+__host__ __device__ __forceinline__ void int_stage_taps(const IntParams &p, IntTap *wc, int tid)
+{
+    for (int i = tid; i < p.nw; i += kIntThreads) wc[i] = IntTap{p.w[i], p.c[i]};
+}
+
 // KIND: +1 symmetric, -1 antisymmetric, 0 general.  `s` addresses the element
 // under tap 0 of the first of four consecutive outputs, `step` is the element
 // distance between consecutive positions of the line.  Reads s[0 .. (nw+2)*step].
 // Element q of the line lives in window slot A[q & 3]; element (L - 1 + q') in
 // B[q' & 3]; the tap loop is unrolled four times so that the slots are static.
 template <typename TS, int KIND>
-__host__ __device__ __forceinline__ void int_line_quad(const TS *s, int step, const IntParams &p, double (&acc)[4])
+__host__ __device__ __forceinline__ void int_line_quad(const TS *s, int step, const IntParams &p, const IntTap *wc,
+                                                       double (&acc)[4])
 {
     constexpr bool SV = KIND < 0 || std::is_signed<TS>::value;
     const int L = p.nw;
     const int ns = p.nsteps;
     {
-        const double w = p.w[p.centre], c = p.c[p.centre];
+        const IntTap q = wc[p.centre];
+        const double w = q.w, c = q.c;
         const TS *sc = s + p.centre * step;
 #pragma unroll
         for (int m = 0; m < 4; ++m) acc[m] = int_product<std::is_signed<TS>::value>((int)sc[m * step], w, c);
@@ -190,7 +205,8 @@ __host__ __device__ __forceinline__ void int_line_quad(const TS *s, int step, co
             B[m] = KIND != 0 ? (int)s[(L - 1 + m) * step] : 0;
         }
         run([&]<int U>(int k) {
-            const double w = p.w[k], c = p.c[k];
+            const IntTap q = wc[k];
+            const double w = q.w, c = q.c;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const int a = A[(U + m) & 3];
@@ -211,7 +227,8 @@ __host__ __device__ __forceinline__ void int_line_quad(const TS *s, int step, co
 #pragma unroll
         for (int m = 0; m < 4; ++m) A[m] = int_pattern(hi, (uint32_t)s[m * step]);
         run([&]<int U>(int k) {
-            const double w = p.w[k], c = p.c[k];
+            const IntTap q = wc[k];
+            const double w = q.w, c = q.c;
 #pragma unroll
             for (int m = 0; m < 4; ++m) acc[m] = int_add(acc[m], int_pattern_product(A[(U + m) & 3], w, c));
             A[U] = int_pattern(hi, (uint32_t)*sa);
@@ -290,22 +307,24 @@ __host__ __device__ __forceinline__ void int_strided_stage(const IntParams &p, T
 }
 
 template <typename TS, int KIND>
-__host__ __device__ __forceinline__ void int_strided_compute(const IntParams &p, const TS *tile, int tid,
-                                                             int64_t bid)
+__host__ __device__ __forceinline__ void int_strided_compute(const IntParams &p, const TS *tile, const IntTap *wc,
+                                                             int tid, int64_t bid)
 {
     constexpr int W = kIntStridedW;
     const IntStridedTile t(p, bid);
+    // (no early exit for the columns past the array: the tap loop stays convergent,
+    // which keeps the weights on the uniform datapath; only the stores are predicated)
     const int64_t col = t.col0 + tid;
-    if (col >= p.inner) return;
+    const bool live = col < p.inner;
     TS *out_col = (TS *)p.out + t.o * p.n * p.inner + col;
     for (int r0 = 0; r0 < p.tile_out; r0 += 4) {
         if (t.row0 + r0 >= p.n) break;
         double acc[4];
-        int_line_quad<TS, KIND>(tile + r0 * W + tid, W, p, acc);
+        int_line_quad<TS, KIND>(tile + r0 * W + tid, W, p, wc, acc);
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int64_t row = t.row0 + r0 + m;
-            if (row < p.n) {
+            if (live && row < p.n) {
                 TS *dst = out_col + row * p.inner;
                 *dst = int_finish<TS>(acc[m], dst, p.epilogue);
             }
@@ -366,8 +385,8 @@ __host__ __device__ __forceinline__ void int_contig_stage(const IntParams &p, TS
 }
 
 template <typename TS, int KIND>
-__host__ __device__ __forceinline__ void int_contig_compute(const IntParams &p, const TS *tile, TS *otile, int tid,
-                                                            int64_t bid)
+__host__ __device__ __forceinline__ void int_contig_compute(const IntParams &p, const TS *tile, TS *otile,
+                                                            const IntTap *wc, int tid, int64_t bid)
 {
     const IntContigTile t(p, bid);
     const int warp = tid >> 5, lane = tid & 31;
@@ -375,10 +394,11 @@ __host__ __device__ __forceinline__ void int_contig_compute(const IntParams &p, 
     const TS *line = tile + lane * p.pitch + p.shift;
     TS *oline = otile + lane * p.opitch;
     for (int g = 0; g < per_warp; g += 4) {
+        // (groups past the end of a ragged line are computed and dropped: a per-warp
+        // exit would take the weights off the uniform datapath)
         const int xo = warp * per_warp + g;
-        if (t.x0 + xo >= p.n) break;
         double acc[4];
-        int_line_quad<TS, KIND>(line + xo, 1, p, acc);
+        int_line_quad<TS, KIND>(line + xo, 1, p, wc, acc);
         TS r[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) r[m] = cast_out<TS>(acc[m]);
@@ -505,7 +525,7 @@ inline int plan_corr1d_int(const Corr1dArgs &a, IntPlan &pl, int symmetry)
         p.n_tiles = 1;
         const int64_t row_tiles = (p.outer + kIntContigRows - 1) / kIntContigRows;
         pl.blocks = row_tiles * p.c_tiles;
-        pl.smem_bytes = (size_t)kIntContigRows * (p.pitch + p.opitch) * sz;
+        pl.smem_bytes = kIntTapBytes + (size_t)kIntContigRows * (p.pitch + p.opitch) * sz;
     } else {
         if (p.inner >= (1ll << 31) || p.n >= (1ll << 31) - 4096) return -1;
         p.vec = (p.inner % A == 0) && ((uintptr_t)a.in % 16 == 0);
@@ -516,7 +536,7 @@ inline int plan_corr1d_int(const Corr1dArgs &a, IntPlan &pl, int symmetry)
         p.n_tiles = (int)((p.n + p.tile_out - 1) / p.tile_out);
         p.c_tiles = (int)((p.inner + kIntStridedW - 1) / kIntStridedW);
         pl.blocks = p.outer * (int64_t)p.n_tiles * p.c_tiles;
-        pl.smem_bytes = (size_t)p.tile_len * kIntStridedW * sz;
+        pl.smem_bytes = kIntTapBytes + (size_t)p.tile_len * kIntStridedW * sz;
     }
     if (pl.blocks < 1 || pl.blocks >= (1ll << 31)) return -1;
     return 0;

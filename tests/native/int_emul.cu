@@ -21,18 +21,20 @@ static void run_blocks(const IntPlan &pl)
 {
     const IntParams &p = pl.p;
     std::vector<unsigned char> smem(pl.smem_bytes + 16);
-    TS *tile = reinterpret_cast<TS *>(smem.data());
+    IntTap *wc = reinterpret_cast<IntTap *>(smem.data());
+    TS *tile = reinterpret_cast<TS *>(smem.data() + kIntTapBytes);
     for (int64_t bid = 0; bid < pl.blocks; ++bid) {
         // poison the tile so that a read of an element no thread staged shows up
         for (size_t i = 0; i < smem.size(); ++i) smem[i] = 0xA5;
+        for (int t = 0; t < kIntThreads; ++t) int_stage_taps(p, wc, t);
         if (pl.contig) {
             TS *otile = tile + kIntContigRows * p.pitch;
             for (int t = 0; t < kIntThreads; ++t) int_contig_stage<TS>(p, tile, t, bid);
-            for (int t = 0; t < kIntThreads; ++t) int_contig_compute<TS, KIND>(p, tile, otile, t, bid);
+            for (int t = 0; t < kIntThreads; ++t) int_contig_compute<TS, KIND>(p, tile, otile, wc, t, bid);
             for (int t = 0; t < kIntThreads; ++t) int_contig_writeout<TS>(p, otile, t, bid);
         } else {
             for (int t = 0; t < kIntThreads; ++t) int_strided_stage<TS>(p, tile, t, bid);
-            for (int t = 0; t < kIntThreads; ++t) int_strided_compute<TS, KIND>(p, tile, t, bid);
+            for (int t = 0; t < kIntThreads; ++t) int_strided_compute<TS, KIND>(p, tile, wc, t, bid);
         }
     }
 }
