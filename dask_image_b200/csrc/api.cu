@@ -253,6 +253,10 @@ int b200_correlate_nd(const void *in, void *out, int dtype, int ndim, const int6
         int rc = launch_corrnd_tiled(a);
         if (rc >= 0) return rc;
     }
+    if (!is_float && !(flags & B200_FLAG_EXACT)) {
+        int rc = launch_corrnd_int(a);
+        if (rc >= 0) return rc;
+    }
     if (flags & B200_FLAG_FORCE_FAST)
         return set_error(B200_EINVAL, "no tiled kernel is eligible for this call");
     return launch_corrnd_generic(a);

@@ -303,6 +303,8 @@ struct CorrNdArgs {
 };
 int launch_corrnd_generic(const CorrNdArgs &a);
 int launch_corrnd_tiled(const CorrNdArgs &a);
+// exact tiled path of the 8/16-bit integer dtypes, 2-D / 3-D (corrnd_int.cu); -1 = not eligible
+int launch_corrnd_int(const CorrNdArgs &a);
 
 int launch_combine(void *acc, const void *src, int dtype, int64_t n, int op, cudaStream_t stream);
 

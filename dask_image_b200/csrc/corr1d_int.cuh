@@ -164,6 +164,57 @@ __host__ __device__ __forceinline__ void int_stage_taps(const IntParams &p, IntT
     for (int i = tid; i < p.nw; i += kIntThreads) wc[i] = IntTap{p.w[i], p.c[i]};
 }
 
+// Steps 0 .. ns-1 through `one.operator()<U>(k)` with U = k & 3 static: the
+// window slots of the callers rotate with period four.
+template <typename F>
+__host__ __device__ __forceinline__ void int_run_steps(int ns, F &&one)
+{
+    int k = 0;
+    for (; k + 4 <= ns; k += 4) {
+        one.template operator()<0>(k);
+        one.template operator()<1>(k + 1);
+        one.template operator()<2>(k + 2);
+        one.template operator()<3>(k + 3);
+    }
+    if (k < ns) one.template operator()<0>(k);
+    if (k + 1 < ns) one.template operator()<1>(k + 1);
+    if (k + 2 < ns) one.template operator()<2>(k + 2);
+}
+
+// acc[m] += x[m + k] * w[k] for k = 0 .. ns-1, in that order, for four
+// consecutive outputs m: the single-tap walk (general 1-D weights, and every
+// weight row of the N-D correlate).  `s` addresses x[0], `step` is the element
+// distance between consecutive positions.  Reads s[0 .. (ns+3)*step].
+template <typename TS>
+__host__ __device__ __forceinline__ void int_quad_taps(const TS *s, int step, int ns, const IntTap *wc, uint32_t hi,
+                                                       double (&acc)[4])
+{
+    const TS *sa = s + 4 * step;   // next element entering the window
+    if constexpr (std::is_signed<TS>::value) {
+        int A[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) A[m] = (int)s[m * step];
+        int_run_steps(ns, [&]<int U>(int k) {
+            const IntTap q = wc[k];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[m] = int_add(acc[m], int_product<true>(A[(U + m) & 3], q.w, q.c));
+            A[U] = (int)*sa;
+            sa += step;
+        });
+    } else {
+        uint64_t A[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) A[m] = int_pattern(hi, (uint32_t)s[m * step]);
+        int_run_steps(ns, [&]<int U>(int k) {
+            const IntTap q = wc[k];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[m] = int_add(acc[m], int_pattern_product(A[(U + m) & 3], q.w, q.c));
+            A[U] = int_pattern(hi, (uint32_t)*sa);
+            sa += step;
+        });
+    }
+}
+
 // KIND: +1 symmetric, -1 antisymmetric, 0 general.  `s` addresses the element
 // under tap 0 of the first of four consecutive outputs, `step` is the element
 // distance between consecutive positions of the line.  Reads s[0 .. (nw+2)*step].
@@ -175,64 +226,35 @@ __host__ __device__ __forceinline__ void int_line_quad(const TS *s, int step, co
 {
     constexpr bool SV = KIND < 0 || std::is_signed<TS>::value;
     const int L = p.nw;
-    const int ns = p.nsteps;
     {
         const IntTap q = wc[p.centre];
-        const double w = q.w, c = q.c;
         const TS *sc = s + p.centre * step;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) acc[m] = int_product<std::is_signed<TS>::value>((int)sc[m * step], w, c);
+        for (int m = 0; m < 4; ++m) acc[m] = int_product<std::is_signed<TS>::value>((int)sc[m * step], q.w, q.c);
     }
-    const TS *sa = s + 4 * step;         // next element entering the left window
-    const TS *sb = s + (L - 2) * step;   // next element entering the right window
-    auto run = [&](auto &&one) {
-        int k = 0;
-        for (; k + 4 <= ns; k += 4) {
-            one.template operator()<0>(k);
-            one.template operator()<1>(k + 1);
-            one.template operator()<2>(k + 2);
-            one.template operator()<3>(k + 3);
-        }
-        if (k < ns) one.template operator()<0>(k);
-        if (k + 1 < ns) one.template operator()<1>(k + 1);
-        if (k + 2 < ns) one.template operator()<2>(k + 2);
-    };
-    if constexpr (SV || KIND != 0) {
+    if constexpr (KIND == 0) {
+        int_quad_taps<TS>(s, step, p.nsteps, wc, p.hi_word, acc);
+    } else {
+        const TS *sa = s + 4 * step;         // next element entering the left window
+        const TS *sb = s + (L - 2) * step;   // next element entering the right window
         int A[4], B[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             A[m] = (int)s[m * step];
-            B[m] = KIND != 0 ? (int)s[(L - 1 + m) * step] : 0;
+            B[m] = (int)s[(L - 1 + m) * step];
         }
-        run([&]<int U>(int k) {
+        int_run_steps(p.nsteps, [&]<int U>(int k) {
             const IntTap q = wc[k];
-            const double w = q.w, c = q.c;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const int a = A[(U + m) & 3];
                 const int b = B[(m - U) & 3];
-                const int v = KIND > 0 ? a + b : (KIND < 0 ? a - b : a);
-                acc[m] = int_add(acc[m], int_product<SV>(v, w, c));
+                acc[m] = int_add(acc[m], int_product<SV>(KIND > 0 ? a + b : a - b, q.w, q.c));
             }
             A[U] = (int)*sa;
             sa += step;
-            if constexpr (KIND != 0) {
-                B[(3 - U) & 3] = (int)*sb;
-                sb -= step;
-            }
-        });
-    } else {
-        uint64_t A[4];
-        const uint32_t hi = p.hi_word;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) A[m] = int_pattern(hi, (uint32_t)s[m * step]);
-        run([&]<int U>(int k) {
-            const IntTap q = wc[k];
-            const double w = q.w, c = q.c;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) acc[m] = int_add(acc[m], int_pattern_product(A[(U + m) & 3], w, c));
-            A[U] = int_pattern(hi, (uint32_t)*sa);
-            sa += step;
+            B[(3 - U) & 3] = (int)*sb;
+            sb -= step;
         });
     }
 }

@@ -1,0 +1,65 @@
+// corrnd_int.cu -- kernel and launcher of the exact tiled N-D correlate for
+// uint8 / int8 / uint16 / int16 arrays (see corrnd_int.cuh).  Bounded by FP64
+// issue: two FP64 instructions per tap and output.
+#include "corrnd_int.cuh"
+#include <mutex>
+
+namespace b200 {
+
+template <typename TS>
+__global__ void __launch_bounds__(kIntThreads, 8)
+corrnd_int_kernel(const __grid_constant__ IntNdParams p)
+{
+    extern __shared__ __align__(16) unsigned char int_nd_smem[];
+    IntTap *wc = reinterpret_cast<IntTap *>(int_nd_smem);
+    TS *tile = reinterpret_cast<TS *>(int_nd_smem + int_nd_tap_bytes(p.ntaps));
+    TS *otile = tile + p.KZ * p.stage_lines * p.pitch;
+    int_nd_stage_taps(p, wc, threadIdx.x);
+    int_nd_stage<TS>(p, tile, threadIdx.x, blockIdx.x);
+    __syncthreads();
+    int_nd_compute<TS>(p, tile, otile, wc, threadIdx.x, blockIdx.x);
+    __syncthreads();
+    int_nd_writeout<TS>(p, otile, threadIdx.x, blockIdx.x);
+}
+
+template <typename TS>
+static int launch_nd_typed(const IntNdPlan &pl, cudaStream_t stream)
+{
+    static std::once_flag once;
+    static cudaError_t attr = cudaSuccess;
+    std::call_once(once, [] {
+        attr = cudaFuncSetAttribute(corrnd_int_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kIntNdMaxSmem);
+    });
+    if (attr != cudaSuccess) return check_cuda(attr, "corrnd_int shared memory opt-in");
+    corrnd_int_kernel<TS><<<(unsigned)pl.blocks, kIntThreads, pl.smem_bytes, stream>>>(pl.p);
+    return check_cuda(cudaGetLastError(), "corrnd_int launch");
+}
+
+// returns B200_OK when it ran, -1 when the call is not eligible
+int launch_corrnd_int(const CorrNdArgs &a)
+{
+    IntNdPlan pl{};
+    if (plan_corrnd_int(a, pl) != 0) return -1;
+    IntTap *dev = nullptr;
+    const size_t bytes = sizeof(IntTap) * pl.taps.size();
+    B200_CUDA_TRY(cudaMallocAsync((void **)&dev, bytes, a.stream));
+    int rc = check_cuda(cudaMemcpyAsync(dev, pl.taps.data(), bytes, cudaMemcpyHostToDevice, a.stream),
+                        "corrnd_int taps upload");
+    if (!rc) {
+        pl.p.taps = dev;
+        switch (a.dtype) {
+        case B200_U8: rc = launch_nd_typed<uint8_t>(pl, a.stream); break;
+        case B200_I8: rc = launch_nd_typed<int8_t>(pl, a.stream); break;
+        case B200_U16: rc = launch_nd_typed<uint16_t>(pl, a.stream); break;
+        default: rc = launch_nd_typed<int16_t>(pl, a.stream); break;
+        }
+    }
+    cudaFreeAsync(dev, a.stream);
+    if (rc) return rc;
+    count_launch();
+    note_kernel("corrnd_int");
+    return B200_OK;
+}
+
+}  // namespace b200

@@ -6,7 +6,7 @@
 // __syncthreads() in the kernel is the boundary between two loops over the
 // threads here) -- and the CPU test suite compares the result with the oracle.
 // Built by tests/test_int_emul.py with `nvcc -x cu` (host code only; no GPU).
-#include "../../dask_image_b200/csrc/corr1d_int.cuh"
+#include "../../dask_image_b200/csrc/corrnd_int.cuh"
 #include <vector>
 
 namespace b200 {
@@ -69,6 +69,48 @@ extern "C" int emul_correlate1d_int(const void *in, void *out, int dtype, int nd
     case B200_I8: run_kind<int8_t>(pl); break;
     case B200_U16: run_kind<uint16_t>(pl); break;
     default: run_kind<int16_t>(pl); break;
+    }
+    return 0;
+}
+
+template <typename TS>
+static void run_nd_blocks(const IntNdPlan &pl)
+{
+    const IntNdParams &p = pl.p;
+    std::vector<unsigned char> smem(pl.smem_bytes + 16);
+    IntTap *wc = reinterpret_cast<IntTap *>(smem.data());
+    TS *tile = reinterpret_cast<TS *>(smem.data() + int_nd_tap_bytes(p.ntaps));
+    TS *otile = tile + p.KZ * p.stage_lines * p.pitch;
+    for (int64_t bid = 0; bid < pl.blocks; ++bid) {
+        for (size_t i = 0; i < smem.size(); ++i) smem[i] = 0xA5;
+        for (int t = 0; t < kIntThreads; ++t) int_nd_stage_taps(p, wc, t);
+        for (int t = 0; t < kIntThreads; ++t) int_nd_stage<TS>(p, tile, t, bid);
+        for (int t = 0; t < kIntThreads; ++t) int_nd_compute<TS>(p, tile, otile, wc, t, bid);
+        for (int t = 0; t < kIntThreads; ++t) int_nd_writeout<TS>(p, otile, t, bid);
+    }
+}
+
+// Same argument meaning as b200_correlate_nd (host pointers); info = {blocks, smem_bytes, vec, tile_out}.
+extern "C" int emul_correlate_nd_int(const void *in, void *out, int dtype, int ndim, const int64_t *shape,
+                                     const double *weights, const int64_t *wshape, const int64_t *origins, int mode,
+                                     double cval, int64_t pad_lo, int64_t pad_hi, int64_t *info)
+{
+    CorrNdArgs a;
+    a.in = in; a.out = out; a.dtype = dtype; a.ndim = ndim;
+    for (int d = 0; d < ndim; ++d) {
+        a.shape[d] = shape[d]; a.wshape[d] = wshape[d]; a.origins[d] = origins[d];
+    }
+    a.w = weights; a.mode = mode; a.cval = cval; a.pad_lo = pad_lo; a.pad_hi = pad_hi;
+    a.flags = 0; a.stream = nullptr;
+    IntNdPlan pl{};
+    if (plan_corrnd_int(a, pl) != 0) return -1;
+    pl.p.taps = pl.taps.data();
+    info[0] = pl.blocks; info[1] = (int64_t)pl.smem_bytes; info[2] = pl.p.vec; info[3] = pl.p.tile_out;
+    switch (dtype) {
+    case B200_U8: run_nd_blocks<uint8_t>(pl); break;
+    case B200_I8: run_nd_blocks<int8_t>(pl); break;
+    case B200_U16: run_nd_blocks<uint16_t>(pl); break;
+    default: run_nd_blocks<int16_t>(pl); break;
     }
     return 0;
 }

@@ -113,3 +113,48 @@ def test_int_chains_bitwise(b200, dtype):
                                           orc.gaussian_gradient_magnitude(x, 1.0, mode=mode))
             np.testing.assert_array_equal(b200.ndimage.gaussian_laplace(d, 1.0, mode=mode).to_numpy(),
                                           orc.gaussian_laplace(x, 1.0, mode=mode))
+
+
+# ---------------------------------------------------------------------------
+# N-D correlate / convolve (corrnd_int.cu)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_int_correlate_nd_bitwise(b200, dtype):
+    from dask_image_b200 import _lib
+    from test_int_emul import ND_CASES, nd_weights
+
+    for shape, wshape in ND_CASES + [((300, 272), (3, 3)), ((20, 70, 256), (3, 3, 3))]:
+        rng = np.random.default_rng(hash((dtype, shape, wshape)) % (1 << 32))
+        x = data(rng, shape, dtype)
+        d = dev(b200, x)
+        w = nd_weights(rng, wshape)
+        small = np.prod(wshape) < 100
+        for mode in (MODES if small else ["reflect", "wrap"]):
+            origin_sets = [0, [-(k // 2) for k in wshape], [(k - 1) // 2 for k in wshape]]
+            for origin in (origin_sets if small else [0]):
+                cval = 0.0 if mode != "constant" else 9.0
+                got = b200.ndimage.correlate(d, w, mode=mode, cval=cval, origin=origin)
+                assert _lib.last_kernel() == "corrnd_int", _lib.last_kernel()
+                ref = orc.correlate(x, w, mode=mode, cval=cval, origin=origin)
+                np.testing.assert_array_equal(got.to_numpy(), ref, err_msg=str((shape, wshape, mode, origin)))
+        got = b200.ndimage.convolve(d, w, mode="mirror")
+        np.testing.assert_array_equal(got.to_numpy(), orc.convolve(x, w, mode="mirror"))
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "int16"])
+def test_int_correlate_nd_equals_generic_kernel(b200, dtype):
+    from dask_image_b200 import _lib
+
+    rng = np.random.default_rng(12)
+    x = data(rng, (48, 96, 128), dtype)
+    d = dev(b200, x)
+    w = rng.standard_normal((3, 5, 3))
+    fast = b200.ndimage.correlate(d, w, mode="nearest").to_numpy()
+    assert _lib.last_kernel() == "corrnd_int"
+    old = b200.ndimage.set_default_flags(_lib.FLAG_EXACT)
+    try:
+        exact = b200.ndimage.correlate(d, w, mode="nearest").to_numpy()
+        assert _lib.last_kernel() == "corrnd_generic"
+    finally:
+        b200.ndimage.set_default_flags(old)
+    np.testing.assert_array_equal(fast, exact)

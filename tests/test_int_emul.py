@@ -23,7 +23,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "native", "int_emul.cu")
 OUT = os.path.join(HERE, "native", "_build", "libint_emul.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-DEPS = [SRC] + [os.path.join(HERE, "..", "dask_image_b200", "csrc", f) for f in ("corr1d_int.cuh", "common.cuh")]
+DEPS = [SRC] + [os.path.join(HERE, "..", "dask_image_b200", "csrc", f)
+                for f in ("corr1d_int.cuh", "corrnd_int.cuh", "common.cuh")]
 
 MODES = ["reflect", "mirror", "nearest", "wrap", "constant"]
 DTYPES = ["uint8", "int8", "uint16", "int16"]
@@ -40,6 +41,7 @@ def emul():
                                "-Xcompiler", "-fPIC,-fno-strict-aliasing", "-shared", "-x", "cu", SRC, "-o", OUT])
     lib = ctypes.CDLL(OUT)
     lib.emul_correlate1d_int.restype = ctypes.c_int
+    lib.emul_correlate_nd_int.restype = ctypes.c_int
     return lib
 
 
@@ -187,3 +189,85 @@ def test_emulated_kernels_decline_what_they_cannot_hold(emul):
     assert run_emul(emul, x, np.ones(131), 0, "reflect")[0] is None        # more taps than the parameter block holds
     assert run_emul(emul, x, np.array([1.0, np.inf, 1.0]), 0, "reflect")[0] is None
     assert run_emul(emul, x.astype(np.int32), w, 0, "reflect")[0] is None  # 32-bit sums leave the low word
+
+
+# ---------------------------------------------------------------------------
+# N-D correlate (corrnd_int.cuh)
+# ---------------------------------------------------------------------------
+def run_emul_nd(lib, x, w, mode, cval=0.0, origin=0, pad=(0, 0)):
+    x = np.ascontiguousarray(x)
+    shape = list(x.shape)
+    shape[0] -= pad[0] + pad[1]
+    out = np.zeros(shape, dtype=x.dtype)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    origins = [origin] * x.ndim if np.isscalar(origin) else list(origin)
+    plane = int(np.prod(shape[1:])) * x.dtype.itemsize
+    info = (ctypes.c_int64 * 8)()
+    rc = lib.emul_correlate_nd_int(
+        ctypes.c_void_p(x.ctypes.data + pad[0] * plane), ctypes.c_void_p(out.ctypes.data),
+        ctypes.c_int(_lib.DTYPE_CODES[x.dtype.name]), ctypes.c_int(x.ndim), _lib.i64_array(shape),
+        w.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _lib.i64_array(w.shape), _lib.i64_array(origins),
+        ctypes.c_int(_lib.mode_code(mode)), ctypes.c_double(cval), ctypes.c_int64(pad[0]), ctypes.c_int64(pad[1]),
+        info)
+    if rc != 0:
+        return None, None
+    return out, dict(blocks=info[0], smem=info[1], vec=info[2], tile_out=info[3])
+
+
+ND_CASES = [
+    ((70, 144), (3, 3)), ((70, 144), (5, 4)), ((37, 50), (1, 7)), ((37, 50), (6, 1)), ((33, 130), (2, 2)),
+    ((9, 40, 48), (3, 3, 3)), ((6, 35, 21), (2, 3, 4)), ((5, 34, 160), (1, 5, 5)), ((12, 9, 16), (5, 1, 1)),
+    ((3, 4), (5, 7)), ((10, 66, 144), (9, 9, 9)),
+]
+
+
+def nd_weights(rng, wshape):
+    w = rng.standard_normal(wshape)
+    w.reshape(-1)[::5] = 0.0          # taps the reference skips
+    w.reshape(-1)[1::7] = 1e-17       # |w| <= DBL_EPSILON: skipped as well
+    return w
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,wshape", ND_CASES)
+def test_emulated_nd_kernel_matches_oracle(emul, dtype, shape, wshape):
+    rng = np.random.default_rng(hash((dtype, shape, wshape)) % (1 << 32))
+    x = data(rng, shape, dtype)
+    w = nd_weights(rng, wshape)
+    small = np.prod(wshape) < 100
+    for mode in (MODES if small else ["reflect", "wrap"]):
+        origin_sets = [0, [-(k // 2) for k in wshape], [(k - 1) // 2 for k in wshape]]
+        for origin in (origin_sets if small else [0]):
+            cval = 0.0 if mode != "constant" else 9.0
+            got, info = run_emul_nd(emul, x, w, mode, cval, origin)
+            assert got is not None
+            ref = oracle.correlate(x, w, mode=mode, cval=cval, origin=origin)
+            np.testing.assert_array_equal(got, ref, err_msg=str((mode, origin, info)))
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "int16"])
+@pytest.mark.parametrize("shape,wshape", [((41, 6, 32), (5, 3, 3)), ((41, 48), (4, 3))])
+def test_emulated_nd_slab_pads_equal_whole_volume(emul, dtype, shape, wshape):
+    rng = np.random.default_rng(6)
+    x = data(rng, shape, dtype)
+    w = rng.standard_normal(wshape)
+    for mode in ["reflect", "mirror", "nearest", "constant"]:
+        for origin0 in (0, -1):
+            origin = [origin0] + [0] * (len(shape) - 1)
+            ref = oracle.correlate(x, w, mode=mode, cval=4.0, origin=origin)
+            lo, hi = wshape[0] // 2 + origin0, wshape[0] - 1 - wshape[0] // 2 - origin0
+            for a, b in [(0, 13), (13, 29), (29, 41)]:
+                pl = 0 if a == 0 else lo
+                ph = 0 if b == 41 else hi
+                got, _ = run_emul_nd(emul, x[a - pl:b + ph], w, mode, 4.0, origin, pad=(pl, ph))
+                assert got is not None
+                np.testing.assert_array_equal(got, ref[a:b], err_msg=str((mode, origin0, a, b)))
+
+
+def test_emulated_nd_kernel_declines(emul):
+    x = np.zeros((8, 32), dtype=np.uint16)
+    w = np.ones((3, 3))
+    assert run_emul_nd(emul, x, w, "constant", cval=0.5)[0] is None
+    assert run_emul_nd(emul, x.reshape(2, 4, 8, 4), np.ones((1, 3, 3, 3)), "reflect")[0] is None   # 4-D
+    assert run_emul_nd(emul, x.astype(np.uint32), w, "reflect")[0] is None
+    assert run_emul_nd(emul, np.zeros((4, 40, 40), np.uint8), np.ones((11, 11, 11)), "reflect")[0] is None
