@@ -215,6 +215,36 @@ __host__ __device__ __forceinline__ void int_quad_taps(const TS *s, int step, in
     }
 }
 
+// The same walk with the tap count known at compile time (short weight rows of
+// the N-D correlate): the NT + 3 elements are loaded once, no loop, no window
+// rotation.
+template <typename TS, int NT>
+__host__ __device__ __forceinline__ void int_quad_taps_static(const TS *s, const IntTap *wc, uint32_t hi,
+                                                              double (&acc)[4])
+{
+    if constexpr (std::is_signed<TS>::value) {
+        int x[NT + 3];
+#pragma unroll
+        for (int i = 0; i < NT + 3; ++i) x[i] = (int)s[i];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            const IntTap q = wc[k];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[m] = int_add(acc[m], int_product<true>(x[m + k], q.w, q.c));
+        }
+    } else {
+        uint64_t x[NT + 3];
+#pragma unroll
+        for (int i = 0; i < NT + 3; ++i) x[i] = int_pattern(hi, (uint32_t)s[i]);
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            const IntTap q = wc[k];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[m] = int_add(acc[m], int_pattern_product(x[m + k], q.w, q.c));
+        }
+    }
+}
+
 // KIND: +1 symmetric, -1 antisymmetric, 0 general.  `s` addresses the element
 // under tap 0 of the first of four consecutive outputs, `step` is the element
 // distance between consecutive positions of the line.  Reads s[0 .. (nw+2)*step].

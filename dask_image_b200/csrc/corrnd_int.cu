@@ -12,10 +12,13 @@ corrnd_int_kernel(const __grid_constant__ IntNdParams p)
 {
     extern __shared__ __align__(16) unsigned char int_nd_smem[];
     IntTap *wc = reinterpret_cast<IntTap *>(int_nd_smem);
-    TS *tile = reinterpret_cast<TS *>(int_nd_smem + int_nd_tap_bytes(p.ntaps));
+    int64_t *table = reinterpret_cast<int64_t *>(int_nd_smem + int_nd_tap_bytes(p.ntaps));
+    TS *tile = reinterpret_cast<TS *>(int_nd_smem + int_nd_tap_bytes(p.ntaps) + int_nd_table_bytes(p));
     TS *otile = tile + p.KZ * p.stage_lines * p.pitch;
     int_nd_stage_taps(p, wc, threadIdx.x);
-    int_nd_stage<TS>(p, tile, threadIdx.x, blockIdx.x);
+    int_nd_stage_lines(p, table, threadIdx.x, blockIdx.x);
+    __syncthreads();
+    int_nd_stage<TS>(p, tile, table, threadIdx.x, blockIdx.x);
     __syncthreads();
     int_nd_compute<TS>(p, tile, otile, wc, threadIdx.x, blockIdx.x);
     __syncthreads();

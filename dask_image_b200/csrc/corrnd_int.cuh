@@ -39,6 +39,7 @@ struct IntNdParams {
     int vec;
     int c_tiles, y_tiles;
     uint32_t hi_word;
+    uint32_t vpr_magic, ly_magic;   // ceil(2^32 / d) for d = vectors per line, staged lines per plane
 };
 
 struct IntNdTile {
@@ -55,6 +56,40 @@ struct IntNdTile {
 };
 
 __host__ __device__ __forceinline__ size_t int_nd_tap_bytes(int ntaps) { return ((size_t)ntaps * 16 + 127) / 128 * 128; }
+__host__ __device__ __forceinline__ size_t int_nd_table_bytes(const IntNdParams &p)
+{
+    return ((size_t)p.KZ * p.stage_lines * 8 + 127) / 128 * 128;
+}
+
+// v / d for v < 2^16 with magic = ceil(2^32 / d), d <= 2^16 (exact: the error term v * (magic * d - 2^32)
+// stays below 2^32)
+__host__ __device__ __forceinline__ uint32_t int_div_magic(uint32_t v, uint32_t magic)
+{
+#ifdef __CUDA_ARCH__
+    return __umulhi(v, magic);
+#else
+    return (uint32_t)(((uint64_t)v * magic) >> 32);
+#endif
+}
+
+// Source of every staged line: element offset of its row (z, y) in the array, or
+// INT64_MIN when the row lies outside under mode 'constant'.  One entry per line, computed
+// once per tile (the extension map costs 64-bit compares and, on the edges, a modulo).
+__host__ __device__ __forceinline__ void int_nd_stage_lines(const IntNdParams &p, int64_t *table, int tid, int64_t bid)
+{
+    const IntNdTile t(p, bid);
+    const int LY = p.stage_lines;
+    for (int line = tid; line < p.KZ * LY; line += kIntThreads) {
+        const int lz = (int)int_div_magic((uint32_t)line, p.ly_magic), ly = line - lz * LY;
+        const int64_t zpos = t.z - p.loz + lz, ypos = t.y0 - p.loy + ly;
+        const int64_t zs = p.pad_axis == 0 ? ext_index_padded(zpos, p.Z, p.mode, p.pad_lo, p.pad_hi)
+                                           : ext_index_padded(zpos, p.Z, p.mode, 0, 0);
+        const int64_t ys = p.pad_axis == 1 ? ext_index_padded(ypos, p.Y, p.mode, p.pad_lo, p.pad_hi)
+                                           : ext_index_padded(ypos, p.Y, p.mode, 0, 0);
+        // (a padded slab addresses rows in front of `in`: offsets may be negative, the flag is separate)
+        table[line] = (zs == B200_USE_CVAL || ys == B200_USE_CVAL) ? INT64_MIN : (zs * p.Y + ys) * p.X;
+    }
+}
 
 __host__ __device__ __forceinline__ void int_nd_stage_taps(const IntNdParams &p, IntTap *wc, int tid)
 {
@@ -62,31 +97,27 @@ __host__ __device__ __forceinline__ void int_nd_stage_taps(const IntNdParams &p,
 }
 
 template <typename TS>
-__host__ __device__ __forceinline__ void int_nd_stage(const IntNdParams &p, TS *tile, int tid, int64_t bid)
+__host__ __device__ __forceinline__ void int_nd_stage(const IntNdParams &p, TS *tile, const int64_t *table, int tid,
+                                                      int64_t bid)
 {
     constexpr int A = 16 / (int)sizeof(TS);
     const IntNdTile t(p, bid);
     const TS *in = (const TS *)p.in;
-    const int PC = p.tile_len, P = p.pitch, LY = p.stage_lines;
+    const int PC = p.tile_len, P = p.pitch;
     const int VPR = PC / A;
-    const int nvec = p.KZ * LY * VPR;
+    const int nvec = p.KZ * p.stage_lines * VPR;
     TS fill[A];
 #pragma unroll
     for (int e = 0; e < A; ++e) fill[e] = (TS)p.cval;
     uint4 cvec;
     memcpy(&cvec, fill, 16);
     for (int v = tid; v < nvec; v += kIntThreads) {
-        const int line = v / VPR, cv = v - line * VPR;
-        const int lz = line / LY, ly = line - lz * LY;
-        const int64_t zpos = t.z - p.loz + lz, ypos = t.y0 - p.loy + ly;
-        const int64_t zs = p.pad_axis == 0 ? ext_index_padded(zpos, p.Z, p.mode, p.pad_lo, p.pad_hi)
-                                           : ext_index_padded(zpos, p.Z, p.mode, 0, 0);
-        const int64_t ys = p.pad_axis == 1 ? ext_index_padded(ypos, p.Y, p.mode, p.pad_lo, p.pad_hi)
-                                           : ext_index_padded(ypos, p.Y, p.mode, 0, 0);
+        const int line = (int)int_div_magic((uint32_t)v, p.vpr_magic), cv = v - line * VPR;
+        const int64_t off = table[line];
         const int64_t pos = t.g0 + cv * A;
         uint4 val = cvec;
-        if (zs != B200_USE_CVAL && ys != B200_USE_CVAL) {
-            const TS *src = in + (zs * p.Y + ys) * p.X;
+        if (off != INT64_MIN) {
+            const TS *src = in + off;
             if (p.vec && pos >= 0 && pos + A <= p.X) {
                 val = *reinterpret_cast<const uint4 *>(src + pos);
             } else {
@@ -105,9 +136,10 @@ __host__ __device__ __forceinline__ void int_nd_stage(const IntNdParams &p, TS *
     }
 }
 
-template <typename TS>
-__host__ __device__ __forceinline__ void int_nd_compute(const IntNdParams &p, const TS *tile, TS *otile,
-                                                        const IntTap *wc, int tid, int64_t bid)
+// KXS = taps per weight row when it is one of the short static cases, 0 = run-time loop
+template <typename TS, int KXS>
+__host__ __device__ __forceinline__ void int_nd_compute_kx(const IntNdParams &p, const TS *tile, TS *otile,
+                                                           const IntTap *wc, int tid)
 {
     const int warp = tid >> 5, lane = tid & 31;
     const int per_warp = p.tile_out / (kIntThreads / 32);   // multiple of 4
@@ -119,8 +151,10 @@ __host__ __device__ __forceinline__ void int_nd_compute(const IntNdParams &p, co
         const IntTap *wrow = wc;
         for (int kz = 0; kz < p.KZ; ++kz) {
             const TS *row = tile + (kz * LY + lane) * P + p.shift + xo;
-            for (int ky = 0; ky < p.KY; ++ky, row += P, wrow += p.KX)
-                int_quad_taps<TS>(row, 1, p.KX, wrow, p.hi_word, acc);
+            for (int ky = 0; ky < p.KY; ++ky, row += P, wrow += p.KX) {
+                if constexpr (KXS > 0) int_quad_taps_static<TS, KXS>(row, wrow, p.hi_word, acc);
+                else int_quad_taps<TS>(row, 1, p.KX, wrow, p.hi_word, acc);
+            }
         }
         TS r[4];
 #pragma unroll
@@ -133,6 +167,21 @@ __host__ __device__ __forceinline__ void int_nd_compute(const IntNdParams &p, co
             d[0] = (uint32_t)(uint8_t)r[0] | ((uint32_t)(uint8_t)r[1] << 8) | ((uint32_t)(uint8_t)r[2] << 16) |
                    ((uint32_t)(uint8_t)r[3] << 24);
         }
+    }
+}
+
+template <typename TS>
+__host__ __device__ __forceinline__ void int_nd_compute(const IntNdParams &p, const TS *tile, TS *otile,
+                                                        const IntTap *wc, int tid, int64_t)
+{
+    switch (p.KX) {   // uniform over the grid
+    case 1: int_nd_compute_kx<TS, 1>(p, tile, otile, wc, tid); break;
+    case 2: int_nd_compute_kx<TS, 2>(p, tile, otile, wc, tid); break;
+    case 3: int_nd_compute_kx<TS, 3>(p, tile, otile, wc, tid); break;
+    case 4: int_nd_compute_kx<TS, 4>(p, tile, otile, wc, tid); break;
+    case 5: int_nd_compute_kx<TS, 5>(p, tile, otile, wc, tid); break;
+    case 7: int_nd_compute_kx<TS, 7>(p, tile, otile, wc, tid); break;
+    default: int_nd_compute_kx<TS, 0>(p, tile, otile, wc, tid); break;
     }
 }
 
@@ -221,11 +270,15 @@ inline int plan_corrnd_int(const CorrNdArgs &a, IntNdPlan &pl)
         p.tile_len = (p.shift + p.tile_out + p.KX + A - 1) / A * A;
         p.pitch = p.tile_len + 4 / sz;
         p.opitch = p.tile_out + 4 / sz;
-        pl.smem_bytes = int_nd_tap_bytes(p.ntaps) +
+        pl.smem_bytes = int_nd_tap_bytes(p.ntaps) + int_nd_table_bytes(p) +
                         ((size_t)p.KZ * p.stage_lines * p.pitch + (size_t)kIntNdLines * p.opitch) * sz;
         if (pl.smem_bytes <= kIntNdMaxSmem) break;
     }
     if (p.tile_out < 32) return -1;
+    const int64_t nvec = (int64_t)p.KZ * p.stage_lines * (p.tile_len / A);
+    if (nvec >= 65536) return -1;
+    p.vpr_magic = (uint32_t)(((1ull << 32) + (p.tile_len / A) - 1) / (p.tile_len / A));
+    p.ly_magic = (uint32_t)(((1ull << 32) + p.stage_lines - 1) / p.stage_lines);
     p.c_tiles = (int)((p.X + p.tile_out - 1) / p.tile_out);
     p.y_tiles = (int)((p.Y + kIntNdLines - 1) / kIntNdLines);
     pl.blocks = p.Z * (int64_t)p.y_tiles * p.c_tiles;

@@ -79,12 +79,14 @@ static void run_nd_blocks(const IntNdPlan &pl)
     const IntNdParams &p = pl.p;
     std::vector<unsigned char> smem(pl.smem_bytes + 16);
     IntTap *wc = reinterpret_cast<IntTap *>(smem.data());
-    TS *tile = reinterpret_cast<TS *>(smem.data() + int_nd_tap_bytes(p.ntaps));
+    int64_t *table = reinterpret_cast<int64_t *>(smem.data() + int_nd_tap_bytes(p.ntaps));
+    TS *tile = reinterpret_cast<TS *>(smem.data() + int_nd_tap_bytes(p.ntaps) + int_nd_table_bytes(p));
     TS *otile = tile + p.KZ * p.stage_lines * p.pitch;
     for (int64_t bid = 0; bid < pl.blocks; ++bid) {
         for (size_t i = 0; i < smem.size(); ++i) smem[i] = 0xA5;
         for (int t = 0; t < kIntThreads; ++t) int_nd_stage_taps(p, wc, t);
-        for (int t = 0; t < kIntThreads; ++t) int_nd_stage<TS>(p, tile, t, bid);
+        for (int t = 0; t < kIntThreads; ++t) int_nd_stage_lines(p, table, t, bid);
+        for (int t = 0; t < kIntThreads; ++t) int_nd_stage<TS>(p, tile, table, t, bid);
         for (int t = 0; t < kIntThreads; ++t) int_nd_compute<TS>(p, tile, otile, wc, t, bid);
         for (int t = 0; t < kIntThreads; ++t) int_nd_writeout<TS>(p, otile, t, bid);
     }

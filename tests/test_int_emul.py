@@ -217,7 +217,7 @@ def run_emul_nd(lib, x, w, mode, cval=0.0, origin=0, pad=(0, 0)):
 ND_CASES = [
     ((70, 144), (3, 3)), ((70, 144), (5, 4)), ((37, 50), (1, 7)), ((37, 50), (6, 1)), ((33, 130), (2, 2)),
     ((9, 40, 48), (3, 3, 3)), ((6, 35, 21), (2, 3, 4)), ((5, 34, 160), (1, 5, 5)), ((12, 9, 16), (5, 1, 1)),
-    ((3, 4), (5, 7)), ((10, 66, 144), (9, 9, 9)),
+    ((3, 4), (5, 7)), ((10, 66, 144), (9, 9, 9)), ((20, 40), (2, 6)),
 ]
 
 
