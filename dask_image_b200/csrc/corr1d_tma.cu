@@ -736,11 +736,11 @@ static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     const size_t smem = stage_bytes + 128;
     if constexpr (OP == 0) {
         auto kern = corr1d_strided_tma_kernel<T, TS, W, TY, R, MINB, REM>;
-        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
         kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, p);
     } else {
         auto kern = minmax_strided_tma_kernel<TS, W, TY, R, MINB, REM, OP>;
-        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
         kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, p);
     }
     B200_CUDA_TRY(cudaGetLastError());
@@ -900,7 +900,7 @@ static int launch_peer_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
 
     auto kern = corr1d_strided_peer_kernel<T, TS, W, TY, R, MINB, REM>;
     const size_t smem = stage_bytes + 128;
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, hm, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
@@ -1043,7 +1043,7 @@ static int launch_contig_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al,
 
     auto kern = corr1d_contig_tma_kernel<T, TS, SH, REM>;
     const size_t smem = stage_bytes + 128;
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
@@ -1109,7 +1109,7 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int
 
     auto kern = corr1d_contig_static_kernel<TS, NT>;
     const size_t smem = stage_bytes + 128;
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     kern<<<(unsigned)num_tiles, threads == 128 ? 128 : 256, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
@@ -1500,7 +1500,7 @@ static int launch_minmax_contig_cfg(const Corr1dArgs &a, int lo_al, int lead)
 
     auto kern = minmax_contig_static_kernel<TS, NT, IS_MAX>;
     const size_t smem = stage_bytes + 128;
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     kern<<<(unsigned)num_tiles, 128, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();

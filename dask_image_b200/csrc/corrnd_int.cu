@@ -2,7 +2,6 @@
 // uint8 / int8 / uint16 / int16 arrays (see corrnd_int.cuh).  Bounded by FP64
 // issue: two FP64 instructions per tap and output.
 #include "corrnd_int.cuh"
-#include <mutex>
 
 namespace b200 {
 
@@ -28,13 +27,9 @@ corrnd_int_kernel(const __grid_constant__ IntNdParams p)
 template <typename TS>
 static int launch_nd_typed(const IntNdPlan &pl, cudaStream_t stream)
 {
-    static std::once_flag once;
-    static cudaError_t attr = cudaSuccess;
-    std::call_once(once, [] {
-        attr = cudaFuncSetAttribute(corrnd_int_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kIntNdMaxSmem);
-    });
-    if (attr != cudaSuccess) return check_cuda(attr, "corrnd_int shared memory opt-in");
+    // (a constant, set on every launch: the attribute is per function AND per device)
+    B200_CUDA_TRY(cudaFuncSetAttribute(corrnd_int_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kIntNdMaxSmem));
     corrnd_int_kernel<TS><<<(unsigned)pl.blocks, kIntThreads, pl.smem_bytes, stream>>>(pl.p);
     return check_cuda(cudaGetLastError(), "corrnd_int launch");
 }

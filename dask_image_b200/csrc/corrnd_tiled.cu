@@ -360,7 +360,7 @@ static int launch_cfg(const CorrNdArgs &a, int lox_al, int Kx_al)
 
     auto kern = corrnd_tiled_kernel<T, SH, REM>;
     const size_t smem = (size_t)P * BY * BZ * es + 128;
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
@@ -439,7 +439,7 @@ static int launch_static_cfg(const CorrNdArgs &a, int lox_al)
 
     auto kern = corrnd_static_kernel<KXA>;
     const size_t smem = (size_t)P * BY * BZ * es + 128;
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();

@@ -10,6 +10,10 @@
 namespace b200 {
 
 constexpr size_t kSmemPerSm = 227 * 1024;
+// Dynamic shared memory opt-in of every tiled kernel: always the device maximum, never the size of
+// the launch at hand -- the attribute is per function, and concurrent host threads launching the same
+// instantiation with different tile sizes would otherwise lower it under each other's launches.
+constexpr int kSmemOptIn = 227 * 1024;
 
 static inline int env_int(const char *name, int dflt)
 {
