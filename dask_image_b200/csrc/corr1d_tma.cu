@@ -218,6 +218,12 @@ __device__ __forceinline__ void strided_tile_body(const CUtensorMap &tmap, const
         const int j = idx / W, c = idx - j * W;
         const int sr = patch_src[j];
         if (sr < 0) return p.cval;
+        if constexpr (PEER) {
+            // The neighbours' rows are not in local memory.  A row that folds onto one of them lies
+            // beyond the halo of a side that HAS a neighbour: it only feeds outputs past the slab's end,
+            // which are never stored -- and the address next to the slab need not be mapped.
+            if (sr < p.pad_lo || sr - p.pad_lo >= p.n) return TS(0);
+        }
         return (col0 + c < p.inner) ? p.in[(o * p.n + (sr - p.pad_lo)) * p.inner + col0 + c] : TS(0);
     };
     TS pre[kPre];

@@ -13,7 +13,7 @@ constexpr size_t kSmemPerSm = 227 * 1024;
 // Dynamic shared memory opt-in of every tiled kernel: always the device maximum, never the size of
 // the launch at hand -- the attribute is per function, and concurrent host threads launching the same
 // instantiation with different tile sizes would otherwise lower it under each other's launches.
-constexpr int kSmemOptIn = 227 * 1024;
+constexpr int kSmemOptIn = 227 * 1024 - 1152;   // less the kernels' static shared memory (patch table, barrier)
 
 static inline int env_int(const char *name, int dflt)
 {
