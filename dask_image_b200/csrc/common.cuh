@@ -114,7 +114,8 @@ __host__ __device__ __forceinline__ int64_t ext_index_padded(int64_t i, int64_t 
 // ---------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int32_t x86_cvtt32(double v)
 {
-    return (v > -2147483649.0 && v < 2147483648.0) ? (int32_t)v : INT32_MIN;
+    // (one compare: a value in (-2^31 - 1, -2^31] truncates to INT32_MIN, the out-of-range result)
+    return fabs(v) < 2147483648.0 ? (int32_t)v : INT32_MIN;
 }
 __host__ __device__ __forceinline__ int64_t x86_cvtt64(double v)
 {

@@ -15,9 +15,12 @@ corr1d_int_strided_kernel(const __grid_constant__ IntParams p)
 {
     extern __shared__ __align__(16) unsigned char int_smem[];
     IntTap *wc = reinterpret_cast<IntTap *>(int_smem);
-    TS *tile = reinterpret_cast<TS *>(int_smem + kIntTapBytes);
+    int64_t *rows = reinterpret_cast<int64_t *>(int_smem + kIntTapBytes);
+    TS *tile = reinterpret_cast<TS *>(int_smem + kIntTapBytes + kIntRowTableBytes);
     int_stage_taps(p, wc, threadIdx.x);
-    int_strided_stage<TS>(p, tile, threadIdx.x, blockIdx.x);
+    int_strided_stage_rows(p, rows, threadIdx.x, blockIdx.x);
+    __syncthreads();
+    int_strided_stage<TS>(p, tile, rows, threadIdx.x, blockIdx.x);
     __syncthreads();
     int_strided_compute<TS, KIND>(p, tile, wc, threadIdx.x, blockIdx.x);
 }

@@ -41,6 +41,7 @@ constexpr int kMaxTapsInt = 129;
 constexpr int kIntThreads = 128;
 constexpr int kIntStridedW = 128;   // strided tiles: columns per tile, one per thread
 constexpr int kIntContigRows = 32;  // contiguous tiles: lines per tile, one per lane
+constexpr int kIntContigOut = 128;  // contiguous tiles: outputs per line
 constexpr int kIntTapBytes = ((kMaxTapsInt * 16 + 127) / 128) * 128;   // shared {w, c} table in front of the tile
 
 struct IntParams {
@@ -59,6 +60,7 @@ struct IntParams {
     int vec;        // 16-byte global accesses are legal
     int n_tiles, c_tiles;
     int cval;
+    uint32_t vpr_magic;   // contiguous: ceil(2^32 / vectors per staged line)
     uint32_t hi_word;   // kIntHigh (see int_pattern)
     double w[kMaxTapsInt];
     double c[kMaxTapsInt];   // -(2^52 * w)
@@ -107,6 +109,17 @@ __host__ __device__ __forceinline__ double int_add(double a, double b)
     return __dadd_rn(a, b);
 #else
     return a + b;
+#endif
+}
+
+// v / d for v < 2^16 with magic = ceil(2^32 / d), d <= 2^16 (exact: the error term v * (magic * d - 2^32)
+// stays below 2^32)
+__host__ __device__ __forceinline__ uint32_t int_div_magic(uint32_t v, uint32_t magic)
+{
+#ifdef __CUDA_ARCH__
+    return __umulhi(v, magic);
+#else
+    return (uint32_t)(((uint64_t)v * magic) >> 32);
 #endif
 }
 
@@ -307,25 +320,43 @@ __host__ __device__ __forceinline__ TS int_finish(double acc, TS *dst, int epilo
 // ---------------------------------------------------------------------------
 struct IntStridedTile {
     int64_t o, row0, col0, g0;
-    __host__ __device__ __forceinline__ IntStridedTile(const IntParams &p, int64_t bid)
+    __host__ __device__ __forceinline__ IntStridedTile(const IntParams &p, uint32_t bid)
     {
-        const int tn = (int)(bid % p.n_tiles);
-        const int64_t q = bid / p.n_tiles;
-        const int tc = (int)(q % p.c_tiles);
-        o = q / p.c_tiles;
+        // (the grid is below 2^31 blocks: 32-bit divisions)
+        const uint32_t q = bid / (uint32_t)p.n_tiles;
+        const int tn = (int)(bid - q * (uint32_t)p.n_tiles);
+        const uint32_t oo = q / (uint32_t)p.c_tiles;
+        const int tc = (int)(q - oo * (uint32_t)p.c_tiles);
+        o = oo;
         row0 = (int64_t)tn * p.tile_out;
         col0 = (int64_t)tc * kIntStridedW;
         g0 = row0 - p.lo;
     }
 };
 
+// Source of every staged row: element offset of the row in the array (negative
+// for the planes a padded slab keeps in front of `in`), or INT64_MIN for "cval".
+// Computed once per tile: the extension map is 64-bit compares and, on the
+// array's edges, a modulo.
+constexpr int kIntRowTableBytes = (32 + kMaxTapsInt + 15) / 16 * 16 * 8;
+
+__host__ __device__ __forceinline__ void int_strided_stage_rows(const IntParams &p, int64_t *rows, int tid, uint32_t bid)
+{
+    const IntStridedTile t(p, bid);
+    for (int r = tid; r < p.tile_len; r += kIntThreads) {
+        const int64_t src = ext_index_padded(t.g0 + r, p.n, p.mode, p.pad_lo, p.pad_hi);
+        rows[r] = src == B200_USE_CVAL ? INT64_MIN : (t.o * p.n + src) * p.inner;
+    }
+}
+
 template <typename TS>
-__host__ __device__ __forceinline__ void int_strided_stage(const IntParams &p, TS *tile, int tid, int64_t bid)
+__host__ __device__ __forceinline__ void int_strided_stage(const IntParams &p, TS *tile, const int64_t *rows, int tid,
+                                                           uint32_t bid)
 {
     constexpr int W = kIntStridedW;
     constexpr int A = 16 / (int)sizeof(TS);
     const IntStridedTile t(p, bid);
-    const TS *plane = (const TS *)p.in + t.o * p.n * p.inner;
+    const TS *in = (const TS *)p.in;
     const int SR = p.tile_len;
     if (p.vec) {
         constexpr int VPR = W / A;
@@ -339,8 +370,8 @@ __host__ __device__ __forceinline__ void int_strided_stage(const IntParams &p, T
             const int64_t col = t.col0 + cv * A;
             uint4 val = make_uint4(0u, 0u, 0u, 0u);
             if (col < p.inner) {
-                const int64_t src = ext_index_padded(t.g0 + r, p.n, p.mode, p.pad_lo, p.pad_hi);
-                val = src == B200_USE_CVAL ? cvec : *reinterpret_cast<const uint4 *>(plane + src * p.inner + col);
+                const int64_t off = rows[r];
+                val = off == INT64_MIN ? cvec : *reinterpret_cast<const uint4 *>(in + off + col);
             }
             *reinterpret_cast<uint4 *>(tile + r * W + cv * A) = val;
         }
@@ -350,8 +381,8 @@ __host__ __device__ __forceinline__ void int_strided_stage(const IntParams &p, T
             const int64_t col = t.col0 + cc;
             TS val = TS(0);
             if (col < p.inner) {
-                const int64_t src = ext_index_padded(t.g0 + r, p.n, p.mode, p.pad_lo, p.pad_hi);
-                val = src == B200_USE_CVAL ? (TS)p.cval : plane[src * p.inner + col];
+                const int64_t off = rows[r];
+                val = off == INT64_MIN ? (TS)p.cval : in[off + col];
             }
             tile[e] = val;
         }
@@ -360,7 +391,7 @@ __host__ __device__ __forceinline__ void int_strided_stage(const IntParams &p, T
 
 template <typename TS, int KIND>
 __host__ __device__ __forceinline__ void int_strided_compute(const IntParams &p, const TS *tile, const IntTap *wc,
-                                                             int tid, int64_t bid)
+                                                             int tid, uint32_t bid)
 {
     constexpr int W = kIntStridedW;
     const IntStridedTile t(p, bid);
@@ -368,18 +399,17 @@ __host__ __device__ __forceinline__ void int_strided_compute(const IntParams &p,
     // which keeps the weights on the uniform datapath; only the stores are predicated)
     const int64_t col = t.col0 + tid;
     const bool live = col < p.inner;
-    TS *out_col = (TS *)p.out + t.o * p.n * p.inner + col;
-    for (int r0 = 0; r0 < p.tile_out; r0 += 4) {
-        if (t.row0 + r0 >= p.n) break;
+    const bool plain = p.epilogue == B200_EPI_STORE;
+    TS *dst = (TS *)p.out + (t.o * p.n + t.row0) * p.inner + col;
+    const int64_t left = p.n - t.row0;
+    const int rows_here = left < p.tile_out ? (int)left : p.tile_out;   // rows of the array in this tile
+    for (int r0 = 0; r0 < rows_here; r0 += 4) {
         double acc[4];
         int_line_quad<TS, KIND>(tile + r0 * W + tid, W, p, wc, acc);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int64_t row = t.row0 + r0 + m;
-            if (live && row < p.n) {
-                TS *dst = out_col + row * p.inner;
-                *dst = int_finish<TS>(acc[m], dst, p.epilogue);
-            }
+        for (int m = 0; m < 4; ++m, dst += p.inner) {
+            if (live && r0 + m < rows_here)
+                *dst = plain ? cast_out<TS>(acc[m]) : int_finish<TS>(acc[m], dst, p.epilogue);
         }
     }
 }
@@ -393,17 +423,18 @@ __host__ __device__ __forceinline__ void int_strided_compute(const IntParams &p,
 // ---------------------------------------------------------------------------
 struct IntContigTile {
     int64_t row0, x0, g0;
-    __host__ __device__ __forceinline__ IntContigTile(const IntParams &p, int64_t bid)
+    __host__ __device__ __forceinline__ IntContigTile(const IntParams &p, uint32_t bid)
     {
-        const int tcx = (int)(bid % p.c_tiles);
-        row0 = (bid / p.c_tiles) * kIntContigRows;
+        const uint32_t q = bid / (uint32_t)p.c_tiles;
+        const int tcx = (int)(bid - q * (uint32_t)p.c_tiles);
+        row0 = (int64_t)q * kIntContigRows;
         x0 = (int64_t)tcx * p.tile_out;
         g0 = x0 - p.lo - p.shift;
     }
 };
 
 template <typename TS>
-__host__ __device__ __forceinline__ void int_contig_stage(const IntParams &p, TS *tile, int tid, int64_t bid)
+__host__ __device__ __forceinline__ void int_contig_stage(const IntParams &p, TS *tile, int tid, uint32_t bid)
 {
     constexpr int TR = kIntContigRows;
     constexpr int A = 16 / (int)sizeof(TS);
@@ -412,7 +443,7 @@ __host__ __device__ __forceinline__ void int_contig_stage(const IntParams &p, TS
     const int PC = p.tile_len, P = p.pitch;
     const int VPR = PC / A;
     for (int v = tid; v < TR * VPR; v += kIntThreads) {
-        const int r = v / VPR, cv = v - r * VPR;
+        const int r = (int)int_div_magic((uint32_t)v, p.vpr_magic), cv = v - r * VPR;
         const int64_t row = t.row0 + r;
         const int64_t pos = t.g0 + cv * A;
         uint4 val = make_uint4(0u, 0u, 0u, 0u);
@@ -438,7 +469,7 @@ __host__ __device__ __forceinline__ void int_contig_stage(const IntParams &p, TS
 
 template <typename TS, int KIND>
 __host__ __device__ __forceinline__ void int_contig_compute(const IntParams &p, const TS *tile, TS *otile,
-                                                            const IntTap *wc, int tid, int64_t bid)
+                                                            const IntTap *wc, int tid, uint32_t bid)
 {
     const IntContigTile t(p, bid);
     const int warp = tid >> 5, lane = tid & 31;
@@ -467,15 +498,16 @@ __host__ __device__ __forceinline__ void int_contig_compute(const IntParams &p, 
 
 template <typename TS>
 __host__ __device__ __forceinline__ void int_contig_writeout(const IntParams &p, const TS *otile, int tid,
-                                                             int64_t bid)
+                                                             uint32_t bid)
 {
     constexpr int TR = kIntContigRows;
     constexpr int A = 16 / (int)sizeof(TS);
     const IntContigTile t(p, bid);
     TS *out = (TS *)p.out;
-    const int SX = p.tile_out, PO = p.opitch;
+    constexpr int SX = kIntContigOut;
+    const int PO = p.opitch;
     if (p.vec) {
-        const int VR = SX / A;
+        constexpr int VR = SX / A;
         for (int v = tid; v < TR * VR; v += kIntThreads) {
             const int r = v / VR, cv = v - r * VR;
             const int64_t row = t.row0 + r, x = t.x0 + cv * A;
@@ -568,11 +600,12 @@ inline int plan_corr1d_int(const Corr1dArgs &a, IntPlan &pl, int symmetry)
         if (a.pad_lo || a.pad_hi) return -1;
         if (p.n >= (1ll << 31) - 4096) return -1;
         p.vec = (p.n % A == 0) && ((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.out % 16 == 0);
-        p.tile_out = 128;
+        p.tile_out = kIntContigOut;
         p.shift = (A - p.lo % A) % A;
         p.tile_len = (p.shift + p.tile_out + L - 1 + A - 1) / A * A;
         p.pitch = p.tile_len + 4 / sz;
         p.opitch = p.tile_out + 4 / sz;
+        p.vpr_magic = (uint32_t)(((1ull << 32) + (p.tile_len / A) - 1) / (p.tile_len / A));
         p.c_tiles = (int)((p.n + p.tile_out - 1) / p.tile_out);
         p.n_tiles = 1;
         const int64_t row_tiles = (p.outer + kIntContigRows - 1) / kIntContigRows;
@@ -588,7 +621,7 @@ inline int plan_corr1d_int(const Corr1dArgs &a, IntPlan &pl, int symmetry)
         p.n_tiles = (int)((p.n + p.tile_out - 1) / p.tile_out);
         p.c_tiles = (int)((p.inner + kIntStridedW - 1) / kIntStridedW);
         pl.blocks = p.outer * (int64_t)p.n_tiles * p.c_tiles;
-        pl.smem_bytes = kIntTapBytes + (size_t)p.tile_len * kIntStridedW * sz;
+        pl.smem_bytes = kIntTapBytes + kIntRowTableBytes + (size_t)p.tile_len * kIntStridedW * sz;
     }
     if (pl.blocks < 1 || pl.blocks >= (1ll << 31)) return -1;
     return 0;

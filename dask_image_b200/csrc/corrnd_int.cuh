@@ -44,12 +44,14 @@ struct IntNdParams {
 
 struct IntNdTile {
     int64_t z, y0, x0, g0;
-    __host__ __device__ __forceinline__ IntNdTile(const IntNdParams &p, int64_t bid)
+    __host__ __device__ __forceinline__ IntNdTile(const IntNdParams &p, uint32_t bid)
     {
-        const int tcx = (int)(bid % p.c_tiles);
-        const int64_t q = bid / p.c_tiles;
-        y0 = (q % p.y_tiles) * kIntNdLines;
-        z = q / p.y_tiles;
+        // (the grid is below 2^31 blocks: 32-bit divisions)
+        const uint32_t q = bid / (uint32_t)p.c_tiles;
+        const int tcx = (int)(bid - q * (uint32_t)p.c_tiles);
+        const uint32_t zz = q / (uint32_t)p.y_tiles;
+        y0 = (int64_t)(q - zz * (uint32_t)p.y_tiles) * kIntNdLines;
+        z = zz;
         x0 = (int64_t)tcx * p.tile_out;
         g0 = x0 - p.lox - p.shift;
     }
@@ -61,21 +63,10 @@ __host__ __device__ __forceinline__ size_t int_nd_table_bytes(const IntNdParams 
     return ((size_t)p.KZ * p.stage_lines * 8 + 127) / 128 * 128;
 }
 
-// v / d for v < 2^16 with magic = ceil(2^32 / d), d <= 2^16 (exact: the error term v * (magic * d - 2^32)
-// stays below 2^32)
-__host__ __device__ __forceinline__ uint32_t int_div_magic(uint32_t v, uint32_t magic)
-{
-#ifdef __CUDA_ARCH__
-    return __umulhi(v, magic);
-#else
-    return (uint32_t)(((uint64_t)v * magic) >> 32);
-#endif
-}
-
 // Source of every staged line: element offset of its row (z, y) in the array, or
 // INT64_MIN when the row lies outside under mode 'constant'.  One entry per line, computed
 // once per tile (the extension map costs 64-bit compares and, on the edges, a modulo).
-__host__ __device__ __forceinline__ void int_nd_stage_lines(const IntNdParams &p, int64_t *table, int tid, int64_t bid)
+__host__ __device__ __forceinline__ void int_nd_stage_lines(const IntNdParams &p, int64_t *table, int tid, uint32_t bid)
 {
     const IntNdTile t(p, bid);
     const int LY = p.stage_lines;
@@ -98,7 +89,7 @@ __host__ __device__ __forceinline__ void int_nd_stage_taps(const IntNdParams &p,
 
 template <typename TS>
 __host__ __device__ __forceinline__ void int_nd_stage(const IntNdParams &p, TS *tile, const int64_t *table, int tid,
-                                                      int64_t bid)
+                                                      uint32_t bid)
 {
     constexpr int A = 16 / (int)sizeof(TS);
     const IntNdTile t(p, bid);
@@ -172,7 +163,7 @@ __host__ __device__ __forceinline__ void int_nd_compute_kx(const IntNdParams &p,
 
 template <typename TS>
 __host__ __device__ __forceinline__ void int_nd_compute(const IntNdParams &p, const TS *tile, TS *otile,
-                                                        const IntTap *wc, int tid, int64_t)
+                                                        const IntTap *wc, int tid, uint32_t)
 {
     switch (p.KX) {   // uniform over the grid
     case 1: int_nd_compute_kx<TS, 1>(p, tile, otile, wc, tid); break;
@@ -186,16 +177,17 @@ __host__ __device__ __forceinline__ void int_nd_compute(const IntNdParams &p, co
 }
 
 template <typename TS>
-__host__ __device__ __forceinline__ void int_nd_writeout(const IntNdParams &p, const TS *otile, int tid, int64_t bid)
+__host__ __device__ __forceinline__ void int_nd_writeout(const IntNdParams &p, const TS *otile, int tid, uint32_t bid)
 {
     constexpr int A = 16 / (int)sizeof(TS);
     const IntNdTile t(p, bid);
     TS *plane = (TS *)p.out + t.z * p.Y * p.X;
     const int SX = p.tile_out, PO = p.opitch;
     if (p.vec) {
-        const int VR = SX / A;
+        const int VR = SX / A;   // a power of two
+        const int vr_shift = 31 - __builtin_clz((unsigned)VR);
         for (int v = tid; v < kIntNdLines * VR; v += kIntThreads) {
-            const int r = v / VR, cv = v - r * VR;
+            const int r = v >> vr_shift, cv = v - r * VR;
             const int64_t y = t.y0 + r, x = t.x0 + cv * A;
             if (y >= p.Y || x >= p.X) continue;
             const uint32_t *sw = reinterpret_cast<const uint32_t *>(otile + r * PO + cv * A);

@@ -23,7 +23,7 @@ static void run_blocks(const IntPlan &pl)
     std::vector<unsigned char> smem(pl.smem_bytes + 16);
     IntTap *wc = reinterpret_cast<IntTap *>(smem.data());
     TS *tile = reinterpret_cast<TS *>(smem.data() + kIntTapBytes);
-    for (int64_t bid = 0; bid < pl.blocks; ++bid) {
+    for (uint32_t bid = 0; bid < (uint32_t)pl.blocks; ++bid) {
         // poison the tile so that a read of an element no thread staged shows up
         for (size_t i = 0; i < smem.size(); ++i) smem[i] = 0xA5;
         for (int t = 0; t < kIntThreads; ++t) int_stage_taps(p, wc, t);
@@ -33,8 +33,11 @@ static void run_blocks(const IntPlan &pl)
             for (int t = 0; t < kIntThreads; ++t) int_contig_compute<TS, KIND>(p, tile, otile, wc, t, bid);
             for (int t = 0; t < kIntThreads; ++t) int_contig_writeout<TS>(p, otile, t, bid);
         } else {
-            for (int t = 0; t < kIntThreads; ++t) int_strided_stage<TS>(p, tile, t, bid);
-            for (int t = 0; t < kIntThreads; ++t) int_strided_compute<TS, KIND>(p, tile, wc, t, bid);
+            int64_t *rows = reinterpret_cast<int64_t *>(smem.data() + kIntTapBytes);
+            TS *stile = reinterpret_cast<TS *>(smem.data() + kIntTapBytes + kIntRowTableBytes);
+            for (int t = 0; t < kIntThreads; ++t) int_strided_stage_rows(p, rows, t, bid);
+            for (int t = 0; t < kIntThreads; ++t) int_strided_stage<TS>(p, stile, rows, t, bid);
+            for (int t = 0; t < kIntThreads; ++t) int_strided_compute<TS, KIND>(p, stile, wc, t, bid);
         }
     }
 }
@@ -82,7 +85,7 @@ static void run_nd_blocks(const IntNdPlan &pl)
     int64_t *table = reinterpret_cast<int64_t *>(smem.data() + int_nd_tap_bytes(p.ntaps));
     TS *tile = reinterpret_cast<TS *>(smem.data() + int_nd_tap_bytes(p.ntaps) + int_nd_table_bytes(p));
     TS *otile = tile + p.KZ * p.stage_lines * p.pitch;
-    for (int64_t bid = 0; bid < pl.blocks; ++bid) {
+    for (uint32_t bid = 0; bid < (uint32_t)pl.blocks; ++bid) {
         for (size_t i = 0; i < smem.size(); ++i) smem[i] = 0xA5;
         for (int t = 0; t < kIntThreads; ++t) int_nd_stage_taps(p, wc, t);
         for (int t = 0; t < kIntThreads; ++t) int_nd_stage_lines(p, table, t, bid);
