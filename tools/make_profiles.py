@@ -24,6 +24,9 @@ KEYS = [
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
     ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe busy %"),
+    ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "FP64 pipe busy %"),
+    ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe busy %"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe busy %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
     ("launch__registers_per_thread", "registers / thread"),
     ("launch__occupancy_limit_registers", "CTA/SM limit (registers)"),
@@ -96,7 +99,11 @@ def main():
                          r"corr1d_strided_tma_kernelIftLi256ELi8ELi4ELi3ELi3E", r"corr1d_contig_static_kernelItLi16E",
                          r"corr1d_strided_peer_kernelIffLi128ELi8ELi4ELi3ELi1E", r"corr1d_contig_tma_kernelIffLi0ELi1E"],
         "corrnd_tiled.o": [r"corrnd_static_kernelILi9E"],
+        "corr1d_int.o": [r"corr1d_int_strided_kernelItLi1E"],
+        "corrnd_int.o": [r"corrnd_int_kernelItE"],
     }
+    if os.environ.get("SASS_ONLY"):
+        wanted = {k: v for k, v in wanted.items() if k in os.environ["SASS_ONLY"].split(",")}
     for obj, pats in wanted.items():
         path = os.path.join(ROOT, "dask_image_b200", "build", obj)
         if not os.path.exists(path):
