@@ -74,7 +74,9 @@ typedef enum {
 #define B200_ENODEVICE     6   /* no sm_100 device / kernels unavailable     */
 
 /* flags */
-#define B200_FLAG_EXACT      1u  /* force the scipy-order fp64 path (bit-exact) */
+#define B200_FLAG_EXACT      1u  /* force the one-thread-per-output scipy-order fp64 kernels: bit-exact for
+                                   * floats too; for 8/16-bit integers the tiled kernels are bit-exact as
+                                   * well and this flag selects their cross-check */
 #define B200_FLAG_NO_TMA     2u  /* never pick a TMA-tiled kernel (debug/tests) */
 #define B200_FLAG_FORCE_FAST 4u  /* fail instead of falling back to generic     */
 

@@ -271,3 +271,43 @@ def test_emulated_nd_kernel_declines(emul):
     assert run_emul_nd(emul, x.reshape(2, 4, 8, 4), np.ones((1, 3, 3, 3)), "reflect")[0] is None   # 4-D
     assert run_emul_nd(emul, x.astype(np.uint32), w, "reflect")[0] is None
     assert run_emul_nd(emul, np.zeros((4, 40, 40), np.uint8), np.ones((11, 11, 11)), "reflect")[0] is None
+
+
+# ---------------------------------------------------------------------------
+# randomised: emulated kernels vs scipy itself (what the reference calls per chunk)
+# ---------------------------------------------------------------------------
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+import scipy.ndimage as ndi  # noqa: E402
+
+
+@settings(max_examples=150, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(st.data())
+def test_emulated_kernels_fuzz_against_scipy(emul, data):
+    nd = data.draw(st.integers(1, 3))
+    shape = tuple(data.draw(st.sampled_from([1, 2, 3, 5, 8, 16, 31, 40, 67, 130])) for _ in range(nd))
+    dt = np.dtype(data.draw(st.sampled_from(DTYPES)))
+    mode = data.draw(st.sampled_from(MODES))
+    cval = float(data.draw(st.sampled_from([0, 1, 100, -7]))) if mode == "constant" else 0.0
+    if dt.kind == "u" and cval < 0:
+        cval = 7.0
+    rng = np.random.default_rng(data.draw(st.integers(0, 2 ** 16)))
+    ii = np.iinfo(dt)
+    a = rng.integers(ii.min, ii.max + 1, size=shape, dtype=np.int64).astype(dt)
+    axis = data.draw(st.integers(0, nd - 1))
+    nw = data.draw(st.integers(1, 40))
+    origin = data.draw(st.integers(-(nw // 2), (nw - 1) // 2))
+    w = rng.standard_normal(nw)
+    if nw % 2 and data.draw(st.booleans()):
+        w = (w + w[::-1]) / 2 if data.draw(st.booleans()) else (w - w[::-1]) / 2     # the folded branches
+    got, info = run_emul(emul, a, w, axis, mode, cval, origin)
+    assert got is not None
+    np.testing.assert_array_equal(got, ndi.correlate1d(a, w, axis=axis, mode=mode, cval=cval, origin=origin),
+                                  err_msg=str((shape, dt, axis, mode, nw, origin, info)))
+    if nd >= 2:
+        wshape = tuple(data.draw(st.integers(1, 5)) for _ in range(nd))
+        wn = rng.standard_normal(wshape)
+        origins = [data.draw(st.integers(-(s // 2), (s - 1) // 2)) for s in wshape]
+        got, info = run_emul_nd(emul, a, wn, mode, cval, origins)
+        assert got is not None
+        np.testing.assert_array_equal(got, ndi.correlate(a, wn, mode=mode, cval=cval, origin=origins),
+                                      err_msg=str((shape, dt, wshape, mode, origins, info)))
