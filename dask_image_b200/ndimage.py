@@ -77,16 +77,32 @@ def _check_output(output, x):
 # --------------------------------------------------------------------------
 # raw launches
 # --------------------------------------------------------------------------
+_dtype_codes = {}
+
+
+def _dtype_code(np_dtype):
+    """``_lib.DTYPE_CODES[np_dtype.name]`` without numpy's (slow) name property on every launch."""
+    code = _dtype_codes.get(np_dtype)
+    if code is None:
+        code = _dtype_codes[np_dtype] = _lib.DTYPE_CODES[np_dtype.name]
+    return code
+
+
 def _launch_correlate1d(src, dst, shape, np_dtype, axis, weights, mode, cval, origin,
-                        pad=(0, 0), epilogue=_lib.EPI_STORE, flags=None):
+                        pad=(0, 0), epilogue=_lib.EPI_STORE, flags=None, prepared=None):
     """src/dst: torch tensors (device pointers are taken at element 0 of the
-    UNPADDED array; ``pad`` planes of real data precede/follow it on axis 0)."""
+    UNPADDED array; ``pad`` planes of real data precede/follow it on axis 0).
+    ``prepared`` = ``(float64 taps, ctypes pointer to them)`` of a cached pass."""
     lib = _lib.load()
-    w = np.ascontiguousarray(weights, dtype=np.float64)
+    if prepared is None:
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        wptr = _lib.f64_pointer(w)
+    else:
+        w, wptr = prepared
     with torch.cuda.device(src.device):
         rc = lib.b200_correlate1d(
-            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape),
-            _lib.i64_array(shape), int(axis), _lib.f64_pointer(w), int(w.shape[0]),
+            src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape),
+            _lib.i64_array(shape), int(axis), wptr, int(w.shape[0]),
             _lib.mode_code(mode), float(cval), int(origin), int(pad[0]), int(pad[1]),
             int(epilogue), int(_default_flags if flags is None else flags), _stream_ptr(src))
     _lib.check(rc)
@@ -101,7 +117,7 @@ def _launch_correlate1d_halo(src, dst, shape, np_dtype, weights, mode, cval, ori
     w = np.ascontiguousarray(weights, dtype=np.float64)
     with torch.cuda.device(src.device):
         rc = lib.b200_correlate1d_halo(
-            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape), _lib.i64_array(shape),
+            src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape), _lib.i64_array(shape),
             _lib.f64_pointer(w), int(w.shape[0]), _lib.mode_code(mode), float(cval), int(origin),
             halo_lo.data_ptr() if halo_lo is not None else None, int(halo_lo.shape[0]) if halo_lo is not None else 0,
             halo_hi.data_ptr() if halo_hi is not None else None, int(halo_hi.shape[0]) if halo_hi is not None else 0,
@@ -114,7 +130,7 @@ def _launch_uniform1d_halo(src, dst, shape, np_dtype, size, mode, cval, origin, 
     lib = _lib.load()
     with torch.cuda.device(src.device):
         rc = lib.b200_uniform_filter1d_halo(
-            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape), _lib.i64_array(shape),
+            src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape), _lib.i64_array(shape),
             int(size), _lib.mode_code(mode), float(cval), int(origin),
             halo_lo.data_ptr() if halo_lo is not None else None, int(halo_lo.shape[0]) if halo_lo is not None else 0,
             halo_hi.data_ptr() if halo_hi is not None else None, int(halo_hi.shape[0]) if halo_hi is not None else 0,
@@ -124,12 +140,12 @@ def _launch_uniform1d_halo(src, dst, shape, np_dtype, size, mode, cval, origin, 
 
 def _uniform_halo_eligible(np_dtype, n, inner, size, origin, mode, cval):
     return bool(_lib.load().b200_uniform_filter1d_halo_eligible(
-        _lib.DTYPE_CODES[np_dtype.name], int(n), int(inner), int(size), int(origin), _lib.mode_code(mode),
+        _dtype_code(np_dtype), int(n), int(inner), int(size), int(origin), _lib.mode_code(mode),
         float(cval)))
 
 
 def _halo_eligible(np_dtype, n, inner, nw, origin):
-    return bool(_lib.load().b200_correlate1d_halo_eligible(_lib.DTYPE_CODES[np_dtype.name], int(n), int(inner),
+    return bool(_lib.load().b200_correlate1d_halo_eligible(_dtype_code(np_dtype), int(n), int(inner),
                                                            int(nw), int(origin)))
 
 
@@ -138,7 +154,7 @@ def _launch_uniform1d(src, dst, shape, np_dtype, axis, size, mode, cval, origin,
     lib = _lib.load()
     with torch.cuda.device(src.device):
         rc = lib.b200_uniform_filter1d(
-            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape),
+            src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape),
             _lib.i64_array(shape), int(axis), int(size), _lib.mode_code(mode), float(cval),
             int(origin), int(pad[0]), int(pad[1]),
             int(_default_flags if flags is None else flags), _stream_ptr(src))
@@ -151,7 +167,7 @@ def _launch_correlate_nd(src, dst, shape, np_dtype, weights, origins, mode, cval
     w = np.ascontiguousarray(weights, dtype=np.float64)
     with torch.cuda.device(src.device):
         rc = lib.b200_correlate_nd(
-            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape),
+            src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape),
             _lib.i64_array(shape), _lib.f64_pointer(w), _lib.i64_array(w.shape),
             _lib.i64_array(origins), _lib.mode_code(mode), float(cval), int(pad[0]), int(pad[1]),
             int(_default_flags if flags is None else flags), _stream_ptr(src))
@@ -162,7 +178,7 @@ def _launch_minmax1d(src, dst, shape, np_dtype, axis, size, is_max, mode, cval, 
     lib = _lib.load()
     with torch.cuda.device(src.device):
         rc = lib.b200_minmax_filter1d(
-            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape),
+            src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape),
             _lib.i64_array(shape), int(axis), int(size), int(bool(is_max)), _lib.mode_code(mode), float(cval),
             int(origin), int(pad[0]), int(pad[1]),
             int(_default_flags if flags is None else flags), _stream_ptr(src))
@@ -176,7 +192,7 @@ def _launch_minmax_nd(src, dst, shape, np_dtype, footprint, origins, is_max, mod
     fp = np.ascontiguousarray(footprint, dtype=np.uint8)
     with torch.cuda.device(src.device):
         rc = lib.b200_minmax_filter_nd(
-            src.data_ptr(), dst.data_ptr(), _lib.DTYPE_CODES[np_dtype.name], len(shape),
+            src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape),
             _lib.i64_array(shape), fp.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _lib.i64_array(fp.shape),
             _lib.i64_array(origins), int(bool(is_max)), _lib.mode_code(mode), float(cval), int(pad[0]), int(pad[1]),
             int(_default_flags if flags is None else flags) & ~_lib.FLAG_FORCE_FAST, _stream_ptr(src))
@@ -186,7 +202,7 @@ def _launch_minmax_nd(src, dst, shape, np_dtype, footprint, origins, is_max, mod
 def _launch_combine(acc, src, np_dtype, op):
     lib = _lib.load()
     with torch.cuda.device(acc.device):
-        rc = lib.b200_combine(acc.data_ptr(), src.data_ptr(), _lib.DTYPE_CODES[np_dtype.name],
+        rc = lib.b200_combine(acc.data_ptr(), src.data_ptr(), _dtype_code(np_dtype),
                               int(acc.numel()), int(op), _stream_ptr(acc))
     _lib.check(rc)
 
@@ -250,15 +266,35 @@ def _gaussian_kernel1d(sigma, order, radius):
     return poly * phi
 
 
+_taps_cache = {}
+_TAPS_CACHE_MAX = 512
+
+
 def _gaussian_weights(sigma, order, truncate, radius=None):
-    """Taps handed to correlate1d by scipy's gaussian_filter1d (:745-754)."""
+    """Taps handed to correlate1d by scipy's gaussian_filter1d (:745-754).
+    Cached per (type and value of sigma, order, radius): scipy squares sigma in
+    sigma's OWN type, so a float32 scalar and the equal Python float give
+    different taps and are different keys.  Cached arrays are read-only."""
     sd = float(sigma)
     lw = int(truncate * sd + 0.5)
     if radius is not None:
         lw = radius
     if not isinstance(lw, numbers.Integral) or lw < 0:
         raise ValueError("Radius must be a nonnegative integer.")
-    return _gaussian_kernel1d(sigma, order, lw)[::-1]
+    key = None
+    if isinstance(order, numbers.Integral) and isinstance(sigma, (numbers.Real, np.generic)):
+        key = (type(sigma), sd, int(order), int(lw))
+        hit = _taps_cache.get(key)
+        if hit is not None:
+            return hit
+    w = _gaussian_kernel1d(sigma, order, lw)[::-1]
+    if key is not None:
+        w = np.ascontiguousarray(w)
+        w.flags.writeable = False
+        if len(_taps_cache) >= _TAPS_CACHE_MAX:
+            _taps_cache.clear()
+        _taps_cache[key] = w
+    return w
 
 
 def gaussian_filter1d(input, sigma, axis=-1, order=0, output=None, mode="reflect", cval=0.0,
@@ -286,11 +322,21 @@ def uniform_filter1d(input, size, axis=-1, output=None, mode="reflect", cval=0.0
 # pass chains
 # --------------------------------------------------------------------------
 class _Pass:
-    __slots__ = ("kind", "axis", "weights", "size", "origin", "mode")
+    """One 1-D pass of a plan.  Immutable once built (plans are cached and shared
+    between threads): the signature and the ctypes view of the taps are computed
+    once."""
+    __slots__ = ("kind", "axis", "weights", "size", "origin", "mode", "sig", "prepared")
 
     def __init__(self, kind, axis, mode, weights=None, size=0, origin=0):
         self.kind, self.axis, self.mode = kind, axis, mode
         self.weights, self.size, self.origin = weights, size, origin
+        self.prepared = None
+        wbytes = None
+        if weights is not None:
+            w = np.ascontiguousarray(weights, dtype=np.float64)
+            self.prepared = (w, _lib.f64_pointer(w))
+            wbytes = w.tobytes()
+        self.sig = (kind, axis, mode, origin, size, wbytes)
 
 
 def _chain_targets(n_passes, epilogue):
@@ -305,8 +351,7 @@ def _chain_targets(n_passes, epilogue):
 
 
 def _pass_signature(ps):
-    return (ps.kind, ps.axis, ps.mode, ps.origin, ps.size,
-            None if ps.weights is None else np.asarray(ps.weights, dtype=np.float64).tobytes())
+    return ps.sig
 
 
 def _run_chain(x_tensor, shape, np_dtype, passes, cval, out_tensor, final_epilogue=_lib.EPI_STORE,
@@ -344,7 +389,7 @@ def _run_chain(x_tensor, shape, np_dtype, passes, cval, out_tensor, final_epilog
         epi = final_epilogue if last else _lib.EPI_STORE
         if ps.kind == "corr":
             _launch_correlate1d(src, dst, shape, np_dtype, ps.axis, ps.weights, ps.mode, cval,
-                                ps.origin, use_pad, epi, flags)
+                                ps.origin, use_pad, epi, flags, prepared=ps.prepared)
         else:
             if epi != _lib.EPI_STORE:
                 raise RuntimeError("only correlation passes have a fused epilogue")
@@ -598,10 +643,43 @@ def _plan_maximum_filter(ndim, size=None, footprint=None, mode="reflect", cval=0
     return _plan_minmax(ndim, True, size, footprint, mode, cval, origin, axes)
 
 
+_plan_cache = {}
+_PLAN_CACHE_MAX = 256
+
+
+def _freeze(v):
+    """Hashable, type-preserving image of a plan argument, or raise TypeError
+    (arrays and other unhashable objects: the plan is then built afresh)."""
+    if isinstance(v, (list, tuple)):
+        return (type(v).__name__,) + tuple(_freeze(e) for e in v)
+    if isinstance(v, np.generic):
+        return (v.dtype.str, v.item())
+    if v is None or isinstance(v, (bool, int, float, str)):
+        return (type(v).__name__, v)
+    raise TypeError("not cacheable")
+
+
+def _cached_plan(plan_fn, ndim, args, kwargs):
+    """Plans depend on the call's parameters only, never on the data: chunk-wise
+    callers (dask runs the same filter on every chunk, from several threads)
+    build each plan once.  Plans and their passes are never mutated."""
+    try:
+        key = (plan_fn.__name__, ndim, _freeze(args), _freeze(sorted(kwargs.items())))
+    except TypeError:
+        return plan_fn(ndim, *args, **kwargs)
+    plan = _plan_cache.get(key)
+    if plan is None:
+        plan = plan_fn(ndim, *args, **kwargs)
+        if len(_plan_cache) >= _PLAN_CACHE_MAX:
+            _plan_cache.clear()
+        _plan_cache[key] = plan
+    return plan
+
+
 def _run(plan_fn, input, output, *args, **kwargs):
     x = as_b200(input)
     _zero_dim_guard(x)
-    plan = plan_fn(x.ndim, *args, **kwargs)
+    plan = _cached_plan(plan_fn, x.ndim, args, kwargs)
     out = _check_output(output, x) or x.empty_like()
     return _execute(plan, x, out)
 

@@ -81,6 +81,69 @@ def test_gaussian_taps_bit_identical_to_scipy(sigma, order):
         assert np.array_equal(ref[::-1], ndimage._gaussian_weights(sigma, order, truncate))
 
 
+def test_gaussian_taps_cache_keeps_sigma_type_and_is_read_only():
+    """scipy squares sigma in sigma's own type: a float32 scalar and the equal Python float give
+    different taps, so they are different cache entries; cached taps cannot be modified."""
+    ndimage._taps_cache.clear()
+    s32, s64 = np.float32(2.1), float(np.float32(2.1))
+    for _ in range(2):          # second round is served from the cache
+        w32 = ndimage._gaussian_weights(s32, 0, 4.0)
+        w64 = ndimage._gaussian_weights(s64, 0, 4.0)
+        assert np.array_equal(w32, scipy.ndimage._filters._gaussian_kernel1d(s32, 0, 8)[::-1])
+        assert np.array_equal(w64, scipy.ndimage._filters._gaussian_kernel1d(s64, 0, 8)[::-1])
+        assert not np.array_equal(w32, w64)
+    assert ndimage._gaussian_weights(s64, 0, 4.0) is w64
+    assert ndimage._gaussian_weights(s64, 1, 4.0) is not w64
+    assert ndimage._gaussian_weights(s64, 0, 4.0, radius=3).shape == (7,)
+    with pytest.raises(ValueError):
+        w64[0] = 1.0
+    with pytest.raises(ValueError):
+        ndimage._gaussian_weights(2.0, 0, 4.0, radius=-1)
+    with pytest.raises(ValueError):
+        ndimage._gaussian_weights(2.0, -1, 4.0)
+
+
+def test_plan_cache_is_keyed_by_value_and_type():
+    ndimage._plan_cache.clear()
+    p1 = ndimage._cached_plan(ndimage._plan_gaussian_filter, 3, (2.0, 0, "reflect", 0.0, 4.0, None, None), {})
+    p2 = ndimage._cached_plan(ndimage._plan_gaussian_filter, 3, (2.0, 0, "reflect", 0.0, 4.0, None, None), {})
+    assert p1 is p2 and len(p1.chains[0][0]) == 3
+    # other values, other types (np.float32 sigma, a tuple, an int), other rank: other plans
+    others = [
+        ndimage._cached_plan(ndimage._plan_gaussian_filter, 3, (2.5, 0, "reflect", 0.0, 4.0, None, None), {}),
+        ndimage._cached_plan(ndimage._plan_gaussian_filter, 3, (np.float32(2.0), 0, "reflect", 0.0, 4.0, None, None), {}),
+        ndimage._cached_plan(ndimage._plan_gaussian_filter, 3, ((2.0, 2.0, 2.0), 0, "reflect", 0.0, 4.0, None, None), {}),
+        ndimage._cached_plan(ndimage._plan_gaussian_filter, 3, (2, 0, "reflect", 0.0, 4.0, None, None), {}),
+        ndimage._cached_plan(ndimage._plan_gaussian_filter, 2, (2.0, 0, "reflect", 0.0, 4.0, None, None), {}),
+        ndimage._cached_plan(ndimage._plan_gaussian_filter, 3, (2.0, 0, "mirror", 0.0, 4.0, None, None), {}),
+    ]
+    assert all(o is not p1 for o in others) and len({id(o) for o in others}) == len(others)
+    # the cached plan is what a fresh build gives
+    fresh = ndimage._plan_gaussian_filter(3, 2.0, 0, "reflect", 0.0, 4.0, None, None)
+    assert [ps.sig for ps in fresh.chains[0][0]] == [ps.sig for ps in p1.chains[0][0]]
+    # keyword arguments take part; unhashable arguments (arrays) bypass the cache
+    k1 = ndimage._cached_plan(ndimage._plan_gaussian_gradient_magnitude, 2, (1.0, "reflect", 0.0, None), {"truncate": 3.0})
+    k2 = ndimage._cached_plan(ndimage._plan_gaussian_gradient_magnitude, 2, (1.0, "reflect", 0.0, None), {"truncate": 2.0})
+    assert k1 is not k2
+    n = len(ndimage._plan_cache)
+    a1 = ndimage._cached_plan(ndimage._plan_uniform_filter, 2, (np.array([3, 5]),), {})
+    a2 = ndimage._cached_plan(ndimage._plan_uniform_filter, 2, (np.array([3, 5]),), {})
+    assert a1 is not a2 and len(ndimage._plan_cache) == n
+    # invalid parameters raise every time and are not cached
+    for _ in range(2):
+        with pytest.raises(RuntimeError):
+            ndimage._cached_plan(ndimage._plan_gaussian_filter, 2, (1.0, 0, "bogus", 0.0, 4.0, None, None), {})
+
+
+def test_pass_prepares_signature_and_taps_once():
+    w = np.array([1, 2, 1], dtype=np.float32)          # any real dtype in, float64 taps out
+    ps = ndimage._Pass("corr", 1, "reflect", weights=w, origin=0)
+    assert ps.prepared[0].dtype == np.float64 and np.array_equal(ps.prepared[0], [1.0, 2.0, 1.0])
+    assert ndimage._pass_signature(ps) == ("corr", 1, "reflect", 0, 0, np.array([1.0, 2.0, 1.0]).tobytes())
+    box = ndimage._Pass("uniform", 0, "wrap", size=5, origin=1)
+    assert box.prepared is None and ndimage._pass_signature(box) == ("uniform", 0, "wrap", 1, 5, None)
+
+
 # ---- wrapper metadata (reference test__utils.py:11-60) -----------------------
 def test__get_docstring_and_update_wrapper():
     f = lambda: 0  # noqa: E731
