@@ -1,0 +1,155 @@
+"""The host side of the single-array path, end to end on the CPU.
+
+The product has no CPU fallback; here -- test infrastructure only -- the six raw
+launch helpers of ``dask_image_b200.ndimage`` are replaced by the oracle (the C
+ABI's contract restated on numpy views of CPU tensors) and ``B200Array`` is
+allowed to wrap CPU tensors, so that everything ABOVE the C ABI runs for real:
+argument handling, the cached plans and taps, pass chains, scratch ping-pong,
+prefix sharing between chains, fused epilogues.  With exact arithmetic below
+it, the public functions must reproduce scipy bit for bit, for every dtype.
+"""
+import numpy as np
+import pytest
+import scipy.ndimage as ndi
+import torch
+
+from _oracle_backend import _fold, _np
+from dask_image_b200 import _array, _lib, ndimage
+from oracle import oracle as orc
+
+
+def _view(t, shape):
+    return _np(t).reshape(tuple(shape))
+
+
+@pytest.fixture
+def cpu_path(monkeypatch):
+    calls = []
+
+    def init(self, tensor):
+        self.tensor = tensor if tensor.is_contiguous() else tensor.contiguous()
+
+    def corr1d(src, dst, shape, np_dtype, axis, weights, mode, cval, origin, pad=(0, 0),
+               epilogue=_lib.EPI_STORE, flags=None, prepared=None):
+        assert tuple(pad) == (0, 0)
+        if prepared is not None:      # the cached view of the taps is the taps
+            assert prepared[0].dtype == np.float64 and np.array_equal(prepared[0], np.asarray(weights, np.float64))
+        calls.append(("corr", axis, len(weights), epilogue))
+        r = orc.correlate1d(_view(src, shape), weights, axis, mode, cval, origin)
+        _fold(_view(dst, shape), r.copy(), epilogue)
+
+    def uniform1d(src, dst, shape, np_dtype, axis, size, mode, cval, origin, pad=(0, 0), flags=None):
+        calls.append(("uniform", axis, size))
+        _view(dst, shape)[...] = orc.uniform_filter1d(_view(src, shape), size, axis, mode, cval, origin)
+
+    def corrnd(src, dst, shape, np_dtype, weights, origins, mode, cval, pad=(0, 0), flags=None):
+        calls.append(("nd",))
+        _view(dst, shape)[...] = orc.correlate(_view(src, shape), weights, mode, cval, list(origins))
+
+    def minmax1d(src, dst, shape, np_dtype, axis, size, is_max, mode, cval, origin, pad=(0, 0), flags=None):
+        calls.append(("minmax", axis, size))
+        f = ndi.maximum_filter1d if is_max else ndi.minimum_filter1d
+        _view(dst, shape)[...] = f(_view(src, shape), size, axis=axis, mode=mode, cval=cval, origin=origin)
+
+    def minmaxnd(src, dst, shape, np_dtype, footprint, origins, is_max, mode, cval, pad=(0, 0), flags=None):
+        calls.append(("minmax_nd",))
+        f = ndi.maximum_filter if is_max else ndi.minimum_filter
+        _view(dst, shape)[...] = f(_view(src, shape), footprint=footprint, mode=mode, cval=cval, origin=list(origins))
+
+    def combine(acc, src, np_dtype, op):
+        calls.append(("combine", op))
+        _fold(_np(acc), _np(src).copy(), op)
+
+    monkeypatch.setattr(_array.B200Array, "__init__", init)
+    monkeypatch.setattr(_array, "default_device", lambda: torch.device("cpu"))
+    for name, fn in [("_launch_correlate1d", corr1d), ("_launch_uniform1d", uniform1d),
+                     ("_launch_correlate_nd", corrnd), ("_launch_minmax1d", minmax1d),
+                     ("_launch_minmax_nd", minmaxnd), ("_launch_combine", combine)]:
+        monkeypatch.setattr(ndimage, name, fn)
+    ndimage._plan_cache.clear()
+    return calls
+
+
+DTYPES = [np.float32, np.float64, np.uint8, np.uint16, np.int16, np.int32]
+
+
+def _data(rng, shape, dtype):
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        return (rng.random(shape) * 100 - 30).astype(dt)
+    ii = np.iinfo(dt)
+    return rng.integers(max(ii.min, -3000), min(ii.max, 3000), shape, endpoint=True).astype(dt)
+
+
+def _same(got, ref):
+    got = got.to_numpy()
+    assert got.dtype == ref.dtype and got.shape == ref.shape
+    np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(19, 23), (7, 9, 11)])
+def test_public_functions_reproduce_scipy_bitwise(cpu_path, dtype, shape):
+    rng = np.random.default_rng(17)
+    a = _data(rng, shape, dtype)
+    x = _array.B200Array.from_numpy(a)
+    nd = len(shape)
+    with np.errstate(all="ignore"):
+        for _ in range(2):      # second round: every plan comes out of the cache
+            _same(ndimage.gaussian_filter(x, 1.3), ndi.gaussian_filter(a, 1.3))
+            _same(ndimage.gaussian_filter(x, (1.0, 0.0, 2.0)[:nd], order=(0, 1, 2)[:nd], mode="wrap"),
+                  ndi.gaussian_filter(a, (1.0, 0.0, 2.0)[:nd], order=(0, 1, 2)[:nd], mode="wrap"))
+            _same(ndimage.gaussian_filter(x, np.float32(0.9), mode="constant", cval=3.0, truncate=2.5),
+                  ndi.gaussian_filter(a, np.float32(0.9), mode="constant", cval=3.0, truncate=2.5))
+            _same(ndimage.uniform_filter(x, 3, mode="mirror"), ndi.uniform_filter(a, 3, mode="mirror"))
+            _same(ndimage.uniform_filter(x, (4, 1, 5)[:nd], origin=(1, 0, -2)[:nd]),
+                  ndi.uniform_filter(a, (4, 1, 5)[:nd], origin=(1, 0, -2)[:nd]))
+            _same(ndimage.gaussian_gradient_magnitude(x, 1.1), ndi.gaussian_gradient_magnitude(a, 1.1))
+            _same(ndimage.gaussian_gradient_magnitude(x, 0.8, mode="nearest", truncate=3.0),
+                  ndi.gaussian_gradient_magnitude(a, 0.8, mode="nearest", truncate=3.0))
+            _same(ndimage.gaussian_laplace(x, 1.2, mode="reflect"), ndi.gaussian_laplace(a, 1.2, mode="reflect"))
+            _same(ndimage.laplace(x), ndi.laplace(a))
+            _same(ndimage.sobel(x, axis=0), ndi.sobel(a, axis=0))
+            _same(ndimage.prewitt(x, axis=-1, mode="constant", cval=1.0), ndi.prewitt(a, axis=-1, mode="constant", cval=1.0))
+            w = rng.random((3,) * nd) - 0.3
+            _same(ndimage.correlate(x, w, mode="wrap"), ndi.correlate(a, w, mode="wrap"))
+            _same(ndimage.convolve(x, w, origin=(1, -1, 0)[:nd]), ndi.convolve(a, w, origin=(1, -1, 0)[:nd]))
+            _same(ndimage.minimum_filter(x, size=3), ndi.minimum_filter(a, size=3))
+            _same(ndimage.maximum_filter(x, footprint=np.eye(3, dtype=bool) if nd == 2 else None,
+                                         size=None if nd == 2 else (1, 3, 2)),
+                  ndi.maximum_filter(a, footprint=np.eye(3, dtype=bool) if nd == 2 else None,
+                                     size=None if nd == 2 else (1, 3, 2)))
+            w1 = rng.random(5) - 0.5
+            _same(ndimage.correlate1d(x, w1, axis=0, origin=-1), ndi.correlate1d(a, w1, axis=0, origin=-1))
+            _same(ndimage.gaussian_filter1d(x, 1.7, axis=-1, order=1), ndi.gaussian_filter1d(a, 1.7, axis=-1, order=1))
+
+
+def test_gradient_magnitude_shares_chain_prefixes(cpu_path):
+    """3-D gradient magnitude / laplace: 8 launches for scipy's 9 passes (the chains along the last two
+    axes start with the same smoothing pass along axis 0), epilogues fused into each chain's last pass."""
+    a = np.random.default_rng(3).random((6, 7, 8)).astype(np.float32)
+    x = _array.B200Array.from_numpy(a)
+    del cpu_path[:]
+    _same(ndimage.gaussian_gradient_magnitude(x, 1.0), ndi.gaussian_gradient_magnitude(a, 1.0))
+    corr = [c for c in cpu_path if c[0] == "corr"]
+    assert len(corr) == 8 and not [c for c in cpu_path if c[0] == "combine"]
+    assert [c[3] for c in corr if c[3] != _lib.EPI_STORE] == [_lib.EPI_SQ_STORE, _lib.EPI_SQ_ACC, _lib.EPI_SQ_ACC_SQRT]
+    del cpu_path[:]
+    _same(ndimage.gaussian_laplace(x, 1.0), ndi.gaussian_laplace(a, 1.0))
+    corr = [c for c in cpu_path if c[0] == "corr"]
+    assert len(corr) == 8
+    assert [c[3] for c in corr if c[3] != _lib.EPI_STORE] == [_lib.EPI_ACC, _lib.EPI_ACC]
+
+
+def test_output_argument_and_input_untouched(cpu_path):
+    a = np.random.default_rng(4).integers(0, 255, (12, 14)).astype(np.uint8)
+    x = _array.B200Array.from_numpy(a)
+    out = x.empty_like()
+    r = ndimage.gaussian_filter(x, 2.0, output=out)
+    assert r is out
+    _same(out, ndi.gaussian_filter(a, 2.0))
+    np.testing.assert_array_equal(x.to_numpy(), a)          # the input is never written
+    # all sigmas ~ 0: identity copy, no launch
+    del cpu_path[:]
+    _same(ndimage.gaussian_filter(x, 0.0), a)
+    assert cpu_path == []
