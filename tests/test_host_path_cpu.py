@@ -153,3 +153,36 @@ def test_output_argument_and_input_untouched(cpu_path):
     del cpu_path[:]
     _same(ndimage.gaussian_filter(x, 0.0), a)
     assert cpu_path == []
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.uint16])
+def test_ndfilters_layer_chunked_equals_whole_array_scipy(cpu_path, dtype):
+    """The mirror of dask_image.ndfilters over HaloChunked (the eager map_overlap stand-in): halo depths,
+    boundary handling and trimming per ref:_gaussian.py:47-81, _smooth.py:17-40, _conv.py:15-66 --
+    chunk-wise results are the whole-array scipy results, bit for bit."""
+    import dask_image_b200 as b200
+
+    rng = np.random.default_rng(23)
+    a = _data(rng, (37, 41), dtype)
+    with np.errstate(all="ignore"):
+        for chunks in [(10, 13), (37, 41), (5, 40)]:
+            d = b200.from_array(a, chunks=chunks)
+            for mode in ("reflect", "constant", "wrap", "nearest", "mirror"):
+                # (gaussian / uniform keep boundary="none" as the reference does, ref:_gaussian.py:70-81: 'wrap'
+                # then wraps inside each edge chunk; only convolve / correlate rewrite it to a periodic halo)
+                if mode != "wrap" or chunks == a.shape:
+                    np.testing.assert_array_equal(
+                        np.asarray(b200.ndfilters.gaussian_filter(d, 1.2, mode=mode).compute()),
+                        ndi.gaussian_filter(a, 1.2, mode=mode), err_msg=str((chunks, mode)))
+                    np.testing.assert_array_equal(
+                        np.asarray(b200.ndfilters.uniform_filter(d, (3, 4), mode=mode, origin=(0, -1)).compute()),
+                        ndi.uniform_filter(a, (3, 4), mode=mode, origin=(0, -1)), err_msg=str((chunks, mode)))
+                w = rng.random((3, 4)) - 0.2
+                np.testing.assert_array_equal(
+                    np.asarray(b200.ndfilters.convolve(d, b200.B200Array.from_numpy(w), mode=mode).compute()),
+                    ndi.convolve(a, w, mode=mode), err_msg=str((chunks, mode)))
+            np.testing.assert_array_equal(np.asarray(b200.ndfilters.gaussian_gradient_magnitude(d, 1.0).compute()),
+                                          ndi.gaussian_gradient_magnitude(a, 1.0))
+            np.testing.assert_array_equal(np.asarray(b200.ndfilters.sobel(d, axis=1).compute()), ndi.sobel(a, axis=1))
+            np.testing.assert_array_equal(np.asarray(b200.ndfilters.maximum_filter(d, size=3).compute()),
+                                          ndi.maximum_filter(a, size=3))
