@@ -24,6 +24,10 @@ FLAGS = [
 ]
 
 
+# extra nvcc arguments for experiments (e.g. NVCC_EXTRA=-DB200_INT_NQ8); empty for the shipped build
+EXTRA = os.environ.get("NVCC_EXTRA", "").split()
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
@@ -47,7 +51,7 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + FLAGS + EXTRA + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False

@@ -6,6 +6,7 @@
 // 2 * taps - 1 FP64 instructions per output (taps when the weights are
 // symmetric or antisymmetric).
 #include "corr1d_int.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -41,9 +42,56 @@ corr1d_int_contig_kernel(const __grid_constant__ IntParams p)
     int_contig_writeout<TS>(p, otile, threadIdx.x, blockIdx.x);
 }
 
+#ifdef B200_INT_NQ8
+// Experiment (build with NVCC_EXTRA=-DB200_INT_NQ8, select with B200_INT_NQ=8): eight outputs per lane
+// and walk -- half the window loads, tap-table reads and loop overhead per output, twice the accumulators
+// (6 CTAs per SM instead of 8).  Same phases, same arithmetic; tests/test_int_emul.py runs both widths.
+template <typename TS, int KIND>
+__global__ void __launch_bounds__(kIntThreads, 6)
+corr1d_int_strided_kernel_nq8(const __grid_constant__ IntParams p)
+{
+    extern __shared__ __align__(16) unsigned char int_smem[];
+    IntTap *wc = reinterpret_cast<IntTap *>(int_smem);
+    int64_t *rows = reinterpret_cast<int64_t *>(int_smem + kIntTapBytes);
+    TS *tile = reinterpret_cast<TS *>(int_smem + kIntTapBytes + kIntRowTableBytes);
+    int_stage_taps(p, wc, threadIdx.x);
+    int_strided_stage_rows(p, rows, threadIdx.x, blockIdx.x);
+    __syncthreads();
+    int_strided_stage<TS>(p, tile, rows, threadIdx.x, blockIdx.x);
+    __syncthreads();
+    int_strided_compute<TS, KIND, 8>(p, tile, wc, threadIdx.x, blockIdx.x);
+}
+
+template <typename TS, int KIND>
+__global__ void __launch_bounds__(kIntThreads, 6)
+corr1d_int_contig_kernel_nq8(const __grid_constant__ IntParams p)
+{
+    extern __shared__ __align__(16) unsigned char int_smem[];
+    IntTap *wc = reinterpret_cast<IntTap *>(int_smem);
+    TS *tile = reinterpret_cast<TS *>(int_smem + kIntTapBytes);
+    TS *otile = tile + kIntContigRows * p.pitch;
+    int_stage_taps(p, wc, threadIdx.x);
+    int_contig_stage<TS>(p, tile, threadIdx.x, blockIdx.x);
+    __syncthreads();
+    int_contig_compute<TS, KIND, 8>(p, tile, otile, wc, threadIdx.x, blockIdx.x);
+    __syncthreads();
+    int_contig_writeout<TS>(p, otile, threadIdx.x, blockIdx.x);
+}
+#endif
+
 template <typename TS, int KIND>
 static int launch_int_typed(const IntPlan &pl, cudaStream_t stream)
 {
+#ifdef B200_INT_NQ8
+    static const bool nq8 = [] { const char *e = getenv("B200_INT_NQ"); return e && atoi(e) == 8; }();
+    if (nq8) {
+        if (pl.contig)
+            corr1d_int_contig_kernel_nq8<TS, KIND><<<(unsigned)pl.blocks, kIntThreads, pl.smem_bytes, stream>>>(pl.p);
+        else
+            corr1d_int_strided_kernel_nq8<TS, KIND><<<(unsigned)pl.blocks, kIntThreads, pl.smem_bytes, stream>>>(pl.p);
+        return check_cuda(cudaGetLastError(), "corr1d_int launch");
+    }
+#endif
     if (pl.contig)
         corr1d_int_contig_kernel<TS, KIND><<<(unsigned)pl.blocks, kIntThreads, pl.smem_bytes, stream>>>(pl.p);
     else

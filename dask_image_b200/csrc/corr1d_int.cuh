@@ -177,51 +177,66 @@ __host__ __device__ __forceinline__ void int_stage_taps(const IntParams &p, IntT
     for (int i = tid; i < p.nw; i += kIntThreads) wc[i] = IntTap{p.w[i], p.c[i]};
 }
 
-// Steps 0 .. ns-1 through `one.operator()<U>(k)` with U = k & 3 static: the
-// window slots of the callers rotate with period four.
-template <typename F>
+// Steps 0 .. ns-1 through `one.operator()<U>(k)` with U = k % NQ static: the
+// window slots of the callers rotate with period NQ (the outputs per lane).
+template <int NQ, typename F>
 __host__ __device__ __forceinline__ void int_run_steps(int ns, F &&one)
 {
+    static_assert(NQ == 4 || NQ == 8, "four or eight outputs per lane");
     int k = 0;
-    for (; k + 4 <= ns; k += 4) {
+    for (; k + NQ <= ns; k += NQ) {
         one.template operator()<0>(k);
         one.template operator()<1>(k + 1);
         one.template operator()<2>(k + 2);
         one.template operator()<3>(k + 3);
+        if constexpr (NQ == 8) {
+            one.template operator()<4>(k + 4);
+            one.template operator()<5>(k + 5);
+            one.template operator()<6>(k + 6);
+            one.template operator()<7>(k + 7);
+        }
     }
     if (k < ns) one.template operator()<0>(k);
     if (k + 1 < ns) one.template operator()<1>(k + 1);
     if (k + 2 < ns) one.template operator()<2>(k + 2);
+    if constexpr (NQ == 8) {
+        if (k + 3 < ns) one.template operator()<3>(k + 3);
+        if (k + 4 < ns) one.template operator()<4>(k + 4);
+        if (k + 5 < ns) one.template operator()<5>(k + 5);
+        if (k + 6 < ns) one.template operator()<6>(k + 6);
+    }
 }
 
-// acc[m] += x[m + k] * w[k] for k = 0 .. ns-1, in that order, for four
+// acc[m] += x[m + k] * w[k] for k = 0 .. ns-1, in that order, for NQ
 // consecutive outputs m: the single-tap walk (general 1-D weights, and every
 // weight row of the N-D correlate).  `s` addresses x[0], `step` is the element
-// distance between consecutive positions.  Reads s[0 .. (ns+3)*step].
-template <typename TS>
+// distance between consecutive positions.  Reads s[0 .. (ns+NQ-1)*step].
+template <typename TS, int NQ = 4>
 __host__ __device__ __forceinline__ void int_quad_taps(const TS *s, int step, int ns, const IntTap *wc, uint32_t hi,
-                                                       double (&acc)[4])
+                                                       double (&acc)[NQ])
 {
-    const TS *sa = s + 4 * step;   // next element entering the window
+    const TS *sa = s + NQ * step;   // next element entering the window
     if constexpr (std::is_signed<TS>::value) {
-        int A[4];
+        int A[NQ];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) A[m] = (int)s[m * step];
-        int_run_steps(ns, [&]<int U>(int k) {
+        for (int m = 0; m < NQ; ++m) A[m] = (int)s[m * step];
+        int_run_steps<NQ>(ns, [&]<int U>(int k) {
             const IntTap q = wc[k];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) acc[m] = int_add(acc[m], int_product<true>(A[(U + m) & 3], q.w, q.c));
+            for (int m = 0; m < NQ; ++m)
+                acc[m] = int_add(acc[m], int_product<true>(A[(U + m) & (NQ - 1)], q.w, q.c));
             A[U] = (int)*sa;
             sa += step;
         });
     } else {
-        uint64_t A[4];
+        uint64_t A[NQ];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) A[m] = int_pattern(hi, (uint32_t)s[m * step]);
-        int_run_steps(ns, [&]<int U>(int k) {
+        for (int m = 0; m < NQ; ++m) A[m] = int_pattern(hi, (uint32_t)s[m * step]);
+        int_run_steps<NQ>(ns, [&]<int U>(int k) {
             const IntTap q = wc[k];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) acc[m] = int_add(acc[m], int_pattern_product(A[(U + m) & 3], q.w, q.c));
+            for (int m = 0; m < NQ; ++m)
+                acc[m] = int_add(acc[m], int_pattern_product(A[(U + m) & (NQ - 1)], q.w, q.c));
             A[U] = int_pattern(hi, (uint32_t)*sa);
             sa += step;
         });
@@ -259,13 +274,13 @@ __host__ __device__ __forceinline__ void int_quad_taps_static(const TS *s, const
 }
 
 // KIND: +1 symmetric, -1 antisymmetric, 0 general.  `s` addresses the element
-// under tap 0 of the first of four consecutive outputs, `step` is the element
-// distance between consecutive positions of the line.  Reads s[0 .. (nw+2)*step].
-// Element q of the line lives in window slot A[q & 3]; element (L - 1 + q') in
-// B[q' & 3]; the tap loop is unrolled four times so that the slots are static.
-template <typename TS, int KIND>
+// under tap 0 of the first of NQ consecutive outputs, `step` is the element
+// distance between consecutive positions of the line.  Reads s[0 .. (nw+NQ-2)*step].
+// Element q of the line lives in window slot A[q % NQ]; element (L - 1 + q') in
+// B[q' % NQ]; the tap loop is unrolled NQ times so that the slots are static.
+template <typename TS, int KIND, int NQ = 4>
 __host__ __device__ __forceinline__ void int_line_quad(const TS *s, int step, const IntParams &p, const IntTap *wc,
-                                                       double (&acc)[4])
+                                                       double (&acc)[NQ])
 {
     constexpr bool SV = KIND < 0 || std::is_signed<TS>::value;
     const int L = p.nw;
@@ -273,30 +288,30 @@ __host__ __device__ __forceinline__ void int_line_quad(const TS *s, int step, co
         const IntTap q = wc[p.centre];
         const TS *sc = s + p.centre * step;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) acc[m] = int_product<std::is_signed<TS>::value>((int)sc[m * step], q.w, q.c);
+        for (int m = 0; m < NQ; ++m) acc[m] = int_product<std::is_signed<TS>::value>((int)sc[m * step], q.w, q.c);
     }
     if constexpr (KIND == 0) {
-        int_quad_taps<TS>(s, step, p.nsteps, wc, p.hi_word, acc);
+        int_quad_taps<TS, NQ>(s, step, p.nsteps, wc, p.hi_word, acc);
     } else {
-        const TS *sa = s + 4 * step;         // next element entering the left window
+        const TS *sa = s + NQ * step;        // next element entering the left window
         const TS *sb = s + (L - 2) * step;   // next element entering the right window
-        int A[4], B[4];
+        int A[NQ], B[NQ];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
+        for (int m = 0; m < NQ; ++m) {
             A[m] = (int)s[m * step];
             B[m] = (int)s[(L - 1 + m) * step];
         }
-        int_run_steps(p.nsteps, [&]<int U>(int k) {
+        int_run_steps<NQ>(p.nsteps, [&]<int U>(int k) {
             const IntTap q = wc[k];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int a = A[(U + m) & 3];
-                const int b = B[(m - U) & 3];
+            for (int m = 0; m < NQ; ++m) {
+                const int a = A[(U + m) & (NQ - 1)];
+                const int b = B[(m - U) & (NQ - 1)];
                 acc[m] = int_add(acc[m], int_product<SV>(KIND > 0 ? a + b : a - b, q.w, q.c));
             }
             A[U] = (int)*sa;
             sa += step;
-            B[(3 - U) & 3] = (int)*sb;
+            B[(NQ - 1 - U) & (NQ - 1)] = (int)*sb;
             sb -= step;
         });
     }
@@ -389,7 +404,8 @@ __host__ __device__ __forceinline__ void int_strided_stage(const IntParams &p, T
     }
 }
 
-template <typename TS, int KIND>
+// NQ = outputs per lane and walk (4, or 8 in the B200_INT_NQ8 build)
+template <typename TS, int KIND, int NQ = 4>
 __host__ __device__ __forceinline__ void int_strided_compute(const IntParams &p, const TS *tile, const IntTap *wc,
                                                              int tid, uint32_t bid)
 {
@@ -403,11 +419,11 @@ __host__ __device__ __forceinline__ void int_strided_compute(const IntParams &p,
     TS *dst = (TS *)p.out + (t.o * p.n + t.row0) * p.inner + col;
     const int64_t left = p.n - t.row0;
     const int rows_here = left < p.tile_out ? (int)left : p.tile_out;   // rows of the array in this tile
-    for (int r0 = 0; r0 < rows_here; r0 += 4) {
-        double acc[4];
-        int_line_quad<TS, KIND>(tile + r0 * W + tid, W, p, wc, acc);
+    for (int r0 = 0; r0 < rows_here; r0 += NQ) {
+        double acc[NQ];
+        int_line_quad<TS, KIND, NQ>(tile + r0 * W + tid, W, p, wc, acc);
 #pragma unroll
-        for (int m = 0; m < 4; ++m, dst += p.inner) {
+        for (int m = 0; m < NQ; ++m, dst += p.inner) {
             if (live && r0 + m < rows_here)
                 *dst = plain ? cast_out<TS>(acc[m]) : int_finish<TS>(acc[m], dst, p.epilogue);
         }
@@ -467,31 +483,34 @@ __host__ __device__ __forceinline__ void int_contig_stage(const IntParams &p, TS
     }
 }
 
-template <typename TS, int KIND>
+template <typename TS, int KIND, int NQ = 4>
 __host__ __device__ __forceinline__ void int_contig_compute(const IntParams &p, const TS *tile, TS *otile,
                                                             const IntTap *wc, int tid, uint32_t bid)
 {
     const IntContigTile t(p, bid);
     const int warp = tid >> 5, lane = tid & 31;
-    const int per_warp = p.tile_out / (kIntThreads / 32);   // multiple of 4
+    const int per_warp = p.tile_out / (kIntThreads / 32);   // multiple of 8
     const TS *line = tile + lane * p.pitch + p.shift;
     TS *oline = otile + lane * p.opitch;
-    for (int g = 0; g < per_warp; g += 4) {
+    for (int g = 0; g < per_warp; g += NQ) {
         // (groups past the end of a ragged line are computed and dropped: a per-warp
         // exit would take the weights off the uniform datapath)
         const int xo = warp * per_warp + g;
-        double acc[4];
-        int_line_quad<TS, KIND>(line + xo, 1, p, wc, acc);
-        TS r[4];
+        double acc[NQ];
+        int_line_quad<TS, KIND, NQ>(line + xo, 1, p, wc, acc);
+        TS r[NQ];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) r[m] = cast_out<TS>(acc[m]);
+        for (int m = 0; m < NQ; ++m) r[m] = cast_out<TS>(acc[m]);
         uint32_t *d = reinterpret_cast<uint32_t *>(oline + xo);
-        if constexpr (sizeof(TS) == 2) {
-            d[0] = (uint32_t)(uint16_t)r[0] | ((uint32_t)(uint16_t)r[1] << 16);
-            d[1] = (uint32_t)(uint16_t)r[2] | ((uint32_t)(uint16_t)r[3] << 16);
-        } else {
-            d[0] = (uint32_t)(uint8_t)r[0] | ((uint32_t)(uint8_t)r[1] << 8) | ((uint32_t)(uint8_t)r[2] << 16) |
-                   ((uint32_t)(uint8_t)r[3] << 24);
+#pragma unroll
+        for (int h = 0; h < NQ / 4; ++h) {
+            if constexpr (sizeof(TS) == 2) {
+                d[2 * h] = (uint32_t)(uint16_t)r[4 * h] | ((uint32_t)(uint16_t)r[4 * h + 1] << 16);
+                d[2 * h + 1] = (uint32_t)(uint16_t)r[4 * h + 2] | ((uint32_t)(uint16_t)r[4 * h + 3] << 16);
+            } else {
+                d[h] = (uint32_t)(uint8_t)r[4 * h] | ((uint32_t)(uint8_t)r[4 * h + 1] << 8) |
+                       ((uint32_t)(uint8_t)r[4 * h + 2] << 16) | ((uint32_t)(uint8_t)r[4 * h + 3] << 24);
+            }
         }
     }
 }

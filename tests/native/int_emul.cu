@@ -8,6 +8,7 @@
 // Built by tests/test_int_emul.py with `nvcc -x cu` (host code only; no GPU).
 #include "../../dask_image_b200/csrc/corrnd_int.cuh"
 #include <vector>
+#include <cstdlib>
 
 namespace b200 {
 // the launchers' diagnostics are not linked into this harness
@@ -16,7 +17,8 @@ int set_error(int code, const char *, ...) { return code; }
 
 using namespace b200;
 
-template <typename TS, int KIND>
+// NQ = outputs per lane and walk: 4 is the shipped kernel, 8 the B200_INT_NQ8 experiment
+template <typename TS, int KIND, int NQ>
 static void run_blocks(const IntPlan &pl)
 {
     const IntParams &p = pl.p;
@@ -30,24 +32,32 @@ static void run_blocks(const IntPlan &pl)
         if (pl.contig) {
             TS *otile = tile + kIntContigRows * p.pitch;
             for (int t = 0; t < kIntThreads; ++t) int_contig_stage<TS>(p, tile, t, bid);
-            for (int t = 0; t < kIntThreads; ++t) int_contig_compute<TS, KIND>(p, tile, otile, wc, t, bid);
+            for (int t = 0; t < kIntThreads; ++t) int_contig_compute<TS, KIND, NQ>(p, tile, otile, wc, t, bid);
             for (int t = 0; t < kIntThreads; ++t) int_contig_writeout<TS>(p, otile, t, bid);
         } else {
             int64_t *rows = reinterpret_cast<int64_t *>(smem.data() + kIntTapBytes);
             TS *stile = reinterpret_cast<TS *>(smem.data() + kIntTapBytes + kIntRowTableBytes);
             for (int t = 0; t < kIntThreads; ++t) int_strided_stage_rows(p, rows, t, bid);
             for (int t = 0; t < kIntThreads; ++t) int_strided_stage<TS>(p, stile, rows, t, bid);
-            for (int t = 0; t < kIntThreads; ++t) int_strided_compute<TS, KIND>(p, stile, wc, t, bid);
+            for (int t = 0; t < kIntThreads; ++t) int_strided_compute<TS, KIND, NQ>(p, stile, wc, t, bid);
         }
     }
+}
+
+template <typename TS, int NQ>
+static void run_kind_nq(const IntPlan &pl)
+{
+    if (pl.kind > 0) run_blocks<TS, 1, NQ>(pl);
+    else if (pl.kind < 0) run_blocks<TS, -1, NQ>(pl);
+    else run_blocks<TS, 0, NQ>(pl);
 }
 
 template <typename TS>
 static void run_kind(const IntPlan &pl)
 {
-    if (pl.kind > 0) run_blocks<TS, 1>(pl);
-    else if (pl.kind < 0) run_blocks<TS, -1>(pl);
-    else run_blocks<TS, 0>(pl);
+    const char *e = getenv("B200_INT_NQ");
+    if (e && atoi(e) == 8) run_kind_nq<TS, 8>(pl);
+    else run_kind_nq<TS, 4>(pl);
 }
 
 // Same argument meaning as b200_correlate1d (host pointers).  Returns 0 when the

@@ -110,6 +110,38 @@ def test_emulated_kernels_match_oracle(emul, dtype, kind, nw):
                     np.testing.assert_array_equal(got, ref, err_msg=str((shape, axis, mode, origin, info)))
 
 
+@pytest.fixture
+def eight_wide(monkeypatch):
+    """Run the emulation with eight outputs per lane and walk (the B200_INT_NQ8 experiment of
+    corr1d_int.cu; tests/native/int_emul.cu reads the variable on every call)."""
+    monkeypatch.setenv("B200_INT_NQ", "8")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kind,nw", [("gauss", 17), ("gauss", 3), ("gauss", 1), ("gauss", 27), ("dgauss", 9),
+                                     ("dgauss", 15), ("random", 8), ("random", 5), ("random", 2), ("random", 21)])
+def test_emulated_eight_wide_walk_matches_oracle(emul, eight_wide, dtype, kind, nw):
+    rng = np.random.default_rng(hash((dtype, kind, nw, 8)) % (1 << 32))
+    w = weights(kind, nw, rng)
+    for shape in [(37, 144), (5, 40, 48), (70, 19)]:
+        x = data(rng, shape, dtype)
+        for axis in range(len(shape)):
+            for mode in ("reflect", "constant", "wrap"):
+                for origin in sorted({0, -(nw // 2), (nw - 1) // 2}):
+                    got, info = run_emul(emul, x, w, axis, mode, 5.0, origin)
+                    assert got is not None
+                    ref = oracle.correlate1d(x, w, axis=axis, mode=mode, cval=5.0, origin=origin)
+                    np.testing.assert_array_equal(got, ref, err_msg=str((shape, axis, mode, origin, info)))
+    # fused epilogue through the eight-wide store path
+    x = data(rng, (24, 48), dtype)
+    prev = data(rng, (24, 48), dtype)
+    for axis in (0, 1):
+        r = oracle.correlate1d(x, w, axis=axis).astype(np.int64)
+        out = prev.copy()
+        got, _ = run_emul(emul, x, w, axis, "reflect", epilogue=_lib.EPI_SQ_ACC, out=out)
+        np.testing.assert_array_equal(got, _wrap(prev.astype(np.int64) + r * r, dtype))
+
+
 @pytest.mark.parametrize("dtype", ["uint8", "uint16", "int16"])
 def test_emulated_kernels_long_filters_and_small_extents(emul, dtype):
     rng = np.random.default_rng(11)
