@@ -19,13 +19,10 @@ FLAGS = [
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
     "-cudart", "static",
 ]
-# corr1d_tma.cu holds ~250 kernel instantiations: optimise / assemble it on all host cores (2 min -> 70 s).
-# Split compilation is NOT reproducible -- repeated runs of one command give one of two SASS variants of the
-# same source (measured on corr1d_int.cu: 78824 vs 78120 instruction lines) -- so every other translation unit,
-# each a few seconds of work, is compiled in one piece and its SASS is a function of the source alone.
-SPLIT = {"corr1d_tma.cu": ["--split-compile=0"]}
-
-
+# Every translation unit is compiled in one piece: nvcc's --split-compile is NOT reproducible (repeated
+# runs of one command give one of two SASS variants of the same source), and with one unit per kernel
+# family (corr1d_strided.cu / corr1d_contig.cu / ...) the units already build in parallel.
+SPLIT = {}
 # extra nvcc arguments for experiments (e.g. NVCC_EXTRA=-DB200_INT_NQ8); empty for the shipped build
 EXTRA = os.environ.get("NVCC_EXTRA", "").split()
 

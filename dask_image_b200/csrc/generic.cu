@@ -4,8 +4,9 @@
 // accepts, accumulate in fp64 in exactly the order scipy's compiled loops use
 // (no FMA contraction: __dmul_rn/__dadd_rn) and store with the reference's
 // cast rules, so their results are bit-identical to scipy.ndimage for every
-// dtype.  They are the integer path, the B200_FLAG_EXACT path, and the
-// fallback for shapes the TMA-tiled kernels (corr1d_tma.cu, uniform_fast.cu,
+// dtype.  They are the path of the 32/64-bit integer dtypes (8/16-bit ones have exact
+// tiled kernels: corr1d_int.cu, corrnd_int.cu), the B200_FLAG_EXACT path, and the
+// fallback for shapes the TMA-tiled kernels (corr1d_strided.cu, corr1d_contig.cu,
 // corrnd_tiled.cu) do not take.  Loads are coalesced along the contiguous
 // axis and overlapping windows are served by L1/L2.
 #include "common.cuh"

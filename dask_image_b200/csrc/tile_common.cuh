@@ -1,5 +1,5 @@
 // tile_common.cuh -- device building blocks shared by the TMA-tiled kernels
-// (corr1d_tma.cu: 1-D passes and box filter; corrnd_tiled.cu: direct N-D
+// (corr1d_strided.cu / corr1d_contig.cu: 1-D passes and box filter; corrnd_tiled.cu: direct N-D
 // correlate): 16-byte register vectors, packed-FFMA2 accumulators, storage
 // widening loads, the contiguous-axis tap engine and wide global stores.
 #pragma once

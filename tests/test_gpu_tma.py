@@ -1,4 +1,4 @@
-"""GPU tests of the TMA-tiled kernels (corr1d_tma.cu): forced onto the tiled
+"""GPU tests of the TMA-tiled kernels (corr1d_strided.cu, corr1d_contig.cu, corr1d_minmax.cu): forced onto the tiled
 path with B200_FLAG_FORCE_FAST so that small, edge-heavy shapes exercise tile
 edges, patched halos, tap tails and both axis orientations; compared against
 the CPU oracle within the north_star tolerances (fp32 1e-5, fp64 1e-12)."""

@@ -95,9 +95,11 @@ def main():
     sass_dir = os.path.join(PROF, "sass")
     os.makedirs(sass_dir, exist_ok=True)
     wanted = {
-        "corr1d_tma.o": [r"corr1d_strided_tma_kernelIffLi128ELi8ELi4ELi3ELi1E", r"corr1d_contig_static_kernelIfLi17E",
-                         r"corr1d_strided_tma_kernelIftLi256ELi8ELi4ELi3ELi3E", r"corr1d_contig_static_kernelItLi16E",
-                         r"corr1d_strided_peer_kernelIffLi128ELi8ELi4ELi3ELi1E", r"corr1d_contig_tma_kernelIffLi0ELi1E"],
+        "corr1d_strided.o": [r"corr1d_strided_tma_kernelIffLi128ELi8ELi4ELi3ELi1E",
+                             r"corr1d_strided_tma_kernelIftLi256ELi8ELi4ELi3ELi3E",
+                             r"corr1d_strided_peer_kernelIffLi128ELi8ELi4ELi3ELi1E"],
+        "corr1d_contig.o": [r"corr1d_contig_static_kernelIfLi17E", r"corr1d_contig_static_kernelItLi16E",
+                            r"corr1d_contig_tma_kernelIffLi0ELi1E"],
         "corrnd_tiled.o": [r"corrnd_static_kernelILi9E"],
         "corr1d_int.o": [r"corr1d_int_strided_kernelItLi1E"],
         "corrnd_int.o": [r"corrnd_int_kernelItE"],
