@@ -51,6 +51,13 @@ def main():
          lambda v: f.gaussian_filter(v, 2.0)),
         ("H4 gaussian s=4 2048^3 f32", (2048 // scale,) * 3, np.float32, 24,
          lambda v: f.gaussian_filter(v, 4.0)),
+        # integer images: the exact tiled integer kernels (instruction-issue bound, not HBM bound)
+        ("I16 gaussian s=2 2048^3 u16", (2048 // scale,) * 3, np.uint16, 12,
+         lambda v: f.gaussian_filter(v, 2.0)),
+        ("I8 gaussian s=2 2048^3 u8", (2048 // scale,) * 3, np.uint8, 6,
+         lambda v: f.gaussian_filter(v, 2.0)),
+        ("I16g ggm s=2 1024^3 u16", (1024 // scale,) * 3, np.uint16, 36,
+         lambda v: f.gaussian_gradient_magnitude(v, 2.0)),
     ]
     for name, shape, dt, bpv, fn in cfgs:
         if only and name.split()[0] not in only:
