@@ -12,6 +12,8 @@ bash tools/capture_raw.sh prof_${tag}_corrnd_int_u16 corrnd_int env DTYPES=u2 py
 ls -la gpurun_out/prof_${tag}_*int*_raw.csv
 # the eight-outputs-per-lane experiment: rebuild with the flag, rerun the parity tests and the scan with it selected
 # (uncomment for an A/B run; the default build does not contain these kernels)
-# NVCC_EXTRA=-DB200_INT_NQ8 python -m dask_image_b200.build --force > /dev/null 2>&1
+# NVCC_EXTRA="-DB200_INT_NQ8 -DB200_INT_FIXED" python -m dask_image_b200.build --force > /dev/null 2>&1
 # B200_INT_NQ=8 python -m pytest tests/test_gpu_int.py -q 2>&1 | tail -1
 # (cd tools && B200_INT_NQ=8 DTYPES=u2 python int_scan.py 2 | cut -c1-120)
+# B200_INT_FIXED=1 python -m pytest tests/test_gpu_int.py -q 2>&1 | tail -1
+# (cd tools && B200_INT_FIXED=1 DTYPES=u2 python int_scan.py 2 | cut -c1-120; B200_INT_FIXED=1 B200_INT_NQ=8 DTYPES=u2 python int_scan.py 2 | cut -c1-120)
