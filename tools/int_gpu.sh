@@ -16,4 +16,4 @@ ls -la gpurun_out/prof_${tag}_*int*_raw.csv
 # B200_INT_NQ=8 python -m pytest tests/test_gpu_int.py -q 2>&1 | tail -1
 # (cd tools && B200_INT_NQ=8 DTYPES=u2 python int_scan.py 2 | cut -c1-120)
 # B200_INT_FIXED=1 python -m pytest tests/test_gpu_int.py -q 2>&1 | tail -1
-# (cd tools && B200_INT_FIXED=1 DTYPES=u2 python int_scan.py 2 | cut -c1-120; B200_INT_FIXED=1 B200_INT_NQ=8 DTYPES=u2 python int_scan.py 2 | cut -c1-120)
+# (cd tools && B200_INT_FIXED=1 DTYPES=u2 python int_scan.py 2 | cut -c1-120; B200_INT_NQ=8 DTYPES=u2 python int_scan.py 2 | cut -c1-120)
