@@ -83,8 +83,8 @@ corr1d_int_contig_kernel_nq8(const __grid_constant__ IntParams p)
 // Experiment (build with NVCC_EXTRA=-DB200_INT_FIXED, select with B200_INT_FIXED=1): the certified
 // fixed-point walk of corr1d_int.cuh -- one IMAD.WIDE per tap pair, the exact FP64 sequence only for the
 // outputs whose integer sum lies within the proven error band of an integer.
-template <typename TS, int KIND>
-__global__ void __launch_bounds__(kIntThreads, 8)
+template <typename TS, int KIND, int NQ = 4>
+__global__ void __launch_bounds__(kIntThreads, NQ == 8 ? 6 : 8)
 corr1d_int_strided_kernel_fx(const __grid_constant__ IntParams p, const __grid_constant__ IntFixedParams fx)
 {
     extern __shared__ __align__(16) unsigned char int_smem[];
@@ -96,11 +96,11 @@ corr1d_int_strided_kernel_fx(const __grid_constant__ IntParams p, const __grid_c
     __syncthreads();
     int_strided_stage<TS>(p, tile, rows, threadIdx.x, blockIdx.x);
     __syncthreads();
-    int_strided_compute_fixed<TS, KIND>(p, fx, tile, wc, threadIdx.x, blockIdx.x);
+    int_strided_compute_fixed<TS, KIND, NQ>(p, fx, tile, wc, threadIdx.x, blockIdx.x);
 }
 
-template <typename TS, int KIND>
-__global__ void __launch_bounds__(kIntThreads, 8)
+template <typename TS, int KIND, int NQ = 4>
+__global__ void __launch_bounds__(kIntThreads, NQ == 8 ? 6 : 8)
 corr1d_int_contig_kernel_fx(const __grid_constant__ IntParams p, const __grid_constant__ IntFixedParams fx)
 {
     extern __shared__ __align__(16) unsigned char int_smem[];
@@ -110,7 +110,7 @@ corr1d_int_contig_kernel_fx(const __grid_constant__ IntParams p, const __grid_co
     int_stage_taps(p, wc, threadIdx.x);
     int_contig_stage<TS>(p, tile, threadIdx.x, blockIdx.x);
     __syncthreads();
-    int_contig_compute_fixed<TS, KIND>(p, fx, tile, otile, wc, threadIdx.x, blockIdx.x);
+    int_contig_compute_fixed<TS, KIND, NQ>(p, fx, tile, otile, wc, threadIdx.x, blockIdx.x);
     __syncthreads();
     int_contig_writeout<TS>(p, otile, threadIdx.x, blockIdx.x);
 }
@@ -121,6 +121,16 @@ static int launch_int_typed(const IntPlan &pl, const IntFixedParams &fx, cudaStr
 {
 #ifdef B200_INT_FIXED
     static const bool fixed = [] { const char *e = getenv("B200_INT_FIXED"); return e && atoi(e) == 1; }();
+#ifdef B200_INT_NQ8
+    static const bool fixed8 = [] { const char *e = getenv("B200_INT_NQ"); return e && atoi(e) == 8; }();
+    if (fixed && fx.on && fixed8) {
+        if (pl.contig)
+            corr1d_int_contig_kernel_fx<TS, KIND, 8><<<(unsigned)pl.blocks, kIntThreads, pl.smem_bytes, stream>>>(pl.p, fx);
+        else
+            corr1d_int_strided_kernel_fx<TS, KIND, 8><<<(unsigned)pl.blocks, kIntThreads, pl.smem_bytes, stream>>>(pl.p, fx);
+        return check_cuda(cudaGetLastError(), "corr1d_int launch");
+    }
+#endif
     if (fixed && fx.on) {
         if (pl.contig)
             corr1d_int_contig_kernel_fx<TS, KIND><<<(unsigned)pl.blocks, kIntThreads, pl.smem_bytes, stream>>>(pl.p, fx);

@@ -14,6 +14,6 @@ ls -la gpurun_out/prof_${tag}_*int*_raw.csv
 # (uncomment for an A/B run; the default build does not contain these kernels)
 # NVCC_EXTRA="-DB200_INT_NQ8 -DB200_INT_FIXED" python -m dask_image_b200.build --force > /dev/null 2>&1
 # B200_INT_NQ=8 python -m pytest tests/test_gpu_int.py -q 2>&1 | tail -1
-# (cd tools && B200_INT_NQ=8 DTYPES=u2 python int_scan.py 2 | cut -c1-120)
+# (cd tools && B200_INT_NQ=8 DTYPES=u2 python int_scan.py 2 | cut -c1-120; B200_INT_FIXED=1 B200_INT_NQ=8 DTYPES=u2 python int_scan.py 2 | cut -c1-120)
 # B200_INT_FIXED=1 python -m pytest tests/test_gpu_int.py -q 2>&1 | tail -1
-# (cd tools && B200_INT_FIXED=1 DTYPES=u2 python int_scan.py 2 | cut -c1-120; B200_INT_NQ=8 DTYPES=u2 python int_scan.py 2 | cut -c1-120)
+# (cd tools && B200_INT_FIXED=1 DTYPES=u2 python int_scan.py 2 | cut -c1-120; B200_INT_NQ=8 DTYPES=u2 python int_scan.py 2 | cut -c1-120; B200_INT_FIXED=1 B200_INT_NQ=8 DTYPES=u2 python int_scan.py 2 | cut -c1-120)
