@@ -33,6 +33,7 @@ EXPORTS = (
     "b200_correlate1d", "b200_uniform_filter1d", "b200_correlate_nd", "b200_combine",
     "b200_minmax_filter1d", "b200_minmax_filter_nd", "b200_correlate1d_halo", "b200_correlate1d_halo_eligible",
     "b200_enable_peer_access", "b200_uniform_filter1d_halo", "b200_uniform_filter1d_halo_eligible",
+    "b200_correlate1d_pair", "b200_correlate1d_pair_eligible",
     "b200_last_kernel", "b200_last_error", "b200_version", "b200_launch_count",
 )
 
@@ -80,6 +81,10 @@ def load():
     lib.b200_uniform_filter1d_halo.restype = ci
     lib.b200_uniform_filter1d_halo_eligible.argtypes = [ci, i64, i64, i64, i64, ci, dbl]
     lib.b200_uniform_filter1d_halo_eligible.restype = ci
+    lib.b200_correlate1d_pair.argtypes = [vp, vp, ci, ci, i64p, dblp, i64, ci, i64, dblp, i64, ci, i64, dbl, ci, cu, vp]
+    lib.b200_correlate1d_pair.restype = ci
+    lib.b200_correlate1d_pair_eligible.argtypes = [ci, ci, i64p, i64, i64, i64, i64]
+    lib.b200_correlate1d_pair_eligible.restype = ci
     lib.b200_enable_peer_access.argtypes = [ci]
     lib.b200_enable_peer_access.restype = ci
     lib.b200_correlate1d_halo_eligible.argtypes = [ci, i64, i64, i64, i64]

@@ -145,6 +145,47 @@ int b200_correlate1d_halo(const void *in, void *out, int dtype, int ndim, const 
     return rc;
 }
 
+int b200_correlate1d_pair_eligible(int dtype, int ndim, const int64_t *shape, int64_t nw1, int64_t origin1,
+                                   int64_t nw2, int64_t origin2)
+{
+    if (ndim < 2 || ndim > B200_MAXDIM || !shape) return 0;
+    if (nw1 < 1 || nw1 > 4096 || nw2 < 1 || nw2 > 4096) return 0;
+    return corr2d_fused_eligible(dtype, shape[ndim - 2], shape[ndim - 1], (int)nw1, (int)origin1, (int)nw2,
+                                 (int)origin2);
+}
+
+int b200_correlate1d_pair(const void *in, void *out, int dtype, int ndim, const int64_t *shape, const double *w1,
+                          int64_t nw1, int mode1, int64_t origin1, const double *w2, int64_t nw2, int mode2,
+                          int64_t origin2, double cval, int epilogue, unsigned flags, void *stream)
+{
+    int64_t total;
+    if (int rc = check_common(in, out, dtype, ndim, shape, mode1, &total)) return rc;
+    if (mode2 < B200_MODE_NEAREST || mode2 > B200_MODE_CONSTANT)
+        return set_error(B200_EMODE, "boundary mode not supported");
+    if (ndim < 2) return set_error(B200_EINVAL, "a pass pair needs at least two axes");
+    if (!w1 || nw1 < 1 || !w2 || nw2 < 1) return set_error(B200_EINVAL, "no filter weights given");
+    if (origin1 < -(nw1 / 2) || origin1 > (nw1 - 1) / 2 || origin2 < -(nw2 / 2) || origin2 > (nw2 - 1) / 2)
+        return set_error(B200_EORIGIN, "Invalid origin; origin must satisfy "
+                                       "-(len(weights) // 2) <= origin <= (len(weights)-1) // 2");
+    if (epilogue < B200_EPI_STORE || epilogue > B200_EPI_SQ_ACC_SQRT)
+        return set_error(B200_EINVAL, "unknown epilogue");
+    if (total == 0) return B200_OK;
+    if (flags & B200_FLAG_EXACT) return set_error(B200_EINVAL, "not eligible: the fused pass pair is a tiled kernel");
+    if (!b200_correlate1d_pair_eligible(dtype, ndim, shape, nw1, origin1, nw2, origin2))
+        return set_error(B200_EINVAL, "not eligible: no fused kernel for this pair of filters");
+    Corr2dArgs a;
+    a.in = in; a.out = out; a.dtype = dtype;
+    a.outer = 1;
+    for (int d = 0; d < ndim - 2; ++d) a.outer *= shape[d];
+    a.ny = shape[ndim - 2]; a.nx = shape[ndim - 1];
+    a.w1 = w1; a.nw1 = (int)nw1; a.origin1 = (int)origin1; a.mode1 = mode1;
+    a.w2 = w2; a.nw2 = (int)nw2; a.origin2 = (int)origin2; a.mode2 = mode2;
+    a.cval = cval; a.epilogue = epilogue; a.flags = flags; a.stream = (cudaStream_t)stream;
+    int rc = launch_corr2d_fused(a);
+    if (rc < 0) return set_error(B200_EINVAL, "not eligible: no fused kernel for this pair of filters");
+    return rc;
+}
+
 int b200_enable_peer_access(int peer_device)
 {
     int dev = -1;

@@ -269,6 +269,26 @@ int launch_corr1d_tma(const Corr1dArgs &a);
 // exact tiled path of the 8/16-bit integer dtypes (corr1d_int.cu); -1 = not eligible
 int launch_corr1d_int(const Corr1dArgs &a);
 
+// two consecutive float32 passes along the last two axes in one launch (corr2d_fused.cu):
+// the array is viewed as [outer][ny][nx]
+struct Corr2dArgs {
+    const void *in;
+    void *out;
+    int dtype;
+    int64_t outer, ny, nx;
+    const double *w1;  // host: taps of the pass along axis ndim-2
+    int nw1, origin1, mode1;
+    const double *w2;  // host: taps of the pass along axis ndim-1
+    int nw2, origin2, mode2;
+    double cval;
+    int epilogue;
+    unsigned flags;
+    cudaStream_t stream;
+};
+// -1 = no fused kernel for this pair of filters (the caller runs the two passes one by one)
+int launch_corr2d_fused(const Corr2dArgs &a);
+int corr2d_fused_eligible(int dtype, int64_t ny, int64_t nx, int nw1, int origin1, int nw2, int origin2);
+
 struct Uniform1dArgs {
     const void *in;
     void *out;

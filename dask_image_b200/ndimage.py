@@ -108,6 +108,63 @@ def _launch_correlate1d(src, dst, shape, np_dtype, axis, weights, mode, cval, or
     _lib.check(rc)
 
 
+def _launch_correlate1d_pair(src, dst, shape, np_dtype, ps1, ps2, cval, epilogue=_lib.EPI_STORE, flags=None):
+    """The passes ``ps1`` (axis ndim-2) and ``ps2`` (axis ndim-1) in one launch
+    (corr2d_fused.cu); bit-identical to the two launches."""
+    lib = _lib.load()
+    (w1, p1), (w2, p2) = ps1.prepared, ps2.prepared
+    with torch.cuda.device(src.device):
+        rc = lib.b200_correlate1d_pair(
+            src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape), _lib.i64_array(shape),
+            p1, int(w1.shape[0]), _lib.mode_code(ps1.mode), int(ps1.origin),
+            p2, int(w2.shape[0]), _lib.mode_code(ps2.mode), int(ps2.origin),
+            float(cval), int(epilogue), int(_default_flags if flags is None else flags), _stream_ptr(src))
+    _lib.check(rc)
+
+
+_FUSE_PAIRS = os.environ.get("B200_FUSE_PAIRS", "1") not in ("", "0")
+
+
+def set_pair_fusion(on):
+    """Enable / disable the fused two-pass kernel (tests compare both paths); returns the old value."""
+    global _FUSE_PAIRS
+    old, _FUSE_PAIRS = _FUSE_PAIRS, bool(on)
+    return old
+
+
+def _pair_eligible(shape, np_dtype, ps1, ps2, flags=None):
+    """Can the consecutive passes ``ps1``, ``ps2`` run as one fused launch?  Depends
+    on the dtype, the LAST TWO extents and the two filters only -- never on the
+    leading extents, so every slab / chunk of a volume takes the same path."""
+    if not _FUSE_PAIRS or np_dtype != np.float32 or len(shape) < 2:
+        return False
+    if ps1.kind != "corr" or ps2.kind != "corr" or ps1.axis != len(shape) - 2 or ps2.axis != len(shape) - 1:
+        return False
+    fl = _default_flags if flags is None else flags
+    if fl & (_lib.FLAG_EXACT | _lib.FLAG_NO_TMA):
+        return False
+    return bool(_lib.load().b200_correlate1d_pair_eligible(
+        _dtype_code(np_dtype), len(shape), _lib.i64_array(shape), len(ps1.weights), int(ps1.origin),
+        len(ps2.weights), int(ps2.origin)))
+
+
+def _chain_steps(passes, shape, np_dtype, flags=None, axis0_local=True):
+    """Group the 1-D passes of a chain into launches: ``[(pass,)]`` or, where the
+    fused kernel applies, ``[(pass, pass)]`` for the passes along the last two
+    axes.  ``axis0_local`` = False says axis 0 reaches beyond the resident planes
+    (slab halos / streamed chunks): a pass along axis 0 then stays on its own."""
+    steps, i = [], 0
+    while i < len(passes):
+        if (i + 1 < len(passes) and (axis0_local or passes[i].axis != 0)
+                and _pair_eligible(shape, np_dtype, passes[i], passes[i + 1], flags)):
+            steps.append((passes[i], passes[i + 1]))
+            i += 2
+        else:
+            steps.append((passes[i],))
+            i += 1
+    return steps
+
+
 def _launch_correlate1d_halo(src, dst, shape, np_dtype, weights, mode, cval, origin, halo_lo, halo_hi,
                              epilogue=_lib.EPI_STORE, flags=None):
     """Axis-0 pass of a slab whose neighbour planes are read in place:
@@ -369,11 +426,13 @@ def _run_chain(x_tensor, shape, np_dtype, passes, cval, out_tensor, final_epilog
     of scipy's 9 passes -- same arithmetic, computed once."""
     scratch = scratch if scratch is not None else []
     src, src_pad = x_tensor, pad
-    targets = _chain_targets(len(passes), final_epilogue)
+    steps = _chain_steps(passes, shape, np_dtype, flags, axis0_local=tuple(pad) == (0, 0))
+    targets = _chain_targets(len(steps), final_epilogue)
     sig = ()
-    for i, ps in enumerate(passes):
-        last = i == len(passes) - 1
-        sig = sig + (_pass_signature(ps),)
+    for i, step in enumerate(steps):
+        last = i == len(steps) - 1
+        for ps in step:
+            sig = sig + (_pass_signature(ps),)
         if targets[i] == "out":
             dst = out_tensor
         else:
@@ -385,9 +444,12 @@ def _run_chain(x_tensor, shape, np_dtype, passes, cval, out_tensor, final_epilog
             if prov is not None and prov.get(k) == sig:
                 src, src_pad = dst, (0, 0)      # this prefix of the input is already there
                 continue
+        ps = step[0]
         use_pad = src_pad if ps.axis == 0 else (0, 0)
         epi = final_epilogue if last else _lib.EPI_STORE
-        if ps.kind == "corr":
+        if len(step) == 2:
+            _launch_correlate1d_pair(src, dst, shape, np_dtype, step[0], step[1], cval, epi, flags)
+        elif ps.kind == "corr":
             _launch_correlate1d(src, dst, shape, np_dtype, ps.axis, ps.weights, ps.mode, cval,
                                 ps.origin, use_pad, epi, flags, prepared=ps.prepared)
         else:

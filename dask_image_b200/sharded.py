@@ -70,6 +70,11 @@ class CudaBackend:
                                 flags)
 
     @staticmethod
+    def correlate1d_pair(src_full, s0, dst_full, d0, n, shape, np_dtype, ps1, ps2, cval, epilogue, flags=None):
+        _nd._launch_correlate1d_pair(src_full[s0:s0 + n], dst_full[d0:d0 + n], (n,) + tuple(shape[1:]),
+                                     np_dtype, ps1, ps2, cval, epilogue, flags)
+
+    @staticmethod
     def uniform1d(src_full, s0, dst_full, d0, n, pad, shape, np_dtype, ps, cval, flags=None):
         _nd._launch_uniform1d(src_full[s0:s0 + n], dst_full[d0:d0 + n], (n,) + tuple(shape[1:]),
                               np_dtype, ps.axis, ps.size, ps.mode, cval, ps.origin, pad, flags)
@@ -462,11 +467,18 @@ class ShardedVolume:
                 be.combine(out.interior, src0.interior, dt, op)
                 continue
             src = src0
-            targets = _nd._chain_targets(len(passes), op)
+            # passes along the last two axes pair up into one fused launch where the kernel exists
+            # (never the axis-0 pass of a sharded volume: it reaches into the neighbours' planes)
+            fuse_ok = hasattr(be, "correlate1d_pair")
+            steps = (_nd._chain_steps(passes, shape, dt, flags, axis0_local=self.world == 1) if fuse_ok
+                     else [(ps,) for ps in passes])
+            targets = _nd._chain_targets(len(steps), op)
             sig = ()
-            for i, ps in enumerate(passes):
-                last = i == len(passes) - 1
-                sig = sig + (_nd._pass_signature(ps),)
+            for i, step in enumerate(steps):
+                last = i == len(steps) - 1
+                for ps in step:
+                    sig = sig + (_nd._pass_signature(ps),)
+                ps = step[0]
                 if targets[i] == "out":
                     dst = out
                 else:
@@ -481,6 +493,11 @@ class ShardedVolume:
                 epi = op if last else _lib.EPI_STORE
                 if ps.kind != "corr" and epi != _lib.EPI_STORE:
                     raise RuntimeError("only correlation passes have a fused epilogue")
+                if len(step) == 2:
+                    be.correlate1d_pair(src.full, src.cap, dst.full, dst.cap, self.n_local, shape, dt,
+                                        step[0], step[1], plan.cval, epi, flags)
+                    src = dst
+                    continue
 
                 def call(p0, p1, pad, src=src, dst=dst, ps=ps, epi=epi):
                     if ps.kind == "corr":

@@ -214,7 +214,8 @@ class HostVolume:
             d_out = [torch.empty((C,) + tail, dtype=h_in.dtype, device=dev) for _ in range(nslot)]
             need = 0
             for passes, op in plan.chains:
-                for tgt in _nd._chain_targets(len(passes), op):
+                nsteps = len(_nd._chain_steps(passes, (C,) + tail, dt, axis0_local=False))
+                for tgt in _nd._chain_targets(nsteps, op):
                     if tgt != "out":
                         need = max(need, tgt + 1)
             scratch = [torch.empty((C,) + tail, dtype=h_in.dtype, device=dev) for _ in range(need)]

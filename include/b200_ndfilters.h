@@ -117,6 +117,29 @@ int b200_correlate1d_halo(const void *in, void *out, int dtype, int ndim,
                           const void *halo_hi, int64_t n_hi, int epilogue,
                           unsigned flags, void *stream);
 
+/* Two consecutive b200_correlate1d passes in ONE launch: along axis ndim-2 with
+ * taps `w1` (mode1, origin1), then along axis ndim-1 with taps `w2` (mode2,
+ * origin2); `epilogue` applies to the store of the second pass.  This is the
+ * tail of scipy's gaussian_filter loop (scipy/ndimage/_filters.py:852-858:
+ * one correlate1d per axis, each pass stored in the array dtype): the
+ * intermediate pass lives in shared memory, rounded to float32 exactly as the
+ * stored pass would be, and both passes sum in the order of the one-pass
+ * kernels, so the result is bit-identical to the two calls -- at 8 B/voxel of
+ * HBM traffic instead of 16.  float32 only, ndim >= 2; rows that are not
+ * 16-byte multiples are staged with plain loads instead of TMA.  Returns
+ * B200_EINVAL ("not eligible") when no fused kernel exists for this pair of
+ * filters; the _eligible query is host-only and depends on the dtype, the last
+ * two extents and the filters alone (never on the leading extents, so every
+ * slab of a volume takes the same path). */
+int b200_correlate1d_pair(const void *in, void *out, int dtype, int ndim,
+                          const int64_t *shape, const double *w1, int64_t nw1,
+                          int mode1, int64_t origin1, const double *w2,
+                          int64_t nw2, int mode2, int64_t origin2, double cval,
+                          int epilogue, unsigned flags, void *stream);
+int b200_correlate1d_pair_eligible(int dtype, int ndim, const int64_t *shape,
+                                   int64_t nw1, int64_t origin1, int64_t nw2,
+                                   int64_t origin2);
+
 /* Let kernels on the current device read memory of `peer_device` (needed once
  * per device pair before b200_correlate1d_halo is given a peer GPU's planes;
  * cudaDeviceEnablePeerAccess, "already enabled" is success). */

@@ -38,6 +38,13 @@ def cpu_path(monkeypatch):
         r = orc.correlate1d(_view(src, shape), weights, axis, mode, cval, origin)
         _fold(_view(dst, shape), r.copy(), epilogue)
 
+    def corr_pair(src, dst, shape, np_dtype, ps1, ps2, cval, epilogue=_lib.EPI_STORE, flags=None):
+        # the fused launch IS the two passes, the intermediate stored in the array dtype
+        calls.append(("pair", ps1.axis, ps2.axis, len(ps1.weights), len(ps2.weights), epilogue))
+        mid = orc.correlate1d(_view(src, shape), ps1.weights, ps1.axis, ps1.mode, cval, ps1.origin)
+        r = orc.correlate1d(mid, ps2.weights, ps2.axis, ps2.mode, cval, ps2.origin)
+        _fold(_view(dst, shape), r.copy(), epilogue)
+
     def uniform1d(src, dst, shape, np_dtype, axis, size, mode, cval, origin, pad=(0, 0), flags=None):
         calls.append(("uniform", axis, size))
         _view(dst, shape)[...] = orc.uniform_filter1d(_view(src, shape), size, axis, mode, cval, origin)
@@ -62,7 +69,8 @@ def cpu_path(monkeypatch):
 
     monkeypatch.setattr(_array.B200Array, "__init__", init)
     monkeypatch.setattr(_array, "default_device", lambda: torch.device("cpu"))
-    for name, fn in [("_launch_correlate1d", corr1d), ("_launch_uniform1d", uniform1d),
+    for name, fn in [("_launch_correlate1d", corr1d), ("_launch_correlate1d_pair", corr_pair),
+                     ("_launch_uniform1d", uniform1d),
                      ("_launch_correlate_nd", corrnd), ("_launch_minmax1d", minmax1d),
                      ("_launch_minmax_nd", minmaxnd), ("_launch_combine", combine)]:
         monkeypatch.setattr(ndimage, name, fn)
@@ -125,20 +133,56 @@ def test_public_functions_reproduce_scipy_bitwise(cpu_path, dtype, shape):
 
 
 def test_gradient_magnitude_shares_chain_prefixes(cpu_path):
-    """3-D gradient magnitude / laplace: 8 launches for scipy's 9 passes (the chains along the last two
-    axes start with the same smoothing pass along axis 0), epilogues fused into each chain's last pass."""
+    """3-D gradient magnitude / laplace, unfused: 8 launches for scipy's 9 passes (the chains along the last
+    two axes start with the same smoothing pass along axis 0), epilogues fused into each chain's last pass.
+    With the fused pass pair (float32): 2 axis-0 passes + 3 pair launches."""
     a = np.random.default_rng(3).random((6, 7, 8)).astype(np.float32)
     x = _array.B200Array.from_numpy(a)
-    del cpu_path[:]
-    _same(ndimage.gaussian_gradient_magnitude(x, 1.0), ndi.gaussian_gradient_magnitude(a, 1.0))
-    corr = [c for c in cpu_path if c[0] == "corr"]
-    assert len(corr) == 8 and not [c for c in cpu_path if c[0] == "combine"]
-    assert [c[3] for c in corr if c[3] != _lib.EPI_STORE] == [_lib.EPI_SQ_STORE, _lib.EPI_SQ_ACC, _lib.EPI_SQ_ACC_SQRT]
-    del cpu_path[:]
-    _same(ndimage.gaussian_laplace(x, 1.0), ndi.gaussian_laplace(a, 1.0))
-    corr = [c for c in cpu_path if c[0] == "corr"]
-    assert len(corr) == 8
-    assert [c[3] for c in corr if c[3] != _lib.EPI_STORE] == [_lib.EPI_ACC, _lib.EPI_ACC]
+    old = ndimage.set_pair_fusion(False)
+    try:
+        del cpu_path[:]
+        _same(ndimage.gaussian_gradient_magnitude(x, 1.0), ndi.gaussian_gradient_magnitude(a, 1.0))
+        corr = [c for c in cpu_path if c[0] == "corr"]
+        assert len(corr) == 8 and not [c for c in cpu_path if c[0] in ("combine", "pair")]
+        assert [c[3] for c in corr if c[3] != _lib.EPI_STORE] == [_lib.EPI_SQ_STORE, _lib.EPI_SQ_ACC,
+                                                                 _lib.EPI_SQ_ACC_SQRT]
+        del cpu_path[:]
+        _same(ndimage.gaussian_laplace(x, 1.0), ndi.gaussian_laplace(a, 1.0))
+        corr = [c for c in cpu_path if c[0] == "corr"]
+        assert len(corr) == 8
+        assert [c[3] for c in corr if c[3] != _lib.EPI_STORE] == [_lib.EPI_ACC, _lib.EPI_ACC]
+    finally:
+        ndimage.set_pair_fusion(old)
+    ndimage.set_pair_fusion(True)
+    try:
+        del cpu_path[:]
+        _same(ndimage.gaussian_gradient_magnitude(x, 1.0), ndi.gaussian_gradient_magnitude(a, 1.0))
+        assert [c[:3] for c in cpu_path] == [("corr", 0, 9), ("pair", 1, 2), ("corr", 0, 9), ("pair", 1, 2),
+                                             ("pair", 1, 2)]
+        assert [c[-1] for c in cpu_path if c[0] == "pair"] == [_lib.EPI_SQ_STORE, _lib.EPI_SQ_ACC,
+                                                              _lib.EPI_SQ_ACC_SQRT]
+        del cpu_path[:]
+        _same(ndimage.gaussian_laplace(x, 1.0), ndi.gaussian_laplace(a, 1.0))
+        assert [c[0] for c in cpu_path] == ["corr", "pair", "corr", "pair", "pair"]
+        assert [c[-1] for c in cpu_path if c[0] == "pair"] == [_lib.EPI_STORE, _lib.EPI_ACC, _lib.EPI_ACC]
+        # a 3-D gaussian is an axis-0 pass and one pair; a 2-D one is a single launch; float64 / integers and
+        # filters without a fused kernel (anisotropic radii) stay on single passes
+        del cpu_path[:]
+        _same(ndimage.gaussian_filter(x, 1.0), ndi.gaussian_filter(a, 1.0))
+        assert [c[0] for c in cpu_path] == ["corr", "pair"]
+        del cpu_path[:]
+        x2 = _array.B200Array.from_numpy(a[0])
+        _same(ndimage.gaussian_filter(x2, 1.0), ndi.gaussian_filter(a[0], 1.0))
+        assert [c[0] for c in cpu_path] == ["pair"]
+        del cpu_path[:]
+        _same(ndimage.gaussian_filter(x, (1.0, 1.0, 1.5)), ndi.gaussian_filter(a, (1.0, 1.0, 1.5)))
+        assert [c[0] for c in cpu_path] == ["corr", "corr", "corr"]
+        del cpu_path[:]
+        x64 = _array.B200Array.from_numpy(a.astype(np.float64))
+        _same(ndimage.gaussian_filter(x64, 1.0), ndi.gaussian_filter(a.astype(np.float64), 1.0))
+        assert [c[0] for c in cpu_path] == ["corr", "corr", "corr"]
+    finally:
+        ndimage.set_pair_fusion(old)
 
 
 def test_output_argument_and_input_untouched(cpu_path):
