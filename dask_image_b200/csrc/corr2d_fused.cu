@@ -30,90 +30,80 @@ namespace b200 {
 
 constexpr int kFusedPX = 256;       // staged tile width in floats (TMA box limit)
 constexpr int kFusedPI = 260;       // pitch of the intermediate tile: 16 bytes * odd
+constexpr int kFusedPO = 244;       // pitch of the spare output block (240 columns at most): 16 bytes * odd
 constexpr int kFusedMaxTaps = 48;
 
 struct Corr2dParams {
     const float *in;
     float *out;
-    int64_t outer, ny, nx;
+    int outer, ny, nx;
     int lo1, mode1;       // rows read above an output row: nw1/2 + origin1
     int lo2, mode2;       // staged column 0 is array column x0 - lo2 (lo2 = reach in front, rounded up to 4)
     int hi1, hi2;         // rows / columns read beyond an output
     int epilogue, wide_store;
     int y_tiles, x_tiles;
+    int ncg;              // 16-output column groups per tile in use: tiles are ncg * 16 columns wide
     float cval;
     float w1[kFusedMaxTaps];   // taps along axis ndim-2
     float w2[kFusedMaxTaps];   // taps along axis ndim-1, alignment zeros in front
 };
 
-template <int L1, int NTX, int TYO, int NWARPS, int RA, bool ALIAS, int MINB, bool TMA>
-__global__ void __launch_bounds__(NWARPS * 32, MINB)
-corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr2dParams p)
+// 32-bit form of ext_index() (common.cuh) for tile coordinates: |i| and n are below 2^31 here
+__device__ __forceinline__ int ext_index32(int i, int n, int mode)
 {
-    constexpr int PX = kFusedPX, PI = kFusedPI;
-    constexpr int TYIN = TYO + L1 - 1;
-    constexpr int NTHR = NWARPS * 32;
-    constexpr int NCG = (PX - (NTX - 1)) / 16;   // 16-output column groups per tile
-    constexpr int TXO = NCG * 16;
-    constexpr int NF = (16 + NTX + 3) / 4 * 4;   // row window of a thread: whole 16-byte blocks
-    constexpr int ITEMS_A = (TYO / RA) * 2;
-    constexpr int ITEMS_B = TYO * NCG;
-    static_assert(TYO % RA == 0 && TYO % 8 == 0, "tile rows");
-    static_assert(!ALIAS || ITEMS_A == NWARPS, "aliased tiles need one phase-A item per warp");
-    static_assert(16 * (NCG - 1) + NF <= PI, "row window inside the intermediate tile");
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *tin = aligned_smem<float>(smem_raw);
-    float *mid = ALIAS ? tin : tin + TYIN * PX;
-    __shared__ __align__(8) uint64_t full_bar;
-    __shared__ int row_src[TYIN];
-    __shared__ int col_src[PX];
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-
-    const int64_t t = blockIdx.x;
-    const int txi = (int)(t % p.x_tiles);
-    const int64_t q = t / p.x_tiles;
-    const int tyi = (int)(q % p.y_tiles);
-    const int64_t z = q / p.y_tiles;
-    const int64_t x0 = (int64_t)txi * TXO, y0 = (int64_t)tyi * TYO;
-    const int64_t gx0 = x0 - p.lo2, gy0 = y0 - p.lo1;   // array position of staged element (0, 0)
-
-    if constexpr (TMA) {
-        if (tid == 0) {
-            mbar_init(&full_bar, 1);
-            fence_barrier_init();
-            mbar_arrive_expect_tx(&full_bar, (uint32_t)(TYIN * PX * (int)sizeof(float)));
-            tma_load_3d(tin, &tmap, &full_bar, (int)gx0, (int)gy0, (int)z);
-        }
+    if (i >= 0 && i < n) return i;
+    switch (mode) {
+    case B200_MODE_NEAREST:
+        return i < 0 ? 0 : n - 1;
+    case B200_MODE_WRAP: {
+        int t = i % n;
+        return t < 0 ? t + n : t;
     }
+    case B200_MODE_REFLECT: {
+        const long long pp = 2ll * n;
+        long long t = i % pp;
+        if (t < 0) t += pp;
+        return (int)(t < n ? t : pp - 1 - t);
+    }
+    case B200_MODE_MIRROR: {
+        if (n == 1) return 0;
+        const long long pp = 2ll * n - 2;
+        long long t = i % pp;
+        if (t < 0) t += pp;
+        return (int)(t < n ? t : pp - t);
+    }
+    default:
+        return -1;
+    }
+}
 
-    // Staged rows / columns that are actually read by outputs inside the array
-    // (a tile on the far edges may hang over): [0, rows_need) x [0, cols_need)
-    const int rows_need = (int)(p.ny - gy0 + p.hi1 < TYIN ? p.ny - gy0 + p.hi1 : TYIN);
-    const int cols_need = (int)(p.nx - gx0 + p.hi2 < PX ? p.nx - gx0 + p.hi2 : PX);
-    // ... and the part of that which lies inside the array (TMA delivers it; the rest is zero-filled)
-    const int r_lo = (int)(gy0 < 0 ? (-gy0 < rows_need ? -gy0 : rows_need) : 0);
-    const int r_hi = (int)(p.ny - gy0 < rows_need ? (p.ny - gy0 > r_lo ? p.ny - gy0 : r_lo) : rows_need);
-    const int c_lo = (int)(gx0 < 0 ? (-gx0 < cols_need ? -gx0 : cols_need) : 0);
-    const int c_hi = (int)(p.nx - gx0 < cols_need ? (p.nx - gx0 > c_lo ? p.nx - gx0 : c_lo) : cols_need);
-    const bool edge = r_lo > 0 || r_hi < rows_need || c_lo > 0 || c_hi < cols_need;
+// Edge tiles (and every tile of the plain-load variant): fill the staged elements that lie outside
+// the array -- TMA zero-fills them -- through the extension maps of the two axes.  Kept out of line:
+// interior CTAs never come here, and the hot path keeps its registers.
+template <int TYIN, int NTHR, bool TMA>
+__device__ __noinline__ void fused_stage_edges(const Corr2dParams &p, float *tin, int *row_src, int *col_src,
+                                               const float *plane, int gx0, int gy0, uint64_t *full_bar)
+{
+    constexpr int PX = kFusedPX;
+    const int tid = threadIdx.x;
+    const int nx = p.nx, ny = p.ny;
+    // staged rows / columns that outputs inside the array actually read: [0, rows_need) x [0, cols_need)
+    const int rows_need = min(ny - gy0 + p.hi1, TYIN);
+    const int cols_need = min(nx - gx0 + p.hi2, PX);
+    // ... and the part of them that lies inside the array (TMA delivers it)
+    const int r_lo = min(max(-gy0, 0), rows_need), r_hi = max(min(ny - gy0, rows_need), r_lo);
+    const int c_lo = min(max(-gx0, 0), cols_need), c_hi = max(min(nx - gx0, cols_need), c_lo);
     const bool zero_ok = p.mode1 == B200_MODE_CONSTANT && p.mode2 == B200_MODE_CONSTANT && p.cval == 0.f;
-    const bool patch = TMA ? (edge && !zero_ok) : true;
-    const float *plane = p.in + z * p.ny * p.nx;
-
-    if (patch && (edge || !TMA)) {
-        // source row / column of every staged row / column under the extension maps (-1 = cval);
-        // identity inside the array
-        for (int i = tid; i < TYIN; i += NTHR) row_src[i] = (int)ext_index(gy0 + i, p.ny, p.mode1);
-        for (int c = tid; c < PX; c += NTHR) col_src[c] = (int)ext_index(gx0 + c, p.nx, p.mode2);
+    const bool any = r_lo > 0 || r_hi < rows_need || c_lo > 0 || c_hi < cols_need;
+    const bool patch = TMA ? (any && !zero_ok) : true;
+    if (patch) {
+        // source row / column of every staged row / column (-1 = cval; identity inside the array)
+        for (int i = tid; i < TYIN; i += NTHR) row_src[i] = ext_index32(gy0 + i, ny, p.mode1);
+        for (int c = tid; c < PX; c += NTHR) col_src[c] = ext_index32(gx0 + c, nx, p.mode2);
     }
     __syncthreads();
-
     if constexpr (TMA) {
-        // one warp polls the mbarrier; the others sleep at the CTA barrier
-        if (tid < 32) mbar_wait(&full_bar, 0);
+        if (tid < 32) mbar_wait(full_bar, 0);
         __syncthreads();
         if (patch) {
             // rows outside the array, full width
@@ -123,7 +113,7 @@ corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 if (c >= cols_need) continue;
                 const int i = k < r_lo ? k : r_hi + (k - r_lo);
                 const int ry = row_src[i], cx = col_src[c];
-                tin[i * PX + c] = (ry < 0 || cx < 0) ? p.cval : plane[(int64_t)ry * p.nx + cx];
+                tin[i * PX + c] = (ry < 0 || cx < 0) ? p.cval : plane[(int64_t)ry * nx + cx];
             }
             // columns outside the array on the rows inside it
             const int nbad_c = c_lo + (cols_need - c_hi);
@@ -133,9 +123,8 @@ corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 const int c = k < c_lo ? k : c_hi + (k - c_lo);
                 const int i = r_lo + r;
                 const int cx = col_src[c];
-                tin[i * PX + c] = cx < 0 ? p.cval : plane[(gy0 + i) * p.nx + cx];
+                tin[i * PX + c] = cx < 0 ? p.cval : plane[(int64_t)(gy0 + i) * nx + cx];
             }
-            __syncthreads();
         }
     } else {
         // rows that are not 16-byte multiples (or an unaligned base): the same tile, staged with
@@ -147,10 +136,77 @@ corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             float v = 0.f;
             if (c < cols_need) {
                 const int ry = row_src[i], cx = col_src[c];
-                v = (ry < 0 || cx < 0) ? p.cval : plane[(int64_t)ry * p.nx + cx];
+                v = (ry < 0 || cx < 0) ? p.cval : plane[(int64_t)ry * nx + cx];
             }
             tin[idx] = v;
         }
+    }
+    __syncthreads();
+}
+
+// mode 'constant' along the contiguous axis: the unfused second pass reads cval beyond the ends of
+// the STORED first pass, not the first pass of cval columns (they differ unless the taps of the
+// first pass sum to exactly 1) -- overwrite those columns of the intermediate tile
+template <int TYO, int NTHR>
+__device__ __noinline__ void fused_fix_constant_columns(const Corr2dParams &p, float *mid, int gx0)
+{
+    constexpr int PX = kFusedPX, PI = kFusedPI;
+    const int cols_need = min(p.nx - gx0 + p.hi2, PX);
+    const int c_lo = min(max(-gx0, 0), cols_need), c_hi = max(min(p.nx - gx0, cols_need), c_lo);
+    const int nbad_c = c_lo + (cols_need - c_hi);
+    for (int idx = threadIdx.x; idx < TYO * nbad_c; idx += NTHR) {
+        const int r = idx / nbad_c, k = idx - r * nbad_c;
+        mid[r * PI + (k < c_lo ? k : c_hi + (k - c_lo))] = p.cval;
+    }
+    __syncthreads();
+}
+
+template <int L1, int NTX, int TYO, int NWARPS, int RA, bool ALIAS, int MINB, bool TMA>
+__global__ void __launch_bounds__(NWARPS * 32, MINB)
+corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr2dParams p)
+{
+    constexpr int PX = kFusedPX, PI = kFusedPI;
+    constexpr int TYIN = TYO + L1 - 1;
+    constexpr int NTHR = NWARPS * 32;
+    constexpr int NCG = (PX - (NTX - 1)) / 16;   // 16-output column groups per tile, at most
+    constexpr int NF = (16 + NTX + 3) / 4 * 4;   // row window of a thread: whole 16-byte blocks
+    constexpr int ITEMS_A = (TYO / RA) * 2;
+    static_assert(TYO % RA == 0 && TYO % 8 == 0, "tile rows");
+    static_assert(!ALIAS || ITEMS_A == NWARPS, "aliased tiles need one phase-A item per warp");
+    static_assert(16 * (NCG - 1) + NF <= PI, "row window inside the intermediate tile");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tin = aligned_smem<float>(smem_raw);
+    float *mid = ALIAS ? tin : tin + TYIN * PX;
+    float *spare = mid + TYO * PI;   // NTHR/16 rows of pitch kFusedPO: staged results of the first row block
+    __shared__ __align__(8) uint64_t full_bar;
+    __shared__ int row_src[TYIN];
+    __shared__ int col_src[PX];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nx = p.nx, ny = p.ny;
+    const int z = blockIdx.z;
+    const int x0 = blockIdx.x * (p.ncg * 16), y0 = blockIdx.y * TYO;
+    const int gx0 = x0 - p.lo2, gy0 = y0 - p.lo1;   // array position of staged element (0, 0)
+
+    if constexpr (TMA) {
+        if (tid == 0) {
+            mbar_init(&full_bar, 1);
+            fence_barrier_init();
+            mbar_arrive_expect_tx(&full_bar, (uint32_t)(TYIN * PX * (int)sizeof(float)));
+            tma_load_3d(tin, &tmap, &full_bar, gx0, gy0, z);
+        }
+    }
+    // a tile whose staged box lies inside the array needs nothing beyond the TMA load
+    const bool edge = !TMA || gx0 < 0 || gy0 < 0 || gx0 + PX > nx || gy0 + TYIN > ny;
+    if (edge) {
+        fused_stage_edges<TYIN, NTHR, TMA>(p, tin, row_src, col_src, p.in + (int64_t)z * ny * nx, gx0, gy0,
+                                           &full_bar);
+    } else {
+        __syncthreads();
+        // one warp polls the mbarrier; the others sleep at the CTA barrier
+        if (tid < 32) mbar_wait(&full_bar, 0);
         __syncthreads();
     }
 
@@ -183,104 +239,109 @@ corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             *reinterpret_cast<float4 *>(d + j * PI) = make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y);
     }
     __syncthreads();
-    // mode 'constant' along the contiguous axis: the unfused second pass reads cval beyond the
-    // ends of the STORED first pass, not the first pass of cval columns (they differ unless the
-    // taps of the first pass sum to exactly 1) -- overwrite those columns of the intermediate
-    if (p.mode2 == B200_MODE_CONSTANT && p.cval != 0.f && (c_lo > 0 || c_hi < cols_need)) {
-        const int nbad_c = c_lo + (cols_need - c_hi);
-        for (int idx = tid; idx < TYO * nbad_c; idx += NTHR) {
-            const int r = idx / nbad_c, k = idx - r * nbad_c;
-            mid[r * PI + (k < c_lo ? k : c_hi + (k - c_lo))] = p.cval;
-        }
-        __syncthreads();
-    }
+    if (edge && p.mode2 == B200_MODE_CONSTANT && p.cval != 0.f) fused_fix_constant_columns<TYO, NTHR>(p, mid, gx0);
 
     // ---- phase B: the pass along the contiguous axis, mid -> out ---------------
-    // item = (column group, row): the 8 lanes of a quarter warp sit on 8 rows of one
-    // column group, which the odd 16-byte pitch spreads over all bank groups
-    for (int item = tid; item < ITEMS_B; item += NTHR) {
-        const int cg = item / TYO, r = item - cg * TYO;
+    // ROWS_B rows at a time: thread = (column group, row); the 8 lanes of a quarter warp sit on 8
+    // rows of one column group, which the odd 16-byte pitch spreads over all bank groups.  Results are
+    // staged in shared memory -- the first row block in a spare block behind the intermediate tile,
+    // every later one over the rows the PREVIOUS block has consumed -- and leave the SM row by row
+    // through the bulk-copy engine (cp.async.bulk shared -> global): no per-lane global stores, whose
+    // 32 half-sectors on 32 different rows cost ~50 LSU wavefronts per instruction.  Epilogues that
+    // read `out`, and unaligned rows, take a coalesced cooperative copy-out instead.
+    constexpr int ROWS_B = NTHR / 16;
+    static_assert(TYO % ROWS_B == 0, "phase B row blocks");
+    const int ncg = p.ncg;                       // column groups in use (<= NCG): tile width ncg * 16
+    const bool bulk = TMA && p.epilogue == B200_EPI_STORE;
+    const int tile_cols = min(nx - x0, ncg * 16);   // columns of this tile inside the array
+    for (int hb = 0; hb < TYO / ROWS_B; ++hb) {
+        const int r = hb * ROWS_B + (tid % ROWS_B);
+        const int cg = tid / ROWS_B;
+        const bool live = y0 + r < ny && cg * 16 < tile_cols;
         const float *srow = mid + r * PI + cg * 16;
+        float *const oblk = hb == 0 ? spare : mid + (hb - 1) * ROWS_B * PI;   // staged results of this block
+        const int opitch = hb == 0 ? kFusedPO : PI;
         float f[NF];
+        if (live) {
 #pragma unroll
-        for (int b = 0; b < NF / 4; ++b) {
-            const float4 v = *reinterpret_cast<const float4 *>(srow + 4 * b);
-            f[4 * b] = v.x; f[4 * b + 1] = v.y; f[4 * b + 2] = v.z; f[4 * b + 3] = v.w;
-        }
-        float2 e[8], o[9];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) o[i] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int tt = 0; tt < NTX; ++tt) {
-            const float wk = p.w2[tt];
-            const float2 w2 = make_float2(wk, wk);
-            if (tt < 3 && wk == 0.f) continue;   // alignment zeros (as corr1d_contig_static_kernel)
-            if ((tt & 1) == 0) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    e[i] = __ffma2_rn(make_float2(f[2 * i + tt], f[2 * i + tt + 1]), w2, e[i]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 9; ++i)
-                    o[i] = __ffma2_rn(make_float2(f[2 * i - 1 + tt], f[2 * i + tt]), w2, o[i]);
+            for (int b = 0; b < NF / 4; ++b) {
+                const float4 v = *reinterpret_cast<const float4 *>(srow + 4 * b);
+                f[4 * b] = v.x; f[4 * b + 1] = v.y; f[4 * b + 2] = v.z; f[4 * b + 3] = v.w;
             }
         }
-        const int64_t row = y0 + r;
-        const int64_t x = x0 + cg * 16;
-        if (row < p.ny && x < p.nx) {
-            float *dst0 = p.out + (z * p.ny + row) * p.nx + x;
-            float res[16];
+        if (live) {
+            float2 e[8], o[9];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                res[j] = ((j & 1) ? e[j >> 1].y : e[j >> 1].x) + ((j & 1) ? o[(j + 1) >> 1].x : o[j >> 1].y);
-            if (p.wide_store && x + 16 <= p.nx) {
+            for (int i = 0; i < 8; ++i) e[i] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) o[i] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int tt = 0; tt < NTX; ++tt) {
+                const float wk = p.w2[tt];
+                const float2 w2 = make_float2(wk, wk);
+                if (tt < 3 && wk == 0.f) continue;   // alignment zeros (as corr1d_contig_static_kernel)
+                if ((tt & 1) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        e[i] = __ffma2_rn(make_float2(f[2 * i + tt], f[2 * i + tt + 1]), w2, e[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i)
+                        o[i] = __ffma2_rn(make_float2(f[2 * i - 1 + tt], f[2 * i + tt]), w2, o[i]);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                float4 r4;
+                r4.x = e[2 * h].x + o[2 * h].y;
+                r4.y = e[2 * h].y + o[2 * h + 1].x;
+                r4.z = e[2 * h + 1].x + o[2 * h + 1].y;
+                r4.w = e[2 * h + 1].y + o[2 * h + 2].x;
+                *reinterpret_cast<float4 *>(oblk + (tid % ROWS_B) * opitch + cg * 16 + 4 * h) = r4;
+            }
+        }
+        if (bulk) fence_proxy_async();   // the stores above become visible to the bulk-copy engine
+        __syncthreads();
+        if (bulk) {
+            if (tid < ROWS_B && y0 + hb * ROWS_B + tid < ny)
+                bulk_store_row(p.out + ((int64_t)z * ny + y0 + hb * ROWS_B + tid) * nx + x0, oblk + tid * opitch,
+                               tile_cols * 4);
+            continue;
+        }
+        float *orow0 = p.out + ((int64_t)z * ny + y0 + hb * ROWS_B) * nx + x0;
+        if constexpr (TMA) {
+            // 16-byte vectors, lanes along the row: coalesced read-modify-write with the epilogue
+            const int nvec = tile_cols >> 2;
+            const bool reads_out = epilogue_reads_out(p.epilogue);
+            for (int idx = tid; idx < ROWS_B * nvec; idx += NTHR) {
+                const int rr = idx / nvec, v = idx - rr * nvec;
+                if (y0 + hb * ROWS_B + rr >= ny) continue;
+                float4 r4 = *reinterpret_cast<const float4 *>(oblk + rr * opitch + 4 * v);
+                float4 *dst = reinterpret_cast<float4 *>(orow0 + (int64_t)rr * nx + 4 * v);
                 if (p.epilogue != B200_EPI_STORE) {
-                    const bool reads_out = epilogue_reads_out(p.epilogue);
-                    float prev[16];
-                    if (reads_out) {
-                        ld_global_256(dst0, reinterpret_cast<float(&)[8]>(prev[0]));
-                        ld_global_256(dst0 + 8, reinterpret_cast<float(&)[8]>(prev[8]));
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        res[j] = apply_epilogue<float>(p.epilogue, reads_out ? prev[j] : 0.f, res[j]);
+                    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (reads_out) pv = *dst;
+                    r4.x = apply_epilogue<float>(p.epilogue, pv.x, r4.x);
+                    r4.y = apply_epilogue<float>(p.epilogue, pv.y, r4.y);
+                    r4.z = apply_epilogue<float>(p.epilogue, pv.z, r4.z);
+                    r4.w = apply_epilogue<float>(p.epilogue, pv.w, r4.w);
                 }
-                st_global_256(dst0, reinterpret_cast<const float(&)[8]>(res[0]));
-                st_global_256(dst0 + 8, reinterpret_cast<const float(&)[8]>(res[8]));
-            } else if constexpr (TMA) {
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    if (x + h * 4 < p.nx) {   // rows are whole multiples of 16 bytes
-                        float4 *dst = reinterpret_cast<float4 *>(dst0 + h * 4);
-                        float4 r4 = make_float4(res[4 * h], res[4 * h + 1], res[4 * h + 2], res[4 * h + 3]);
-                        if (p.epilogue != B200_EPI_STORE) {
-                            const bool reads_out = epilogue_reads_out(p.epilogue);
-                            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (reads_out) pv = *dst;
-                            r4.x = apply_epilogue<float>(p.epilogue, pv.x, r4.x);
-                            r4.y = apply_epilogue<float>(p.epilogue, pv.y, r4.y);
-                            r4.z = apply_epilogue<float>(p.epilogue, pv.z, r4.z);
-                            r4.w = apply_epilogue<float>(p.epilogue, pv.w, r4.w);
-                        }
-                        *dst = r4;
-                    }
-                }
-            } else {
-                const bool reads_out = epilogue_reads_out(p.epilogue);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (x + j < p.nx) {
-                        float v = res[j];
-                        if (p.epilogue != B200_EPI_STORE)
-                            v = apply_epilogue<float>(p.epilogue, reads_out ? dst0[j] : 0.f, v);
-                        dst0[j] = v;
-                    }
-                }
+                *dst = r4;
+            }
+        } else {
+            const bool reads_out = epilogue_reads_out(p.epilogue);
+            for (int idx = tid; idx < ROWS_B * tile_cols; idx += NTHR) {
+                const int rr = idx / tile_cols, c = idx - rr * tile_cols;
+                if (y0 + hb * ROWS_B + rr >= ny) continue;
+                float v = oblk[rr * opitch + c];
+                float *dst = orow0 + (int64_t)rr * nx + c;
+                if (p.epilogue != B200_EPI_STORE) v = apply_epilogue<float>(p.epilogue, reads_out ? *dst : 0.f, v);
+                *dst = v;
             }
         }
     }
+    // the tile must stay intact until the bulk copies have read it
+    if (bulk && tid < ROWS_B) bulk_store_wait_read();
 }
 
 // ---------------------------------------------------------------------------
@@ -297,12 +358,13 @@ static int launch_fused_cfg(const Corr2dArgs &a, const Corr2dParams &p0)
     constexpr int TXO = NCG * 16;
     constexpr int TYIN = TYO + L1 - 1;
     Corr2dParams p = p0;
+    // as few tile columns as the widest tile allows, then the narrowest tile that still covers the row
     p.x_tiles = (int)((a.nx + TXO - 1) / TXO);
+    p.ncg = (int)((a.nx + 16ll * p.x_tiles - 1) / (16ll * p.x_tiles));
     p.y_tiles = (int)((a.ny + TYO - 1) / TYO);
-    const int64_t num_tiles = (int64_t)p.x_tiles * p.y_tiles * a.outer;
-    if (num_tiles >= (1ll << 31)) return -1;
+    if (a.outer > 65535 || p.y_tiles > 65535) return -1;   // grid = (x tiles, y tiles, planes)
     const size_t in_bytes = (size_t)TYIN * kFusedPX * sizeof(float);
-    const size_t mid_bytes = (size_t)TYO * kFusedPI * sizeof(float);
+    const size_t mid_bytes = ((size_t)TYO * kFusedPI + (size_t)(NWARPS * 2) * kFusedPO) * sizeof(float);
     const size_t smem = (ALIAS ? (in_bytes > mid_bytes ? in_bytes : mid_bytes) : in_bytes + mid_bytes) + 128;
     if (smem + 2048 > kSmemPerSm) return -1;
     CUtensorMap tmap;
@@ -315,7 +377,7 @@ static int launch_fused_cfg(const Corr2dArgs &a, const Corr2dParams &p0)
     }
     auto kern = corr2d_fused_kernel<L1, NTX, TYO, NWARPS, RA, ALIAS, MINB, TMA>;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn - 2048));
-    kern<<<(unsigned)num_tiles, NWARPS * 32, smem, a.stream>>>(tmap, p);
+    kern<<<dim3((unsigned)p.x_tiles, (unsigned)p.y_tiles, (unsigned)a.outer), NWARPS * 32, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
     note_kernel(TMA ? "corr2d_fused_tma_f32" : "corr2d_fused_ldg_f32");
@@ -343,7 +405,7 @@ static int launch_fused_taps(const Corr2dArgs &a, const Corr2dParams &p)
 #else
     (void)variant;
 #endif
-    return launch_fused_cfg<L1, NTX, 32, 8, 8, true, 3, TMA>(a, p);
+    return launch_fused_cfg<L1, NTX, 32, 8, 8, true, 4, TMA>(a, p);
 }
 
 // (L1, NTX) pairs with a compiled kernel: the two passes of an isotropic odd
@@ -389,7 +451,7 @@ int launch_corr2d_fused(const Corr2dArgs &a)
     Corr2dParams p;
     memset(&p, 0, sizeof(p));
     p.in = (const float *)a.in; p.out = (float *)a.out;
-    p.outer = a.outer; p.ny = a.ny; p.nx = a.nx;
+    p.outer = (int)a.outer; p.ny = (int)a.ny; p.nx = (int)a.nx;
     p.lo1 = a.nw1 / 2 + a.origin1; p.mode1 = a.mode1; p.hi1 = a.nw1 - 1 - p.lo1;
     p.lo2 = lo2_al; p.mode2 = a.mode2; p.hi2 = ntx - 1 - lo2_al;
     p.epilogue = a.epilogue;

@@ -68,6 +68,21 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *t
         : "memory");
 }
 
+// one contiguous run of `bytes` (a multiple of 16, both addresses 16-byte aligned) from shared to
+// global memory through the bulk-copy engine; completion is tracked per thread in bulk groups
+__device__ __forceinline__ void bulk_store_row(void *gmem_dst, const void *smem_src, int bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                 "cp.async.bulk.commit_group;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+
+// wait until the bulk copies issued by this thread have finished READING shared memory
+__device__ __forceinline__ void bulk_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
