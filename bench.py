@@ -7,11 +7,19 @@ GVoxels/s on a 2048^3 fp32 volume at 1/2/4/8 B200, % of HBM roofline).
     torchrun --nproc-per-node N bench.py --gpus N ...        # N > 1 (one rank per GPU)
 
 One "step" = one whole ``gaussian_filter`` over the synthetic volume (every 1-D
-pass of scipy's chain; for N > 1 including the NCCL halo exchange).  ``value``
-is device-resident throughput (inputs already in HBM), ``e2e`` is the same
-public call fed from / drained to pinned HOST buffers inside the timed region.
-The volume is the same for every N ("strong" scaling: fixed total work).
-Prints exactly one JSON line on rank 0.
+pass of scipy's chain; for N > 1 including the neighbour-halo reads over NVLink).
+``value`` is device-resident throughput (inputs already in HBM), ``e2e`` is the
+same public call fed from / drained to pinned HOST buffers inside the timed
+region, next to the host<->device copy ceiling measured in the same process
+(``e2e.roofline``).  The volume is the same for every N ("strong" scaling).
+
+The one JSON line printed by rank 0 also carries
+  * ``verify``: a 64-bit checksum of the result's bits (identical for every GPU
+    count -- the partition-invariance proof) and the maximum error of two blocks
+    of the big result (a volume corner and a block across the middle slab faces)
+    against scipy run on the host;
+  * ``configs``: every BASELINE.json config (C1 ... C5) timed device-resident for
+    a few steps, with its algorithmic bytes per voxel and roofline fraction.
 """
 import argparse
 import json
@@ -179,99 +187,187 @@ def run_reference(args, wl, rank, world):
 # ---------------------------------------------------------------------------
 # CUDA arm
 # ---------------------------------------------------------------------------
-def run_b200(args, wl, rank, world, local_rank):
+class Ctx:
+    """Rank / device / collective helpers shared by the legs of the CUDA arm."""
+
+    def __init__(self, rank, world, local_rank):
+        import torch
+
+        self.torch = torch
+        self.rank, self.world = rank, world
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_int(self, x):
+        if self.dist is None:
+            return int(x)
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.int64)
+        self.dist.all_reduce(t)
+        return int(t.item())
+
+    def time_steps(self, step, steps, warmup):
+        """W warm-up calls, then K calls between CUDA events with a barrier and a
+        device sync on both sides; returns (ms per step, max over ranks; launches)."""
+        from dask_image_b200 import _lib
+
+        torch = self.torch
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        self.barrier()
+        _lib.launch_count(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps, self.sum_int(_lib.launch_count())
+
+
+def result_checksum(ctx, vol):
+    """Sum of the result's 32-bit words as unsigned integers, modulo 2^64, over the
+    whole (sharded) volume: independent of the partition, so it must be the same
+    number at 1, 2, 4 and 8 GPUs."""
+    torch = ctx.torch
+    loc = vol.local.reshape(-1)
+    es = loc.element_size()
+    words = loc.view({1: torch.uint8, 2: torch.int16}.get(es, torch.int32))
+    mask = {1: 0xFF, 2: 0xFFFF}.get(es, 0xFFFFFFFF)
+    total = 0
+    step = 1 << 28
+    for o in range(0, words.numel(), step):
+        total += int((words[o:o + step].to(torch.int64) & mask).sum().item())
+    # (int64 all-reduce over <= 8 ranks: keep every partial sum below 2^56)
+    return ctx.sum_int(total % (1 << 56)) % (1 << 56)
+
+
+def fetch_block(ctx, vol, z0, z1, ys, xs):
+    """Planes [z0, z1) x ys x xs of a sharded result as one host array on rank 0."""
+    s, e = vol.bounds[vol.rank]
+    part = None
+    a, b = max(z0, s), min(z1, e)
+    if b > a:
+        part = (a, vol.local[a - s:b - s, ys, xs].contiguous().cpu().numpy())
+    if ctx.dist is None:
+        parts = [part]
+    else:
+        parts = [None] * ctx.world
+        ctx.dist.all_gather_object(parts, part)
+    if ctx.rank != 0:
+        return None
+    parts = sorted([p for p in parts if p is not None], key=lambda p: p[0])
+    return np.concatenate([p[1] for p in parts], axis=0)
+
+
+def host_input_block(shape, seed, z0, z1, y0, y1, x0, x1):
+    """The synthetic input (ShardedVolume.random: a hash of the global voxel index)
+    regenerated on the host for one block."""
     import torch
 
-    import dask_image_b200 as b200
-    from dask_image_b200 import _lib, ndimage
-    from dask_image_b200.sharded import ShardedVolume, slab_bounds
+    from dask_image_b200.sharded import _hash_values
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
+    zz = torch.arange(z0, z1, dtype=torch.int64)[:, None, None]
+    yy = torch.arange(y0, y1, dtype=torch.int64)[None, :, None]
+    xx = torch.arange(x0, x1, dtype=torch.int64)[None, None, :]
+    idx = (zz * shape[1] + yy) * shape[2] + xx
+    return _hash_values(idx.reshape(-1), seed, torch.float32).reshape(idx.shape).numpy()
 
-        # keep stdout for the one JSON line: NCCL's banner / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-    shape = tuple(wl["shape"])
-    sigma, mode = wl["sigma"], wl["mode"]
-    voxels = int(np.prod(shape))
-    warmup = max(args.warmup, 3)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+def verify_headline(ctx, res, shape, sigma, mode, seed):
+    """scipy on the host for two blocks of the big result: the (0,0,0) corner (three
+    volume faces) and a block across the middle of axis 0 -- the slab face of every
+    even GPU count -- each cut with the filter's reach around it, so the block's
+    result equals the whole-volume result there."""
+    import scipy.ndimage as ndi
 
-    # ---- device-resident: the public call on a (sharded) resident volume ---
+    out = {"checksum": "%016x" % result_checksum(ctx, res)}
     halo = max(int(4.0 * s + 0.5) for s in sigma)
-    vol = ShardedVolume.random(shape, np.float32, seed=1234, device=dev, halo=halo)
-    res = None
+    side = min(128, min(shape) // 2)
+    mid = shape[0] // 2
+    blocks = {"corner": (0, side, 0, side, 0, side),
+              "mid_slab_face": (mid - side // 2, mid + side // 2, shape[1] // 4, shape[1] // 4 + side,
+                                shape[2] // 4, shape[2] // 4 + side)}
+    worst = 0.0
+    for name, (z0, z1, y0, y1, x0, x1) in blocks.items():
+        got = fetch_block(ctx, res, z0, z1, slice(y0, y1), slice(x0, x1))
+        if ctx.rank != 0:
+            continue
+        lo = [max(0, v - halo) for v in (z0, y0, x0)]
+        hi = [min(n, v + halo) for n, v in zip(shape, (z1, y1, x1))]
+        a = host_input_block(shape, seed, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2])
+        ref = ndi.gaussian_filter(a.astype(np.float64), sigma, mode=mode)
+        ref = ref[z0 - lo[0]:z1 - lo[0], y0 - lo[1]:y1 - lo[1], x0 - lo[2]:x1 - lo[2]]
+        err = float(np.max(np.abs(got.astype(np.float64) - ref)) / np.max(np.abs(ref)))
+        out["%s_max_rel_err" % name] = err
+        worst = max(worst, err)
+    if ctx.rank == 0:
+        out["subvolume_max_rel_err"] = worst
+        out["tolerance"] = 1e-5
+        out["ok"] = bool(worst <= 1e-5)
+        out["reference"] = "scipy.ndimage.gaussian_filter in float64 on the blocks' input + halo (%d^3 blocks)" % side
+    return out
 
-    def step():
-        nonlocal res
-        res = None                      # release the previous result first
-        res = b200.ndfilters.gaussian_filter(vol, sigma, mode=mode)
 
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    _lib.launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    launches = _lib.launch_count()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
-        dist.all_reduce(lt)
-        launches = int(lt.item())
-    ms_per_step = ms / args.steps
-    value = voxels / (ms_per_step * 1e-3) / 1e9
+def kernel_roofline(ctx, args, vol, res, sigma, mode, peak, peak_src):
+    """Launch duration of every kernel of one step on this rank's slab (CUDA events
+    on the launching stream), algorithmic bytes per launch = one read + one write of
+    the float32 slab, whatever the launch fuses."""
+    import torch
 
-    # ---- per-kernel launch durations (CUDA events, same stream, same slab) --
+    from dask_image_b200 import _lib, ndimage
+
     n_loc = vol.n_local
-    lshape = (n_loc,) + shape[1:]
+    lshape = (n_loc,) + tuple(vol.shape[1:])
     lvox = int(np.prod(lshape))
     x_t, out_t = vol.local, res.local
+    f32 = np.dtype(np.float32)
     passes = ndimage._gaussian_passes(3, sigma, 0, mode, 4.0)
-    per_pass = []
-    for ps in passes:
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-        ndimage._launch_correlate1d(x_t, out_t, lshape, np.dtype(np.float32), ps.axis, ps.weights, ps.mode, 0.0, 0)
+    steps = ndimage._chain_steps(passes, lshape, f32)
+    per_step = []
+    for st in steps:
+        if len(st) == 2:
+            def launch(st=st):
+                ndimage._launch_correlate1d_pair(x_t, out_t, lshape, f32, st[0], st[1], 0.0)
+        else:
+            def launch(ps=st[0]):
+                ndimage._launch_correlate1d(x_t, out_t, lshape, f32, ps.axis, ps.weights, ps.mode, 0.0, 0)
+        launch()
         torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         evs[0].record()
         for k in range(args.steps):
-            ndimage._launch_correlate1d(x_t, out_t, lshape, np.dtype(np.float32), ps.axis, ps.weights, ps.mode,
-                                        0.0, 0)
+            launch()
             evs[k + 1].record()
         torch.cuda.synchronize()
         t = float(np.mean([evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]))
-        per_pass.append((_lib.last_kernel(), ps.axis, len(ps.weights), t))
-    peak, peak_src = measured_peaks()
-    alg_bytes = 2 * 4 * lvox               # one read + one write of the f32 slab per pass
-    by_kernel, passes_info = {}, []
-    for name, ax, taps, t in per_pass:
+        per_step.append((_lib.last_kernel(), [ps.axis for ps in st], [len(ps.weights) for ps in st], t))
+    alg_bytes = 2 * 4 * lvox
+    by_kernel, info = {}, []
+    for name, axes, taps, t in per_step:
         by_kernel.setdefault(name, []).append(t)
-        passes_info.append({"kernel": name, "axis": ax, "taps": taps, "ms": t,
-                            "gb_s": alg_bytes / (t * 1e-3) / 1e9})
+        info.append({"kernel": name, "axes": axes, "taps": taps, "ms": t, "gb_s": alg_bytes / (t * 1e-3) / 1e9,
+                     "scipy_passes": len(axes)})
     dom = max(by_kernel, key=lambda k: sum(by_kernel[k]))
     t_dom = float(np.mean(by_kernel[dom]))
     achieved = alg_bytes / (t_dom * 1e-3) / 1e9
@@ -280,71 +376,247 @@ def run_b200(args, wl, rank, world, local_rank):
                 "traffic": measured_traffic(dom, lvox), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": t_dom,
                 "launches_per_step": {k: len(v) for k, v in by_kernel.items()},
-                "kernel_share_of_step": sum(by_kernel[dom]) / sum(t for _, _, _, t in per_pass)}
+                "kernel_share_of_step": sum(by_kernel[dom]) / sum(t for _, _, _, t in per_step),
+                "note": ("the dominant launch runs TWO of scipy's 1-D passes (axes 1 and 2) out of one read + one "
+                         "write of the slab; it is FP32-issue / shared-memory bound, not HBM bound"
+                         if dom.startswith("corr2d_fused") else None)}
+    return roofline, info, len(passes), len(steps)
+
+
+def pcie_ceiling(ctx, h_in, h_out, d_buf, chunk=256 << 20, budget_bytes=8 << 30):
+    """Plain pinned cudaMemcpyAsync in both directions at once (one stream per
+    direction, one copy per 256 MiB) on the buffers of the e2e leg: the ceiling
+    the streamed path is measured against.  Aggregate GB/s per direction."""
+    torch = ctx.torch
+    hi, ho, dv = (t.reshape(-1).view(torch.uint8) for t in (h_in, h_out, d_buf))
+    n = int(min(hi.numel(), dv.numel() // 2, budget_bytes))
+    s_up, s_down = torch.cuda.Stream(ctx.dev), torch.cuda.Stream(ctx.dev)
+
+    def run():
+        torch.cuda.synchronize()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for o in range(0, n, chunk):
+            e = min(n, o + chunk)
+            with torch.cuda.stream(s_up):
+                dv[o:e].copy_(hi[o:e], non_blocking=True)
+            with torch.cuda.stream(s_down):
+                ho[o:e].copy_(dv[n + o:n + e], non_blocking=True)
+        torch.cuda.synchronize()
+        return ctx.max_over_ranks(time.perf_counter() - t0)
+
+    run()
+    best = None
+    for c in (chunk, chunk // 2, chunk * 2):      # the ceiling should not depend on the copy size: take the best
+        chunk = c
+        dt = min(run(), run())
+        best = dt if best is None else min(best, dt)
+    return ctx.world * n / best / 1e9
+
+
+def e2e_leg(ctx, args, wl, vol_local, lshape):
+    """Pinned host slab -> ndfilters.gaussian_filter(HostVolume) -> pinned host result."""
+    import torch
+
+    import dask_image_b200 as b200
+    from dask_image_b200 import _numa
+
+    shape, sigma, mode = tuple(wl["shape"]), wl["sigma"], wl["mode"]
+    voxels = int(np.prod(shape))
+    numa = _numa.bind_host_to_device(ctx.dev)      # pinned pages next to this GPU's root port
+    h_in = torch.empty(lshape, dtype=torch.float32, pin_memory=True)
+    h_out = torch.empty(lshape, dtype=torch.float32, pin_memory=True)
+    h_in.copy_(vol_local)                          # realistic content
+    torch.cuda.synchronize()
+    hv = b200.HostVolume(h_in, out=h_out, device=ctx.dev, global_shape=shape if ctx.world > 1 else None)
+
+    def step():
+        b200.ndfilters.gaussian_filter(hv, sigma, mode=mode)
+
+    step()
+    torch.cuda.synchronize()
+    ctx.barrier()
+    n_e2e = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        step()
+    torch.cuda.synchronize()
+    ctx.barrier()
+    t_e2e = ctx.max_over_ranks((time.perf_counter() - t0) / n_e2e)
+    # the copy ceiling of this box at this N, on the same pinned buffers
+    d_buf = torch.empty(min(h_in.numel(), 4 << 30), dtype=torch.float32, device=ctx.dev)
+    ceiling = pcie_ceiling(ctx, h_in, h_out, d_buf)
+    del d_buf
+    achieved = voxels * 4 / t_e2e / 1e9
+    how = ("pinned host volume (one axis-0 slab per rank) -> ndfilters.gaussian_filter(HostVolume) -> pinned "
+           "host result: chunked H2D | filter | D2H pipeline on three streams%s; wall clock with device sync, "
+           "max over ranks" % (", NCCL halo faces" if ctx.world > 1 else ""))
+    return {"value": voxels / t_e2e / 1e9, "unit": UNIT, "h2d_bytes_per_step": voxels * 4,
+            "d2h_bytes_per_step": voxels * 4, "ms_per_step": t_e2e * 1e3, "steps": n_e2e, "how": how,
+            "roofline": {"bound": "pcie", "unit": "GB/s per direction, all GPUs", "achieved_gbs": achieved,
+                         "peak_gbs": ceiling, "frac": achieved / ceiling,
+                         "peak_source": "measured in this run: pinned cudaMemcpyAsync H2D and D2H at once, one "
+                                        "stream per direction, 256 MiB per copy, on the same host buffers"},
+            "host_placement": numa}
+
+
+def configs_leg(ctx, args, peak):
+    """Every BASELINE.json config, device-resident, a few steps each."""
+    import torch
+
+    import dask_image_b200 as b200
+    from dask_image_b200 import _lib
+    from dask_image_b200.sharded import ShardedVolume
+
+    f = b200.ndfilters
+    rng = np.random.default_rng(1234)
+    w9 = rng.random((9, 9, 9), dtype=np.float32)
+    scale = int(os.environ.get("B200_CFG_SCALE", "1"))
+    n_steps = max(1, min(args.steps, 5))
+    cfgs = [
+        ("C1", "gaussian_filter sigma=2 on 4096^2 float32, whole array", (4096 // scale,) * 2, np.float32, 16, 2,
+         lambda v: f.gaussian_filter(v, 2.0)),
+        ("C2", "gaussian_filter sigma=(4,4,4) reflect on 1024^3 float32", (1024 // scale,) * 3, np.float32, 24, 3,
+         lambda v: f.gaussian_filter(v, (4.0, 4.0, 4.0))),
+        ("C3", "uniform_filter size=7 on 2048^3 uint16", (2048 // scale,) * 3, np.uint16, 12, 3,
+         lambda v: f.uniform_filter(v, 7)),
+        ("C4a", "gaussian_gradient_magnitude sigma=3 on 2048^3 float32", (2048 // scale,) * 3, np.float32, 72, 9,
+         lambda v: f.gaussian_gradient_magnitude(v, 3.0)),
+        ("C4b", "gaussian_laplace sigma=3 on 2048^3 float32", (2048 // scale,) * 3, np.float32, 72, 9,
+         lambda v: f.gaussian_laplace(v, 3.0)),
+        ("C5", "convolve 9x9x9 float32 weights mode=wrap on 1536^3 float32", (1536 // scale,) * 3, np.float32, 8, 1,
+         lambda v: f.convolve(v, w9, mode="wrap")),
+    ]
+    out = []
+    for name, desc, shape, dt, bpv, scipy_passes, fn in cfgs:
+        entry = {"name": name, "workload": desc, "bytes_per_voxel": bpv, "scipy_passes": scipy_passes}
+        try:
+            vol = ShardedVolume.random(shape, dt, seed=1234, device=ctx.dev, halo=16)
+            holder = [None]
+
+            def step():
+                holder[0] = None
+                holder[0] = fn(vol)
+
+            ms, launches = ctx.time_steps(step, 1 if name == "C5" else n_steps, 1 if name == "C5" else 2)
+            vox = float(np.prod(shape))
+            entry.update(ms=ms, gvox_s=vox / ms / 1e6, launches=launches // (1 if name == "C5" else n_steps),
+                         kernel=_lib.last_kernel(), alg_gbs_per_gpu=vox * bpv / ctx.world / ms / 1e6,
+                         frac_of_measured_peak=vox * bpv / ctx.world / ms / 1e6 / peak,
+                         checksum="%016x" % result_checksum(ctx, holder[0]))
+            if name == "C5":
+                entry["bound"] = "fp32 issue (1458 flop/voxel), not HBM"
+                entry["tfma_s"] = vox * 729 / ms / 1e9
+            holder[0] = None
+            del vol
+        except Exception as exc:
+            entry["error"] = repr(exc)[:200]
+        torch.cuda.empty_cache()
+        out.append(entry)
+    # C1 as the config names it: 16 chunks of 1024^2 through the dispatch boundary (map_overlap semantics,
+    # halo 8, one chunk function call per chunk) -- one GPU, chunk-wise like dask would drive it
+    if ctx.rank == 0:
+        entry = {"name": "C1_chunked", "workload": "gaussian_filter sigma=2 on 4096^2 float32 in 16 chunks of 1024^2 "
+                 "through from_array(...).map_overlap (dispatch boundary)", "bytes_per_voxel": 16, "scipy_passes": 2}
+        try:
+            side = 4096 // scale
+            a = torch.rand((side, side), device=ctx.dev)
+            d = b200.from_array(b200.B200Array(a), chunks=(side // 4, side // 4))
+            for _ in range(2):
+                f.gaussian_filter(d, 2.0)
+            torch.cuda.synchronize()
+            _lib.launch_count(reset=True)
+            t0 = time.perf_counter()
+            for _ in range(n_steps):
+                f.gaussian_filter(d, 2.0)
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) / n_steps * 1e3
+            entry.update(ms=ms, gvox_s=side * side / ms / 1e6, launches=_lib.launch_count() // n_steps,
+                         kernel=_lib.last_kernel(), frac_of_measured_peak=side * side * 16 / ms / 1e6 / peak,
+                         timing="wall clock incl. the halo assembly / trim copies of the map_overlap stand-in")
+        except Exception as exc:
+            entry["error"] = repr(exc)[:200]
+        out.append(entry)
+    ctx.barrier()
+    return out
+
+
+def run_b200(args, wl, rank, world, local_rank):
+    import torch
+
+    import dask_image_b200 as b200
+    from dask_image_b200.sharded import ShardedVolume
+
+    ctx = Ctx(rank, world, local_rank)
+    shape = tuple(wl["shape"])
+    sigma, mode = wl["sigma"], wl["mode"]
+    voxels = int(np.prod(shape))
+    warmup = max(args.warmup, 3)
+    seed = 1234
+
+    # ---- device-resident: the public call on a (sharded) resident volume ---
+    halo = max(int(4.0 * s + 0.5) for s in sigma)
+    vol = ShardedVolume.random(shape, np.float32, seed=seed, device=ctx.dev, halo=halo)
+    holder = [None]
+
+    def step():
+        holder[0] = None                      # release the previous result first
+        holder[0] = b200.ndfilters.gaussian_filter(vol, sigma, mode=mode)
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(warmup):
+        step()
+    if rank == 0:
+        sampler.start()
+    ms_per_step, launches = ctx.time_steps(step, args.steps, 0)
+    clocks = sampler.stop() if rank == 0 else None
+    value = voxels / (ms_per_step * 1e-3) / 1e9
+    res = holder[0]
+
+    verify = verify_headline(ctx, res, shape, sigma, mode, seed) if not args.no_verify else None
+    peak, peak_src = measured_peaks()
+    roofline, passes_info, n_passes, n_launch = kernel_roofline(ctx, args, vol, res, sigma, mode, peak, peak_src)
+    n_loc = vol.n_local
+    lshape = (n_loc,) + shape[1:]
+    lvox = int(np.prod(lshape))
 
     # ---- end to end: pinned host in -> device -> public call -> pinned host out
     e2e = None
     if not args.no_e2e:
         try:
-            s0, s1 = slab_bounds(shape[0], world)[rank]
-            h_in = torch.empty(lshape, dtype=torch.float32).pin_memory()
-            h_out = torch.empty(lshape, dtype=torch.float32).pin_memory()
-            h_in.copy_(vol.local)                     # realistic content
-            res = None
-            vol = None
-            x_t = out_t = None
-            torch.cuda.empty_cache()
-
-            # host volume (this rank's slab) streamed through the GPU: H2D | filter | D2H
-            # overlapped on three streams, neighbour faces over NCCL for N > 1
-            hv = b200.HostVolume(h_in, out=h_out, device=dev,
-                                 global_shape=shape if world > 1 else None)
-
-            def e2e_step():
-                b200.ndfilters.gaussian_filter(hv, sigma, mode=mode)
-
-            how = ("pinned host volume (one axis-0 slab per rank) -> ndfilters.gaussian_filter(HostVolume) -> "
-                   "pinned host result: chunked H2D | filter | D2H pipeline on three streams%s; wall clock "
-                   "with device sync, max over ranks" % (", NCCL halo faces" if world > 1 else ""))
-
-            e2e_step()
-            torch.cuda.synchronize()
-            barrier()
-            n_e2e = max(1, min(args.steps, 5))
-            t0 = time.perf_counter()
-            for _ in range(n_e2e):
-                e2e_step()
-            torch.cuda.synchronize()
-            barrier()
-            t_e2e = (time.perf_counter() - t0) / n_e2e
-            if dist is not None:
-                t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                t_e2e = float(t.item())
-            e2e = {"value": voxels / t_e2e / 1e9, "unit": UNIT, "h2d_bytes_per_step": voxels * 4,
-                   "d2h_bytes_per_step": voxels * 4, "ms_per_step": t_e2e * 1e3, "steps": n_e2e,
-                   "how": how}
+            vol_local = vol.local
+            holder[0] = res = None
+            e2e = e2e_leg(ctx, args, wl, vol_local, lshape)
         except Exception as exc:  # e.g. not enough pinnable host memory
             e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:200]}
+    holder[0] = res = vol = vol_local = None
+    torch.cuda.empty_cache()
+
+    configs = configs_leg(ctx, args, peak) if not args.no_configs else None
 
     if rank != 0:
         return
     cpu = None
     if world == 1 and not args.no_cpu:
-        gv, dt, cores, sample = cpu_reference_run(wl, 1, 1, budget_seconds=25.0)
+        gv, dt, cores, sample = cpu_reference_run(wl, 2, 1, budget_seconds=25.0)
         cpu = {"value": gv, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "shape": list(shape), "sigma": list(sigma), "mode": mode,
-                   "passes": len(passes),
+                   "scipy_passes": n_passes, "launches_per_step": n_launch,
                    "l2": "per-GPU slab (%.1f GiB) larger than L2; no flush needed" % (lvox * 4 / 2 ** 30),
-                   "decomposition": ("axis-0 slabs (%d planes/GPU), NCCL send/recv halo exchange overlapped "
-                                     "with interior compute" % n_loc) if world > 1 else "single GPU"},
+                   "decomposition": ("axis-0 slabs (%d planes/GPU); the axis-0 pass reads the neighbour slabs' halo "
+                                     "planes in place over NVLink (CUDA IPC mappings, TMA loads inside the kernel), "
+                                     "two 1-element NCCL all-reduces order it; passes along axes 1 and 2 are one "
+                                     "slab-local fused launch" % n_loc) if world > 1 else
+                                    "single GPU: axis-0 pass + one fused launch for axes 1 and 2"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks, "passes": passes_info,
-        "op_level_roofline_frac": (8.0 * len(passes) * voxels / world / (ms_per_step * 1e-3) / 1e9) / peak,
+        "clocks": clocks, "passes": passes_info, "verify": verify, "configs": configs,
+        # scipy's algorithmic traffic (one read + one write per 1-D pass) over the measured step time: above 1.0
+        # because two of the three passes share one HBM round trip
+        "op_level_roofline_frac": (8.0 * n_passes * voxels / world / (ms_per_step * 1e-3) / 1e9) / peak,
     }
     print(json.dumps(line))
 
@@ -358,6 +630,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs leg")
+    ap.add_argument("--no-verify", action="store_true", help="skip the checksum / scipy block check")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -384,8 +384,9 @@ static int launch_fused_cfg(const Corr2dArgs &a, const Corr2dParams &p0)
     return B200_OK;
 }
 
-// tile geometry: 32 output rows, 8 warps, 8 rows per lane in phase A, the
-// intermediate tile aliased onto the input tile (B200 sweep: tools/sweep_fused.py)
+// tile geometry: 32 output rows x up to 240 columns, 8 warps, 8 rows per lane in phase A, the
+// intermediate tile aliased onto the input tile (B200 sweep: tools/sweep_fused.py with a
+// -DB200_FUSED_SWEEP build, profiles/r2_sweep_fused.log)
 template <int L1, int NTX, bool TMA>
 static int launch_fused_taps(const Corr2dArgs &a, const Corr2dParams &p)
 {
@@ -405,7 +406,9 @@ static int launch_fused_taps(const Corr2dArgs &a, const Corr2dParams &p)
 #else
     (void)variant;
 #endif
-    return launch_fused_cfg<L1, NTX, 32, 8, 8, true, 4, TMA>(a, p);
+    // short filters: 4 CTAs of 8 warps per SM (<= 64 registers); from 25 taps on the pass is FP32-issue
+    // bound, the tiles are bigger and 3 resident CTAs with more registers do better (B200 sweep)
+    return launch_fused_cfg<L1, NTX, 32, 8, 8, true, (NTX < 25 ? 4 : 2), TMA>(a, p);
 }
 
 // (L1, NTX) pairs with a compiled kernel: the two passes of an isotropic odd

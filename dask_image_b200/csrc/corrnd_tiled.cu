@@ -187,7 +187,7 @@ corrnd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 // covers 64 x 8 outputs, lanes of a quarter warp sit on 8 different rows so the
 // odd 16-byte pitch makes every LDS.128 conflict-free.
 // ===========================================================================
-template <int KXA>
+template <int KXA, bool SKIPZ>
 __global__ void __launch_bounds__(256, 2)
 corrnd_static_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CorrNdTiledParams<float> p)
 {
@@ -248,9 +248,12 @@ corrnd_static_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                 for (int tt = 0; tt < KXA; ++tt) {
                     const float wk = wrow[tt];
                     const float2 w2 = make_float2(wk, wk);
-                    // alignment padding in front of the row: a warp-uniform skip, so
-                    // non-finite neighbours outside the footprint cannot leak in
-                    if (tt < 3 && wk == 0.f) continue;
+                    // Zero taps are SKIPPED, as the reference iterates over the non-zero
+                    // footprint only (|w| > DBL_EPSILON): 0 * NaN / 0 * Inf must not reach the
+                    // sum.  The alignment padding in front of a row (tt < 3) is always tested;
+                    // kernels with genuine zero weights run the SKIPZ instantiation, which tests
+                    // every tap (warp-uniform branch), dense kernels keep the untested form.
+                    if ((SKIPZ || tt < 3) && wk == 0.f) continue;
                     if ((tt & 1) == 0) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
@@ -368,7 +371,7 @@ static int launch_cfg(const CorrNdArgs &a, int lox_al, int Kx_al)
     return B200_OK;
 }
 
-template <int KXA>
+template <int KXA, bool SKIPZ>
 static int launch_static_cfg(const CorrNdArgs &a, int lox_al)
 {
     constexpr int R = 16, SX = 4 * R;
@@ -437,7 +440,7 @@ static int launch_static_cfg(const CorrNdArgs &a, int lox_al)
             p.w[rw * KXA + lead + kx] = std::fabs(w) > DBL_EPSILON ? (float)w : 0.f;
         }
 
-    auto kern = corrnd_static_kernel<KXA>;
+    auto kern = corrnd_static_kernel<KXA, SKIPZ>;
     const size_t smem = (size_t)P * BY * BZ * es + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
@@ -445,6 +448,17 @@ static int launch_static_cfg(const CorrNdArgs &a, int lox_al)
     count_launch();
     note_kernel("corrnd_tiled_f32");
     return B200_OK;
+}
+
+// Does the kernel hold taps the reference skips (|w| <= DBL_EPSILON), or taps that underflow to
+// zero in float32?  Such kernels must not multiply them into the sum (non-finite data).
+static bool nd_weights_have_zeros(const CorrNdArgs &a)
+{
+    size_t n = 1;
+    for (int d = 0; d < a.ndim; ++d) n *= (size_t)a.wshape[d];
+    for (size_t i = 0; i < n; ++i)
+        if (!(std::fabs(a.w[i]) > DBL_EPSILON) || (a.dtype == B200_F32 && (float)a.w[i] == 0.f)) return true;
+    return false;
 }
 
 // float32 with at most 16 taps per weight row (alignment zeros included)
@@ -458,8 +472,10 @@ static int launch_static(const CorrNdArgs &a)
     const int lox = Kx / 2 + (int)a.origins[nd - 1];
     const int lox_al = (lox + 3) / 4 * 4;
     const int kxa = Kx + (lox_al - lox);
+    const bool zeros = nd_weights_have_zeros(a);
     switch (kxa) {
-#define B200_ND_CASE(K) case K: return launch_static_cfg<K>(a, lox_al);
+#define B200_ND_CASE(K) \
+    case K: return zeros ? launch_static_cfg<K, true>(a, lox_al) : launch_static_cfg<K, false>(a, lox_al);
     B200_ND_CASE(1) B200_ND_CASE(2) B200_ND_CASE(3) B200_ND_CASE(4) B200_ND_CASE(5) B200_ND_CASE(6)
     B200_ND_CASE(7) B200_ND_CASE(8) B200_ND_CASE(9) B200_ND_CASE(10) B200_ND_CASE(11) B200_ND_CASE(12)
     B200_ND_CASE(13) B200_ND_CASE(14) B200_ND_CASE(15) B200_ND_CASE(16)
@@ -514,10 +530,14 @@ int launch_corrnd_tiled(const CorrNdArgs &a)
     for (int d = 0; d < a.ndim; ++d)
         if (a.wshape[d] > 128) return -1;
     if (a.dtype == B200_F32) {
-        // (which engine runs depends on the weights' row length only)
+        // (which engine runs depends on the weights alone)
         const int rc = env_int("B200_ND_STATIC", 1) ? launch_static(a) : -2;
-        return rc == -2 ? launch_typed<float>(a) : rc;
+        if (rc != -2) return rc;
     }
+    // the run-time row engine multiplies every tap of a row: kernels with zero taps go to the
+    // scipy-order kernel (generic.cu), which skips them like the reference
+    if (nd_weights_have_zeros(a)) return -1;
+    if (a.dtype == B200_F32) return launch_typed<float>(a);
     if (a.dtype == B200_F64) return launch_typed<double>(a);
     return -1;
 }

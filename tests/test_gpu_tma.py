@@ -127,10 +127,20 @@ def test_launch_counter_and_kernel_names(b200):
     a = np.random.default_rng(5).random((64, 64, 64), dtype=np.float32)
     _lib.launch_count(reset=True)
     b200.ndimage.gaussian_filter(dev(b200, a), 2.0)
-    assert _lib.launch_count() == 3
+    assert _lib.launch_count() == 2      # axis-0 pass + the fused pair of the last two axes
     _lib.launch_count(reset=True)
     b200.ndimage.gaussian_laplace(dev(b200, a), 2.0)
-    assert _lib.launch_count() == 8      # scipy's 9 passes; the shared axis-0 smoothing runs once
+    assert _lib.launch_count() == 5      # scipy's 9 passes: 2 axis-0 passes (one shared) + 3 fused pairs
+    old = b200.ndimage.set_pair_fusion(False)
+    try:
+        _lib.launch_count(reset=True)
+        b200.ndimage.gaussian_filter(dev(b200, a), 2.0)
+        assert _lib.launch_count() == 3
+        _lib.launch_count(reset=True)
+        b200.ndimage.gaussian_laplace(dev(b200, a), 2.0)
+        assert _lib.launch_count() == 8  # the shared axis-0 smoothing runs once
+    finally:
+        b200.ndimage.set_pair_fusion(old)
 
 
 # ---------------------------------------------------------------------------
@@ -239,7 +249,6 @@ def test_tiled_correlate_nd(b200, dtype, mode, shape, wshape, origin):
     rng = np.random.default_rng(hash((shape, wshape, mode)) % (2 ** 32))
     a = (rng.random(shape) - 0.25).astype(dtype)
     w = rng.random(wshape) - 0.3
-    w.flat[1] = 0.0                       # a tap the reference skips
     d = dev(b200, a)
     for name in ("correlate", "convolve"):
         with forced(b200, _lib.FLAG_FORCE_FAST):
@@ -247,6 +256,47 @@ def test_tiled_correlate_nd(b200, dtype, mode, shape, wshape, origin):
         assert _lib.last_kernel().startswith("corrnd_tiled_"), _lib.last_kernel()
         ref = getattr(orc, name)(a, w, mode=mode, cval=0.6, origin=origin)
         assert_parity(got.to_numpy(), ref, what=name, data=a)
+    # a tap the reference skips (|w| <= DBL_EPSILON): float32 rows of <= 16 taps stay on the tiled kernel
+    # (its zero-skipping instantiation); everything else goes to the scipy-order kernel, which skips too
+    w.flat[1] = 0.0
+    got = b200.ndimage.correlate(d, w, mode=mode, cval=0.6, origin=origin)
+    short_rows = wshape[-1] + 3 <= 16
+    if dtype == np.float32 and short_rows:
+        assert _lib.last_kernel() == "corrnd_tiled_f32", _lib.last_kernel()
+    elif dtype == np.float64:
+        assert _lib.last_kernel() == "corrnd_generic", _lib.last_kernel()
+    assert_parity(got.to_numpy(), orc.correlate(a, w, mode=mode, cval=0.6, origin=origin), data=a)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_sparse_kernel_on_non_finite_data(b200, dtype):
+    """scipy's N-D correlate iterates over the NON-ZERO footprint only, so a zero weight never meets the data:
+    a cross-shaped Laplacian (zero corners) next to a NaN / Inf voxel stays finite exactly where scipy's does."""
+    from dask_image_b200 import _lib
+
+    rng = np.random.default_rng(77)
+    a = rng.random((40, 72)).astype(dtype)
+    a[10, 20] = np.nan
+    a[25, 60] = np.inf
+    a[0, 0] = -np.inf
+    w2 = np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]], dtype=np.float64)
+    got = b200.ndimage.correlate(dev(b200, a), w2).to_numpy()
+    ref = ndi.correlate(a, w2)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(np.isinf(got), np.isinf(ref))
+    ok = np.isfinite(ref)
+    assert_parity(np.where(ok, got, 0).astype(dtype), np.where(ok, ref, 0).astype(dtype), data=a[np.isfinite(a)])
+    assert _lib.last_kernel() == ("corrnd_tiled_f32" if dtype == np.float32 else "corrnd_generic")
+    # 3-D, convolve, a whole zero plane and a tiny-but-kept weight
+    a3 = rng.random((12, 20, 40)).astype(dtype)
+    a3[5, 7, 9] = np.inf
+    w3 = rng.random((3, 3, 3)) - 0.5
+    w3[0] = 0.0
+    w3[1, 1, 2] = 1e-17          # below DBL_EPSILON: skipped by the reference
+    got = b200.ndimage.convolve(dev(b200, a3), w3, mode="mirror").to_numpy()
+    ref = ndi.convolve(a3, w3, mode="mirror")
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    ok = np.isfinite(ref)
+    assert_parity(np.where(ok, got, 0).astype(dtype), np.where(ok, ref, 0).astype(dtype), data=a3[np.isfinite(a3)])
 
 
 def test_config5_convolve_9cubed_wrap(b200):
