@@ -140,7 +140,7 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 // warp 64 x 8; the lanes of a quarter warp sit on 8 different rows, which the
 // odd 16-byte pitch spreads over all bank groups.  TS = uint16_t / uint8_t is
 // the exact integer box filter (taps 0/1, quotient epilogue).
-template <typename TS, int NT>
+template <typename TS, int NT, bool LDG = false>
 __global__ void __launch_bounds__(256, 3)
 corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
                             const __grid_constant__ Corr1dTmaParams<float, TS> p)
@@ -168,7 +168,7 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
     const int64_t row0 = trow * TR;
     const int64_t g0 = x0t - p.lo;
 
-    contig_stage_tile<TS, 8>(tmap, tile, &full_bar, p.in, g0, row0, p.n, nrows, P, TR, p.mode, p.cval);
+    contig_stage_tile<TS, 8, LDG>(tmap, tile, &full_bar, p.in, g0, row0, p.n, nrows, P, TR, p.mode, p.cval);
 
     // a warp keeps one 64-column group and walks the 8-row groups (uniform trip
     // count); CTAs have 8 or 4 warps
@@ -235,7 +235,22 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
 #pragma unroll
             for (int j = 0; j < R; ++j)
                 res[j] = ((j & 1) ? e[j >> 1].y : e[j >> 1].x) + ((j & 1) ? o[(j + 1) >> 1].x : o[j >> 1].y);
-            if constexpr (kBox) {
+            if constexpr (LDG) {
+                // unaligned rows: element stores, the row may end anywhere
+                const bool reads_out = epilogue_reads_out(p.epilogue);
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    if (x + j < p.n) {
+                        if constexpr (kBox) {
+                            dst0[j] = (TS)box_quotient_bits<float>(res[j], p.qinv, p.qc0);
+                        } else {
+                            dst0[j] = p.epilogue == B200_EPI_STORE
+                                          ? res[j]
+                                          : apply_epilogue<float>(p.epilogue, reads_out ? dst0[j] : 0.f, res[j]);
+                        }
+                    }
+                }
+            } else if constexpr (kBox) {
                 // rows are whole multiples of 16 bytes and x is a multiple of 16 elements
                 store_box_quotients<float, TS, 8>(dst0, reinterpret_cast<const float(&)[8]>(res[0]), p.qinv, p.qc0);
                 if (x + 8 < p.n)
@@ -352,7 +367,7 @@ static int launch_contig_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al,
     return B200_OK;
 }
 
-template <typename TS, int NT>
+template <typename TS, int NT, bool LDG = false>
 static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al, int lead)
 {
     constexpr int EB = 16 / (int)sizeof(TS);   // elements per 16 bytes of storage
@@ -390,10 +405,13 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int
     const size_t stage_bytes = (size_t)tr * pitch * es;
 
     CUtensorMap tmap;
-    uint64_t dims[2] = {(uint64_t)g.n, (uint64_t)g.outer};
-    uint64_t strides[1] = {(uint64_t)g.n * es};
-    uint32_t bx[2] = {(uint32_t)pitch, (uint32_t)tr};
-    if (encode_tensor_map(&tmap, dtype_code<TS>(), (void *)a.in, 2, dims, strides, bx) != 0) return -1;
+    memset(&tmap, 0, sizeof(tmap));
+    if constexpr (!LDG) {
+        uint64_t dims[2] = {(uint64_t)g.n, (uint64_t)g.outer};
+        uint64_t strides[1] = {(uint64_t)g.n * es};
+        uint32_t bx[2] = {(uint32_t)pitch, (uint32_t)tr};
+        if (encode_tensor_map(&tmap, dtype_code<TS>(), (void *)a.in, 2, dims, strides, bx) != 0) return -1;
+    }
 
     Corr1dTmaParams<float, TS> p;
     p.in = (const TS *)a.in; p.out = (TS *)a.out;
@@ -401,20 +419,20 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int
     p.pad_lo = 0; p.pad_hi = 0;
     p.nw = NT; p.lo = lo_al; p.mode = a.mode; p.epilogue = a.epilogue;
     p.tile_rows = tr; p.smem_rows = tr; p.nb = 1; p.pitch = pitch; p.shift = 0; p.ncg = ncg;
-    p.wide_store = (((g.n * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
+    p.wide_store = (!LDG && ((g.n * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
     p.n_tiles = (int)r_tiles; p.c_tiles = (int)c_tiles;
     p.cval = (TS)a.cval;
     p.qinv = box.qinv; p.qc0 = box.qc0;
     for (int i = 0; i < NT; ++i) p.w[i] = 0.f;
     for (int i = 0; i < a.nw; ++i) p.w[lead + i] = (float)a.w[i];
 
-    auto kern = corr1d_contig_static_kernel<TS, NT>;
+    auto kern = corr1d_contig_static_kernel<TS, NT, LDG>;
     const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     kern<<<(unsigned)num_tiles, threads == 128 ? 128 : 256, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
-    note_kernel(kernel_name<float, TS>(false));
+    note_kernel(kernel_name<float, TS>(false, LDG));
     return B200_OK;
 }
 
@@ -425,17 +443,20 @@ static int launch_contig_static(const Corr1dArgs &a)
 {
     const LineGeom &g = a.g;
     if (a.pad_lo || a.pad_hi) return -1;
-    if ((g.n * 4) % 16 != 0) return -1;
     if (g.n >= (1ll << 31) || g.outer >= (1ll << 31)) return -1;
-    if (((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15)) return -1;
+    // rows / bases that are not 16-byte multiples: the same tiles staged with plain loads
+    const bool ldg = (g.n * 4) % 16 != 0 || ((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15);
     const int lo = a.nw / 2 + a.origin;
     const int lo_al = (lo + 3) / 4 * 4;
     const int lead = lo_al - lo;
     const int nt = lead + a.nw;
-    if (nt > kStaticTaps) return -2;
+    if (nt > kStaticTaps) return ldg ? -1 : -2;
     const BoxInfo none;
     switch (nt) {
-#define B200_C1_CASE(K) case K: return launch_contig_static_cfg<float, K>(a, none, lo_al, lead);
+#define B200_C1_CASE(K)                                                                  \
+    case K:                                                                              \
+        return ldg ? launch_contig_static_cfg<float, K, true>(a, none, lo_al, lead)      \
+                   : launch_contig_static_cfg<float, K, false>(a, none, lo_al, lead);
 #define B200_C1_CASE4(K) B200_C1_CASE(K) B200_C1_CASE(K + 1) B200_C1_CASE(K + 2) B200_C1_CASE(K + 3)
     B200_C1_CASE4(1) B200_C1_CASE4(5) B200_C1_CASE4(9) B200_C1_CASE4(13) B200_C1_CASE4(17) B200_C1_CASE4(21)
     B200_C1_CASE4(25) B200_C1_CASE4(29) B200_C1_CASE4(33) B200_C1_CASE4(37) B200_C1_CASE4(41) B200_C1_CASE4(45)
@@ -498,25 +519,29 @@ static int launch_contig_box(const Corr1dArgs &a, const BoxInfo &box)
     const int es = (int)sizeof(TS);
     const LineGeom &g = a.g;
     if (a.pad_lo || a.pad_hi) return -1;
-    if ((g.n * es) % 16 != 0) return -1;
     if (g.n >= (1ll << 31) || g.outer >= (1ll << 31)) return -1;
-    if (((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15)) return -1;
+    const bool ldg = (g.n * es) % 16 != 0 || ((uintptr_t)a.in & 15) || ((uintptr_t)a.out & 15);
     const int lo = a.nw / 2 + a.origin;
     const int lo_al = (lo + U16B - 1) / U16B * U16B;
     const int lead = lo_al - lo;
-    if (env_int("B200_TMA_STATIC", 1)) {
+    if (ldg || env_int("B200_TMA_STATIC", 1)) {
         // compile-time tap engine: taps padded to whole 16-byte blocks of storage
         const int la = (lead + a.nw + U16B - 1) / U16B * U16B;
+#define B200_BOX_CASE(K)                                                              \
+    return ldg ? launch_contig_static_cfg<TS, K, true>(a, box, lo_al, lead)           \
+               : launch_contig_static_cfg<TS, K, false>(a, box, lo_al, lead);
         switch (la) {
-        case 8: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 8>(a, box, lo_al, lead); break;
-        case 16: return launch_contig_static_cfg<TS, 16>(a, box, lo_al, lead);
-        case 24: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 24>(a, box, lo_al, lead); break;
-        case 32: return launch_contig_static_cfg<TS, 32>(a, box, lo_al, lead);
-        case 40: if constexpr (U16B == 8) return launch_contig_static_cfg<TS, 40>(a, box, lo_al, lead); break;
-        case 48: return launch_contig_static_cfg<TS, 48>(a, box, lo_al, lead);
+        case 8: if constexpr (U16B == 8) { B200_BOX_CASE(8) } break;
+        case 16: B200_BOX_CASE(16)
+        case 24: if constexpr (U16B == 8) { B200_BOX_CASE(24) } break;
+        case 32: B200_BOX_CASE(32)
+        case 40: if constexpr (U16B == 8) { B200_BOX_CASE(40) } break;
+        case 48: B200_BOX_CASE(48)
         default: break;
         }
+#undef B200_BOX_CASE
     }
+    if (ldg) return -1;
     int L = a.nw + lead;
     L = (L + V - 1) / V * V;
     if (L > kMaxTapsTma) return -1;

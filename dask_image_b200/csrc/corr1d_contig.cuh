@@ -24,14 +24,15 @@ struct ContigEdge {
     __device__ __forceinline__ int column(int k) const { return k < nlow ? k : hstart + (k - nlow); }
 };
 
-template <typename TS, int KPRE>
+// LDG = stage with plain element loads instead of TMA (rows / bases that are not 16-byte multiples)
+template <typename TS, int KPRE, bool LDG = false>
 __device__ __forceinline__ void contig_stage_tile(const CUtensorMap &tmap, TS *tile, uint64_t *full_bar, const TS *in,
                                                   int64_t g0, int64_t row0, int64_t n, int64_t nrows, int P, int TR,
                                                   int mode, TS cval)
 {
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
-    if (tid == 0) {
+    if (!LDG && tid == 0) {
         mbar_init(full_bar, 1);
         fence_barrier_init();
         mbar_arrive_expect_tx(full_bar, (uint32_t)(TR * P * (int)sizeof(TS)));
@@ -62,7 +63,27 @@ __device__ __forceinline__ void contig_stage_tile(const CUtensorMap &tmap, TS *t
         }
     }
     __syncthreads();
-    if (tid < 32) mbar_wait(full_bar, 0);
+    if constexpr (LDG) {
+        // the columns of the tile that lie inside the row, element by element; the rest is zero
+        // (a warp walks along one tile row: coalesced, and no division per element)
+        const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+        for (int r = wid; r < TR; r += nw) {
+            const bool row_ok = row0 + r < nrows;
+            const TS *src = in + (row0 + r) * n + g0;
+            for (int c = lane; c < P; c += 32) {
+                const int64_t col = g0 + c;
+                const bool ok = row_ok && col >= 0 && col < n;
+                if constexpr (sizeof(TS) == 4) {
+                    cp_async_f32(tile + r * P + c, ok ? src + c : in, ok);
+                } else {
+                    tile[r * P + c] = ok ? src[c] : TS(0);
+                }
+            }
+        }
+        if constexpr (sizeof(TS) == 4) cp_async_wait_all();
+    } else {
+        if (tid < 32) mbar_wait(full_bar, 0);
+    }
     __syncthreads();
     if (patch) {
 #pragma unroll

@@ -17,8 +17,10 @@
 
 namespace b200 {
 
-template <typename T, typename TS, int W, int TY, int R, int REM, bool PEER, int OP = 0>
-__device__ __forceinline__ void strided_tile_body(const CUtensorMap &tmap, const Corr1dTmaParams<T, TS> &p,
+// LDG = the tile is staged with plain element loads instead of TMA (rows or bases that are not
+// 16-byte multiples) and stored element-wise: same tile, same arithmetic, no alignment needs.
+template <typename T, typename TS, int W, int TY, int R, int REM, bool PEER, int OP = 0, bool LDG = false>
+__device__ __forceinline__ void strided_tile_body(const CUtensorMap *tmap, const Corr1dTmaParams<T, TS> &p,
                                                   const PeerMaps *hm)
 {
     constexpr int V = StridedV<T, TS>::V;
@@ -44,7 +46,7 @@ __device__ __forceinline__ void strided_tile_body(const CUtensorMap &tmap, const
     const int64_t col0 = (int64_t)tc * W;
     const int64_t g0 = row0 - p.lo;                  // array row held by smem row 0
 
-    if (tid == 0) {
+    if (!LDG && tid == 0) {
         mbar_init(&full_bar, 1);
         fence_barrier_init();
         if constexpr (PEER) {
@@ -59,11 +61,11 @@ __device__ __forceinline__ void strided_tile_body(const CUtensorMap &tmap, const
                 tma_load_3d(tile + hm->k_last * W, &hm->hi, &full_bar, (int)col0, 0, 0);
             } else {
                 mbar_arrive_expect_tx(&full_bar, (uint32_t)(p.smem_rows * W * (int)sizeof(TS)));
-                tma_load_3d(tile, &tmap, &full_bar, (int)col0, (int)g0, (int)o);
+                tma_load_3d(tile, tmap, &full_bar, (int)col0, (int)g0, (int)o);
             }
         } else {
             mbar_arrive_expect_tx(&full_bar, (uint32_t)(p.smem_rows * W * (int)sizeof(TS)));
-            tma_load_3d(tile, &tmap, &full_bar, (int)col0, (int)(g0 + p.pad_lo), (int)o);
+            tma_load_3d(tile, tmap, &full_bar, (int)col0, (int)(g0 + p.pad_lo), (int)o);
         }
     }
 
@@ -112,8 +114,29 @@ __device__ __forceinline__ void strided_tile_body(const CUtensorMap &tmap, const
         }
     }
     __syncthreads();
-    // one warp polls the mbarrier; the others sleep at the CTA barrier
-    if (tid < 32) mbar_wait(&full_bar, 0);
+    if constexpr (LDG) {
+        // resident rows of the tile, element by element (coalesced along the row); the rest is zero
+        if constexpr (sizeof(TS) == 4) {
+            // 4-byte asynchronous copies: the whole tile is in flight before anybody waits
+            const TS *src = p.in + (o * p.n + g0) * p.inner + col0;
+            for (int idx = tid; idx < p.smem_rows * W; idx += NTHREADS) {
+                const int r = idx / W, c = idx - r * W;
+                const bool ok = r >= nlo && r < rhi && col0 + c < p.inner;
+                cp_async_f32(tile + idx, ok ? src + (int64_t)r * p.inner + c : p.in, ok);
+            }
+            cp_async_wait_all();
+        } else {
+            for (int idx = tid; idx < p.smem_rows * W; idx += NTHREADS) {
+                const int r = idx / W, c = idx - r * W;
+                TS v = TS(0);
+                if (r >= nlo && r < rhi && col0 + c < p.inner) v = p.in[(o * p.n + (g0 + r)) * p.inner + col0 + c];
+                tile[idx] = v;
+            }
+        }
+    } else {
+        // one warp polls the mbarrier; the others sleep at the CTA barrier
+        if (tid < 32) mbar_wait(&full_bar, 0);
+    }
     __syncthreads();
     if (patch) {
 #pragma unroll
@@ -161,7 +184,22 @@ __device__ __forceinline__ void strided_tile_body(const CUtensorMap &tmap, const
                 const int64_t row = row0 + r0 + j;
                 if (row < p.n) {
                     TS *dst = out_col + row * p.inner;
-                    if constexpr (kBox) {
+                    if constexpr (LDG) {
+                        // unaligned rows: element stores, the row may end inside the vector
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            if (col + v < p.inner) {
+                                if constexpr (kBox) {
+                                    dst[v] = (TS)box_quotient_bits<T>(acc[j].get(v), p.qinv, p.qc0);
+                                } else {
+                                    const T prev = reads_out ? dst[v] : T(0);
+                                    dst[v] = p.epilogue == B200_EPI_STORE
+                                                 ? acc[j].get(v)
+                                                 : apply_epilogue<T>(p.epilogue, prev, acc[j].get(v));
+                                }
+                            }
+                        }
+                    } else if constexpr (kBox) {
                         T sums[V];
 #pragma unroll
                         for (int v = 0; v < V; ++v) sums[v] = acc[j].get(v);
@@ -192,7 +230,15 @@ template <typename T, typename TS, int W, int TY, int R, int MINB, int REM>
 __global__ void __launch_bounds__((W / StridedV<T, TS>::V) * TY, MINB)
 corr1d_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr1dTmaParams<T, TS> p)
 {
-    strided_tile_body<T, TS, W, TY, R, REM, false>(tmap, p, nullptr);
+    strided_tile_body<T, TS, W, TY, R, REM, false>(&tmap, p, nullptr);
+}
+
+// the same pass for rows / bases that are not 16-byte multiples: plain loads and stores
+template <typename T, typename TS, int W, int TY, int R, int MINB, int REM>
+__global__ void __launch_bounds__((W / StridedV<T, TS>::V) * TY, MINB)
+corr1d_strided_ldg_kernel(const __grid_constant__ Corr1dTmaParams<T, TS> p)
+{
+    strided_tile_body<T, TS, W, TY, R, REM, false, 0, true>(nullptr, p, nullptr);
 }
 
 // minimum (OP = 1) / maximum (OP = 2) filter along a non-contiguous axis: the
@@ -202,7 +248,7 @@ __global__ void __launch_bounds__((W / StridedV<float, TS>::V) * TY, MINB)
 minmax_strided_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                           const __grid_constant__ Corr1dTmaParams<float, TS> p)
 {
-    strided_tile_body<float, TS, W, TY, R, REM, false, OP>(tmap, p, nullptr);
+    strided_tile_body<float, TS, W, TY, R, REM, false, OP>(&tmap, p, nullptr);
 }
 
 template <typename T, typename TS, int W, int TY, int R, int MINB, int REM>
@@ -210,13 +256,13 @@ __global__ void __launch_bounds__((W / StridedV<T, TS>::V) * TY, MINB)
 corr1d_strided_peer_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PeerMaps hm,
                            const __grid_constant__ Corr1dTmaParams<T, TS> p)
 {
-    strided_tile_body<T, TS, W, TY, R, REM, true>(tmap, p, &hm);
+    strided_tile_body<T, TS, W, TY, R, REM, true>(&tmap, p, &hm);
 }
 
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
-template <typename T, typename TS, int R, int MINB, int REM, int TY = 8, int OP = 0>
+template <typename T, typename TS, int R, int MINB, int REM, int TY = 8, int OP = 0, bool LDG = false>
 static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
 {
     constexpr int V = StridedV<T, TS>::V;
@@ -242,10 +288,12 @@ static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     if (num_tiles >= (1ll << 31)) return -1;
 
     CUtensorMap tmap;
-    uint64_t dims[3] = {(uint64_t)g.inner, (uint64_t)n_tot, (uint64_t)g.outer};
-    uint64_t strides[2] = {(uint64_t)g.inner * es, (uint64_t)g.inner * es * (uint64_t)n_tot};
-    uint32_t bx[3] = {(uint32_t)W, (uint32_t)smem_rows, 1u};
-    if (encode_tensor_map(&tmap, dtype_code<TS>(), (void *)base, 3, dims, strides, bx) != 0) return -1;
+    if constexpr (!LDG) {
+        uint64_t dims[3] = {(uint64_t)g.inner, (uint64_t)n_tot, (uint64_t)g.outer};
+        uint64_t strides[2] = {(uint64_t)g.inner * es, (uint64_t)g.inner * es * (uint64_t)n_tot};
+        uint32_t bx[3] = {(uint32_t)W, (uint32_t)smem_rows, 1u};
+        if (encode_tensor_map(&tmap, dtype_code<TS>(), (void *)base, 3, dims, strides, bx) != 0) return -1;
+    }
 
     Corr1dTmaParams<T, TS> p;
     p.in = (const TS *)a.in; p.out = (TS *)a.out;
@@ -260,7 +308,12 @@ static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     for (int i = 0; i < L; ++i) p.w[i] = (T)a.w[i];
 
     const size_t smem = stage_bytes + 128;
-    if constexpr (OP == 0) {
+    if constexpr (LDG) {
+        static_assert(OP == 0, "plain-load staging is built for the weighted pass and the box filter");
+        auto kern = corr1d_strided_ldg_kernel<T, TS, W, TY, R, MINB, REM>;
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
+        kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(p);
+    } else if constexpr (OP == 0) {
         auto kern = corr1d_strided_tma_kernel<T, TS, W, TY, R, MINB, REM>;
         B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
         kern<<<(unsigned)num_tiles, (W / V) * TY, smem, a.stream>>>(tmap, p);
@@ -271,7 +324,7 @@ static int launch_strided_cfg(const Corr1dArgs &a, const BoxInfo &box, int nb)
     }
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
-    note_kernel(OP == 0 ? kernel_name<T, TS>(true) : (OP == 1 ? "min1d_tma_strided" : "max1d_tma_strided"));
+    note_kernel(OP == 0 ? kernel_name<T, TS>(true, LDG) : (OP == 1 ? "min1d_tma_strided" : "max1d_tma_strided"));
     return B200_OK;
 }
 
@@ -285,12 +338,27 @@ static int launch_strided_r(const Corr1dArgs &a, const BoxInfo &box)
     const LineGeom &g = a.g;
     const int L = a.nw;
     if (L > kMaxTapsTma || 8 * R + L - 1 > 256) return -1;
-    if ((g.inner * es) % 16 != 0) return -1;
     const int64_t n_tot = a.pad_lo + g.n + a.pad_hi;
     if (g.inner >= (1ll << 31) || n_tot >= (1ll << 31) || g.outer >= (1ll << 31)) return -1;
     if ((a.pad_lo || a.pad_hi) && g.outer != 1) return -1;   // pads exist only for axis 0
     const char *base = (const char *)a.in - a.pad_lo * g.inner * es;
-    if (((uintptr_t)base & 15) || ((uintptr_t)a.out & 15)) return -1;
+    // TMA needs 16-byte rows and bases; anything else takes the same tiles with plain loads / stores
+    // (the choice depends on the row length and the pointers only, never on the plane count)
+    const bool unaligned = (g.inner * es) % 16 != 0 || ((uintptr_t)base & 15) || ((uintptr_t)a.out & 15);
+    if (unaligned) {
+        if constexpr (R == 4 && OP == 0) {
+            int nbl = ((int)((kSmemPerSm - 3072) / MINB) / row_bytes - (L - 1)) / (8 * R);
+            nbl = nbl < 1 ? 1 : nbl;
+            switch (L % R) {
+            case 0: return launch_strided_cfg<T, TS, R, MINB, 0, 8, 0, true>(a, box, nbl);
+            case 1: return launch_strided_cfg<T, TS, R, MINB, 1, 8, 0, true>(a, box, nbl);
+            case 2: return launch_strided_cfg<T, TS, R, MINB, 2, 8, 0, true>(a, box, nbl);
+            default: return launch_strided_cfg<T, TS, R, MINB, 3, 8, 0, true>(a, box, nbl);
+            }
+        } else {
+            return -1;
+        }
+    }
 
     // nb = row blocks (of 8*R rows) per CTA tile: the tallest tile that still
     // leaves MINB CTAs resident per SM (B200 sweeps in profiles/: more, smaller
@@ -498,9 +566,12 @@ int launch_corr1d_peer(const Corr1dArgs &a)
 template <typename T, typename TS>
 static int launch_strided(const Corr1dArgs &a, const BoxInfo &box)
 {
+    const int es = (int)sizeof(TS);
+    const char *base = (const char *)a.in - a.pad_lo * a.g.inner * es;
+    const bool unaligned = (a.g.inner * es) % 16 != 0 || ((uintptr_t)base & 15) || ((uintptr_t)a.out & 15);
     if constexpr (sizeof(T) == sizeof(TS)) {
-        if (a.g.n <= 8) return launch_strided_r<T, TS, 1>(a, box);
-        if (a.g.n <= 16) return launch_strided_r<T, TS, 2>(a, box);
+        if (!unaligned && a.g.n <= 8) return launch_strided_r<T, TS, 1>(a, box);
+        if (!unaligned && a.g.n <= 16) return launch_strided_r<T, TS, 2>(a, box);
     }
     return launch_strided_r<T, TS, 4>(a, box);
 }

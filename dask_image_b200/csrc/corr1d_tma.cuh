@@ -78,8 +78,15 @@ struct BoxInfo {
 };
 
 template <typename T, typename TS>
-static const char *kernel_name(bool strided)
+static const char *kernel_name(bool strided, bool ldg = false)
 {
+    if (ldg) {   // the tiled kernels staged with plain loads (rows / bases not 16-byte multiples)
+        if (sizeof(TS) != sizeof(T))
+            return strided ? (sizeof(TS) == 2 ? "uniform1d_ldg_strided_u16" : "uniform1d_ldg_strided_u8")
+                           : (sizeof(TS) == 2 ? "uniform1d_ldg_contig_u16" : "uniform1d_ldg_contig_u8");
+        return strided ? (sizeof(T) == 4 ? "corr1d_ldg_strided_f32" : "corr1d_ldg_strided_f64")
+                       : (sizeof(T) == 4 ? "corr1d_ldg_contig_f32" : "corr1d_ldg_contig_f64");
+    }
     if (sizeof(TS) != sizeof(T))
         return strided ? (sizeof(TS) == 2 ? "uniform1d_tma_strided_u16" : "uniform1d_tma_strided_u8")
                        : (sizeof(TS) == 2 ? "uniform1d_tma_contig_u16" : "uniform1d_tma_contig_u8");

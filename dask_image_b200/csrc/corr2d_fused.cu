@@ -96,7 +96,7 @@ __device__ __noinline__ void fused_stage_edges(const Corr2dParams &p, float *tin
     const bool zero_ok = p.mode1 == B200_MODE_CONSTANT && p.mode2 == B200_MODE_CONSTANT && p.cval == 0.f;
     const bool any = r_lo > 0 || r_hi < rows_need || c_lo > 0 || c_hi < cols_need;
     const bool patch = TMA ? (any && !zero_ok) : true;
-    if (patch) {
+    if (patch && (TMA || any)) {
         // source row / column of every staged row / column (-1 = cval; identity inside the array)
         for (int i = tid; i < TYIN; i += NTHR) row_src[i] = ext_index32(gy0 + i, ny, p.mode1);
         for (int c = tid; c < PX; c += NTHR) col_src[c] = ext_index32(gx0 + c, nx, p.mode2);
@@ -129,17 +129,30 @@ __device__ __noinline__ void fused_stage_edges(const Corr2dParams &p, float *tin
     } else {
         // rows that are not 16-byte multiples (or an unaligned base): the same tile, staged with
         // plain 4-byte loads through the extension maps
+        // plain 4-byte asynchronous copies (all of the tile in flight at once): straight from the rows
+        // when the needed box lies inside the array, else through the extension maps (cval positions
+        // are written directly)
         const int total = rows_need * PX;
-#pragma unroll 4
+        if (!any) {
+            const int lane = tid & 31;
+            for (int i = tid >> 5; i < rows_need; i += NTHR / 32) {
+                const float *src = plane + (int64_t)(gy0 + i) * nx + gx0;
+                float *dst = tin + i * PX;
+#pragma unroll
+                for (int c = lane; c < PX; c += 32) cp_async_f32(dst + c, c < cols_need ? src + c : plane, c < cols_need);
+            }
+        } else
         for (int idx = tid; idx < total; idx += NTHR) {
             const int i = idx / PX, c = idx - i * PX;
-            float v = 0.f;
-            if (c < cols_need) {
-                const int ry = row_src[i], cx = col_src[c];
-                v = (ry < 0 || cx < 0) ? p.cval : plane[(int64_t)ry * nx + cx];
+            const int ry = row_src[i], cx = c < cols_need ? col_src[c] : 0;
+            if (c < cols_need && (ry < 0 || cx < 0)) {
+                tin[idx] = p.cval;
+            } else {
+                const bool ok = c < cols_need;
+                cp_async_f32(tin + idx, ok ? plane + (int64_t)ry * nx + cx : plane, ok);
             }
-            tin[idx] = v;
         }
+        cp_async_wait_all();
     }
     __syncthreads();
 }
@@ -329,14 +342,18 @@ corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 *dst = r4;
             }
         } else {
+            // a warp per row, lanes along it: coalesced element stores
             const bool reads_out = epilogue_reads_out(p.epilogue);
-            for (int idx = tid; idx < ROWS_B * tile_cols; idx += NTHR) {
-                const int rr = idx / tile_cols, c = idx - rr * tile_cols;
-                if (y0 + hb * ROWS_B + rr >= ny) continue;
-                float v = oblk[rr * opitch + c];
-                float *dst = orow0 + (int64_t)rr * nx + c;
-                if (p.epilogue != B200_EPI_STORE) v = apply_epilogue<float>(p.epilogue, reads_out ? *dst : 0.f, v);
-                *dst = v;
+            for (int rr = warp; rr < ROWS_B; rr += NWARPS) {
+                if (y0 + hb * ROWS_B + rr >= ny) break;
+                const float *srcr = oblk + rr * opitch;
+                float *dst = orow0 + (int64_t)rr * nx;
+                if (p.epilogue == B200_EPI_STORE) {
+                    for (int c = lane; c < tile_cols; c += 32) dst[c] = srcr[c];
+                } else {
+                    for (int c = lane; c < tile_cols; c += 32)
+                        dst[c] = apply_epilogue<float>(p.epilogue, reads_out ? dst[c] : 0.f, srcr[c]);
+                }
             }
         }
     }

@@ -83,6 +83,20 @@ __device__ __forceinline__ void bulk_store_wait_read()
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// 4-byte asynchronous copy global -> shared (LDGSTS); `valid` = false writes zeros and reads nothing.
+// The staging path of tiles whose rows are not 16-byte multiples: no registers, no round trip
+// through the LSU return path, and all copies of a tile are in flight at once.
+__device__ __forceinline__ void cp_async_f32(void *smem_dst, const void *gmem_src, bool valid)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(valid ? 4 : 0)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");

@@ -73,17 +73,68 @@ def test_tma_constant_cval_zero_uses_tma_zero_fill(b200, mode):
         assert_parity(got.to_numpy(), orc.correlate1d(a, w, axis=axis, mode=mode, cval=0.0))
 
 
-def test_unaligned_shapes_fall_back_or_fail_loudly(b200):
+UNALIGNED_WIDTHS = list(range(1, 68)) + [110, 1023, 1034]
+
+
+@pytest.mark.parametrize("width", UNALIGNED_WIDTHS)
+def test_unaligned_rows_stay_on_the_tiled_kernels(b200, width):
+    """Rows that are not 16-byte multiples (dask chunks with odd halos: ceil(4 sigma) = 5, 7, 9 ...) cannot be
+    TMA-staged; the same tiles are then filled with plain loads and stored element-wise -- the arithmetic is
+    that of the tiled kernels, never the one-thread-per-output kernel (a ~20x cliff in round 1)."""
     from dask_image_b200 import _lib
 
-    a = np.random.default_rng(2).random((64, 1023)).astype(np.float32)   # rows not 16-byte multiples
-    w = np.ones(5) / 5
-    got = b200.ndimage.correlate1d(dev(b200, a), w, axis=0)
-    assert _lib.last_kernel() == "corr1d_generic"
-    assert_parity(got.to_numpy(), orc.correlate1d(a, w, axis=0))
-    with forced(b200, _lib.FLAG_FORCE_FAST):
-        with pytest.raises(RuntimeError, match="no tiled kernel"):
-            b200.ndimage.correlate1d(dev(b200, a), w, axis=0)
+    rng = np.random.default_rng(width)
+    a = (rng.random((37, width)) - 0.25).astype(np.float32)
+    d = dev(b200, a)
+    aligned = width % 4 == 0
+    for nw, origin, mode in ((5, 0, "reflect"), (17, 0, "mirror"), (9, -2, "wrap"), (12, 3, "constant"), (25, 0, "nearest")):
+        w = rng.random(nw) - 0.3
+        for axis in (0, 1):
+            with forced(b200, _lib.FLAG_FORCE_FAST):
+                got = b200.ndimage.correlate1d(d, w, axis=axis, mode=mode, cval=0.7, origin=origin)
+            k = _lib.last_kernel()
+            if width == 1 and axis == 0:
+                want = "corr1d_ldg_contig_f32"     # a single column IS a contiguous line (37 * 4 bytes: unaligned)
+            else:
+                want = "corr1d_%s_%s_f32" % ("tma" if aligned else "ldg", "strided" if axis == 0 else "contig")
+            assert k == want, (width, axis, k)
+            assert_parity(got.to_numpy(), orc.correlate1d(a, w, axis=axis, mode=mode, cval=0.7, origin=origin),
+                          what="width=%d nw=%d axis=%d" % (width, nw, axis))
+    # uint16 / uint8: the exact box filter, and the weighted integer kernels (plain loads by construction)
+    for dt in (np.uint16, np.uint8):
+        u = rng.integers(0, np.iinfo(dt).max, (21, 19, width), dtype=dt, endpoint=True)
+        du = dev(b200, u)
+        got = b200.ndimage.uniform_filter(du, 5, mode="mirror")
+        assert "generic" not in _lib.last_kernel(), (width, _lib.last_kernel())
+        assert np.array_equal(got.to_numpy(), orc.uniform_filter(u, 5, mode="mirror"))
+        got = b200.ndimage.gaussian_filter(du, 1.0)
+        assert _lib.last_kernel().startswith("corr1d_int_"), (width, _lib.last_kernel())
+        assert np.array_equal(got.to_numpy(), orc.gaussian_filter(u, 1.0))
+    # float32 volume: axis-0 pass + fused pair, whatever the width
+    v = rng.random((9, 23, width)).astype(np.float32)
+    _lib.launch_count(reset=True)
+    got = b200.ndimage.gaussian_filter(dev(b200, v), 1.5, mode="reflect")
+    assert _lib.launch_count() == 2 and _lib.last_kernel().startswith("corr2d_fused_"), _lib.last_kernel()
+    assert_parity(got.to_numpy(), orc.gaussian_filter(v, 1.5, mode="reflect"))
+
+
+def test_unaligned_base_pointer(b200):
+    """A view that starts 4 bytes into an allocation: 16-byte rows, unaligned base -> plain-load staging."""
+    import torch
+
+    from dask_image_b200 import _lib, ndimage
+
+    rng = np.random.default_rng(12)
+    a = rng.random((40 * 64 + 1,)).astype(np.float32)
+    t = torch.from_numpy(a).cuda()
+    x = t[1:].view(40, 64)
+    assert x.data_ptr() % 16 == 4 and x.is_contiguous()
+    w = rng.random(7)
+    for axis in (0, 1):
+        out = torch.empty(40, 64, device="cuda")
+        ndimage._launch_correlate1d(x, out, (40, 64), np.dtype(np.float32), axis, w, "reflect", 0.0, 0)
+        assert _lib.last_kernel() == "corr1d_ldg_%s_f32" % ("strided" if axis == 0 else "contig")
+        assert_parity(out.cpu().numpy(), orc.correlate1d(a[1:].reshape(40, 64), w, axis=axis))
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
