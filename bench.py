@@ -258,6 +258,8 @@ def result_checksum(ctx, vol):
     step = 1 << 28
     for o in range(0, words.numel(), step):
         total += int((words[o:o + step].to(torch.int64) & mask).sum().item())
+    if getattr(vol, "replicated", False):     # every rank holds the whole (small) volume
+        return total % (1 << 56)
     # (int64 all-reduce over <= 8 ranks: keep every partial sum below 2^56)
     return ctx.sum_int(total % (1 << 56)) % (1 << 56)
 
@@ -500,6 +502,8 @@ def configs_leg(ctx, args, peak):
 
             ms, launches = ctx.time_steps(step, 1 if name == "C5" else n_steps, 1 if name == "C5" else 2)
             vox = float(np.prod(shape))
+            if vol.replicated:
+                entry["replicated"] = "below ShardedVolume.REPLICATE_BELOW_BYTES: every rank filters the whole volume"
             entry.update(ms=ms, gvox_s=vox / ms / 1e6, launches=launches // (1 if name == "C5" else n_steps),
                          kernel=_lib.last_kernel(), alg_gbs_per_gpu=vox * bpv / ctx.world / ms / 1e6,
                          frac_of_measured_peak=vox * bpv / ctx.world / ms / 1e6 / peak,

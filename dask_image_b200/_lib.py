@@ -34,6 +34,7 @@ EXPORTS = (
     "b200_minmax_filter1d", "b200_minmax_filter_nd", "b200_correlate1d_halo", "b200_correlate1d_halo_eligible",
     "b200_enable_peer_access", "b200_uniform_filter1d_halo", "b200_uniform_filter1d_halo_eligible",
     "b200_correlate1d_pair", "b200_correlate1d_pair_eligible",
+    "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_last_kernel", "b200_last_error", "b200_version", "b200_launch_count",
 )
 
@@ -85,6 +86,12 @@ def load():
     lib.b200_correlate1d_pair.restype = ci
     lib.b200_correlate1d_pair_eligible.argtypes = [ci, ci, i64p, i64, i64, i64, i64]
     lib.b200_correlate1d_pair_eligible.restype = ci
+    lib.b200_ipc_export.argtypes = [vp, vp, i64p]
+    lib.b200_ipc_export.restype = ci
+    lib.b200_ipc_open.argtypes = [vp, ci, ctypes.POINTER(vp)]
+    lib.b200_ipc_open.restype = ci
+    lib.b200_ipc_close.argtypes = [vp]
+    lib.b200_ipc_close.restype = ci
     lib.b200_enable_peer_access.argtypes = [ci]
     lib.b200_enable_peer_access.restype = ci
     lib.b200_correlate1d_halo_eligible.argtypes = [ci, i64, i64, i64, i64]

@@ -2,6 +2,7 @@
 // argument validation (same conditions and error classes as the scipy drivers
 // the reference calls), kernel-family selection, thread-local diagnostics.
 #include "common.cuh"
+#include <cuda.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -200,6 +201,58 @@ int b200_enable_peer_access(int peer_device)
         return B200_OK;
     }
     return check_cuda(e, "cudaDeviceEnablePeerAccess");
+}
+
+// ---- CUDA IPC: neighbour slabs mapped for the in-place halo reads ------------
+typedef CUresult (*PFN_memGetAddressRange)(CUdeviceptr *, size_t *, CUdeviceptr);
+
+int b200_ipc_export(const void *dev_ptr, void *handle_out, int64_t *offset_out)
+{
+    if (!dev_ptr || !handle_out || !offset_out) return set_error(B200_EINVAL, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200_IPC_HANDLE_BYTES, "IPC handle size");
+    static PFN_memGetAddressRange get_range = nullptr;
+    static std::atomic<int> looked{0};
+    if (!looked.load()) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            get_range = (PFN_memGetAddressRange)fp;
+        looked.store(1);
+    }
+    if (!get_range) return set_error(B200_ECUDA, "cuMemGetAddressRange is not available");
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (get_range(&base, &size, (CUdeviceptr)(uintptr_t)dev_ptr) != CUDA_SUCCESS)
+        return set_error(B200_ECUDA, "cuMemGetAddressRange failed for %p", dev_ptr);
+    cudaIpcMemHandle_t h;
+    B200_CUDA_TRY(cudaIpcGetMemHandle(&h, (void *)(uintptr_t)base));
+    memcpy(handle_out, &h, sizeof(h));
+    *offset_out = (int64_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+    return B200_OK;
+}
+
+int b200_ipc_open(const void *handle, int owner_device, void **base_out)
+{
+    if (!handle || !base_out) return set_error(B200_EINVAL, "null argument");
+    int dev = -1;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    if (owner_device >= 0 && owner_device != dev) {
+        if (int rc = b200_enable_peer_access(owner_device)) return rc;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    B200_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *base_out = p;
+    return B200_OK;
+}
+
+int b200_ipc_close(void *base)
+{
+    if (!base) return B200_OK;
+    B200_CUDA_TRY(cudaIpcCloseMemHandle(base));
+    return B200_OK;
 }
 
 int b200_correlate1d_halo_eligible(int dtype, int64_t n, int64_t inner, int64_t nw, int64_t origin)

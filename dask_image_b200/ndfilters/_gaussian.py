@@ -9,6 +9,7 @@ from ..dispatch._dispatch_ndfilters import (dispatch_gaussian_filter,
                                             dispatch_gaussian_gradient_magnitude,
                                             dispatch_gaussian_laplace)
 from . import _utils
+from ..ndimage import _freeze
 
 __all__ = ["gaussian_filter", "gaussian_gradient_magnitude", "gaussian_laplace", "gaussian"]
 
@@ -35,10 +36,26 @@ def _get_border(image, sigma, truncate):
     return tuple(np.ceil(sigmas * truncate).astype(int))
 
 
+_halo_cache = {}
+
+
 def _halo(image, sigma, truncate):
+    """(sigmas, depth, boundary) of a call.  Depends on (ndim, sigma, truncate) only: chunk-wise
+    callers repeat the same call per chunk, so validated results are remembered (errors are not)."""
+    try:
+        key = (image.ndim, _freeze(sigma), _freeze(truncate))
+        hit = _halo_cache.get(key)
+        if hit is not None:
+            return hit[0], dict(hit[1]), dict(hit[2])
+    except TypeError:
+        key = None
     sigma = _get_sigmas(image, sigma)
     depth = _get_border(image, sigma, truncate)
     depth, boundary = _utils._get_depth_boundary(image.ndim, depth, "none")
+    if key is not None:
+        if len(_halo_cache) >= 256:
+            _halo_cache.clear()
+        _halo_cache[key] = (sigma, depth, boundary)
     return sigma, depth, boundary
 
 

@@ -59,6 +59,26 @@ def _stream_ptr(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+class _NoCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_CTX = _NoCtx()
+
+
+def _on_device(t):
+    """Context that makes ``t``'s device current -- free when it already is (the per-launch cost of
+    ``torch.cuda.device`` is several microseconds, as much as a small chunk's kernel)."""
+    idx = t.device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_CTX
+    return torch.cuda.device(idx)
+
+
 def _new_like(x):
     return torch.empty_like(x.tensor)
 
@@ -66,12 +86,22 @@ def _new_like(x):
 def _check_output(output, x):
     if output is None:
         return None
+    if isinstance(output, torch.Tensor) and not output.is_contiguous():
+        # B200Array would wrap a contiguous COPY: the result would never reach the caller's tensor
+        raise RuntimeError("output must be C-contiguous")
     out = as_b200(output)
     if out.shape != x.shape or out.dtype != x.dtype:
         raise RuntimeError("output shape / dtype not correct")
     if out.tensor.data_ptr() == x.tensor.data_ptr() and x.size:
         raise RuntimeError("input and output must not share memory")
     return out
+
+
+def _output_or_new(output, x):
+    """The caller's ``output`` (validated) or a new array like ``x``.  (Not ``a or b``: the truth value
+    of a B200Array is its length, so an output with a zero-length first axis would be replaced.)"""
+    out = _check_output(output, x)
+    return x.empty_like() if out is None else out
 
 
 # --------------------------------------------------------------------------
@@ -99,7 +129,7 @@ def _launch_correlate1d(src, dst, shape, np_dtype, axis, weights, mode, cval, or
         wptr = _lib.f64_pointer(w)
     else:
         w, wptr = prepared
-    with torch.cuda.device(src.device):
+    with _on_device(src):
         rc = lib.b200_correlate1d(
             src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape),
             _lib.i64_array(shape), int(axis), wptr, int(w.shape[0]),
@@ -113,7 +143,7 @@ def _launch_correlate1d_pair(src, dst, shape, np_dtype, ps1, ps2, cval, epilogue
     (corr2d_fused.cu); bit-identical to the two launches."""
     lib = _lib.load()
     (w1, p1), (w2, p2) = ps1.prepared, ps2.prepared
-    with torch.cuda.device(src.device):
+    with _on_device(src):
         rc = lib.b200_correlate1d_pair(
             src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape), _lib.i64_array(shape),
             p1, int(w1.shape[0]), _lib.mode_code(ps1.mode), int(ps1.origin),
@@ -148,11 +178,19 @@ def _pair_eligible(shape, np_dtype, ps1, ps2, flags=None):
         len(ps2.weights), int(ps2.origin)))
 
 
+_steps_cache = {}
+
+
 def _chain_steps(passes, shape, np_dtype, flags=None, axis0_local=True):
     """Group the 1-D passes of a chain into launches: ``[(pass,)]`` or, where the
     fused kernel applies, ``[(pass, pass)]`` for the passes along the last two
     axes.  ``axis0_local`` = False says axis 0 reaches beyond the resident planes
     (slab halos / streamed chunks): a pass along axis 0 then stays on its own."""
+    key = (tuple(ps.sig for ps in passes), len(shape), tuple(shape[-2:]), np_dtype, flags, _default_flags,
+           axis0_local, _FUSE_PAIRS)
+    hit = _steps_cache.get(key)
+    if hit is not None:
+        return hit
     steps, i = [], 0
     while i < len(passes):
         if (i + 1 < len(passes) and (axis0_local or passes[i].axis != 0)
@@ -162,6 +200,9 @@ def _chain_steps(passes, shape, np_dtype, flags=None, axis0_local=True):
         else:
             steps.append((passes[i],))
             i += 1
+    if len(_steps_cache) >= 1024:
+        _steps_cache.clear()
+    _steps_cache[key] = steps
     return steps
 
 
@@ -172,7 +213,7 @@ def _launch_correlate1d_halo(src, dst, shape, np_dtype, weights, mode, cval, ori
     peer GPU's planes mapped through CUDA IPC) or None for a volume boundary."""
     lib = _lib.load()
     w = np.ascontiguousarray(weights, dtype=np.float64)
-    with torch.cuda.device(src.device):
+    with _on_device(src):
         rc = lib.b200_correlate1d_halo(
             src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape), _lib.i64_array(shape),
             _lib.f64_pointer(w), int(w.shape[0]), _lib.mode_code(mode), float(cval), int(origin),
@@ -185,7 +226,7 @@ def _launch_correlate1d_halo(src, dst, shape, np_dtype, weights, mode, cval, ori
 def _launch_uniform1d_halo(src, dst, shape, np_dtype, size, mode, cval, origin, halo_lo, halo_hi, flags=None):
     """Box filter along axis 0 of a slab, neighbour planes read in place."""
     lib = _lib.load()
-    with torch.cuda.device(src.device):
+    with _on_device(src):
         rc = lib.b200_uniform_filter1d_halo(
             src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape), _lib.i64_array(shape),
             int(size), _lib.mode_code(mode), float(cval), int(origin),
@@ -209,7 +250,7 @@ def _halo_eligible(np_dtype, n, inner, nw, origin):
 def _launch_uniform1d(src, dst, shape, np_dtype, axis, size, mode, cval, origin, pad=(0, 0),
                       flags=None):
     lib = _lib.load()
-    with torch.cuda.device(src.device):
+    with _on_device(src):
         rc = lib.b200_uniform_filter1d(
             src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape),
             _lib.i64_array(shape), int(axis), int(size), _lib.mode_code(mode), float(cval),
@@ -222,7 +263,7 @@ def _launch_correlate_nd(src, dst, shape, np_dtype, weights, origins, mode, cval
                          flags=None):
     lib = _lib.load()
     w = np.ascontiguousarray(weights, dtype=np.float64)
-    with torch.cuda.device(src.device):
+    with _on_device(src):
         rc = lib.b200_correlate_nd(
             src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape),
             _lib.i64_array(shape), _lib.f64_pointer(w), _lib.i64_array(w.shape),
@@ -233,7 +274,7 @@ def _launch_correlate_nd(src, dst, shape, np_dtype, weights, origins, mode, cval
 
 def _launch_minmax1d(src, dst, shape, np_dtype, axis, size, is_max, mode, cval, origin, pad=(0, 0), flags=None):
     lib = _lib.load()
-    with torch.cuda.device(src.device):
+    with _on_device(src):
         rc = lib.b200_minmax_filter1d(
             src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape),
             _lib.i64_array(shape), int(axis), int(size), int(bool(is_max)), _lib.mode_code(mode), float(cval),
@@ -247,7 +288,7 @@ def _launch_minmax_nd(src, dst, shape, np_dtype, footprint, origins, is_max, mod
 
     lib = _lib.load()
     fp = np.ascontiguousarray(footprint, dtype=np.uint8)
-    with torch.cuda.device(src.device):
+    with _on_device(src):
         rc = lib.b200_minmax_filter_nd(
             src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape),
             _lib.i64_array(shape), fp.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _lib.i64_array(fp.shape),
@@ -258,7 +299,7 @@ def _launch_minmax_nd(src, dst, shape, np_dtype, footprint, origins, is_max, mod
 
 def _launch_combine(acc, src, np_dtype, op):
     lib = _lib.load()
-    with torch.cuda.device(acc.device):
+    with _on_device(acc):
         rc = lib.b200_combine(acc.data_ptr(), src.data_ptr(), _dtype_code(np_dtype),
                               int(acc.numel()), int(op), _stream_ptr(acc))
     _lib.check(rc)
@@ -283,7 +324,7 @@ def correlate1d(input, weights, axis=-1, output=None, mode="reflect", cval=0.0, 
     if w.ndim != 1 or w.shape[0] < 1:
         raise RuntimeError("no filter weights given")
     axis = _axis_index(axis, x.ndim)
-    out = _check_output(output, x) or x.empty_like()
+    out = _output_or_new(output, x)
     _launch_correlate1d(x.tensor, out.tensor, x.shape, x.dtype, axis, w, mode, cval, origin)
     return out
 
@@ -370,7 +411,7 @@ def uniform_filter1d(input, size, axis=-1, output=None, mode="reflect", cval=0.0
         raise RuntimeError("incorrect filter size")
     if (size // 2 + origin < 0) or (size // 2 + origin >= size):
         raise ValueError("invalid origin")
-    out = _check_output(output, x) or x.empty_like()
+    out = _output_or_new(output, x)
     _launch_uniform1d(x.tensor, out.tensor, x.shape, x.dtype, axis, size, mode, cval, origin)
     return out
 
@@ -742,7 +783,7 @@ def _run(plan_fn, input, output, *args, **kwargs):
     x = as_b200(input)
     _zero_dim_guard(x)
     plan = _cached_plan(plan_fn, x.ndim, args, kwargs)
-    out = _check_output(output, x) or x.empty_like()
+    out = _output_or_new(output, x)
     return _execute(plan, x, out)
 
 
@@ -796,7 +837,7 @@ def _correlate_or_convolve(input, weights, output, mode, cval, origin, convoluti
     x = as_b200(input)
     _zero_dim_guard(x)
     plan = _plan_correlate_nd(x.ndim, x.dtype, weights, mode, cval, origin, convolution)
-    out = _check_output(output, x) or x.empty_like()
+    out = _output_or_new(output, x)
     return _execute(plan, x, out)
 
 
@@ -859,7 +900,7 @@ def _minmax1d(input, size, axis, output, mode, cval, origin, is_max):
         raise RuntimeError("incorrect filter size")
     if (size // 2 + origin < 0) or (size // 2 + origin >= size):
         raise ValueError("invalid origin")
-    out = _check_output(output, x) or x.empty_like()
+    out = _output_or_new(output, x)
     if x.size:
         _launch_minmax1d(x.tensor, out.tensor, x.shape, x.dtype, axis, size, is_max, mode, cval, origin)
     return out

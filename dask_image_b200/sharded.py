@@ -41,16 +41,24 @@ from ._array import _NP_TO_TORCH, _TORCH_TO_NP, torch_dtype
 __all__ = ["ShardedVolume", "slab_bounds", "FUNCTIONS"]
 
 
+import functools
+
+
 def slab_bounds(n0, world):
     """``[(start, stop)]`` of every rank's planes: as even as possible, the
     first ``n0 % world`` ranks hold one plane more."""
+    return list(_slab_bounds(int(n0), int(world)))
+
+
+@functools.lru_cache(maxsize=256)
+def _slab_bounds(n0, world):
     base, rem = divmod(int(n0), int(world))
     out, s = [], 0
     for r in range(world):
         e = s + base + (1 if r < rem else 0)
         out.append((s, e))
         s = e
-    return out
+    return tuple(out)
 
 
 # --------------------------------------------------------------------------
@@ -104,11 +112,42 @@ class CudaBackend:
 # --------------------------------------------------------------------------
 # slab buffers
 # --------------------------------------------------------------------------
+class _PeerPlanes:
+    """``count`` planes of a neighbour's slab, mapped into this process: what the
+    halo launches need of a tensor (``data_ptr()``, ``shape[0]``)."""
+    __slots__ = ("ptr", "shape")
+
+    def __init__(self, ptr, count):
+        self.ptr, self.shape = int(ptr), (int(count),)
+
+    def data_ptr(self):
+        return self.ptr
+
+
+class _PeerSlab:
+    """A neighbour rank's slab buffer opened through ``b200_ipc_open``: ``base`` is the
+    mapping of the allocation, the buffer starts ``offset`` bytes into it."""
+    __slots__ = ("base", "ptr", "cap", "n", "plane_bytes")
+
+    def __init__(self, base, offset, cap, n, plane_bytes):
+        self.base, self.ptr = int(base), int(base) + int(offset)
+        self.cap, self.n, self.plane_bytes = int(cap), int(n), int(plane_bytes)
+
+    def planes(self, p0, p1):
+        """Planes [p0, p1) of the neighbour's interior."""
+        return _PeerPlanes(self.ptr + (self.cap + p0) * self.plane_bytes, p1 - p0)
+
+    def close(self):
+        if self.base:
+            _lib.load().b200_ipc_close(self.base)
+            self.base = 0
+
+
 class _SlabBuf:
     """``cap`` pad planes + ``n`` interior planes + ``cap`` pad planes, one
     allocation; ``full[cap + p]`` is local plane ``p`` (``p`` may be negative
     or >= n: a received neighbour plane)."""
-    __slots__ = ("full", "cap", "n")
+    __slots__ = ("full", "cap", "n", "__weakref__")
 
     def __init__(self, n, tail_shape, dtype, device, cap):
         self.cap, self.n = int(cap), int(n)
@@ -135,13 +174,22 @@ class ShardedVolume:
 
     DEFAULT_HALO = 16
 
-    def __init__(self, buf, global_shape, group=None, backend=None):
+    # Volumes smaller than this are REPLICATED instead of cut: every rank holds (and filters) the whole
+    # volume, nothing is exchanged, and the result is the 1-GPU result by construction.  A slab
+    # exchange costs ~0.1-0.2 ms of latency (rendezvous + first remote loads); below a few hundred
+    # MiB the whole filter takes less than that on one B200 (BASELINE configs[0], 4096^2 float32 =
+    # 64 MiB: 0.04 ms), so cutting would only slow it down.
+    REPLICATE_BELOW_BYTES = int(os.environ.get("B200_REPLICATE_BELOW", str(256 << 20)))
+
+    def __init__(self, buf, global_shape, group=None, backend=None, replicated=False):
         self._buf = buf
         self.shape = tuple(int(s) for s in global_shape)
         self.group = group
         self.backend = backend or CudaBackend
-        self.rank = dist.get_rank(group) if _dist_on() else 0
-        self.world = dist.get_world_size(group) if _dist_on() else 1
+        self.replicated = bool(replicated)
+        on = _dist_on() and not self.replicated
+        self.rank = dist.get_rank(group) if on else 0
+        self.world = dist.get_world_size(group) if on else 1
         self.bounds = slab_bounds(self.shape[0], self.world)
         lo, hi = self.bounds[self.rank]
         if hi - lo != buf.n:
@@ -149,40 +197,49 @@ class ShardedVolume:
 
     # ---- construction ---------------------------------------------------
     @classmethod
-    def _alloc(cls, global_shape, torch_dt, device, group, backend, halo):
+    def _alloc(cls, global_shape, torch_dt, device, group, backend, halo, replicate=None):
         world = dist.get_world_size(group) if _dist_on() else 1
         rank = dist.get_rank(group) if _dist_on() else 0
+        if replicate is None:
+            nbytes = int(np.prod(global_shape, dtype=np.int64)) * torch.empty((), dtype=torch_dt).element_size()
+            replicate = world > 1 and nbytes < cls.REPLICATE_BELOW_BYTES
+        if replicate:
+            world, rank = 1, 0
         s, e = slab_bounds(global_shape[0], world)[rank]
         cap = 0 if world == 1 else int(halo)
         buf = _SlabBuf(e - s, global_shape[1:], torch_dt, device, cap)
-        return cls(buf, global_shape, group, backend)
+        return cls(buf, global_shape, group, backend, replicated=replicate)
 
     @classmethod
-    def empty(cls, global_shape, dtype, device=None, group=None, backend=None, halo=None):
+    def empty(cls, global_shape, dtype, device=None, group=None, backend=None, halo=None, replicate=None):
+        """``replicate``: None = volumes below ``REPLICATE_BELOW_BYTES`` are held whole by every rank,
+        False = always cut into slabs, True = always replicate."""
         device = _default_device() if device is None else torch.device(device)
         return cls._alloc(tuple(global_shape), torch_dtype(dtype), device, group, backend,
-                          cls.DEFAULT_HALO if halo is None else halo)
+                          cls.DEFAULT_HALO if halo is None else halo, replicate)
 
     @classmethod
-    def from_global(cls, array, device=None, group=None, backend=None, halo=None):
+    def from_global(cls, array, device=None, group=None, backend=None, halo=None, replicate=None):
         a = np.ascontiguousarray(array)
-        vol = cls.empty(a.shape, a.dtype, device, group, backend, halo)
+        vol = cls.empty(a.shape, a.dtype, device, group, backend, halo, replicate)
         s, e = vol.bounds[vol.rank]
         vol.local.copy_(torch.from_numpy(a[s:e].copy()))
         return vol
 
     @classmethod
     def from_local(cls, tensor, global_shape, group=None, backend=None, halo=None):
-        vol = cls.empty(global_shape, _TORCH_TO_NP[tensor.dtype], tensor.device, group, backend, halo)
+        vol = cls.empty(global_shape, _TORCH_TO_NP[tensor.dtype], tensor.device, group, backend, halo,
+                        replicate=False)
         vol.local.copy_(tensor)
         return vol
 
     @classmethod
-    def random(cls, global_shape, dtype, seed=1234, device=None, group=None, backend=None, halo=None):
+    def random(cls, global_shape, dtype, seed=1234, device=None, group=None, backend=None, halo=None,
+               replicate=None):
         """Synthetic volume (uniform [0,1) floats / full-range integers) from a
         counter hash of the GLOBAL voxel index: the same volume for any number
         of ranks, generated in place on the device."""
-        vol = cls.empty(global_shape, dtype, device, group, backend, halo)
+        vol = cls.empty(global_shape, dtype, device, group, backend, halo, replicate)
         s, _ = vol.bounds[vol.rank]
         plane = int(np.prod(vol.shape[1:], dtype=np.int64))
         loc = vol.local
@@ -204,7 +261,10 @@ class ShardedVolume:
 
     @property
     def size(self):
-        return int(np.prod(self.shape, dtype=np.int64))
+        n = 1
+        for v in self.shape:
+            n *= v
+        return n
 
     @property
     def device(self):
@@ -221,12 +281,14 @@ class ShardedVolume:
 
     def astype(self, dtype):
         """A copy of the volume in another dtype (same partition)."""
-        out = ShardedVolume.empty(self.shape, dtype, self.device, self.group, self.backend, self._buf.cap)
+        out = ShardedVolume.empty(self.shape, dtype, self.device, self.group, self.backend, self._buf.cap,
+                                  self.replicated)
         out.local.copy_(self.local.to(torch_dtype(dtype)))
         return out
 
     def __sub__(self, other):
-        out = ShardedVolume.empty(self.shape, self.dtype, self.device, self.group, self.backend, self._buf.cap)
+        out = ShardedVolume.empty(self.shape, self.dtype, self.device, self.group, self.backend, self._buf.cap,
+                                  self.replicated)
         torch.sub(self.local, other, out=out.local)
         return out
 
@@ -267,55 +329,70 @@ class ShardedVolume:
     # ---- neighbour slabs mapped through CUDA IPC ------------------------------
     def _peer_views(self, buf):
         """Map the slab buffers of the two axis-0 neighbours into this process
-        (CUDA IPC, once per buffer; collective).  Returns ``{"prev": (full, cap,
-        n), "next": (...)}`` or None when any rank could not share / open."""
+        (CUDA IPC through the C ABI: ``b200_ipc_export`` / ``b200_ipc_open``; once
+        per buffer; collective).  Returns ``{"prev": _PeerSlab, "next": _PeerSlab}``
+        or None when any rank could not share / open -- reported with a warning,
+        the engine then uses the NCCL exchange."""
         cache = self.__dict__.setdefault("_peer_cache", {})
-        key = id(buf)
-        if key in cache and cache[key][0] is buf:
-            return cache[key][1]
+        key = buf.full.data_ptr()
+        hit = cache.get(key)
+        if hit is not None and hit[0]() is buf:
+            return hit[1]
+        import ctypes
+        import warnings
+        import weakref
+
+        lib = _lib.load()
         G, r = self.world, self.rank
-        info, ok = None, True
-        try:
-            from torch.multiprocessing.reductions import reduce_tensor
-
-            fn, args = reduce_tensor(buf.full)
-            info = (args, buf.cap, buf.n)
-        except Exception:
-            ok = False
+        info, err = None, None
+        handle = ctypes.create_string_buffer(64)
+        off = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            rc = lib.b200_ipc_export(buf.full.data_ptr(), handle, ctypes.byref(off))
+        if rc == 0:
+            plane_bytes = int(np.prod(self.shape[1:], dtype=np.int64)) * self.dtype.itemsize
+            info = (handle.raw, int(off.value), buf.cap, buf.n, plane_bytes, int(self.device.index))
+        else:
+            err = lib.b200_last_error().decode()
         gathered = [None] * G
-        dist.all_gather_object(gathered, (ok, info), group=self.group)
-        views = None
-        if all(g[0] for g in gathered):
-            try:
-                from torch.multiprocessing.reductions import rebuild_cuda_tensor
-
-                opened, views = {}, {}
-                for name, peer in (("prev", (r - 1) % G), ("next", (r + 1) % G)):
-                    if peer == r:
-                        continue
-                    if peer not in opened:
-                        args, cap, n = gathered[peer][1]
-                        owner = int(args[6])
-                        with torch.cuda.device(self.device):
-                            if owner != self.device.index:
-                                _lib.check(_lib.load().b200_enable_peer_access(owner))
-                            # Open the handle in THIS device's context (args[6] is the
-                            # storage device): cudaIpcOpenMemHandle then maps the
-                            # neighbour's allocation for kernels running here; opened
-                            # under the owner's context it is visible to that device only.
-                            args = list(args)
-                            args[6] = self.device.index
-                            full = rebuild_cuda_tensor(*args)
-                        opened[peer] = (full, cap, n)
-                    views[name] = opened[peer]
-            except Exception:
-                views = None
+        dist.all_gather_object(gathered, info, group=self.group)
+        views, opened = None, {}
+        if all(g is not None for g in gathered):
+            views = {}
+            for name, peer in (("prev", (r - 1) % G), ("next", (r + 1) % G)):
+                if peer == r:
+                    continue
+                if peer not in opened:
+                    raw, offset, cap, n, plane_bytes, owner = gathered[peer]
+                    base = ctypes.c_void_p()
+                    with torch.cuda.device(self.device):
+                        rc = lib.b200_ipc_open(raw, owner, ctypes.byref(base))
+                    if rc != 0:
+                        err = lib.b200_last_error().decode()
+                        views = None
+                        break
+                    opened[peer] = _PeerSlab(base.value, offset, cap, n, plane_bytes)
+                views[name] = opened[peer]
         # every rank must take the same path
         flag = torch.tensor([1 if views is not None else 0], device=self.device, dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 0:
+            if views is not None or err is not None:
+                warnings.warn("dask_image_b200: neighbour slabs could not be mapped through CUDA IPC (%s); "
+                              "the axis-0 pass falls back to the NCCL halo exchange (slower at 8 GPUs)"
+                              % (err or "another rank failed"), RuntimeWarning, stacklevel=2)
+            for slab in opened.values():
+                slab.close()
             views = None
-        cache[key] = (buf, views)
+        # the mappings live as long as the buffer they were opened for
+        mappings = list(opened.values()) if views is not None else []
+
+        def retire(key=key, mappings=mappings, cache=cache):
+            cache.pop(key, None)
+            for slab in mappings:
+                slab.close()
+
+        cache[key] = (weakref.ref(buf), views, weakref.finalize(buf, retire))
         return views
 
     def _peer_sync(self):
@@ -411,7 +488,7 @@ class ShardedVolume:
                     depth = max(depth, lo, hi)
         self._ensure_cap(depth)
         out = self._like(depth)
-        result = ShardedVolume(out, self.shape, self.group, self.backend)
+        result = ShardedVolume(out, self.shape, self.group, self.backend, replicated=self.replicated)
         if self.size == 0:
             return result
         src0 = self._buf
@@ -518,11 +595,9 @@ class ShardedVolume:
                         peer_synced = True
                     halo_lo = halo_hi = None
                     if lo > 0 and (ring or self.rank > 0):
-                        full, cap, n_p = peers["prev"]
-                        halo_lo = full[cap + n_p - lo:cap + n_p]
+                        halo_lo = peers["prev"].planes(peers["prev"].n - lo, peers["prev"].n)
                     if hi > 0 and (ring or self.rank < self.world - 1):
-                        full, cap, n_p = peers["next"]
-                        halo_hi = full[cap:cap + hi]
+                        halo_hi = peers["next"].planes(0, hi)
                     if ps.kind == "corr":
                         _nd._launch_correlate1d_halo(src.interior, dst.interior, shape, dt, ps.weights, ps.mode,
                                                      plan.cval, ps.origin, halo_lo, halo_hi, epi, flags)
@@ -591,24 +666,23 @@ def _check(vol):
 def gaussian_filter(input, sigma, order=0, mode="reflect", cval=0.0, truncate=4.0, *,
                     radius=None, axes=None):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_gaussian_filter(vol.ndim, sigma, order, mode, cval, truncate,
-                                                   radius, axes))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_gaussian_filter, vol.ndim, (sigma, order, mode, cval, truncate,
+                                                   radius, axes,), {}))
 
 
 def uniform_filter(input, size=3, mode="reflect", cval=0.0, origin=0, *, axes=None):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_uniform_filter(vol.ndim, size, mode, cval, origin, axes))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_uniform_filter, vol.ndim, (size, mode, cval, origin, axes,), {}))
 
 
 def gaussian_gradient_magnitude(input, sigma, mode="reflect", cval=0.0, *, axes=None, **kwargs):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_gaussian_gradient_magnitude(vol.ndim, sigma, mode, cval, axes,
-                                                               **kwargs))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_gaussian_gradient_magnitude, vol.ndim, (sigma, mode, cval, axes,), kwargs))
 
 
 def gaussian_laplace(input, sigma, mode="reflect", cval=0.0, *, axes=None, **kwargs):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_gaussian_laplace(vol.ndim, sigma, mode, cval, axes, **kwargs))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_gaussian_laplace, vol.ndim, (sigma, mode, cval, axes,), kwargs))
 
 
 def correlate(input, weights, mode="reflect", cval=0.0, origin=0):
@@ -623,17 +697,17 @@ def convolve(input, weights, mode="reflect", cval=0.0, origin=0):
 
 def laplace(input, mode="reflect", cval=0.0, *, axes=None):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_laplace(vol.ndim, mode, cval, axes))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_laplace, vol.ndim, (mode, cval, axes,), {}))
 
 
 def prewitt(input, axis=-1, mode="reflect", cval=0.0):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_prewitt(vol.ndim, axis, mode, cval))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_prewitt, vol.ndim, (axis, mode, cval,), {}))
 
 
 def sobel(input, axis=-1, mode="reflect", cval=0.0):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_sobel(vol.ndim, axis, mode, cval))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_sobel, vol.ndim, (axis, mode, cval,), {}))
 
 
 def minimum_filter(input, size=None, footprint=None, mode="reflect", cval=0.0, origin=0, *, axes=None):

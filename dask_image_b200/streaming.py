@@ -352,22 +352,22 @@ def _check(vol):
 
 def gaussian_filter(input, sigma, order=0, mode="reflect", cval=0.0, truncate=4.0, *, radius=None, axes=None):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_gaussian_filter(vol.ndim, sigma, order, mode, cval, truncate, radius, axes))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_gaussian_filter, vol.ndim, (sigma, order, mode, cval, truncate, radius, axes,), {}))
 
 
 def uniform_filter(input, size=3, mode="reflect", cval=0.0, origin=0, *, axes=None):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_uniform_filter(vol.ndim, size, mode, cval, origin, axes))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_uniform_filter, vol.ndim, (size, mode, cval, origin, axes,), {}))
 
 
 def gaussian_gradient_magnitude(input, sigma, mode="reflect", cval=0.0, *, axes=None, **kwargs):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_gaussian_gradient_magnitude(vol.ndim, sigma, mode, cval, axes, **kwargs))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_gaussian_gradient_magnitude, vol.ndim, (sigma, mode, cval, axes,), kwargs))
 
 
 def gaussian_laplace(input, sigma, mode="reflect", cval=0.0, *, axes=None, **kwargs):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_gaussian_laplace(vol.ndim, sigma, mode, cval, axes, **kwargs))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_gaussian_laplace, vol.ndim, (sigma, mode, cval, axes,), kwargs))
 
 
 def correlate(input, weights, mode="reflect", cval=0.0, origin=0):
@@ -382,17 +382,17 @@ def convolve(input, weights, mode="reflect", cval=0.0, origin=0):
 
 def laplace(input, mode="reflect", cval=0.0, *, axes=None):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_laplace(vol.ndim, mode, cval, axes))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_laplace, vol.ndim, (mode, cval, axes,), {}))
 
 
 def prewitt(input, axis=-1, mode="reflect", cval=0.0):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_prewitt(vol.ndim, axis, mode, cval))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_prewitt, vol.ndim, (axis, mode, cval,), {}))
 
 
 def sobel(input, axis=-1, mode="reflect", cval=0.0):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_sobel(vol.ndim, axis, mode, cval))
+    return vol._run_plan(_nd._cached_plan(_nd._plan_sobel, vol.ndim, (axis, mode, cval,), {}))
 
 
 def minimum_filter(input, size=None, footprint=None, mode="reflect", cval=0.0, origin=0, *, axes=None):

@@ -145,6 +145,22 @@ int b200_correlate1d_pair_eligible(int dtype, int ndim, const int64_t *shape,
  * cudaDeviceEnablePeerAccess, "already enabled" is success). */
 int b200_enable_peer_access(int peer_device);
 
+/* Sharing a slab with the neighbouring ranks (one process per GPU) so that their
+ * axis-0 passes can read its edge planes in place (b200_correlate1d_halo):
+ * b200_ipc_export fills the 64-byte CUDA IPC handle of the ALLOCATION that holds
+ * `dev_ptr` and the byte offset of `dev_ptr` inside it (device buffers come from a
+ * caching allocator: the pointer is rarely the allocation's base); the consumer
+ * calls b200_ipc_open with the handle on ITS current device -- the mapping is then
+ * valid for kernels of that device (peer access is enabled as needed) -- adds the
+ * offset, and calls b200_ipc_close(base) when the slab is retired.  A process
+ * cannot open its own handles.  Allocations made with CUDA's virtual memory API
+ * (e.g. PYTORCH_CUDA_ALLOC_CONF=expandable_segments) cannot be exported:
+ * B200_ECUDA, and the callers fall back to the NCCL exchange. */
+#define B200_IPC_HANDLE_BYTES 64
+int b200_ipc_export(const void *dev_ptr, void *handle_out, int64_t *offset_out);
+int b200_ipc_open(const void *handle, int owner_device, void **base_out);
+int b200_ipc_close(void *base);
+
 /* 1 if b200_correlate1d_halo can take an axis-0 pass over `n` planes of `inner`
  * elements each with these taps, else 0 (host-only query, no CUDA call: every
  * rank of a slab decomposition evaluates it for every slab size so that all of

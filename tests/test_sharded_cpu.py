@@ -101,6 +101,24 @@ def _worker(rank, world, port, q):
             from _oracle_backend import _np
             if not np.array_equal(g.ravel(), _np(exp).ravel()):
                 failures.append("random(%s) depends on the partition" % np.dtype(dt))
+        # small volumes may be REPLICATED instead of cut (the default below REPLICATE_BELOW_BYTES; the test
+        # session switches the rule off, so ask for it): every rank holds and filters the whole volume, no
+        # exchange, same result -- even for a halo deeper than a slab would be
+        rng = np.random.default_rng(5)
+        a = rng.random((world * 2 + 1, 9, 10)).astype(np.float32)
+        for kw in (dict(replicate=True), dict()):
+            old_limit = ShardedVolume.REPLICATE_BELOW_BYTES
+            if not kw:
+                ShardedVolume.REPLICATE_BELOW_BYTES = 1 << 20       # the automatic rule
+            try:
+                vol = ShardedVolume.from_global(a, device="cpu", backend=OracleBackend, **kw)
+            finally:
+                ShardedVolume.REPLICATE_BELOW_BYTES = old_limit
+            res = ndfilters.gaussian_filter(vol, sigma=3.0)
+            if not (vol.replicated and res.replicated and vol.n_local == a.shape[0] and vol.world == 1):
+                failures.append("small volume was not replicated (%s)" % (kw,))
+            if not np.array_equal(res.gather(), _reference("gaussian_filter", a, dict(sigma=3.0))):
+                failures.append("replicated result differs")
         # a halo deeper than the thinnest slab is refused on every rank
         vol = ShardedVolume.from_global(np.zeros((world * 2, 4), np.float32), device="cpu",
                                         backend=OracleBackend)
