@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200ndfilters.so")
+# (B200_NDFILTERS_LIB selects another build of the same library: A/B runs of experimental kernels)
+LIB_PATH = os.environ.get("B200_NDFILTERS_LIB") or os.path.join(_HERE, "libb200ndfilters.so")
 
 # status codes / enums of include/b200_ndfilters.h
 OK, EINVAL, EORIGIN, EMODE, EDTYPE, ECUDA, ENODEVICE = range(7)

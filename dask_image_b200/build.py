@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libb200ndfilters.so")
+OUT = os.environ.get("B200_BUILD_OUT") or os.path.join(HERE, "libb200ndfilters.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++20", "-O3", "-lineinfo",
@@ -43,7 +43,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = os.environ.get("B200_BUILD_OBJDIR") or os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []

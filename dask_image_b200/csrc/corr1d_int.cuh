@@ -317,88 +317,6 @@ __host__ __device__ __forceinline__ void int_line_quad(const TS *s, int step, co
     }
 }
 
-// ---------------------------------------------------------------------------
-// Certified fixed-point walk (experiment, B200_INT_FIXED build).
-// The same tap walk with ONE integer multiply-add per tap (pair): the weights are
-// scaled to round(w * 2^S) and the sum is exact in int64.  The host bounds
-// |acc_reference - sum / 2^S| by delta / 2^S from the actual weights
-// (plan_int_fixed); trunc() is taken from the integer sum wherever its fraction
-// is farther than delta from an integer, and the caller recomputes the rest
-// (about 1e-4 of the outputs on 16-bit data) with the exact FP64 sequence.
-// ---------------------------------------------------------------------------
-struct IntFixedParams {
-    int S;            // weights are round(w * 2^S)
-    int on;           // the launch is eligible for the fixed-point walk
-    uint64_t delta;   // half-width of the ambiguous band around an integer, in units of 2^-S
-    int32_t wq[kMaxTapsInt];
-};
-
-// acc + v * w with 32-bit signed factors: one IMAD.WIDE (left to the compiler, the product of an
-// unsigned pair sum and a sign-extended weight becomes a 64 x 32-bit multiply: two instructions)
-__host__ __device__ __forceinline__ long long int_mad_wide(int v, int w, long long acc)
-{
-#ifdef __CUDA_ARCH__
-    long long r;
-    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(v), "r"(w), "l"(acc));
-    return r;
-#else
-    return acc + (long long)v * (long long)w;
-#endif
-}
-
-// false = at least one of the NQ outputs is ambiguous (r is then not to be used)
-template <typename TS, int KIND, int NQ>
-__host__ __device__ __forceinline__ bool int_line_fixed(const TS *s, int step, const IntParams &p,
-                                                        const IntFixedParams &fx, TS (&r)[NQ])
-{
-    const int L = p.nw;
-    long long acc[NQ];
-    {
-        const int wc = fx.wq[p.centre];
-        const TS *sc = s + p.centre * step;
-#pragma unroll
-        for (int m = 0; m < NQ; ++m) acc[m] = int_mad_wide((int)sc[m * step], wc, 0ll);
-    }
-    const TS *sa = s + NQ * step;
-    const TS *sb = s + (L - 2) * step;
-    int A[NQ], B[NQ];
-#pragma unroll
-    for (int m = 0; m < NQ; ++m) {
-        A[m] = (int)s[m * step];
-        B[m] = KIND != 0 ? (int)s[(L - 1 + m) * step] : 0;
-    }
-    int_run_steps<NQ>(p.nsteps, [&]<int U>(int k) {
-        const int wk = fx.wq[k];
-#pragma unroll
-        for (int m = 0; m < NQ; ++m) {
-            const int a = A[(U + m) & (NQ - 1)];
-            const int b = B[(m - U) & (NQ - 1)];
-            acc[m] = int_mad_wide(KIND > 0 ? a + b : (KIND < 0 ? a - b : a), wk, acc[m]);
-        }
-        A[U] = (int)*sa;
-        sa += step;
-        if constexpr (KIND != 0) {
-            B[(NQ - 1 - U) & (NQ - 1)] = (int)*sb;
-            sb -= step;
-        }
-    });
-    const uint64_t one = 1ull << fx.S, mask = one - 1;
-    bool sure = true;
-#pragma unroll
-    for (int m = 0; m < NQ; ++m) {
-        const bool neg = acc[m] < 0;
-        const uint64_t a = neg ? (uint64_t)(-acc[m]) : (uint64_t)acc[m];
-        const uint64_t q = a >> fx.S, f = a & mask;
-        // near an integer the reference may have landed on either side of it -- except around 0, where
-        // both sides truncate to 0
-        const bool near_lo = f < fx.delta, near_hi = f > one - fx.delta;
-        if ((near_lo && q != 0) || near_hi) sure = false;
-        const int v32 = neg ? -(int)q : (int)q;   // |q| < 2^31 (plan_int_fixed)
-        r[m] = (TS)v32;
-    }
-    return sure;
-}
-
 template <typename TS>
 __host__ __device__ __forceinline__ TS int_finish(double acc, TS *dst, int epilogue)
 {
@@ -512,41 +430,6 @@ __host__ __device__ __forceinline__ void int_strided_compute(const IntParams &p,
     }
 }
 
-template <typename TS, int KIND, int NQ = 4>
-__host__ __device__ __forceinline__ void int_strided_compute_fixed(const IntParams &p, const IntFixedParams &fx,
-                                                                   const TS *tile, const IntTap *wc, int tid,
-                                                                   uint32_t bid)
-{
-    constexpr int W = kIntStridedW;
-    const IntStridedTile t(p, bid);
-    const int64_t col = t.col0 + tid;
-    const bool live = col < p.inner;
-    const bool plain = p.epilogue == B200_EPI_STORE;
-    TS *dst = (TS *)p.out + (t.o * p.n + t.row0) * p.inner + col;
-    const int64_t left = p.n - t.row0;
-    const int rows_here = left < p.tile_out ? (int)left : p.tile_out;
-    for (int r0 = 0; r0 < rows_here; r0 += NQ) {
-        TS r[NQ];
-        if (!int_line_fixed<TS, KIND, NQ>(tile + r0 * W + tid, W, p, fx, r)) {
-            double acc[NQ];                       // ambiguous: the exact sequence decides
-            int_line_quad<TS, KIND, NQ>(tile + r0 * W + tid, W, p, wc, acc);
-#pragma unroll
-            for (int m = 0; m < NQ; ++m) r[m] = cast_out<TS>(acc[m]);
-        }
-#pragma unroll
-        for (int m = 0; m < NQ; ++m, dst += p.inner) {
-            if (live && r0 + m < rows_here) {
-                if (plain) {
-                    *dst = r[m];
-                } else {
-                    const TS prev = epilogue_reads_out(p.epilogue) ? *dst : TS(0);
-                    *dst = apply_epilogue<TS>(p.epilogue, prev, r[m]);
-                }
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------
 // contiguous axis: the array is [outer][n], the filter runs along n.  A tile is
 // kIntContigRows lines of tile_len staged positions, `pitch` elements apart with
@@ -618,38 +501,6 @@ __host__ __device__ __forceinline__ void int_contig_compute(const IntParams &p, 
         TS r[NQ];
 #pragma unroll
         for (int m = 0; m < NQ; ++m) r[m] = cast_out<TS>(acc[m]);
-        uint32_t *d = reinterpret_cast<uint32_t *>(oline + xo);
-#pragma unroll
-        for (int h = 0; h < NQ / 4; ++h) {
-            if constexpr (sizeof(TS) == 2) {
-                d[2 * h] = (uint32_t)(uint16_t)r[4 * h] | ((uint32_t)(uint16_t)r[4 * h + 1] << 16);
-                d[2 * h + 1] = (uint32_t)(uint16_t)r[4 * h + 2] | ((uint32_t)(uint16_t)r[4 * h + 3] << 16);
-            } else {
-                d[h] = (uint32_t)(uint8_t)r[4 * h] | ((uint32_t)(uint8_t)r[4 * h + 1] << 8) |
-                       ((uint32_t)(uint8_t)r[4 * h + 2] << 16) | ((uint32_t)(uint8_t)r[4 * h + 3] << 24);
-            }
-        }
-    }
-}
-
-template <typename TS, int KIND, int NQ = 4>
-__host__ __device__ __forceinline__ void int_contig_compute_fixed(const IntParams &p, const IntFixedParams &fx,
-                                                                  const TS *tile, TS *otile, const IntTap *wc,
-                                                                  int tid, uint32_t bid)
-{
-    const int warp = tid >> 5, lane = tid & 31;
-    const int per_warp = p.tile_out / (kIntThreads / 32);
-    const TS *line = tile + lane * p.pitch + p.shift;
-    TS *oline = otile + lane * p.opitch;
-    for (int g = 0; g < per_warp; g += NQ) {
-        const int xo = warp * per_warp + g;
-        TS r[NQ];
-        if (!int_line_fixed<TS, KIND, NQ>(line + xo, 1, p, fx, r)) {
-            double acc[NQ];                       // ambiguous: the exact sequence decides
-            int_line_quad<TS, KIND, NQ>(line + xo, 1, p, wc, acc);
-#pragma unroll
-            for (int m = 0; m < NQ; ++m) r[m] = cast_out<TS>(acc[m]);
-        }
         uint32_t *d = reinterpret_cast<uint32_t *>(oline + xo);
 #pragma unroll
         for (int h = 0; h < NQ / 4; ++h) {
@@ -793,44 +644,6 @@ inline int plan_corr1d_int(const Corr1dArgs &a, IntPlan &pl, int symmetry)
     }
     if (pl.blocks < 1 || pl.blocks >= (1ll << 31)) return -1;
     return 0;
-}
-
-// Scale, scaled weights and the certified error band of the fixed-point walk.  Everything is exact or
-// rounded UP: w * 2^S is a power-of-two scaling, x - rint(x) of a double is exact, the sums of at most
-// 129 non-negative terms get a relative margin.  `fx.on` stays 0 when the walk cannot be certified.
-inline void plan_int_fixed(const Corr1dArgs &a, const IntPlan &pl, IntFixedParams &fx)
-{
-    fx.on = 0; fx.S = 0; fx.delta = 0;
-    const int L = a.nw;
-    const double M = a.dtype == B200_U8 ? 255.0 : (a.dtype == B200_I8 ? 128.0 : (a.dtype == B200_U16 ? 65535.0 : 32768.0));
-    const double vmax = pl.kind != 0 ? 2.0 * M : M;          // |x[c-j] +- x[c+j]| resp. |x|
-    double wmax = 0.0, wsum = 0.0;
-    for (int i = 0; i < L; ++i) {
-        wmax = std::fmax(wmax, std::fabs(a.w[i]));
-        wsum += std::fabs(a.w[i]);
-    }
-    // the truncated sum must fit the 32-bit conversion the reference's cast goes through
-    if (!(wsum * 2.0 * M * 1.000001 < 2147483648.0)) return;
-    int S = 52;
-    while (S > 0 && !(std::ldexp(wmax, S) < 2147483647.0)) --S;
-    if (!(std::ldexp(wmax, S) < 2147483647.0)) return;
-    double band = 0.0;   // units of 2^-S
-    for (int i = 0; i < L; ++i) {
-        const double x = std::ldexp(a.w[i], S);               // exact
-        const double q = std::rint(x);
-        fx.wq[i] = (int32_t)q;
-        // the taps the walk does not read (right halves of folded pairs) carry no error of their own:
-        // the pair uses the LEFT weight for both, exactly as the reference does
-        const bool used = pl.kind == 0 || i <= L / 2;
-        if (used) band += (i == pl.p.centre && pl.kind != 0 ? M : vmax) * std::fabs(x - q);   // x - q exact
-    }
-    // the reference's own rounding: (terms + 1) * 2^-53 * sum |v w|, scaled to units of 2^-S
-    band += (double)(L + 2) * 0x1p-53 * std::ldexp(wsum, S) * 2.0 * M;
-    band = band * 1.000001 + 2.0;
-    if (!(band < std::ldexp(1.0, S - 2))) return;              // the band must leave most of the unit interval
-    fx.S = S;
-    fx.delta = (uint64_t)std::ceil(band);
-    fx.on = 1;
 }
 
 }  // namespace b200

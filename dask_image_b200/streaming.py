@@ -16,6 +16,12 @@ resident input through the slab contract of the C ABI (``pad_lo`` / ``pad_hi``:
 the planes around it are simply resident), so the result is bit-identical to
 filtering the whole resident volume.
 
+This is a streaming path, not an out-of-core one: the input slab stays resident
+on the device while it is filtered (plus three output chunks and the scratch
+chunks), so a rank's slab must fit its GPU -- with 180 GB per B200 that is a
+~160 GB slab per rank; a larger slab raises ``MemoryError`` up front instead of
+failing somewhere inside the pipeline.
+
 Supported: every plan whose axis-0 passes read the plan's INPUT (gaussian
 filters and their derivative compositions, uniform_filter, laplace, N-D
 correlate / convolve).  Plans that filter along axis 0 after another pass
@@ -208,6 +214,12 @@ class HostVolume:
                 return result
 
             cap_lo, cap_hi = (lo if has_prev else 0), (hi if has_next else 0)
+            need_bytes = (cap_lo + n0 + cap_hi + 5 * C) * plane_bytes
+            free_bytes = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+            if need_bytes > free_bytes:
+                raise MemoryError("HostVolume streams a slab that stays resident while it is filtered: %.1f GiB needed, "
+                                  "%.1f GiB free on %s -- spread the volume over more ranks (global_shape=...)"
+                                  % (need_bytes / 2 ** 30, free_bytes / 2 ** 30, dev))
             d_full = torch.empty((cap_lo + n0 + cap_hi,) + tail, dtype=h_in.dtype, device=dev)
             d_in = d_full[cap_lo:cap_lo + n0]
             nslot = 3

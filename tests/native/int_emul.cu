@@ -17,10 +17,10 @@ int set_error(int code, const char *, ...) { return code; }
 
 using namespace b200;
 
-// NQ = outputs per lane and walk: 4 is the shipped kernel, 8 the B200_INT_NQ8 experiment;
-// fx.on selects the certified fixed-point walk (B200_INT_FIXED experiment)
+// NQ = outputs per lane and walk: 4 is the shipped kernel; 8 (B200_INT_NQ=8) exercises the generic form
+// of the walk (measured slower on the B200, profiles/r2_int_ab.log, and not built into the library)
 template <typename TS, int KIND, int NQ>
-static void run_blocks(const IntPlan &pl, const IntFixedParams &fx)
+static void run_blocks(const IntPlan &pl)
 {
     const IntParams &p = pl.p;
     std::vector<unsigned char> smem(pl.smem_bytes + 16);
@@ -33,38 +33,32 @@ static void run_blocks(const IntPlan &pl, const IntFixedParams &fx)
         if (pl.contig) {
             TS *otile = tile + kIntContigRows * p.pitch;
             for (int t = 0; t < kIntThreads; ++t) int_contig_stage<TS>(p, tile, t, bid);
-            for (int t = 0; t < kIntThreads; ++t) {
-                if (fx.on) int_contig_compute_fixed<TS, KIND, NQ>(p, fx, tile, otile, wc, t, bid);
-                else int_contig_compute<TS, KIND, NQ>(p, tile, otile, wc, t, bid);
-            }
+            for (int t = 0; t < kIntThreads; ++t) int_contig_compute<TS, KIND, NQ>(p, tile, otile, wc, t, bid);
             for (int t = 0; t < kIntThreads; ++t) int_contig_writeout<TS>(p, otile, t, bid);
         } else {
             int64_t *rows = reinterpret_cast<int64_t *>(smem.data() + kIntTapBytes);
             TS *stile = reinterpret_cast<TS *>(smem.data() + kIntTapBytes + kIntRowTableBytes);
             for (int t = 0; t < kIntThreads; ++t) int_strided_stage_rows(p, rows, t, bid);
             for (int t = 0; t < kIntThreads; ++t) int_strided_stage<TS>(p, stile, rows, t, bid);
-            for (int t = 0; t < kIntThreads; ++t) {
-                if (fx.on) int_strided_compute_fixed<TS, KIND, NQ>(p, fx, stile, wc, t, bid);
-                else int_strided_compute<TS, KIND, NQ>(p, stile, wc, t, bid);
-            }
+            for (int t = 0; t < kIntThreads; ++t) int_strided_compute<TS, KIND, NQ>(p, stile, wc, t, bid);
         }
     }
 }
 
 template <typename TS, int NQ>
-static void run_kind_nq(const IntPlan &pl, const IntFixedParams &fx)
+static void run_kind_nq(const IntPlan &pl)
 {
-    if (pl.kind > 0) run_blocks<TS, 1, NQ>(pl, fx);
-    else if (pl.kind < 0) run_blocks<TS, -1, NQ>(pl, fx);
-    else run_blocks<TS, 0, NQ>(pl, fx);
+    if (pl.kind > 0) run_blocks<TS, 1, NQ>(pl);
+    else if (pl.kind < 0) run_blocks<TS, -1, NQ>(pl);
+    else run_blocks<TS, 0, NQ>(pl);
 }
 
 template <typename TS>
-static void run_kind(const IntPlan &pl, const IntFixedParams &fx)
+static void run_kind(const IntPlan &pl)
 {
     const char *e = getenv("B200_INT_NQ");
-    if (e && atoi(e) == 8) run_kind_nq<TS, 8>(pl, fx);
-    else run_kind_nq<TS, 4>(pl, fx);
+    if (e && atoi(e) == 8) run_kind_nq<TS, 8>(pl);
+    else run_kind_nq<TS, 4>(pl);
 }
 
 // Same argument meaning as b200_correlate1d (host pointers).  Returns 0 when the
@@ -83,17 +77,13 @@ extern "C" int emul_correlate1d_int(const void *in, void *out, int dtype, int nd
     IntPlan pl{};
     if (plan_corr1d_int(a, pl, classify_symmetry(a.w, a.nw)) != 0) return -1;
     if (pl.smem_bytes > 48 * 1024) return -1;
-    IntFixedParams fx;
-    fx.on = 0;
-    const char *e = getenv("B200_INT_FIXED");
-    if (e && atoi(e) == 1) plan_int_fixed(a, pl, fx);
     info[0] = pl.contig; info[1] = pl.kind; info[2] = pl.blocks; info[3] = (int64_t)pl.smem_bytes; info[4] = pl.p.vec;
-    info[5] = fx.on; info[6] = fx.on ? fx.S : 0; info[7] = fx.on ? (int64_t)fx.delta : 0;
+    info[5] = 0; info[6] = 0; info[7] = 0;
     switch (dtype) {
-    case B200_U8: run_kind<uint8_t>(pl, fx); break;
-    case B200_I8: run_kind<int8_t>(pl, fx); break;
-    case B200_U16: run_kind<uint16_t>(pl, fx); break;
-    default: run_kind<int16_t>(pl, fx); break;
+    case B200_U8: run_kind<uint8_t>(pl); break;
+    case B200_I8: run_kind<int8_t>(pl); break;
+    case B200_U16: run_kind<uint16_t>(pl); break;
+    default: run_kind<int16_t>(pl); break;
     }
     return 0;
 }

@@ -112,7 +112,10 @@ def test_gaussian_derivative_filters_compare(b200, da_name, order, sigma, trunca
     a = np.arange(float(np.prod(s))).reshape(s)
     d = b200.from_array(a, chunks=(50, 55))
     got = getattr(b200.ndfilters, da_name)(d, sigma, order, truncate=truncate)
-    assert_parity(np.asarray(got), orc.gaussian_filter(a, sigma, order, truncate=truncate))
+    # (a derivative of a linear ramp is EXACTLY zero in scipy's folded sum; the tiled kernels -- which the halo'd
+    # chunks, 63 = 55 + 8 columns wide, now take through the plain-load staging -- leave rounding noise relative
+    # to the data: the scale of the comparison is the input's)
+    assert_parity(np.asarray(got), orc.gaussian_filter(a, sigma, order, truncate=truncate), data=a)
 
 
 @pytest.mark.parametrize("sigma, truncate", [(0.0, 0.0), (0.0, 1.0), (0.0, 4.0), (1.0, 0.0)])

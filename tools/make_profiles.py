@@ -97,10 +97,14 @@ def main():
     wanted = {
         "corr1d_strided.o": [r"corr1d_strided_tma_kernelIffLi128ELi8ELi4ELi3ELi1E",
                              r"corr1d_strided_tma_kernelIftLi256ELi8ELi4ELi3ELi3E",
-                             r"corr1d_strided_peer_kernelIffLi128ELi8ELi4ELi3ELi1E"],
-        "corr1d_contig.o": [r"corr1d_contig_static_kernelIfLi17E", r"corr1d_contig_static_kernelItLi16E",
+                             r"corr1d_strided_peer_kernelIffLi128ELi8ELi4ELi3ELi1E",
+                             r"corr1d_strided_ldg_kernelIffLi128ELi8ELi4ELi3ELi1E"],
+        "corr1d_contig.o": [r"corr1d_contig_static_kernelIfLi17ELb0E", r"corr1d_contig_static_kernelItLi16ELb0E",
                             r"corr1d_contig_tma_kernelIffLi0ELi1E"],
-        "corrnd_tiled.o": [r"corrnd_static_kernelILi9E"],
+        "corr2d_fused.o": [r"corr2d_fused_kernelILi17ELi17ELi32ELi8ELi8ELb1ELi4ELb1E",
+                           r"corr2d_fused_kernelILi33ELi33ELi32ELi8ELi8ELb1ELi2ELb1E",
+                           r"corr2d_fused_kernelILi17ELi17ELi32ELi8ELi8ELb1ELi4ELb0E"],
+        "corrnd_tiled.o": [r"corrnd_static_kernelILi9ELb0E"],
         "corr1d_int.o": [r"corr1d_int_strided_kernelItLi1E"],
         "corrnd_int.o": [r"corrnd_int_kernelItE"],
     }
@@ -117,7 +121,7 @@ def main():
                 m = re.search(r"Function : (\S*%s\S*)" % pat, b)
                 if m:
                     lines = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", ln) for ln in b.splitlines()
-                             if re.search(r"/\*[0-9a-f]{4}\*/|Function :", ln)]
+                             if re.search(r"/\*[0-9a-f]{4,}\*/|Function :", ln)]
                     with open(os.path.join(sass_dir, "%s.sass" % pat), "w") as f:
                         f.write("\n".join(lines) + "\n")
                     break
