@@ -30,8 +30,15 @@ namespace b200 {
 
 constexpr int kFusedPX = 256;       // staged tile width in floats (TMA box limit)
 constexpr int kFusedPI = 260;       // pitch of the intermediate tile: 16 bytes * odd
-constexpr int kFusedPO = 244;       // pitch of the spare output block (240 columns at most): 16 bytes * odd
 constexpr int kFusedMaxTaps = 48;
+
+// floats of one staged buffer when the intermediate tile and the staged results alias the input box
+constexpr int fused_buffer_floats(int l1, int tyo, int nwarps)
+{
+    const int in = (tyo + l1 - 1) * kFusedPX, mid = tyo * kFusedPI;
+    (void)nwarps;
+    return ((in > mid ? in : mid) + 31) / 32 * 32;
+}
 
 struct Corr2dParams {
     const float *in;
@@ -41,7 +48,7 @@ struct Corr2dParams {
     int lo2, mode2;       // staged column 0 is array column x0 - lo2 (lo2 = reach in front, rounded up to 4)
     int hi1, hi2;         // rows / columns read beyond an output
     int epilogue, wide_store;
-    int y_tiles, x_tiles;
+    int y_tiles, x_tiles, n_tiles;
     int ncg;              // 16-output column groups per tile in use: tiles are ncg * 16 columns wide
     float cval;
     float w1[kFusedMaxTaps];   // taps along axis ndim-2
@@ -82,7 +89,8 @@ __device__ __forceinline__ int ext_index32(int i, int n, int mode)
 // interior CTAs never come here, and the hot path keeps its registers.
 template <int TYIN, int NTHR, bool TMA>
 __device__ __noinline__ void fused_stage_edges(const Corr2dParams &p, float *tin, int *row_src, int *col_src,
-                                               const float *plane, int gx0, int gy0, uint64_t *full_bar)
+                                               const float *plane, int gx0, int gy0, uint64_t *full_bar,
+                                               uint32_t parity)
 {
     constexpr int PX = kFusedPX;
     const int tid = threadIdx.x;
@@ -103,7 +111,7 @@ __device__ __noinline__ void fused_stage_edges(const Corr2dParams &p, float *tin
     }
     __syncthreads();
     if constexpr (TMA) {
-        if (tid < 32) mbar_wait(full_bar, 0);
+        if (tid < 32) mbar_wait(full_bar, parity);
         __syncthreads();
         if (patch) {
             // rows outside the array, full width
@@ -174,9 +182,29 @@ __device__ __noinline__ void fused_fix_constant_columns(const Corr2dParams &p, f
     __syncthreads();
 }
 
-template <int L1, int NTX, int TYO, int NWARPS, int RA, bool ALIAS, int MINB, bool TMA>
-__global__ void __launch_bounds__(NWARPS * 32, MINB)
-corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr2dParams p)
+// 64-thread named barrier number 1 + idx with an IMMEDIATE barrier number (NPAIRS of them in use)
+template <int NPAIRS>
+__device__ __forceinline__ void pair_barrier(int idx)
+{
+    static_assert(NPAIRS >= 1 && NPAIRS <= 8, "warp pairs per CTA");
+    if (NPAIRS == 1 || idx == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+    else if (NPAIRS == 2 || idx == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+    else if (NPAIRS == 3 || idx == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+    else if (NPAIRS == 4 || idx == 3) asm volatile("bar.sync 4, 64;" ::: "memory");
+    else if (NPAIRS == 5 || idx == 4) asm volatile("bar.sync 5, 64;" ::: "memory");
+    else if (NPAIRS == 6 || idx == 5) asm volatile("bar.sync 6, 64;" ::: "memory");
+    else if (NPAIRS == 7 || idx == 6) asm volatile("bar.sync 7, 64;" ::: "memory");
+    else asm volatile("bar.sync 8, 64;" ::: "memory");
+}
+
+// One tile, from "the TMA load of the staged box has been issued on `full_bar`" to "its results are
+// on their way to global memory": edge fill, both passes, staged stores.  `tin` is the staged box;
+// the intermediate tile and the staged results alias it (ALIAS) or follow it.  `parity` is the phase
+// of `full_bar` this tile's load completes.  Shared by the one-tile-per-CTA kernel and the persistent,
+// double-buffered one.
+template <int L1, int NTX, int TYO, int NWARPS, int RA, bool ALIAS, bool TMA>
+__device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tin, int *row_src, int *col_src,
+                                           uint64_t *full_bar, uint32_t parity, int x0, int y0, int z)
 {
     constexpr int PX = kFusedPX, PI = kFusedPI;
     constexpr int TYIN = TYO + L1 - 1;
@@ -187,39 +215,21 @@ corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     static_assert(TYO % RA == 0 && TYO % 8 == 0, "tile rows");
     static_assert(!ALIAS || ITEMS_A == NWARPS, "aliased tiles need one phase-A item per warp");
     static_assert(16 * (NCG - 1) + NF <= PI, "row window inside the intermediate tile");
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *tin = aligned_smem<float>(smem_raw);
     float *mid = ALIAS ? tin : tin + TYIN * PX;
-    float *spare = mid + TYO * PI;   // NTHR/16 rows of pitch kFusedPO: staged results of the first row block
-    __shared__ __align__(8) uint64_t full_bar;
-    __shared__ int row_src[TYIN];
-    __shared__ int col_src[PX];
-
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int nx = p.nx, ny = p.ny;
-    const int z = blockIdx.z;
-    const int x0 = blockIdx.x * (p.ncg * 16), y0 = blockIdx.y * TYO;
     const int gx0 = x0 - p.lo2, gy0 = y0 - p.lo1;   // array position of staged element (0, 0)
 
-    if constexpr (TMA) {
-        if (tid == 0) {
-            mbar_init(&full_bar, 1);
-            fence_barrier_init();
-            mbar_arrive_expect_tx(&full_bar, (uint32_t)(TYIN * PX * (int)sizeof(float)));
-            tma_load_3d(tin, &tmap, &full_bar, gx0, gy0, z);
-        }
-    }
     // a tile whose staged box lies inside the array needs nothing beyond the TMA load
     const bool edge = !TMA || gx0 < 0 || gy0 < 0 || gx0 + PX > nx || gy0 + TYIN > ny;
     if (edge) {
         fused_stage_edges<TYIN, NTHR, TMA>(p, tin, row_src, col_src, p.in + (int64_t)z * ny * nx, gx0, gy0,
-                                           &full_bar);
+                                           full_bar, parity);
     } else {
         __syncthreads();
         // one warp polls the mbarrier; the others sleep at the CTA barrier
-        if (tid < 32) mbar_wait(&full_bar, 0);
+        if (tid < 32) mbar_wait(full_bar, parity);
         __syncthreads();
     }
 
@@ -251,38 +261,46 @@ corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         for (int j = 0; j < RA; ++j)
             *reinterpret_cast<float4 *>(d + j * PI) = make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y);
     }
-    __syncthreads();
-    if (edge && p.mode2 == B200_MODE_CONSTANT && p.cval != 0.f) fused_fix_constant_columns<TYO, NTHR>(p, mid, gx0);
-
     // ---- phase B: the pass along the contiguous axis, mid -> out ---------------
-    // ROWS_B rows at a time: thread = (column group, row); the 8 lanes of a quarter warp sit on 8
-    // rows of one column group, which the odd 16-byte pitch spreads over all bank groups.  Results are
-    // staged in shared memory -- the first row block in a spare block behind the intermediate tile,
-    // every later one over the rows the PREVIOUS block has consumed -- and leave the SM row by row
-    // through the bulk-copy engine (cp.async.bulk shared -> global): no per-lane global stores, whose
-    // 32 half-sectors on 32 different rows cost ~50 LSU wavefronts per instruction.  Epilogues that
-    // read `out`, and unaligned rows, take a coalesced cooperative copy-out instead.
-    constexpr int ROWS_B = NTHR / 16;
-    static_assert(TYO % ROWS_B == 0, "phase B row blocks");
-    const int ncg = p.ncg;                       // column groups in use (<= NCG): tile width ncg * 16
+    // Warp w owns rows [4w, 4w + 4) of the tile from here to the end: their intermediate values were
+    // written by this warp and its partner (the two halves of row group w / 2), so ONE 64-thread
+    // named barrier replaces a CTA-wide one, and nothing below synchronises beyond the warp.
+    // Lane = (row, column group): the 8 lanes of a quarter warp sit on 4 rows x 2 adjacent column
+    // groups, which the odd 16-byte pitch spreads over all 8 bank groups; a pass covers 8 column
+    // groups, two passes the tile's 15.  Results go back into the rows IN PLACE (every window of a
+    // pass is in registers before its first store; the second pass reads columns >= 128, the first
+    // writes columns < 128) and leave the SM row by row through the bulk-copy engine (cp.async.bulk
+    // shared -> global) instead of per-lane global stores, whose 32 half-sectors on 32 different
+    // rows cost ~50 LSU wavefronts per instruction.  Epilogues that read `out`, and unaligned rows,
+    // take a coalesced per-warp copy-out instead.
+    static_assert(TYO == 4 * NWARPS && RA == 8 && ITEMS_A == NWARPS,
+                  "a warp owns four rows of the tile in phase B, produced by itself and its partner warp");
+    if (edge && p.mode2 == B200_MODE_CONSTANT && p.cval != 0.f) {
+        __syncthreads();
+        fused_fix_constant_columns<TYO, NTHR>(p, mid, gx0);
+    } else {
+        // (immediate barrier numbers: a register operand makes ptxas reserve all 16 hardware barriers
+        // for the CTA, and an SM has 32 -- two resident CTAs instead of four)
+        pair_barrier<NWARPS / 2>(warp >> 1);
+    }
     const bool bulk = TMA && p.epilogue == B200_EPI_STORE;
-    const int tile_cols = min(nx - x0, ncg * 16);   // columns of this tile inside the array
-    for (int hb = 0; hb < TYO / ROWS_B; ++hb) {
-        const int r = hb * ROWS_B + (tid % ROWS_B);
-        const int cg = tid / ROWS_B;
-        const bool live = y0 + r < ny && cg * 16 < tile_cols;
-        const float *srow = mid + r * PI + cg * 16;
-        float *const oblk = hb == 0 ? spare : mid + (hb - 1) * ROWS_B * PI;   // staged results of this block
-        const int opitch = hb == 0 ? kFusedPO : PI;
+    const int tile_cols = min(nx - x0, p.ncg * 16);   // columns of this tile inside the array
+    const int rw = 4 * warp;                           // first tile row of this warp
+    float *const wrows = mid + rw * PI;
+    const int rl = lane & 3;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int cg = pass * 8 + 2 * (lane >> 3) + ((lane >> 2) & 1);
+        const bool live = y0 + rw + rl < ny && cg * 16 < tile_cols;
+        float *srow = wrows + rl * PI + cg * 16;
         float f[NF];
+        float4 res[4];
         if (live) {
 #pragma unroll
             for (int b = 0; b < NF / 4; ++b) {
                 const float4 v = *reinterpret_cast<const float4 *>(srow + 4 * b);
                 f[4 * b] = v.x; f[4 * b + 1] = v.y; f[4 * b + 2] = v.z; f[4 * b + 3] = v.w;
             }
-        }
-        if (live) {
             float2 e[8], o[9];
 #pragma unroll
             for (int i = 0; i < 8; ++i) e[i] = make_float2(0.f, 0.f);
@@ -305,60 +323,127 @@ corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             }
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                float4 r4;
-                r4.x = e[2 * h].x + o[2 * h].y;
-                r4.y = e[2 * h].y + o[2 * h + 1].x;
-                r4.z = e[2 * h + 1].x + o[2 * h + 1].y;
-                r4.w = e[2 * h + 1].y + o[2 * h + 2].x;
-                *reinterpret_cast<float4 *>(oblk + (tid % ROWS_B) * opitch + cg * 16 + 4 * h) = r4;
+                res[h].x = e[2 * h].x + o[2 * h].y;
+                res[h].y = e[2 * h].y + o[2 * h + 1].x;
+                res[h].z = e[2 * h + 1].x + o[2 * h + 1].y;
+                res[h].w = e[2 * h + 1].y + o[2 * h + 2].x;
             }
         }
-        if (bulk) fence_proxy_async();   // the stores above become visible to the bulk-copy engine
-        __syncthreads();
-        if (bulk) {
-            if (tid < ROWS_B && y0 + hb * ROWS_B + tid < ny)
-                bulk_store_row(p.out + ((int64_t)z * ny + y0 + hb * ROWS_B + tid) * nx + x0, oblk + tid * opitch,
-                               tile_cols * 4);
-            continue;
+        __syncwarp();      // every window of this pass has been read
+        if (live) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) *reinterpret_cast<float4 *>(srow + 4 * h) = res[h];
         }
-        float *orow0 = p.out + ((int64_t)z * ny + y0 + hb * ROWS_B) * nx + x0;
+    }
+    if (bulk) fence_proxy_async();   // the stores above become visible to the bulk-copy engine
+    __syncwarp();
+    if (bulk) {
+        if (lane < 4 && y0 + rw + lane < ny) {
+            bulk_store_row(p.out + ((int64_t)z * ny + y0 + rw + lane) * nx + x0, wrows + lane * PI, tile_cols * 4);
+            bulk_store_wait_read();    // the rows must stay intact until the engine has read them
+        }
+        return;
+    }
+    const bool reads_out = epilogue_reads_out(p.epilogue);
+    for (int rr = 0; rr < 4 && y0 + rw + rr < ny; ++rr) {
+        const float *srcr = wrows + rr * PI;
+        float *dst = p.out + ((int64_t)z * ny + y0 + rw + rr) * nx + x0;
         if constexpr (TMA) {
             // 16-byte vectors, lanes along the row: coalesced read-modify-write with the epilogue
-            const int nvec = tile_cols >> 2;
-            const bool reads_out = epilogue_reads_out(p.epilogue);
-            for (int idx = tid; idx < ROWS_B * nvec; idx += NTHR) {
-                const int rr = idx / nvec, v = idx - rr * nvec;
-                if (y0 + hb * ROWS_B + rr >= ny) continue;
-                float4 r4 = *reinterpret_cast<const float4 *>(oblk + rr * opitch + 4 * v);
-                float4 *dst = reinterpret_cast<float4 *>(orow0 + (int64_t)rr * nx + 4 * v);
+            for (int v = lane; v < (tile_cols >> 2); v += 32) {
+                float4 r4 = *reinterpret_cast<const float4 *>(srcr + 4 * v);
+                float4 *d4 = reinterpret_cast<float4 *>(dst + 4 * v);
                 if (p.epilogue != B200_EPI_STORE) {
                     float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (reads_out) pv = *dst;
+                    if (reads_out) pv = *d4;
                     r4.x = apply_epilogue<float>(p.epilogue, pv.x, r4.x);
                     r4.y = apply_epilogue<float>(p.epilogue, pv.y, r4.y);
                     r4.z = apply_epilogue<float>(p.epilogue, pv.z, r4.z);
                     r4.w = apply_epilogue<float>(p.epilogue, pv.w, r4.w);
                 }
-                *dst = r4;
+                *d4 = r4;
             }
+        } else if (p.epilogue == B200_EPI_STORE) {
+            for (int c = lane; c < tile_cols; c += 32) dst[c] = srcr[c];
         } else {
-            // a warp per row, lanes along it: coalesced element stores
-            const bool reads_out = epilogue_reads_out(p.epilogue);
-            for (int rr = warp; rr < ROWS_B; rr += NWARPS) {
-                if (y0 + hb * ROWS_B + rr >= ny) break;
-                const float *srcr = oblk + rr * opitch;
-                float *dst = orow0 + (int64_t)rr * nx;
-                if (p.epilogue == B200_EPI_STORE) {
-                    for (int c = lane; c < tile_cols; c += 32) dst[c] = srcr[c];
-                } else {
-                    for (int c = lane; c < tile_cols; c += 32)
-                        dst[c] = apply_epilogue<float>(p.epilogue, reads_out ? dst[c] : 0.f, srcr[c]);
-                }
-            }
+            for (int c = lane; c < tile_cols; c += 32)
+                dst[c] = apply_epilogue<float>(p.epilogue, reads_out ? dst[c] : 0.f, srcr[c]);
         }
     }
-    // the tile must stay intact until the bulk copies have read it
-    if (bulk && tid < ROWS_B) bulk_store_wait_read();
+}
+
+template <int L1, int NTX, int TYO, int NWARPS, int RA, bool ALIAS, int MINB, bool TMA>
+__global__ void __launch_bounds__(NWARPS * 32, MINB)
+corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr2dParams p)
+{
+    constexpr int PX = kFusedPX;
+    constexpr int TYIN = TYO + L1 - 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tin = aligned_smem<float>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar;
+    __shared__ int row_src[TYIN];
+    __shared__ int col_src[PX];
+    const int z = blockIdx.z;
+    const int x0 = blockIdx.x * (p.ncg * 16), y0 = blockIdx.y * TYO;
+    if constexpr (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&full_bar, 1);
+            fence_barrier_init();
+            mbar_arrive_expect_tx(&full_bar, (uint32_t)(TYIN * PX * (int)sizeof(float)));
+            tma_load_3d(tin, &tmap, &full_bar, x0 - p.lo2, y0 - p.lo1, z);
+        }
+    }
+    fused_tile<L1, NTX, TYO, NWARPS, RA, ALIAS, TMA>(p, tin, row_src, col_src, &full_bar, 0u, x0, y0, z);
+}
+
+// The same tiles on a PERSISTENT grid (as many CTAs as fit the device, each walking the tile list with
+// the grid's stride) with the staged box double-buffered: the TMA load of a CTA's next-but-one tile is
+// issued as soon as the buffer is free, i.e. a whole tile of arithmetic before it is needed, so no CTA
+// ever sits at the barrier waiting for its data.  Two buffers per CTA halve the resident CTAs (2 x 8
+// warps per SM), which the missing load latency more than pays for with short filters.
+template <int L1, int NTX, int TYO, int NWARPS, int RA>
+__global__ void __launch_bounds__(NWARPS * 32, 2)
+corr2d_fused_persist_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr2dParams p)
+{
+    constexpr int PX = kFusedPX;
+    constexpr int TYIN = TYO + L1 - 1;
+    constexpr int BUF = fused_buffer_floats(L1, TYO, NWARPS);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *base = aligned_smem<float>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ int row_src[TYIN];
+    __shared__ int col_src[PX];
+    const int tid = threadIdx.x;
+    const int G = gridDim.x;
+    const int per_plane = p.x_tiles * p.y_tiles;
+    const int total = p.n_tiles;
+    auto issue = [&](int t, int b) {
+        const int z = t / per_plane, q = t - z * per_plane;
+        const int ty = q / p.x_tiles, tx = q - ty * p.x_tiles;
+        mbar_arrive_expect_tx(&full_bar[b], (uint32_t)(TYIN * PX * (int)sizeof(float)));
+        tma_load_3d(base + b * BUF, &tmap, &full_bar[b], tx * (p.ncg * 16) - p.lo2, ty * TYO - p.lo1, z);
+    };
+    int t = blockIdx.x;
+    if (tid == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        fence_barrier_init();
+        if (t < total) issue(t, 0);
+        if (t + G < total) issue(t + G, 1);
+    }
+    for (int k = 0; t < total; ++k, t += G) {
+        const int b = k & 1;
+        const int z = t / per_plane, q = t - z * per_plane;
+        const int ty = q / p.x_tiles, tx = q - ty * p.x_tiles;
+        fused_tile<L1, NTX, TYO, NWARPS, RA, true, true>(p, base + b * BUF, row_src, col_src, &full_bar[b],
+                                                          (uint32_t)(k >> 1) & 1u, tx * (p.ncg * 16), ty * TYO, z);
+        // (every warp leaves fused_tile with its bulk stores read out of shared memory)
+        __syncthreads();
+        if (tid == 0 && t + 2 * G < total) {
+            fence_proxy_async();     // the threads' accesses to this buffer precede the engine's writes
+            issue(t + 2 * G, b);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -381,7 +466,7 @@ static int launch_fused_cfg(const Corr2dArgs &a, const Corr2dParams &p0)
     p.y_tiles = (int)((a.ny + TYO - 1) / TYO);
     if (a.outer > 65535 || p.y_tiles > 65535) return -1;   // grid = (x tiles, y tiles, planes)
     const size_t in_bytes = (size_t)TYIN * kFusedPX * sizeof(float);
-    const size_t mid_bytes = ((size_t)TYO * kFusedPI + (size_t)(NWARPS * 2) * kFusedPO) * sizeof(float);
+    const size_t mid_bytes = (size_t)TYO * kFusedPI * sizeof(float);
     const size_t smem = (ALIAS ? (in_bytes > mid_bytes ? in_bytes : mid_bytes) : in_bytes + mid_bytes) + 128;
     if (smem + 2048 > kSmemPerSm) return -1;
     CUtensorMap tmap;
@@ -401,6 +486,37 @@ static int launch_fused_cfg(const Corr2dArgs &a, const Corr2dParams &p0)
     return B200_OK;
 }
 
+template <int L1, int NTX>
+static int launch_fused_persist(const Corr2dArgs &a, const Corr2dParams &p0)
+{
+    constexpr int TYO = 32, NWARPS = 8, RA = 8;
+    constexpr int NCG = (kFusedPX - (NTX - 1)) / 16;
+    constexpr int TXO = NCG * 16;
+    constexpr int TYIN = TYO + L1 - 1;
+    constexpr size_t smem = 2 * (size_t)fused_buffer_floats(L1, TYO, NWARPS) * sizeof(float) + 128;
+    Corr2dParams p = p0;
+    p.x_tiles = (int)((a.nx + TXO - 1) / TXO);
+    p.ncg = (int)((a.nx + 16ll * p.x_tiles - 1) / (16ll * p.x_tiles));
+    p.y_tiles = (int)((a.ny + TYO - 1) / TYO);
+    const int64_t n_tiles = (int64_t)p.x_tiles * p.y_tiles * a.outer;
+    if (n_tiles >= (1ll << 31)) return -1;
+    p.n_tiles = (int)n_tiles;
+    CUtensorMap tmap;
+    uint64_t dims[3] = {(uint64_t)a.nx, (uint64_t)a.ny, (uint64_t)a.outer};
+    uint64_t strides[2] = {(uint64_t)a.nx * 4, (uint64_t)a.nx * 4 * (uint64_t)a.ny};
+    uint32_t bx[3] = {(uint32_t)kFusedPX, (uint32_t)TYIN, 1u};
+    if (encode_tensor_map(&tmap, B200_F32, (void *)a.in, 3, dims, strides, bx) != 0) return -1;
+    auto kern = corr2d_fused_persist_kernel<L1, NTX, TYO, NWARPS, RA>;
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn - 2048));
+    const int64_t resident = 2ll * device_sm_count();
+    const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+    kern<<<grid, NWARPS * 32, smem, a.stream>>>(tmap, p);
+    B200_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    note_kernel("corr2d_fused_tma_f32");
+    return B200_OK;
+}
+
 // tile geometry: 32 output rows x up to 240 columns, 8 warps, 8 rows per lane in phase A, the
 // intermediate tile aliased onto the input tile (B200 sweep: tools/sweep_fused.py with a
 // -DB200_FUSED_SWEEP build, profiles/r2_sweep_fused.log)
@@ -415,14 +531,16 @@ static int launch_fused_taps(const Corr2dArgs &a, const Corr2dParams &p)
     case 2: return launch_fused_cfg<L1, NTX, 32, 8, 8, true, 2, TMA>(a, p);
     case 3: return launch_fused_cfg<L1, NTX, 32, 8, 8, true, 4, TMA>(a, p);
     case 4: return launch_fused_cfg<L1, NTX, 16, 4, 8, true, 6, TMA>(a, p);
-    case 5: return launch_fused_cfg<L1, NTX, 64, 8, 8, false, 1, TMA>(a, p);
     case 6: return launch_fused_cfg<L1, NTX, 64, 16, 8, true, 1, TMA>(a, p);
-    case 7: return launch_fused_cfg<L1, NTX, 32, 4, 16, true, 4, TMA>(a, p);
     default: break;
     }
 #else
     (void)variant;
 #endif
+    // persistent double-buffered form where two CTAs with two staged boxes each fit an SM (<= 23 taps)
+    if constexpr (TMA && 2 * (2 * fused_buffer_floats(L1, 32, 8) * 4 + 128 + 2560) <= (int)kSmemPerSm) {
+        if (env_int("B200_FUSED_PERSIST", 0) && a.epilogue == B200_EPI_STORE) return launch_fused_persist<L1, NTX>(a, p);
+    }
     // short filters: 4 CTAs of 8 warps per SM (<= 64 registers); from 25 taps on the pass is FP32-issue
     // bound, the tiles are bigger and 3 resident CTAs with more registers do better (B200 sweep)
     return launch_fused_cfg<L1, NTX, 32, 8, 8, true, (NTX < 25 ? 4 : 2), TMA>(a, p);
