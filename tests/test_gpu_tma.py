@@ -40,7 +40,8 @@ SHAPES_AXES = [
     ((70, 64), 0), ((70, 64), 1), ((5, 130, 36), 1), ((3, 40, 132), 2), ((200, 8, 16), 0),
     ((260, 512), 0), ((260, 512), 1), ((9, 260), 1), ((2, 3, 24, 20), 2), ((1, 4), 1), ((3, 8), 0),
 ]
-TAPS = [(1, 0), (2, -1), (3, 1), (8, 0), (9, 0), (17, 0), (24, 3), (33, 5), (64, -32), (101, 7)]
+TAPS = [(1, 0), (2, -1), (3, 1), (8, 0), (9, 0), (17, 0), (19, 0), (24, 3), (25, -4), (33, 5), (41, 0), (64, -32),
+        (101, 7)]
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
