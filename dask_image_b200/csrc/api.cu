@@ -356,6 +356,50 @@ int b200_correlate_nd(const void *in, void *out, int dtype, int ndim, const int6
     return launch_corrnd_generic(a);
 }
 
+int b200_correlate_nd_halo_eligible(int dtype, int ndim, const int64_t *shape, const int64_t *wshape,
+                                    const int64_t *origins)
+{
+    if (ndim != 3 || !shape || !wshape || !origins) return 0;
+    for (int d = 0; d < ndim; ++d) {
+        if (shape[d] < 1 || wshape[d] < 1) return 0;
+        if (origins[d] < -(wshape[d] / 2) || origins[d] > (wshape[d] - 1) / 2) return 0;
+    }
+    return corrnd_peer_eligible(dtype, ndim, shape, wshape, origins);
+}
+
+int b200_correlate_nd_halo(const void *in, void *out, int dtype, int ndim, const int64_t *shape,
+                           const double *weights, const int64_t *wshape, const int64_t *origins, int mode,
+                           double cval, const void *halo_lo, int64_t n_lo, const void *halo_hi, int64_t n_hi,
+                           unsigned flags, void *stream)
+{
+    int64_t total;
+    if (int rc = check_common(in, out, dtype, ndim, shape, mode, &total)) return rc;
+    if (!weights || !wshape || !origins) return set_error(B200_EINVAL, "no filter weights given");
+    for (int d = 0; d < ndim; ++d) {
+        if (wshape[d] < 1) return set_error(B200_EINVAL, "weights must have non-zero extents");
+        if (origins[d] < -(wshape[d] / 2) || origins[d] > (wshape[d] - 1) / 2)
+            return set_error(B200_EORIGIN, "Invalid origin; origin must satisfy "
+                                           "-(weights.shape[k] // 2) <= origin[k] <= (weights.shape[k]-1) // 2");
+    }
+    if (n_lo < 0 || n_hi < 0 || (n_lo > 0 && !halo_lo) || (n_hi > 0 && !halo_hi))
+        return set_error(B200_EINVAL, "halo planes and their counts do not agree");
+    if (total == 0) return B200_OK;
+    if (!b200_correlate_nd_halo_eligible(dtype, ndim, shape, wshape, origins))
+        return set_error(B200_EINVAL, "not eligible: no in-place halo kernel for this N-D correlate");
+    CorrNdArgs a;
+    a.in = in; a.out = out; a.dtype = dtype; a.ndim = ndim;
+    for (int d = 0; d < ndim; ++d) {
+        a.shape[d] = shape[d]; a.wshape[d] = wshape[d]; a.origins[d] = origins[d];
+    }
+    a.w = weights; a.mode = mode; a.cval = cval; a.pad_lo = 0; a.pad_hi = 0;
+    a.flags = flags; a.stream = (cudaStream_t)stream;
+    a.peer_lo = n_lo > 0 ? halo_lo : nullptr; a.peer_hi = n_hi > 0 ? halo_hi : nullptr;
+    a.n_peer_lo = (int)n_lo; a.n_peer_hi = (int)n_hi;
+    int rc = launch_corrnd_peer(a);
+    if (rc < 0) return set_error(B200_EINVAL, "not eligible: tile geometry cannot place the neighbour planes");
+    return rc;
+}
+
 int b200_minmax_filter1d(const void *in, void *out, int dtype, int ndim, const int64_t *shape, int axis,
                          int64_t size, int is_max, int mode, double cval, int64_t origin, int64_t pad_lo,
                          int64_t pad_hi, unsigned flags, void *stream)

@@ -321,8 +321,14 @@ struct CorrNdArgs {
     int64_t pad_lo, pad_hi;
     unsigned flags;
     cudaStream_t stream;
+    // neighbour planes read in place (b200_correlate_nd_halo); null = none
+    const void *peer_lo = nullptr, *peer_hi = nullptr;
+    int n_peer_lo = 0, n_peer_hi = 0;
 };
 int launch_corrnd_generic(const CorrNdArgs &a);
+// slab whose neighbour planes are read where they live; -1 = geometry not eligible
+int launch_corrnd_peer(const CorrNdArgs &a);
+int corrnd_peer_eligible(int dtype, int ndim, const int64_t *shape, const int64_t *wshape, const int64_t *origins);
 int launch_corrnd_tiled(const CorrNdArgs &a);
 // exact tiled path of the 8/16-bit integer dtypes, 2-D / 3-D (corrnd_int.cu); -1 = not eligible
 int launch_corrnd_int(const CorrNdArgs &a);

@@ -41,16 +41,33 @@ struct CorrNdTiledParams {
     int cx, cy;               // tiles along x and y (z = the rest of the grid)
     int mode, wide_store;
     T cval;
+    // neighbour planes read in place (multi-GPU slab, corrnd_static_peer_kernel): the n_peer_lo planes that
+    // precede plane 0 and the n_peer_hi planes that follow plane Z - 1, in a peer GPU's memory; null = none
+    const T *peer_lo, *peer_hi;
+    int n_peer_lo, n_peer_hi;
     T w[kNdTapBytes / sizeof(T)];
+};
+
+// Tensor maps of the peer-halo form (3-D arrays, slabs along z): the first z tile takes its top `loz`
+// planes from `lo` (the previous rank's last planes) and the rest from a shallower local box; the last
+// z tile takes the planes behind the slab from `hi`.  Every other tile is unchanged.
+struct NdPeerMaps {
+    CUtensorMap first;   // local slab, box depth BZ - loz
+    CUtensorMap last;    // local slab, box depth k_last
+    CUtensorMap lo;      // the planes that precede the slab
+    CUtensorMap hi;      // the planes that follow it
+    int has_lo, has_hi;
+    int lo_planes, k_last, ncz;
 };
 
 // Stage the CTA's input tile: one TMA 3-D box (zero fill outside the resident
 // range), then -- on CTAs that touch an edge -- patch exactly the out-of-range
 // elements through the extension maps.  Ends with the tile visible to all.
-template <typename T, typename PARAMS>
+template <typename T, typename PARAMS, bool PEER = false>
 __device__ __forceinline__ void nd_stage_tile(const PARAMS &p, const CUtensorMap &tmap, T *tile, uint64_t *full_bar,
                                               int P, int BY, int BZ, int64_t g0x, int64_t g0y, int64_t g0z,
-                                              int64_t ylo, int64_t yhi, int64_t zlo, int64_t zhi)
+                                              int64_t ylo, int64_t yhi, int64_t zlo, int64_t zhi,
+                                              const NdPeerMaps *hm = nullptr, int64_t tcz = 0)
 {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -58,8 +75,29 @@ __device__ __forceinline__ void nd_stage_tile(const PARAMS &p, const CUtensorMap
         mbar_init(full_bar, 1);
         fence_barrier_init();
         mbar_arrive_expect_tx(full_bar, (uint32_t)((size_t)P * BY * BZ * sizeof(T)));
-        tma_load_3d(tile, &tmap, full_bar, (int)g0x, (int)(g0y - ylo), (int)(g0z - zlo));
+        if constexpr (PEER) {
+            // (the slab's tensor maps have no pad planes in front: z coordinates are slab planes)
+            if (tcz == 0 && hm->has_lo) {
+                tma_load_3d(tile, &hm->lo, full_bar, (int)g0x, (int)g0y, 0);
+                tma_load_3d(tile + (size_t)hm->lo_planes * BY * P, &hm->first, full_bar, (int)g0x, (int)g0y, 0);
+            } else if (tcz == hm->ncz - 1 && hm->has_hi) {
+                tma_load_3d(tile, &hm->last, full_bar, (int)g0x, (int)g0y, (int)g0z);
+                tma_load_3d(tile + (size_t)hm->k_last * BY * P, &hm->hi, full_bar, (int)g0x, (int)g0y, 0);
+            } else {
+                tma_load_3d(tile, &tmap, full_bar, (int)g0x, (int)g0y, (int)g0z);
+            }
+        } else {
+            tma_load_3d(tile, &tmap, full_bar, (int)g0x, (int)(g0y - ylo), (int)(g0z - zlo));
+        }
     }
+    // plane `sz` of the resident range: local, or one of the neighbours' planes
+    auto plane_base = [&](int64_t sz) -> const T * {
+        if constexpr (PEER) {
+            if (sz < 0) return p.peer_lo + (sz + p.n_peer_lo) * p.Y * p.X;
+            if (sz >= p.Z) return p.peer_hi + (sz - p.Z) * p.Y * p.X;
+        }
+        return p.in + sz * p.Y * p.X;
+    };
     __syncthreads();
     if (tid < 32) mbar_wait(full_bar, 0);
     __syncthreads();
@@ -81,7 +119,7 @@ __device__ __forceinline__ void nd_stage_tile(const PARAMS &p, const CUtensorMap
                                     : ext_index_padded(gz, p.Z, p.mode, 0, 0);
                 row_cval = sy == B200_USE_CVAL || sz == B200_USE_CVAL;
             }
-            const T *srow = row_cval ? nullptr : p.in + (sz * p.Y + sy) * p.X;
+            const T *srow = row_cval ? nullptr : plane_base(sz) + sy * p.X;
             T *trow = tile + (size_t)rr * P;
             for (int c = lane; c < P; c += 32) {
                 const int64_t gx = g0x + c;
@@ -187,9 +225,9 @@ corrnd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 // covers 64 x 8 outputs, lanes of a quarter warp sit on 8 different rows so the
 // odd 16-byte pitch makes every LDS.128 conflict-free.
 // ===========================================================================
-template <int KXA, bool SKIPZ>
-__global__ void __launch_bounds__(256, 2)
-corrnd_static_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CorrNdTiledParams<float> p)
+template <int KXA, bool SKIPZ, bool PEER>
+__device__ __forceinline__ void corrnd_static_body(const CUtensorMap &tmap, const CorrNdTiledParams<float> &p,
+                                                   const NdPeerMaps *hm)
 {
     constexpr int R = 16;
     constexpr int NF = (R + KXA + 3) / 4 * 4;   // floats of a row a thread touches
@@ -212,7 +250,8 @@ corrnd_static_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     const int64_t ylo = p.pad_dim == 1 ? -p.pad_lo : 0, yhi = p.Y + (p.pad_dim == 1 ? p.pad_hi : 0);
     const int64_t zlo = p.pad_dim == 2 ? -p.pad_lo : 0, zhi = p.Z + (p.pad_dim == 2 ? p.pad_hi : 0);
 
-    nd_stage_tile<float>(p, tmap, tile, &full_bar, P, BY, BZ, g0x, g0y, g0z, ylo, yhi, zlo, zhi);
+    nd_stage_tile<float, CorrNdTiledParams<float>, PEER>(p, tmap, tile, &full_bar, P, BY, BZ, g0x, g0y, g0z, ylo, yhi,
+                                                          zlo, zhi, hm, tcz);
 
     // patches: (plane zz, row group yg); TY / 8 is a power of two
     const int nyg = p.TY >> 3;
@@ -288,6 +327,22 @@ corrnd_static_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     }
 }
 
+template <int KXA, bool SKIPZ>
+__global__ void __launch_bounds__(256, 2)
+corrnd_static_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CorrNdTiledParams<float> p)
+{
+    corrnd_static_body<KXA, SKIPZ, false>(tmap, p, nullptr);
+}
+
+// the same kernel for a multi-GPU slab whose neighbour planes are read where they live (NdPeerMaps)
+template <int KXA, bool SKIPZ>
+__global__ void __launch_bounds__(256, 2)
+corrnd_static_peer_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ NdPeerMaps hm,
+                          const __grid_constant__ CorrNdTiledParams<float> p)
+{
+    corrnd_static_body<KXA, SKIPZ, true>(tmap, p, &hm);
+}
+
 template <typename T, int SH, int REM>
 static int launch_cfg(const CorrNdArgs &a, int lox_al, int Kx_al)
 {
@@ -352,6 +407,7 @@ static int launch_cfg(const CorrNdArgs &a, int lox_al, int Kx_al)
     p.TY = TY; p.TZ = TZ; p.ncg = ncg; p.P = P; p.BY = BY; p.BZ = BZ;
     p.cx = (int)cx; p.cy = (int)cy;
     p.mode = a.mode; p.cval = (T)a.cval;
+    p.peer_lo = p.peer_hi = nullptr; p.n_peer_lo = p.n_peer_hi = 0;
     p.wide_store = (((X * es) % 32) == 0 && ((uintptr_t)a.out & 31) == 0) ? 1 : 0;
     const int rows = Ky * Kz;
     for (int i = 0; i < rows * Kx_al; ++i) p.w[i] = T(0);
@@ -371,6 +427,60 @@ static int launch_cfg(const CorrNdArgs &a, int lox_al, int Kx_al)
     return B200_OK;
 }
 
+// Tile geometry of the static engine for a weight row of `kxa` taps (alignment zeros included): the
+// deepest output tile 64 x TY x TZ that keeps two CTAs per SM resident.  false = no geometry.
+static bool nd_static_tile(int nd, int kxa, int Ky, int Kz, int *P_out, int *TY_out, int *TZ_out)
+{
+    constexpr int R = 16, SX = 4 * R;
+    const int NF = (R + kxa + 3) / 4 * 4;
+    int pu = (SX - R + NF + 3) / 4;
+    if (!(pu & 1)) ++pu;
+    const int P = pu * 4;
+    const size_t budget = (kSmemPerSm - 4096) / 2 - 256;
+    static const int cand3[][2] = {{8, 8}, {16, 4}, {32, 2}, {8, 4}, {16, 2}, {8, 2}, {16, 1}, {8, 1}};
+    static const int cand2[][2] = {{64, 1}, {32, 1}, {16, 1}, {8, 1}};
+    const int (*cand)[2] = nd == 3 ? cand3 : cand2;
+    const int ncand = nd == 3 ? 8 : 4;
+    for (int i = 0; i < ncand; ++i) {
+        const size_t bytes = (size_t)P * (cand[i][0] + Ky - 1) * (cand[i][1] + Kz - 1) * 4;
+        if (bytes <= budget && cand[i][0] + Ky - 1 <= 256 && cand[i][1] + Kz - 1 <= 256) {
+            *P_out = P; *TY_out = cand[i][0]; *TZ_out = cand[i][1];
+            return true;
+        }
+    }
+    return false;
+}
+
+// Peer-halo form: neighbour planes may enter the first and the last z tile only.
+static bool nd_peer_tiles_ok(int64_t Z, int TZ, int loz, int hiz)
+{
+    const int64_t ncz = (Z + TZ - 1) / TZ;
+    const int64_t last_planes = Z - (ncz - 1) * TZ;
+    return ncz >= 2 && TZ >= loz && last_planes >= hiz;
+}
+
+// host-only: can launch_corrnd_peer take a slab of this shape with these weights?  (every rank evaluates it
+// for every slab size, so that all of them choose the same path)
+int corrnd_peer_eligible(int dtype, int ndim, const int64_t *shape, const int64_t *wshape, const int64_t *origins)
+{
+    if (dtype != B200_F32 || ndim != 3) return 0;
+    const int64_t X = shape[2], Y = shape[1], Z = shape[0];
+    if ((X * 4) % 16 != 0 || X >= (1ll << 31) || Y >= (1ll << 31) || Z >= (1ll << 31)) return 0;
+    const int Kx = (int)wshape[2], Ky = (int)wshape[1], Kz = (int)wshape[0];
+    if (Kx > 128 || Ky > 128 || Kz > 128) return 0;
+    const int lox = Kx / 2 + (int)origins[2];
+    const int kxa = Kx + ((lox + 3) / 4 * 4 - lox);
+    if (kxa > 16 || (int64_t)Ky * Kz * kxa > (int64_t)(kNdTapBytes / sizeof(float))) return 0;
+    int P, TY, TZ;
+    if (!nd_static_tile(3, kxa, Ky, Kz, &P, &TY, &TZ)) return 0;
+    // the second box of a split tile lands `planes * BY * P` floats into the tile: TMA destinations must
+    // be 128-byte aligned, P * 4 is an odd multiple of 16 bytes => the staged rows per plane must be a
+    // multiple of 8 (Ky = 1, 9, 17 ... with the 8-row tiles)
+    if (((size_t)(TY + Ky - 1) * P * 4) % 128 != 0) return 0;
+    const int loz = Kz / 2 + (int)origins[0], hiz = Kz - 1 - loz;
+    return nd_peer_tiles_ok(Z, TZ, loz, hiz) ? 1 : 0;
+}
+
 template <int KXA, bool SKIPZ>
 static int launch_static_cfg(const CorrNdArgs &a, int lox_al)
 {
@@ -385,25 +495,8 @@ static int launch_static_cfg(const CorrNdArgs &a, int lox_al)
     const int lead = lox_al - (Kx / 2 + (int)a.origins[nd - 1]);
     if ((int64_t)Ky * Kz * KXA > (int64_t)(kNdTapBytes / sizeof(float))) return -1;
 
-    int pu = (SX - R + NF + 3) / 4;
-    if (!(pu & 1)) ++pu;
-    const int P = pu * 4;
-    // output tile: 64 x TY x TZ with (TY / 8) * TZ patches for the 8 warps; the
-    // deepest geometry that keeps two CTAs per SM resident
-    const size_t budget = (kSmemPerSm - 4096) / 2 - 256;
-    static const int cand3[][2] = {{8, 8}, {16, 4}, {32, 2}, {8, 4}, {16, 2}, {8, 2}, {16, 1}, {8, 1}};
-    static const int cand2[][2] = {{64, 1}, {32, 1}, {16, 1}, {8, 1}};
-    int TY = 0, TZ = 0;
-    const int (*cand)[2] = nd == 3 ? cand3 : cand2;
-    const int ncand = nd == 3 ? 8 : 4;
-    for (int i = 0; i < ncand; ++i) {
-        const size_t bytes = (size_t)P * (cand[i][0] + Ky - 1) * (cand[i][1] + Kz - 1) * es;
-        if (bytes <= budget && cand[i][0] + Ky - 1 <= 256 && cand[i][1] + Kz - 1 <= 256) {
-            TY = cand[i][0]; TZ = cand[i][1];
-            break;
-        }
-    }
-    if (!TY) return -1;
+    int P = 0, TY = 0, TZ = 0;
+    if (!nd_static_tile(nd, KXA, Ky, Kz, &P, &TY, &TZ)) return -1;
     const int BY = TY + Ky - 1, BZ = TZ + Kz - 1;
     const int64_t cx = (X + SX - 1) / SX, cy = (Y + TY - 1) / TY, cz = (Z + TZ - 1) / TZ;
     const int64_t num_tiles = cx * cy * cz;
@@ -440,8 +533,47 @@ static int launch_static_cfg(const CorrNdArgs &a, int lox_al)
             p.w[rw * KXA + lead + kx] = std::fabs(w) > DBL_EPSILON ? (float)w : 0.f;
         }
 
-    auto kern = corrnd_static_kernel<KXA, SKIPZ>;
     const size_t smem = (size_t)P * BY * BZ * es + 128;
+    p.peer_lo = p.peer_hi = nullptr; p.n_peer_lo = p.n_peer_hi = 0;
+    if (a.peer_lo || a.peer_hi) {
+        // neighbour planes read in place: extra tensor maps for the first / last z tile
+        const int hiz = Kz - 1 - loz;
+        const bool has_lo = a.peer_lo != nullptr && loz > 0, has_hi = a.peer_hi != nullptr && hiz > 0;
+        if (nd != 3 || a.pad_lo || a.pad_hi || !nd_peer_tiles_ok(Z, TZ, loz, hiz)) return -1;
+        if (((size_t)BY * P * 4) % 128 != 0) return -1;   // 128-byte aligned TMA destinations
+        if ((has_lo && a.n_peer_lo != loz) || (has_hi && a.n_peer_hi != hiz)) return -1;
+        if (((uintptr_t)a.peer_lo & 15) || ((uintptr_t)a.peer_hi & 15)) return -1;
+        NdPeerMaps hm;
+        memset(&hm, 0, sizeof(hm));
+        const int64_t last_planes = Z - (cz - 1) * TZ;
+        hm.has_lo = has_lo; hm.has_hi = has_hi; hm.lo_planes = loz; hm.ncz = (int)cz;
+        hm.k_last = (int)(last_planes + loz);
+        if (has_lo) {
+            uint32_t b1[3] = {(uint32_t)P, (uint32_t)BY, (uint32_t)(BZ - loz)};
+            if (encode_tensor_map(&hm.first, a.dtype, (void *)a.in, 3, dims, strides, b1) != 0) return -1;
+            uint64_t d2[3] = {(uint64_t)X, (uint64_t)Y, (uint64_t)loz};
+            uint32_t b2[3] = {(uint32_t)P, (uint32_t)BY, (uint32_t)loz};
+            if (encode_tensor_map(&hm.lo, a.dtype, (void *)a.peer_lo, 3, d2, strides, b2) != 0) return -1;
+            p.peer_lo = (const float *)a.peer_lo; p.n_peer_lo = loz; p.pad_lo = loz;
+        }
+        if (has_hi) {
+            uint32_t b1[3] = {(uint32_t)P, (uint32_t)BY, (uint32_t)hm.k_last};
+            if (encode_tensor_map(&hm.last, a.dtype, (void *)a.in, 3, dims, strides, b1) != 0) return -1;
+            uint64_t d2[3] = {(uint64_t)X, (uint64_t)Y, (uint64_t)hiz};
+            uint32_t b2[3] = {(uint32_t)P, (uint32_t)BY, (uint32_t)(BZ - hm.k_last)};
+            if (BZ - hm.k_last < 1) return -1;
+            if (encode_tensor_map(&hm.hi, a.dtype, (void *)a.peer_hi, 3, d2, strides, b2) != 0) return -1;
+            p.peer_hi = (const float *)a.peer_hi; p.n_peer_hi = hiz; p.pad_hi = hiz;
+        }
+        auto kern = corrnd_static_peer_kernel<KXA, SKIPZ>;
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
+        kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, hm, p);
+        B200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        note_kernel("corrnd_tiled_peer_f32");
+        return B200_OK;
+    }
+    auto kern = corrnd_static_kernel<KXA, SKIPZ>;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     kern<<<(unsigned)num_tiles, 256, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
@@ -520,6 +652,13 @@ static int launch_typed(const CorrNdArgs &a)
     case 3: if constexpr (V == 4) return launch_sh<T, 3>(a, lox_al, Kx_al);
     }
     return -1;
+}
+
+// N-D correlate of a slab whose neighbour planes are read in place (a.peer_lo / a.peer_hi); -1 = not eligible
+int launch_corrnd_peer(const CorrNdArgs &a)
+{
+    if (!corrnd_peer_eligible(a.dtype, a.ndim, a.shape, a.wshape, a.origins)) return -1;
+    return launch_static(a);
 }
 
 int launch_corrnd_tiled(const CorrNdArgs &a)

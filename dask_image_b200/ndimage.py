@@ -272,6 +272,26 @@ def _launch_correlate_nd(src, dst, shape, np_dtype, weights, origins, mode, cval
     _lib.check(rc)
 
 
+def _launch_correlate_nd_halo(src, dst, shape, np_dtype, weights, origins, mode, cval, halo_lo, halo_hi, flags=None):
+    """N-D correlate of a slab whose neighbour planes are read in place (``halo_lo`` / ``halo_hi``:
+    anything with ``data_ptr()`` and ``shape[0]``, or None at a boundary of the volume)."""
+    lib = _lib.load()
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    with _on_device(src):
+        rc = lib.b200_correlate_nd_halo(
+            src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape), _lib.i64_array(shape),
+            _lib.f64_pointer(w), _lib.i64_array(w.shape), _lib.i64_array(origins), _lib.mode_code(mode), float(cval),
+            halo_lo.data_ptr() if halo_lo is not None else None, int(halo_lo.shape[0]) if halo_lo is not None else 0,
+            halo_hi.data_ptr() if halo_hi is not None else None, int(halo_hi.shape[0]) if halo_hi is not None else 0,
+            int(_default_flags if flags is None else flags), _stream_ptr(src))
+    _lib.check(rc)
+
+
+def _nd_halo_eligible(np_dtype, shape, wshape, origins):
+    return bool(_lib.load().b200_correlate_nd_halo_eligible(
+        _dtype_code(np_dtype), len(shape), _lib.i64_array(shape), _lib.i64_array(wshape), _lib.i64_array(origins)))
+
+
 def _launch_minmax1d(src, dst, shape, np_dtype, axis, size, is_max, mode, cval, origin, pad=(0, 0), flags=None):
     lib = _lib.load()
     with _on_device(src):

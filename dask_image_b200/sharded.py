@@ -504,7 +504,26 @@ class ShardedVolume:
                                      src0.full, src0.cap + p0, out.full, out.cap + p0, p1 - p0, pad,
                                      shape, dt, w, origins, is_max, mode, plan.cval, flags))
                 return result
-            self._axis0_call(src0, lo, hi, mode in ("wrap", "grid-wrap"),
+            ring = mode in ("wrap", "grid-wrap")
+            # fused halo: the kernel reads the neighbours' planes in place (CUDA IPC mappings, TMA loads over
+            # NVLink inside the first / last z tile) instead of an NCCL exchange + separate edge launches
+            if (self.world > 1 and be is CudaBackend and flags is None
+                    and os.environ.get("B200_PEER_HALO", "1") != "0"
+                    and all(_nd._nd_halo_eligible(dt, (e - s,) + self.shape[1:], w.shape, origins)
+                            for s, e in self.bounds)):
+                peers = self._peer_views(src0)
+                if peers is not None:
+                    self._peer_sync()               # the neighbours' inputs are complete
+                    halo_lo = halo_hi = None
+                    if lo > 0 and (ring or self.rank > 0):
+                        halo_lo = peers["prev"].planes(peers["prev"].n - lo, peers["prev"].n)
+                    if hi > 0 and (ring or self.rank < self.world - 1):
+                        halo_hi = peers["next"].planes(0, hi)
+                    _nd._launch_correlate_nd_halo(src0.interior, out.interior, shape, dt, w, origins, mode,
+                                                  plan.cval, halo_lo, halo_hi, flags)
+                    self._peer_sync()               # nobody still reads this rank's input planes
+                    return result
+            self._axis0_call(src0, lo, hi, ring,
                              lambda p0, p1, pad: be.correlate_nd(
                                  src0.full, src0.cap + p0, out.full, out.cap + p0, p1 - p0, pad,
                                  shape, dt, w, origins, mode, plan.cval, flags))

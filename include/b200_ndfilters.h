@@ -197,6 +197,24 @@ int b200_correlate_nd(const void *in, void *out, int dtype, int ndim,
                       double cval, int64_t pad_lo, int64_t pad_hi,
                       unsigned flags, void *stream);
 
+/* b200_correlate_nd over a slab of a 3-D float32 volume (planes along axis 0) whose
+ * neighbour planes are read in place, as b200_correlate1d_halo does for the 1-D
+ * passes: `halo_lo` points at the n_lo = wshape[0]/2 + origins[0] planes that
+ * precede plane 0, `halo_hi` at the n_hi = wshape[0] - 1 - n_lo planes that follow
+ * the last one (peer GPU memory mapped through b200_ipc_open), or NULL / 0 where
+ * the slab ends at a boundary of the volume.  Returns B200_EINVAL ("not eligible")
+ * when the tile geometry cannot place the neighbour planes; the _eligible query is
+ * host-only (all ranks evaluate it for every slab size and choose alike). */
+int b200_correlate_nd_halo(const void *in, void *out, int dtype, int ndim,
+                           const int64_t *shape, const double *weights,
+                           const int64_t *wshape, const int64_t *origins,
+                           int mode, double cval, const void *halo_lo,
+                           int64_t n_lo, const void *halo_hi, int64_t n_hi,
+                           unsigned flags, void *stream);
+int b200_correlate_nd_halo_eligible(int dtype, int ndim, const int64_t *shape,
+                                    const int64_t *wshape,
+                                    const int64_t *origins);
+
 /* replaces the numpy ufuncs of scipy/ndimage/_filters.py:1025-1030,1184-1193:
  * acc (op)= src elementwise over n elements, in the array dtype. */
 int b200_combine(void *acc, const void *src, int dtype, int64_t n, int op,

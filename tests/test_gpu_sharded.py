@@ -119,8 +119,11 @@ def _nccl_worker(rank, world, port, q):
 
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         torch.cuda.set_device(rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world,
-                                device_id=torch.device("cuda", rank))
+        import datetime
+
+        # (a rank that fails must not leave the others waiting in a collective for ever)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                                timeout=datetime.timedelta(seconds=240))
         import dask_image_b200 as b200
 
         rng = np.random.default_rng(21)
@@ -170,6 +173,32 @@ def _nccl_worker(rank, world, port, q):
                     if not np.array_equal(got, one):
                         failures.append("peer=%s %s %s: %d voxels differ from the 1-GPU result" % (
                             flag, name, mode, int((got != one).sum())))
+        # N-D correlate / convolve with the neighbour planes read in place by the tiled kernel's first / last z tile
+        from dask_image_b200 import _lib
+
+        thick9 = rng.random((84 * world, 8, 64), dtype=np.float32)
+        # (in-place halo reads need 8-row-aligned staged planes: 9 or 17 taps along axis 1; other weights take
+        # the NCCL exchange -- checked as well)
+        w9 = rng.random((9, 9, 5)) - 0.4
+        w39 = rng.random((3, 9, 4)) - 0.4
+        for arr, wts, org in ((thick9, w9, 0), (thick, w39, (0, 1, -1)), (thick9, w39, (-1, 0, 1)), (thick, w3, 0)):
+            for mode in MODES:
+                for name in ("convolve", "correlate"):
+                    f = getattr(b200.ndfilters, name)
+                    one = f(b200.B200Array.from_numpy(arr), b200.B200Array.from_numpy(wts), mode=mode, cval=0.3,
+                            origin=org).to_numpy()
+                    for flag in ("1", "0"):
+                        os.environ["B200_PEER_HALO"] = flag
+                        got = f(b200.ShardedVolume.from_global(arr, halo=8), wts, mode=mode, cval=0.3, origin=org).gather()
+                        # (a rank with no neighbour plane to read -- an end slab whose reach towards its only
+                        # neighbour is zero -- runs the plain kernel; with reach on both sides every rank reads)
+                        both = wts.shape == (9, 9, 5)
+                        want = "corrnd_tiled_peer_f32" if flag == "1" and both else "corrnd_tiled_f32"
+                        if (both or flag == "0") and _lib.last_kernel() != want:
+                            failures.append("peer=%s %s %s: kernel %s" % (flag, name, mode, _lib.last_kernel()))
+                        if not np.array_equal(got, one):
+                            failures.append("peer=%s %s %s %s: %d voxels differ from the 1-GPU result" % (
+                                flag, name, wts.shape, mode, int((got != one).sum())))
         thick16 = rng.integers(0, 65536, (80 * world + 3, 8, 64), dtype=np.uint16)
         for mode in MODES:
             for arr in (thick16, thick):
@@ -226,7 +255,7 @@ def test_slab_engine_nccl(world):
     procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=900) for _ in procs]
+    results = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     for rank, failures in results:
@@ -361,3 +390,44 @@ def test_uniform_halo_in_place_equals_whole_call(b200, dtype, mode):
             nd._launch_uniform1d_halo(x[s:e], out[s:e], (e - s,) + tail, dt, size, mode, 5.0, origin, halo_lo, halo_hi)
             assert "_peer_" in _lib.last_kernel(), _lib.last_kernel()
         assert torch.equal(out.view(torch.uint8), whole.view(torch.uint8)), (size, origin, mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_nd_halo_in_place_equals_whole_call(b200, mode):
+    """b200_correlate_nd_halo: slabs of one resident volume whose neighbour planes are passed as pointers (on
+    several GPUs: a peer's memory, read by the kernel's own TMA loads) -- bit-identical to the whole-volume call."""
+    import torch
+    from dask_image_b200 import _lib, ndimage as nd
+
+    rng = np.random.default_rng(29)
+    N, tail = 252, (24, 64)
+    a = (rng.random((N,) + tail) - 0.4).astype(np.float32)
+    x = torch.from_numpy(a).cuda()
+    dt = np.dtype(np.float32)
+    for wshape, origins in (((9, 9, 9), (0, 0, 0)), ((3, 9, 4), (0, 1, -1)), ((5, 9, 3), (-2, 0, 1)), ((4, 1, 7), (1, 0, 0))):
+        w = rng.random(wshape) - 0.3
+        lo = wshape[0] // 2 + origins[0]
+        hi = wshape[0] - 1 - lo
+        whole = torch.empty_like(x)
+        nd._launch_correlate_nd(x, whole, a.shape, dt, w, origins, mode, 0.3)
+        for bounds in ([(0, 124), (124, 252)], [(0, 84), (84, 168), (168, 252)]):
+            assert all(nd._nd_halo_eligible(dt, (e - s,) + tail, wshape, origins) for s, e in bounds), (wshape, bounds)
+            out = torch.zeros_like(x)
+            for k, (s, e) in enumerate(bounds):
+                ring = mode == "wrap"
+                first, last = k == 0, k == len(bounds) - 1
+                halo_lo = halo_hi = None
+                if lo > 0 and (not first or ring):
+                    halo_lo = x[s - lo:s] if not first else x[N - lo:N]
+                if hi > 0 and (not last or ring):
+                    halo_hi = x[e:e + hi] if not last else x[0:hi]
+                nd._launch_correlate_nd_halo(x[s:e], out[s:e], (e - s,) + tail, dt, w, origins, mode, 0.3,
+                                             halo_lo, halo_hi)
+                if halo_lo is not None or halo_hi is not None:
+                    assert _lib.last_kernel() == "corrnd_tiled_peer_f32", _lib.last_kernel()
+            torch.cuda.synchronize()
+            assert torch.equal(out, whole), "%s %s %s: %d voxels differ" % (
+                wshape, bounds, mode, int((out != whole).sum().item()))
+    # weights whose staged planes are not 8-row aligned are refused (the slab engine then exchanges the planes)
+    assert not nd._nd_halo_eligible(dt, (84,) + tail, (3, 5, 4), (0, 0, 0))
+    assert not nd._nd_halo_eligible(np.dtype(np.float64), (84,) + tail, (9, 9, 9), (0, 0, 0))
