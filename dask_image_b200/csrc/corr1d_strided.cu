@@ -152,6 +152,41 @@ __device__ __forceinline__ void strided_tile_body(const CUtensorMap *tmap, const
     const int Lfull = L - REM;
     const int64_t col = col0 + tx * V;
     TS *const out_col = p.out + (o * p.n * p.inner + col);
+    if constexpr (kBox && OP == 0) {
+        // Exact integer box filter: a SLIDING window down a run of consecutive rows.  A thread owns the
+        // tile's rows [ty * run, (ty + 1) * run): it sums the first window once and then, per output
+        // row, adds the row that enters and subtracts the row that leaves -- 2 loads and 2 packed adds
+        // per output instead of `size`.  Window sums are integers below 2^23 held in floats, so every
+        // order of additions and subtractions is exact: the result does not depend on where a run, a
+        // tile or a slab starts (the partition-invariance a floating-point running sum would lose).
+        const int run = p.nb * R;
+        const int r0 = ty * run;
+        const TS *sbase = tile + r0 * W + tx * V;
+        typename TapAcc<T, V, OP>::type acc;
+        acc.zero();
+        for (int k = 0; k < L; ++k) acc.fma(load_block<T, TS, V>(sbase + k * W), T(1));
+        for (int j = 0; j < run; ++j) {
+            if (j > 0) {
+                acc.fma(load_block<T, TS, V>(sbase + (L - 1 + j) * W), T(1));
+                acc.fma(load_block<T, TS, V>(sbase + (j - 1) * W), T(-1));
+            }
+            const int64_t row = row0 + r0 + j;
+            if (col < p.inner && row < p.n) {
+                TS *dst = out_col + row * p.inner;
+                if constexpr (LDG) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v)
+                        if (col + v < p.inner) dst[v] = (TS)box_quotient_bits<T>(acc.get(v), p.qinv, p.qc0);
+                } else {
+                    T sums[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) sums[v] = acc.get(v);
+                    store_box_quotients<T, TS, V>(dst, sums, p.qinv, p.qc0);
+                }
+            }
+        }
+        return;
+    }
     for (int blk = 0; blk < p.nb; ++blk) {
         const int r0 = (blk * TY + ty) * R;
         const TS *sbase = tile + r0 * W + tx * V;
