@@ -37,7 +37,7 @@ EXPORTS = (
     "b200_correlate1d_pair", "b200_correlate1d_pair_eligible",
     "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_correlate_nd_halo", "b200_correlate_nd_halo_eligible",
-    "b200_last_kernel", "b200_last_error", "b200_version", "b200_launch_count",
+    "b200_shutdown", "b200_last_kernel", "b200_last_error", "b200_version", "b200_launch_count",
 )
 
 _lib = None
@@ -112,6 +112,8 @@ def load():
     for name in ("b200_last_kernel", "b200_last_error", "b200_version"):
         getattr(lib, name).argtypes = []
         getattr(lib, name).restype = ctypes.c_char_p
+    lib.b200_shutdown.argtypes = []
+    lib.b200_shutdown.restype = ci
     lib.b200_launch_count.argtypes = [ci]
     lib.b200_launch_count.restype = i64
     _lib = lib

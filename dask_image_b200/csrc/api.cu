@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstring>
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 namespace b200 {
 
@@ -49,6 +51,51 @@ int device_sm_count()
         cached[dev].store(v, std::memory_order_relaxed);
     }
     return v;
+}
+
+namespace {
+struct TableEntry {
+    int dev;
+    uint64_t hash, stamp;
+    std::vector<unsigned char> copy;
+    void *dptr;
+};
+std::mutex g_table_mu;
+std::vector<TableEntry> g_tables;
+uint64_t g_table_stamp = 0;
+}  // namespace
+
+const void *cached_device_table(const void *host, size_t bytes)
+{
+    int dev = 0;
+    if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return nullptr;
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char *b = (const unsigned char *)host;
+    for (size_t i = 0; i < bytes; ++i) h = (h ^ b[i]) * 1099511628211ull;
+    std::lock_guard<std::mutex> lk(g_table_mu);
+    for (auto &e : g_tables)
+        if (e.dev == dev && e.hash == h && e.copy.size() == bytes && memcmp(e.copy.data(), host, bytes) == 0) {
+            e.stamp = ++g_table_stamp;
+            return e.dptr;
+        }
+    if (g_tables.size() >= 32) {
+        size_t lru = 0;
+        for (size_t i = 1; i < g_tables.size(); ++i)
+            if (g_tables[i].stamp < g_tables[lru].stamp) lru = i;
+        cudaFree(g_tables[lru].dptr);      // (synchronises the device: no launch still reads the table)
+        g_tables.erase(g_tables.begin() + lru);
+    }
+    void *d = nullptr;
+    if (check_cuda(cudaMalloc(&d, bytes ? bytes : 1), "cudaMalloc (filter table)")) return nullptr;
+    if (check_cuda(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice), "cudaMemcpy (filter table)")) {
+        cudaFree(d);
+        return nullptr;
+    }
+    TableEntry e;
+    e.dev = dev; e.hash = h; e.stamp = ++g_table_stamp; e.dptr = d;
+    e.copy.assign(b, b + bytes);
+    g_tables.push_back(std::move(e));
+    return d;
 }
 
 static int check_common(const void *in, const void *out, int dtype, int ndim, const int64_t *shape,
@@ -462,6 +509,14 @@ int b200_combine(void *acc, const void *src, int dtype, int64_t n, int op, void 
     if (n < 0) return set_error(B200_EINVAL, "negative length");
     if (n > 0 && (!acc || !src)) return set_error(B200_EINVAL, "null device pointer");
     return launch_combine(acc, src, dtype, n, op, (cudaStream_t)stream);
+}
+
+int b200_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_table_mu);
+    for (auto &e : g_tables) cudaFree(e.dptr);
+    g_tables.clear();
+    return B200_OK;
 }
 
 const char *b200_last_kernel(void) { return tl_kernel; }

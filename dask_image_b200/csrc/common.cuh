@@ -372,4 +372,11 @@ int launch_minmaxnd_generic(const MinMaxNdArgs &a);
 
 int device_sm_count();
 
+// Device copy of a small host table (compacted tap / offset tables of the kernels whose tables do not
+// fit the parameter bank).  Tables are cached by content per device (a chunk-wise caller repeats the same
+// filter on every chunk): a miss costs one cudaMalloc and one synchronous upload, a hit costs a lookup --
+// no allocation, no copy and no host-device serialisation on the launch path.  At most 32 tables stay
+// resident (least recently used first out; freed in b200_shutdown()).  nullptr = CUDA error (set).
+const void *cached_device_table(const void *host, size_t bytes);
+
 }  // namespace b200

@@ -39,21 +39,17 @@ int launch_corrnd_int(const CorrNdArgs &a)
 {
     IntNdPlan pl{};
     if (plan_corrnd_int(a, pl) != 0) return -1;
-    IntTap *dev = nullptr;
-    const size_t bytes = sizeof(IntTap) * pl.taps.size();
-    B200_CUDA_TRY(cudaMallocAsync((void **)&dev, bytes, a.stream));
-    int rc = check_cuda(cudaMemcpyAsync(dev, pl.taps.data(), bytes, cudaMemcpyHostToDevice, a.stream),
-                        "corrnd_int taps upload");
-    if (!rc) {
-        pl.p.taps = dev;
-        switch (a.dtype) {
-        case B200_U8: rc = launch_nd_typed<uint8_t>(pl, a.stream); break;
-        case B200_I8: rc = launch_nd_typed<int8_t>(pl, a.stream); break;
-        case B200_U16: rc = launch_nd_typed<uint16_t>(pl, a.stream); break;
-        default: rc = launch_nd_typed<int16_t>(pl, a.stream); break;
-        }
+    // the tap table lives on the device, cached by content (no allocation or copy per launch)
+    const IntTap *dev = (const IntTap *)cached_device_table(pl.taps.data(), sizeof(IntTap) * pl.taps.size());
+    if (!dev) return B200_ECUDA;
+    int rc;
+    pl.p.taps = dev;
+    switch (a.dtype) {
+    case B200_U8: rc = launch_nd_typed<uint8_t>(pl, a.stream); break;
+    case B200_I8: rc = launch_nd_typed<int8_t>(pl, a.stream); break;
+    case B200_U16: rc = launch_nd_typed<uint16_t>(pl, a.stream); break;
+    default: rc = launch_nd_typed<int16_t>(pl, a.stream); break;
     }
-    cudaFreeAsync(dev, a.stream);
     if (rc) return rc;
     count_launch();
     note_kernel("corrnd_int");

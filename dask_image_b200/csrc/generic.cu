@@ -10,6 +10,7 @@
 // corrnd_tiled.cu) do not take.  Loads are coalesced along the contiguous
 // axis and overlapping windows are served by L1/L2.
 #include "common.cuh"
+#include <cstring>
 #include <vector>
 #include <cmath>
 
@@ -99,13 +100,11 @@ int launch_corr1d_generic(const Corr1dArgs &a)
     p.symmetric = classify_symmetry(a.w, a.nw);
     p.cval = a.cval;
     p.wdev = nullptr;
-    double *wdev = nullptr;
     if (a.nw <= kMaxTaps1D) {
         for (int i = 0; i < a.nw; ++i) p.w[i] = a.w[i];
     } else {
-        B200_CUDA_TRY(cudaMallocAsync((void **)&wdev, sizeof(double) * a.nw, a.stream));
-        B200_CUDA_TRY(cudaMemcpyAsync(wdev, a.w, sizeof(double) * a.nw, cudaMemcpyHostToDevice, a.stream));
-        p.wdev = wdev;
+        p.wdev = (const double *)cached_device_table(a.w, sizeof(double) * a.nw);
+        if (!p.wdev) return B200_ECUDA;
     }
     const int threads = 256;
     const int blocks = grid_for(p.total, threads);
@@ -117,7 +116,6 @@ int launch_corr1d_generic(const Corr1dArgs &a)
             corr1d_generic_kernel<T, int64_t><<<blocks, threads, 0, a.stream>>>(p);
         return check_cuda(cudaGetLastError(), "corr1d_generic launch");
     });
-    if (wdev) cudaFreeAsync(wdev, a.stream);
     if (rc) return rc;
     count_launch();
     note_kernel("corr1d_generic");
@@ -301,14 +299,17 @@ int launch_corrnd_generic(const CorrNdArgs &a)
         }
     }
     p.nnz = (int)tw.size();
-    char *dev = nullptr;
+    const char *dev = nullptr;
     size_t b_tw = sizeof(double) * tw.size(), b_lin = sizeof(int64_t) * tlin.size(),
            b_tk = sizeof(int32_t) * tk.size();
     if (p.nnz > 0) {
-        B200_CUDA_TRY(cudaMallocAsync((void **)&dev, b_tw + b_lin + b_tk, a.stream));
-        B200_CUDA_TRY(cudaMemcpyAsync(dev, tw.data(), b_tw, cudaMemcpyHostToDevice, a.stream));
-        B200_CUDA_TRY(cudaMemcpyAsync(dev + b_tw, tlin.data(), b_lin, cudaMemcpyHostToDevice, a.stream));
-        B200_CUDA_TRY(cudaMemcpyAsync(dev + b_tw + b_lin, tk.data(), b_tk, cudaMemcpyHostToDevice, a.stream));
+        // one blob {weights, linear offsets, per-axis offsets}, cached on the device by content
+        std::vector<unsigned char> blob(b_tw + b_lin + b_tk);
+        memcpy(blob.data(), tw.data(), b_tw);
+        memcpy(blob.data() + b_tw, tlin.data(), b_lin);
+        memcpy(blob.data() + b_tw + b_lin, tk.data(), b_tk);
+        dev = (const char *)cached_device_table(blob.data(), blob.size());
+        if (!dev) return B200_ECUDA;
     }
     p.tw = (const double *)dev;
     p.tlin = (const int64_t *)(dev + b_tw);
@@ -324,7 +325,6 @@ int launch_corrnd_generic(const CorrNdArgs &a)
             corrnd_generic_kernel<T, int64_t><<<blocks, threads, 0, a.stream>>>(p);
         return check_cuda(cudaGetLastError(), "corrnd_generic launch");
     });
-    if (dev) cudaFreeAsync(dev, a.stream);
     if (rc) return rc;
     count_launch();
     note_kernel("corrnd_generic");
@@ -508,12 +508,12 @@ int launch_minmaxnd_generic(const MinMaxNdArgs &a)
     }
     p.nnz = (int)tlin.size();
     if (p.nnz == 0) return set_error(B200_EINVAL, "All-zero footprint is not supported.");
-    char *dev = nullptr;
     const size_t b_lin = sizeof(int64_t) * tlin.size(), b_tk = sizeof(int32_t) * tk.size();
-    B200_CUDA_TRY(cudaMallocAsync((void **)&dev, b_lin + b_tk, a.stream));
-    B200_CUDA_TRY(cudaMemcpyAsync(dev, tlin.data(), b_lin, cudaMemcpyHostToDevice, a.stream));
-    B200_CUDA_TRY(cudaMemcpyAsync(dev + b_lin, tk.data(), b_tk, cudaMemcpyHostToDevice, a.stream));
-    // (pageable sources: cudaMemcpyAsync returns once they are staged, so the vectors may die)
+    std::vector<unsigned char> blob(b_lin + b_tk);
+    memcpy(blob.data(), tlin.data(), b_lin);
+    memcpy(blob.data() + b_lin, tk.data(), b_tk);
+    const char *dev = (const char *)cached_device_table(blob.data(), blob.size());
+    if (!dev) return B200_ECUDA;
     p.tlin = (const int64_t *)dev;
     p.tk = (const int32_t *)(dev + b_lin);
 
@@ -527,7 +527,6 @@ int launch_minmaxnd_generic(const MinMaxNdArgs &a)
             minmaxnd_generic_kernel<T, int64_t><<<blocks, threads, 0, a.stream>>>(p);
         return check_cuda(cudaGetLastError(), "minmaxnd_generic launch");
     });
-    cudaFreeAsync(dev, a.stream);
     if (rc) return rc;
     count_launch();
     note_kernel(a.is_max ? "maxnd_generic" : "minnd_generic");

@@ -821,11 +821,26 @@ def uniform_filter(input, size=3, output=None, mode="reflect", cval=0.0, origin=
 # --------------------------------------------------------------------------
 # N-D correlate / convolve
 # --------------------------------------------------------------------------
+_host_weights = {}
+
+
 def _weights_to_host(weights):
-    if isinstance(weights, B200Array):
-        return weights.to_numpy()
-    if isinstance(weights, torch.Tensor):
-        return weights.cpu().numpy()
+    """Host copy of N-D weights.  Device-resident weights (the reference requires the weights to be of the
+    image's array type, ref:dask_image/dispatch/_utils.py:23-25) would cost a device-to-host copy -- a stream
+    synchronisation -- on EVERY chunk call; the copy is remembered per tensor object and version."""
+    t = weights.tensor if isinstance(weights, B200Array) else weights
+    if isinstance(t, torch.Tensor):
+        import weakref
+
+        hit = _host_weights.get(id(t))
+        if hit is not None and hit[0]() is t and hit[1] == t._version:
+            return hit[2]
+        host = t.cpu().numpy()
+        host.flags.writeable = False
+        if len(_host_weights) >= 32:
+            _host_weights.clear()
+        _host_weights[id(t)] = (weakref.ref(t), t._version, host)
+        return host
     return np.asarray(weights)
 
 

@@ -237,6 +237,10 @@ int b200_minmax_filter_nd(const void *in, void *out, int dtype, int ndim,
                           int is_max, int mode, double cval, int64_t pad_lo,
                           int64_t pad_hi, unsigned flags, void *stream);
 
+/* frees the small device tables the library caches (compacted tap tables of the
+ * generic and integer N-D kernels); optional, safe to call at any time */
+int b200_shutdown(void);
+
 /* name of the kernel family the last successful call on this thread chose
  * ("corr1d_tma_strided_f32", "corr1d_generic", ...); for tests and profiling */
 const char *b200_last_kernel(void);
