@@ -16,11 +16,12 @@ resident input through the slab contract of the C ABI (``pad_lo`` / ``pad_hi``:
 the planes around it are simply resident), so the result is bit-identical to
 filtering the whole resident volume.
 
-This is a streaming path, not an out-of-core one: the input slab stays resident
-on the device while it is filtered (plus three output chunks and the scratch
-chunks), so a rank's slab must fit its GPU -- with 180 GB per B200 that is a
-~160 GB slab per rank; a larger slab raises ``MemoryError`` up front instead of
-failing somewhere inside the pipeline.
+When the volume fits the device (the benchmark case) the input stays resident
+while it is filtered.  A single-process volume that does NOT fit (or is given a
+smaller ``max_device_bytes``) is filtered out of core: axis-0 blocks travel with
+their halo planes through two device windows (``_run_out_of_core``).  A slab of
+a SHARDED volume must fit its GPU (~160 GB per rank); a larger one raises
+``MemoryError`` up front -- spread the volume over more ranks.
 
 Supported: every plan whose axis-0 passes read the plan's INPUT (gaussian
 filters and their derivative compositions, uniform_filter, laplace, N-D
@@ -68,9 +69,13 @@ class HostVolume:
     device : CUDA device to stream through (default: current)
     chunk_bytes : approximate size of one upload / compute / download unit (B200 / PCIe 5 scan,
         tools/e2e_scan.py: 128-512 MiB is the plateau)
+    max_device_bytes : device memory the filter may use (default: what is free).  A volume (one process, not
+        sharded) that does not fit is filtered OUT OF CORE: in axis-0 blocks that are uploaded with their halo
+        planes, filtered and downloaded on three streams, two blocks in flight -- same result, bit for bit.
     """
 
-    def __init__(self, array, out=None, device=None, chunk_bytes=256 << 20, global_shape=None, group=None):
+    def __init__(self, array, out=None, device=None, chunk_bytes=256 << 20, global_shape=None, group=None,
+                 max_device_bytes=None):
         self.tensor = _as_host_tensor(array)
         if self.tensor.dtype not in _TORCH_TO_NP:
             raise RuntimeError("data type not supported")
@@ -84,6 +89,8 @@ class HostVolume:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
         self.chunk_bytes = int(chunk_bytes)
+        # device memory the filter may use; None = what is free on the device when the filter runs
+        self.max_device_bytes = None if max_device_bytes is None else int(max_device_bytes)
         self.group = group
         self.world = self.rank = None
         self.global_shape = None
@@ -135,7 +142,7 @@ class HostVolume:
 
     def _result(self, h_out):
         return HostVolume(h_out, device=self.device, chunk_bytes=self.chunk_bytes,
-                          global_shape=self.global_shape, group=self.group)
+                          global_shape=self.global_shape, group=self.group, max_device_bytes=self.max_device_bytes)
 
     # ------------------------------------------------------------------
     def _run_plan(self, plan):
@@ -196,6 +203,23 @@ class HostVolume:
             if self.group is not None:
                 prev, nxt = dist.get_global_rank(self.group, prev), dist.get_global_rank(self.group, nxt)
 
+        # does the slab fit the device?  (resident input + three output chunks + scratch chunks when pipelined;
+        # input + output + scratch volumes otherwise)
+        cap_lo, cap_hi = (lo if has_prev else 0), (hi if has_next else 0)
+        need_bytes = ((cap_lo + n0 + cap_hi + 5 * C) if pipelined else 4 * n0) * plane_bytes
+        free_bytes = (torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev)
+                      - torch.cuda.memory_allocated(dev))
+        if self.max_device_bytes is not None:
+            free_bytes = min(free_bytes, self.max_device_bytes)
+        if need_bytes > free_bytes:
+            if not sharded and streamable:
+                self._run_out_of_core(plan, h_in, h_out, lo, hi, ring, free_bytes)
+                return result
+            raise MemoryError("HostVolume: %.1f GiB of device memory needed, %.1f GiB available on %s -- %s"
+                              % (need_bytes / 2 ** 30, free_bytes / 2 ** 30, dev,
+                                 "spread the volume over more ranks (global_shape=...)" if sharded else
+                                 "this filter runs along axis 0 after another pass and cannot be cut into blocks"))
+
         with torch.cuda.device(dev):
             cur = torch.cuda.current_stream(dev)
             if not pipelined:
@@ -213,13 +237,6 @@ class HostVolume:
                 cur.synchronize()
                 return result
 
-            cap_lo, cap_hi = (lo if has_prev else 0), (hi if has_next else 0)
-            need_bytes = (cap_lo + n0 + cap_hi + 5 * C) * plane_bytes
-            free_bytes = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-            if need_bytes > free_bytes:
-                raise MemoryError("HostVolume streams a slab that stays resident while it is filtered: %.1f GiB needed, "
-                                  "%.1f GiB free on %s -- spread the volume over more ranks (global_shape=...)"
-                                  % (need_bytes / 2 ** 30, free_bytes / 2 ** 30, dev))
             d_full = torch.empty((cap_lo + n0 + cap_hi,) + tail, dtype=h_in.dtype, device=dev)
             d_in = d_full[cap_lo:cap_lo + n0]
             nslot = 3
@@ -345,6 +362,100 @@ class HostVolume:
                 cur.wait_stream(s)
             cur.synchronize()
         return result
+
+
+def _run_out_of_core(self, plan, h_in, h_out, lo, hi, ring, budget_bytes):
+    """Filter a host volume that does not fit the device: axis-0 blocks of B planes, each uploaded with
+    the ``lo`` / ``hi`` halo planes around it (the volume's own planes; the opposite end's for mode='wrap';
+    none at a boundary of the volume, where the kernels fold by ``mode``), filtered through the slab
+    contract of the C ABI (``pad_lo`` / ``pad_hi`` = the halo planes resident around the block) and
+    downloaded -- upload of block k+1, filter of block k and download of block k-1 overlap on three
+    streams, two windows and two result buffers alternate.  Every voxel sees exactly the operation sequence
+    of the resident path: bit-identical result.  Extra PCIe traffic: (lo + hi) / B of the volume."""
+    dev, dt = self.device, self.dtype
+    n0 = int(h_in.shape[0])
+    tail = tuple(int(v) for v in h_in.shape[1:])
+    plane_bytes = max(1, int(np.prod(tail, dtype=np.int64)) * dt.itemsize)
+    need = 0
+    for passes, op in plan.chains:
+        nsteps = len(_nd._chain_steps(passes, (2,) + tail, dt, axis0_local=False))
+        for tgt in _nd._chain_targets(nsteps, op):
+            if tgt != "out":
+                need = max(need, tgt + 1)
+    planes = int(budget_bytes // plane_bytes)
+    B = (planes - 2 * (lo + hi)) // (4 + need)
+    if B < max(lo, hi, 1):
+        raise MemoryError("HostVolume: %.2f GiB of device memory cannot hold two blocks of %d planes plus halos"
+                          % (budget_bytes / 2 ** 30, max(lo, hi, 1)))
+    B = min(B, n0)
+    blocks = [(s, min(n0, s + B)) for s in range(0, n0, B)]
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        wins = [torch.empty((lo + B + hi,) + tail, dtype=h_in.dtype, device=dev) for _ in range(2)]
+        outs = [torch.empty((B,) + tail, dtype=h_in.dtype, device=dev) for _ in range(2)]
+        scratch = [torch.empty((B,) + tail, dtype=h_in.dtype, device=dev) for _ in range(need)]
+        s_up, s_cmp, s_down = (torch.cuda.Stream(dev) for _ in range(3))
+        for st in (s_up, s_cmp, s_down):
+            st.wait_stream(cur)
+        ev_cmp, ev_down = [None, None], [None, None]
+        for k, (b0, b1) in enumerate(blocks):
+            n, slot = b1 - b0, k % 2
+            w = wins[slot]
+            lo_eff = lo if (b0 > 0 or ring) else 0
+            hi_eff = hi if ring else min(hi, n0 - b1)
+            with torch.cuda.stream(s_up):
+                if ev_cmp[slot] is not None:
+                    s_up.wait_event(ev_cmp[slot])           # the filter of block k-2 has read this window
+                w[lo:lo + n].copy_(h_in[b0:b1], non_blocking=True)
+                if lo_eff:
+                    if b0 >= lo:
+                        w[0:lo].copy_(h_in[b0 - lo:b0], non_blocking=True)
+                    else:                                     # first block of a periodic volume
+                        for j in range(lo):
+                            w[j].copy_(h_in[(b0 - lo + j) % n0], non_blocking=True)
+                if hi_eff:
+                    if b1 + hi_eff <= n0:
+                        w[lo + n:lo + n + hi_eff].copy_(h_in[b1:b1 + hi_eff], non_blocking=True)
+                    else:                                     # last block of a periodic volume
+                        for j in range(hi_eff):
+                            w[lo + n + j].copy_(h_in[(b1 + j) % n0], non_blocking=True)
+                ev_up = torch.cuda.Event()
+                ev_up.record(s_up)
+            src, dst, shape, pad = w[lo:lo + n], outs[slot][:n], (n,) + tail, (lo_eff, hi_eff)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_up)
+                if ev_down[slot] is not None:
+                    s_cmp.wait_event(ev_down[slot])          # the download of block k-2 has left this buffer
+                if plan.extreme is not None:
+                    fp, origins, mode, is_max = plan.extreme
+                    _nd._launch_minmax_nd(src, dst, shape, dt, fp, origins, is_max, mode, plan.cval, pad)
+                elif plan.nd is not None:
+                    wts, origins, mode = plan.nd
+                    _nd._launch_correlate_nd(src, dst, shape, dt, wts, origins, mode, plan.cval, pad)
+                else:
+                    if plan.zero_out:
+                        dst.zero_()
+                    prov = {}
+                    scr = scratch if n == B else [t[:n] for t in scratch]
+                    for passes, op in plan.chains:
+                        if passes:
+                            _nd._run_chain(src, shape, dt, passes, plan.cval, dst, final_epilogue=op, pad=pad,
+                                           scratch=scr, prov=prov)
+                        else:
+                            _nd._launch_combine(dst, src, dt, op)
+                ev_cmp[slot] = torch.cuda.Event()
+                ev_cmp[slot].record(s_cmp)
+            with torch.cuda.stream(s_down):
+                s_down.wait_event(ev_cmp[slot])
+                h_out[b0:b1].copy_(dst, non_blocking=True)
+                ev_down[slot] = torch.cuda.Event()
+                ev_down[slot].record(s_down)
+        for st in (s_up, s_cmp, s_down):
+            cur.wait_stream(st)
+        cur.synchronize()
+
+
+HostVolume._run_out_of_core = _run_out_of_core
 
 
 def _chunk_of(chunks, plane):

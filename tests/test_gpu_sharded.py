@@ -431,3 +431,35 @@ def test_nd_halo_in_place_equals_whole_call(b200, mode):
     # weights whose staged planes are not 8-row aligned are refused (the slab engine then exchanges the planes)
     assert not nd._nd_halo_eligible(dt, (84,) + tail, (3, 5, 4), (0, 0, 0))
     assert not nd._nd_halo_eligible(np.dtype(np.float64), (84,) + tail, (9, 9, 9), (0, 0, 0))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_host_volume_out_of_core_equals_resident(b200, mode):
+    """A host volume that does not fit the device memory it is allowed (max_device_bytes) is filtered in axis-0
+    blocks that travel with their halo planes through two device windows: the result is the resident one, bit for
+    bit -- block seams, volume boundaries and the periodic ring (mode='wrap') included."""
+    rng = np.random.default_rng(31)
+    a = (rng.random((90, 24, 64)) - 0.3).astype(np.float32)
+    u = rng.integers(0, 65536, (75, 16, 32), dtype=np.uint16)
+    w3 = rng.random((3, 5, 4)) - 0.3
+    for arr in (a, u):
+        plane = int(np.prod(arr.shape[1:])) * arr.dtype.itemsize
+        cases = [("gaussian_filter", dict(sigma=2.0, mode=mode, cval=0.2)),
+                 ("uniform_filter", dict(size=(5, 3, 4), mode=mode, origin=(1, 0, -1))),
+                 ("gaussian_laplace", dict(sigma=1.0, mode=mode)),
+                 ("gaussian_gradient_magnitude", dict(sigma=1.5, mode=mode)),
+                 ("convolve", dict(weights=w3, mode=mode, cval=0.4, origin=(1, 0, -1)))]
+        for name, kw in cases:
+            f = getattr(b200.ndfilters, name)
+            kw1 = dict(kw)
+            if "weights" in kw1:
+                kw1["weights"] = b200.B200Array.from_numpy(kw1["weights"])
+            one = f(b200.B200Array.from_numpy(arr), **kw1).to_numpy()
+            for budget_planes in (150, 400):          # ~10 blocks / ~3 blocks
+                hv = b200.HostVolume(arr.copy(), max_device_bytes=budget_planes * plane)
+                got = f(hv, **kw).to_numpy()
+                assert np.array_equal(got, one), "%s %s %s budget=%d: %d voxels differ" % (
+                    name, arr.dtype, mode, budget_planes, int((got != one).sum()))
+    # a budget that cannot hold two blocks and their halos is refused
+    with pytest.raises(MemoryError):
+        b200.ndfilters.gaussian_filter(b200.HostVolume(a.copy(), max_device_bytes=20 * 24 * 64 * 4), 2.0)
