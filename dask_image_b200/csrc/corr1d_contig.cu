@@ -140,7 +140,14 @@ corr1d_contig_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 // warp 64 x 8; the lanes of a quarter warp sit on 8 different rows, which the
 // odd 16-byte pitch spreads over all bank groups.  TS = uint16_t / uint8_t is
 // the exact integer box filter (taps 0/1, quotient epilogue).
-template <typename TS, int NT, bool LDG = false>
+// alignment zeros in front of a box of `size` taps with origin 0 (the TMA box starts on a 16-byte boundary of
+// the storage type: EB elements)
+constexpr int box_lead(int size, int EB) { return (size / 2 + EB - 1) / EB * EB - size / 2; }
+constexpr int box_taps(int size, int EB) { return (box_lead(size, EB) + size + EB - 1) / EB * EB; }
+
+// BS > 0 (integer box filter of BS taps, origin 0): the window slides along the thread's 16 outputs --
+// BS adds for the first, one add and one subtract for every further one -- instead of BS taps each.
+template <typename TS, int NT, bool LDG = false, int BS = 0>
 __global__ void __launch_bounds__(256, 3)
 corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
                             const __grid_constant__ Corr1dTmaParams<float, TS> p)
@@ -205,6 +212,22 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
             }
         }
         float2 e[8], o[9];
+        float slide[R];
+        if constexpr (BS > 0) {
+            // sliding window: sums of integers below 2^23 are exact in fp32 in any order
+            static_assert(kBox, "the sliding window is the exact integer box filter");
+            constexpr int BL = box_lead(BS, EB);
+            static_assert(BL + BS <= NT && R - 1 + BL + BS <= NF, "window inside the staged row");
+            float sacc = 0.f;
+#pragma unroll
+            for (int tt = 0; tt < BS; ++tt) sacc += f[BL + tt];
+            slide[0] = sacc;
+#pragma unroll
+            for (int j = 1; j < R; ++j) {
+                sacc = (sacc + f[j - 1 + BL + BS]) - f[j - 1 + BL];
+                slide[j] = sacc;
+            }
+        } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) e[i] = make_float2(0.f, 0.f);
 #pragma unroll
@@ -228,13 +251,18 @@ corr1d_contig_static_kernel(const __grid_constant__ CUtensorMap tmap,
                     o[i] = __ffma2_rn(make_float2(f[2 * i - 1 + tt], f[2 * i + tt]), w2, o[i]);
             }
         }
+        }
         const int64_t row = row0 + rg * 8 + r_in;
         if (patch_live && row < nrows && x < p.n) {
             TS *dst0 = out_thr + (int64_t)(rg * 8) * p.n;
             float res[R];
 #pragma unroll
-            for (int j = 0; j < R; ++j)
-                res[j] = ((j & 1) ? e[j >> 1].y : e[j >> 1].x) + ((j & 1) ? o[(j + 1) >> 1].x : o[j >> 1].y);
+            for (int j = 0; j < R; ++j) {
+                if constexpr (BS > 0)
+                    res[j] = slide[j];
+                else
+                    res[j] = ((j & 1) ? e[j >> 1].y : e[j >> 1].x) + ((j & 1) ? o[(j + 1) >> 1].x : o[j >> 1].y);
+            }
             if constexpr (LDG) {
                 // unaligned rows: element stores, the row may end anywhere
                 const bool reads_out = epilogue_reads_out(p.epilogue);
@@ -367,7 +395,7 @@ static int launch_contig_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al,
     return B200_OK;
 }
 
-template <typename TS, int NT, bool LDG = false>
+template <typename TS, int NT, bool LDG = false, int BS = 0>
 static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int lo_al, int lead)
 {
     constexpr int EB = 16 / (int)sizeof(TS);   // elements per 16 bytes of storage
@@ -426,7 +454,7 @@ static int launch_contig_static_cfg(const Corr1dArgs &a, const BoxInfo &box, int
     for (int i = 0; i < NT; ++i) p.w[i] = 0.f;
     for (int i = 0; i < a.nw; ++i) p.w[lead + i] = (float)a.w[i];
 
-    auto kern = corr1d_contig_static_kernel<TS, NT, LDG>;
+    auto kern = corr1d_contig_static_kernel<TS, NT, LDG, BS>;
     const size_t smem = stage_bytes + 128;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     kern<<<(unsigned)num_tiles, threads == 128 ? 128 : 256, smem, a.stream>>>(tmap, p);
@@ -524,6 +552,20 @@ static int launch_contig_box(const Corr1dArgs &a, const BoxInfo &box)
     const int lo = a.nw / 2 + a.origin;
     const int lo_al = (lo + U16B - 1) / U16B * U16B;
     const int lead = lo_al - lo;
+    if (!ldg && a.origin == 0 && env_int("B200_BOX_SLIDE", 1)) {
+        // common windows: the sliding-window instantiation (window size and alignment zeros at compile time)
+#define B200_SLIDE_CASE(S)                                                                              \
+    case S:                                                                                             \
+        return launch_contig_static_cfg<TS, box_taps(S, U16B), false, S>(a, box, lo_al, lead);
+        switch (a.nw) {
+        B200_SLIDE_CASE(2) B200_SLIDE_CASE(3) B200_SLIDE_CASE(4) B200_SLIDE_CASE(5) B200_SLIDE_CASE(6)
+        B200_SLIDE_CASE(7) B200_SLIDE_CASE(8) B200_SLIDE_CASE(9) B200_SLIDE_CASE(10) B200_SLIDE_CASE(11)
+        B200_SLIDE_CASE(12) B200_SLIDE_CASE(13) B200_SLIDE_CASE(14) B200_SLIDE_CASE(15) B200_SLIDE_CASE(16)
+        B200_SLIDE_CASE(17) B200_SLIDE_CASE(19) B200_SLIDE_CASE(21) B200_SLIDE_CASE(25) B200_SLIDE_CASE(31)
+        default: break;
+        }
+#undef B200_SLIDE_CASE
+    }
     if (ldg || env_int("B200_TMA_STATIC", 1)) {
         // compile-time tap engine: taps padded to whole 16-byte blocks of storage
         const int la = (lead + a.nw + U16B - 1) / U16B * U16B;
