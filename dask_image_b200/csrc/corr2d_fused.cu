@@ -288,6 +288,29 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tin, in
     const int rw = 4 * warp;                           // first tile row of this warp
     float *const wrows = mid + rw * PI;
     const int rl = lane & 3;
+    // Epilogues that read `out` (laplace / gradient-magnitude sums) fetch the previous values of this warp's
+    // four rows -- 2 x 16 bytes per lane and row -- in one batch after the tap loops.  (Requesting them BEFORE
+    // the tap loops hides their latency but keeps 32 more registers live: 104 registers, 2 CTAs per SM instead
+    // of 3, and every fused launch -- C2 included -- ran 10-15 % slower on the B200.)
+    constexpr bool EARLY_PREV = false;
+    float4 pv[4][2];
+    auto load_prev = [&]() {
+        const bool reads_out = epilogue_reads_out(p.epilogue);
+        const int nvec = tile_cols >> 2;
+        const float *const dst0 = p.out + ((int64_t)z * ny + y0 + rw) * nx + x0;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int v = lane + 32 * u;
+                pv[rr][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (reads_out && y0 + rw + rr < ny && v < nvec)
+                    pv[rr][u] = *reinterpret_cast<const float4 *>(dst0 + (int64_t)rr * nx + 4 * v);
+            }
+    };
+    if constexpr (EARLY_PREV) {
+        if (!bulk) load_prev();
+    }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         const int cg = pass * 8 + 2 * (lane >> 3) + ((lane >> 2) & 1);
@@ -344,26 +367,34 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tin, in
         }
         return;
     }
+    if constexpr (TMA) {
+        // 16-byte vectors, lanes along the row: coalesced read-modify-write with the epilogue.  All eight
+        // loads of the previous values (4 rows x 2 vectors per lane) are issued before the first is used:
+        // one round trip to L2 / HBM per tile instead of eight in a row.
+        if constexpr (!EARLY_PREV) load_prev();
+        const int nvec = tile_cols >> 2;
+        float *const dst0 = p.out + ((int64_t)z * ny + y0 + rw) * nx + x0;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int v = lane + 32 * u;
+                if (y0 + rw + rr < ny && v < nvec) {
+                    float4 r4 = *reinterpret_cast<const float4 *>(wrows + rr * PI + 4 * v);
+                    r4.x = apply_epilogue<float>(p.epilogue, pv[rr][u].x, r4.x);
+                    r4.y = apply_epilogue<float>(p.epilogue, pv[rr][u].y, r4.y);
+                    r4.z = apply_epilogue<float>(p.epilogue, pv[rr][u].z, r4.z);
+                    r4.w = apply_epilogue<float>(p.epilogue, pv[rr][u].w, r4.w);
+                    *reinterpret_cast<float4 *>(dst0 + (int64_t)rr * nx + 4 * v) = r4;
+                }
+            }
+        return;
+    }
     const bool reads_out = epilogue_reads_out(p.epilogue);
     for (int rr = 0; rr < 4 && y0 + rw + rr < ny; ++rr) {
         const float *srcr = wrows + rr * PI;
         float *dst = p.out + ((int64_t)z * ny + y0 + rw + rr) * nx + x0;
-        if constexpr (TMA) {
-            // 16-byte vectors, lanes along the row: coalesced read-modify-write with the epilogue
-            for (int v = lane; v < (tile_cols >> 2); v += 32) {
-                float4 r4 = *reinterpret_cast<const float4 *>(srcr + 4 * v);
-                float4 *d4 = reinterpret_cast<float4 *>(dst + 4 * v);
-                if (p.epilogue != B200_EPI_STORE) {
-                    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (reads_out) pv = *d4;
-                    r4.x = apply_epilogue<float>(p.epilogue, pv.x, r4.x);
-                    r4.y = apply_epilogue<float>(p.epilogue, pv.y, r4.y);
-                    r4.z = apply_epilogue<float>(p.epilogue, pv.z, r4.z);
-                    r4.w = apply_epilogue<float>(p.epilogue, pv.w, r4.w);
-                }
-                *d4 = r4;
-            }
-        } else if (p.epilogue == B200_EPI_STORE) {
+        if (p.epilogue == B200_EPI_STORE) {
             for (int c = lane; c < tile_cols; c += 32) dst[c] = srcr[c];
         } else {
             for (int c = lane; c < tile_cols; c += 32)
