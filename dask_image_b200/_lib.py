@@ -35,6 +35,7 @@ EXPORTS = (
     "b200_minmax_filter1d", "b200_minmax_filter_nd", "b200_correlate1d_halo", "b200_correlate1d_halo_eligible",
     "b200_enable_peer_access", "b200_uniform_filter1d_halo", "b200_uniform_filter1d_halo_eligible",
     "b200_correlate1d_pair", "b200_correlate1d_pair_eligible",
+    "b200_uniform_filter1d_pair", "b200_uniform_filter1d_pair_eligible",
     "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_correlate_nd_halo", "b200_correlate_nd_halo_eligible",
     "b200_shutdown", "b200_last_kernel", "b200_last_error", "b200_version", "b200_launch_count",
@@ -88,6 +89,10 @@ def load():
     lib.b200_correlate1d_pair.restype = ci
     lib.b200_correlate1d_pair_eligible.argtypes = [ci, ci, i64p, i64, i64, i64, i64]
     lib.b200_correlate1d_pair_eligible.restype = ci
+    lib.b200_uniform_filter1d_pair.argtypes = [vp, vp, ci, ci, i64p, i64, ci, i64, i64, ci, i64, dbl, cu, vp]
+    lib.b200_uniform_filter1d_pair.restype = ci
+    lib.b200_uniform_filter1d_pair_eligible.argtypes = [ci, ci, i64p, i64, i64, ci, i64, i64, ci, dbl]
+    lib.b200_uniform_filter1d_pair_eligible.restype = ci
     lib.b200_correlate_nd_halo.argtypes = [vp, vp, ci, ci, i64p, dblp, i64p, i64p, ci, dbl, vp, i64, vp, i64, cu, vp]
     lib.b200_correlate_nd_halo.restype = ci
     lib.b200_correlate_nd_halo_eligible.argtypes = [ci, ci, i64p, i64p, i64p]

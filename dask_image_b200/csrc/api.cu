@@ -363,6 +363,47 @@ int b200_uniform_filter1d_halo_eligible(int dtype, int64_t n, int64_t inner, int
     return uniform1d_peer_eligible(dtype, n, inner, (int)size, (int)origin, mode, cval);
 }
 
+int b200_uniform_filter1d_pair_eligible(int dtype, int ndim, const int64_t *shape, int64_t size1, int64_t origin1,
+                                        int mode1, int64_t size2, int64_t origin2, int mode2, double cval)
+{
+    if (ndim < 2 || ndim > B200_MAXDIM || !shape) return 0;
+    if (size1 < 1 || size1 > 4096 || size2 < 1 || size2 > 4096) return 0;
+    return uniform2d_fused_eligible(dtype, shape[ndim - 2], shape[ndim - 1], (int)size1, (int)origin1, mode1,
+                                    (int)size2, (int)origin2, mode2, cval);
+}
+
+int b200_uniform_filter1d_pair(const void *in, void *out, int dtype, int ndim, const int64_t *shape, int64_t size1,
+                               int mode1, int64_t origin1, int64_t size2, int mode2, int64_t origin2, double cval,
+                               unsigned flags, void *stream)
+{
+    int64_t total;
+    if (int rc = check_common(in, out, dtype, ndim, shape, mode1, &total)) return rc;
+    if (mode2 < B200_MODE_NEAREST || mode2 > B200_MODE_CONSTANT)
+        return set_error(B200_EMODE, "boundary mode not supported");
+    if (ndim < 2) return set_error(B200_EINVAL, "a pass pair needs at least two axes");
+    if (size1 < 1 || size1 > (1 << 20) || size2 < 1 || size2 > (1 << 20))
+        return set_error(B200_EINVAL, "incorrect filter size");
+    if (size1 / 2 + origin1 < 0 || size1 / 2 + origin1 >= size1 || size2 / 2 + origin2 < 0 ||
+        size2 / 2 + origin2 >= size2)
+        return set_error(B200_EORIGIN, "invalid origin");
+    if (total == 0) return B200_OK;
+    if (flags & (B200_FLAG_EXACT | B200_FLAG_NO_TMA))
+        return set_error(B200_EINVAL, "not eligible: the fused box-filter pair is a TMA-tiled kernel");
+    Uniform2dArgs a;
+    a.in = in; a.out = out; a.dtype = dtype;
+    a.outer = 1;
+    for (int d = 0; d < ndim - 2; ++d) a.outer *= shape[d];
+    a.ny = shape[ndim - 2]; a.nx = shape[ndim - 1];
+    a.size1 = (int)size1; a.origin1 = (int)origin1; a.mode1 = mode1;
+    a.size2 = (int)size2; a.origin2 = (int)origin2; a.mode2 = mode2;
+    a.cval = cval; a.flags = flags; a.stream = (cudaStream_t)stream;
+    int rc = launch_uniform2d_fused(a);
+    if (rc < 0)
+        return set_error(B200_EINVAL, "not eligible: no fused kernel for this pair of box filters "
+                                      "(u8 / u16, equal odd sizes, origin 0, 16-byte rows and pointers)");
+    return rc;
+}
+
 int b200_correlate_nd(const void *in, void *out, int dtype, int ndim, const int64_t *shape,
                       const double *weights, const int64_t *wshape, const int64_t *origins, int mode,
                       double cval, int64_t pad_lo, int64_t pad_hi, unsigned flags, void *stream)

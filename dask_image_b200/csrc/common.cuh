@@ -306,6 +306,25 @@ int launch_uniform1d_generic(const Uniform1dArgs &a);
 int launch_uniform1d_peer(const Uniform1dArgs &u, const void *peer_lo, int n_lo, const void *peer_hi, int n_hi);
 int uniform1d_peer_eligible(int dtype, int64_t n, int64_t inner, int size, int origin, int mode, double cval);
 int launch_uniform1d_fast(const Uniform1dArgs &a);
+// can the exact float epilogue (tile_common.cuh: box_quotient_bits) serve this integer box filter?
+bool uniform_box_ok(int dtype, int size, int mode, double cval);
+
+// the box-filter passes along the last two axes of a u8 / u16 array in one launch (corr2d_fused.cu)
+struct Uniform2dArgs {
+    const void *in;
+    void *out;
+    int dtype;
+    int64_t outer, ny, nx;
+    int size1, origin1, mode1;   // axis ndim-2
+    int size2, origin2, mode2;   // axis ndim-1
+    double cval;
+    unsigned flags;
+    cudaStream_t stream;
+};
+// -1 = no fused kernel (the caller runs the two passes one by one)
+int launch_uniform2d_fused(const Uniform2dArgs &a);
+int uniform2d_fused_eligible(int dtype, int64_t ny, int64_t nx, int size1, int origin1, int mode1, int size2, int origin2,
+                             int mode2, double cval);
 
 struct CorrNdArgs {
     const void *in;

@@ -104,7 +104,7 @@ static bool uniform_int_exact(int size, int64_t vmax)
 }
 
 // can the exact float epilogue serve this integer box filter?
-static bool uniform_box_ok(int dtype, int size, int mode, double cval)
+bool uniform_box_ok(int dtype, int size, int mode, double cval)
 {
     if (dtype != B200_U16 && dtype != B200_U8) return false;
     const int64_t vmax = dtype == B200_U16 ? 65535 : 255;

@@ -41,8 +41,8 @@ constexpr int fused_buffer_floats(int l1, int tyo, int nwarps)
 }
 
 struct Corr2dParams {
-    const float *in;
-    float *out;
+    const void *in;       // float, or the storage type of the exact integer box filter
+    void *out;
     int outer, ny, nx;
     int lo1, mode1;       // rows read above an output row: nw1/2 + origin1
     int lo2, mode2;       // staged column 0 is array column x0 - lo2 (lo2 = reach in front, rounded up to 4)
@@ -53,7 +53,17 @@ struct Corr2dParams {
     float cval;
     float w1[kFusedMaxTaps];   // taps along axis ndim-2
     float w2[kFusedMaxTaps];   // taps along axis ndim-1, alignment zeros in front
+    float qinv, qc0;      // integer box filter: the quotient epilogue (tile_common.cuh: box_quotient_bits)
+#ifdef B200_BOX_DEBUG
+    int dbg;              // bring-up: leave the tile after stage `dbg`
+#endif
 };
+
+#ifdef B200_BOX_DEBUG
+#define B200_BOX_STAGE(k) do { if constexpr (BOX) { if (p.dbg == (k)) return; } } while (0)
+#else
+#define B200_BOX_STAGE(k) do { } while (0)
+#endif
 
 // 32-bit form of ext_index() (common.cuh) for tile coordinates: |i| and n are below 2^31 here
 __device__ __forceinline__ int ext_index32(int i, int n, int mode)
@@ -84,12 +94,46 @@ __device__ __forceinline__ int ext_index32(int i, int n, int mode)
     }
 }
 
+// Exact integer box filter (TS = unsigned char / unsigned short): the staged box stays in the storage
+// type (half / a quarter of the shared-memory traffic of a float tile -- the float form of this kernel
+// ran at 90 % of the shared-memory pipe) and is widened in registers where phase A reads it: an
+// integer v < 2^23 is the low mantissa of 2^23 + v, i.e. one byte permute and one exact subtraction
+// per element, no I2F.
+template <typename TS>
+__device__ __forceinline__ float4 box_load4(const TS *ptr)
+{
+    constexpr float kTwo23 = 8388608.f;
+    float4 v;
+    if constexpr (sizeof(TS) == 2) {
+        const uint2 w = *reinterpret_cast<const uint2 *>(ptr);
+        v.x = __uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7410)) - kTwo23;
+        v.y = __uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7432)) - kTwo23;
+        v.z = __uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7410)) - kTwo23;
+        v.w = __uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7432)) - kTwo23;
+    } else {
+        static_assert(sizeof(TS) == 1, "8- or 16-bit storage");
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(ptr);
+        v.x = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)) - kTwo23;
+        v.y = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)) - kTwo23;
+        v.z = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)) - kTwo23;
+        v.w = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)) - kTwo23;
+    }
+    return v;
+}
+
+// bytes of the staged box in the storage type, rounded up so that the float tile behind it stays aligned
+template <typename TS>
+constexpr int box_raw_bytes(int tyin)
+{
+    return (tyin * kFusedPX * (int)sizeof(TS) + 127) / 128 * 128;
+}
+
 // Edge tiles (and every tile of the plain-load variant): fill the staged elements that lie outside
 // the array -- TMA zero-fills them -- through the extension maps of the two axes.  Kept out of line:
 // interior CTAs never come here, and the hot path keeps its registers.
-template <int TYIN, int NTHR, bool TMA>
-__device__ __noinline__ void fused_stage_edges(const Corr2dParams &p, float *tin, int *row_src, int *col_src,
-                                               const float *plane, int gx0, int gy0, uint64_t *full_bar,
+template <int TYIN, int NTHR, bool TMA, typename TS>
+__device__ __noinline__ void fused_stage_edges(const Corr2dParams &p, TS *tin, int *row_src, int *col_src,
+                                               const TS *plane, int gx0, int gy0, uint64_t *full_bar,
                                                uint32_t parity)
 {
     constexpr int PX = kFusedPX;
@@ -121,7 +165,7 @@ __device__ __noinline__ void fused_stage_edges(const Corr2dParams &p, float *tin
                 if (c >= cols_need) continue;
                 const int i = k < r_lo ? k : r_hi + (k - r_lo);
                 const int ry = row_src[i], cx = col_src[c];
-                tin[i * PX + c] = (ry < 0 || cx < 0) ? p.cval : plane[(int64_t)ry * nx + cx];
+                tin[i * PX + c] = (ry < 0 || cx < 0) ? (TS)p.cval : plane[(int64_t)ry * nx + cx];
             }
             // columns outside the array on the rows inside it
             const int nbad_c = c_lo + (cols_need - c_hi);
@@ -131,10 +175,10 @@ __device__ __noinline__ void fused_stage_edges(const Corr2dParams &p, float *tin
                 const int c = k < c_lo ? k : c_hi + (k - c_lo);
                 const int i = r_lo + r;
                 const int cx = col_src[c];
-                tin[i * PX + c] = cx < 0 ? p.cval : plane[(int64_t)(gy0 + i) * nx + cx];
+                tin[i * PX + c] = cx < 0 ? (TS)p.cval : plane[(int64_t)(gy0 + i) * nx + cx];
             }
         }
-    } else {
+    } else if constexpr (std::is_same<TS, float>::value) {
         // rows that are not 16-byte multiples (or an unaligned base): the same tile, staged with
         // plain 4-byte loads through the extension maps
         // plain 4-byte asynchronous copies (all of the tile in flight at once): straight from the rows
@@ -202,10 +246,16 @@ __device__ __forceinline__ void pair_barrier(int idx)
 // the intermediate tile and the staged results alias it (ALIAS) or follow it.  `parity` is the phase
 // of `full_bar` this tile's load completes.  Shared by the one-tile-per-CTA kernel and the persistent,
 // double-buffered one.
-template <int L1, int NTX, int TYO, int NWARPS, int RA, bool ALIAS, bool TMA>
-__device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tin, int *row_src, int *col_src,
+template <int L1, int NTX, int TYO, int NWARPS, int RA, bool ALIAS, bool TMA, typename TS = float, bool SLIDE = false>
+__device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tile, int *row_src, int *col_src,
                                            uint64_t *full_bar, uint32_t parity, int x0, int y0, int z)
 {
+    // BOX: the exact integer box filter (uniform_filter on u8 / u16).  The tile holds the storage values
+    // as floats, window sums stay below 2^23 and are exact in any order, and each pass ends with the
+    // quotient epilogue of the unfused kernels (box_quotient_bits) -- bit-exact by construction.
+    constexpr bool BOX = !std::is_same<TS, float>::value;
+    static_assert(!BOX || TMA, "the integer box pair is staged by TMA only");
+    static_assert(!SLIDE || BOX, "sliding sums are exact for the integer box filter only");
     constexpr int PX = kFusedPX, PI = kFusedPI;
     constexpr int TYIN = TYO + L1 - 1;
     constexpr int NTHR = NWARPS * 32;
@@ -215,7 +265,11 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tin, in
     static_assert(TYO % RA == 0 && TYO % 8 == 0, "tile rows");
     static_assert(!ALIAS || ITEMS_A == NWARPS, "aliased tiles need one phase-A item per warp");
     static_assert(16 * (NCG - 1) + NF <= PI, "row window inside the intermediate tile");
-    float *mid = ALIAS ? tin : tin + TYIN * PX;
+    // the staged box: floats, or the storage type of the integer box filter with the float intermediate
+    // tile behind it (not aliased: phase A stores every row as soon as it is complete)
+    TS *const tin = reinterpret_cast<TS *>(tile);
+    float *mid = BOX ? reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(tile) + box_raw_bytes<TS>(TYIN))
+                     : (ALIAS ? tile : tile + TYIN * PX);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int nx = p.nx, ny = p.ny;
@@ -224,42 +278,100 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tin, in
     // a tile whose staged box lies inside the array needs nothing beyond the TMA load
     const bool edge = !TMA || gx0 < 0 || gy0 < 0 || gx0 + PX > nx || gy0 + TYIN > ny;
     if (edge) {
-        fused_stage_edges<TYIN, NTHR, TMA>(p, tin, row_src, col_src, p.in + (int64_t)z * ny * nx, gx0, gy0,
-                                           full_bar, parity);
+        fused_stage_edges<TYIN, NTHR, TMA, TS>(p, tin, row_src, col_src,
+                                               static_cast<const TS *>(p.in) + (int64_t)z * ny * nx, gx0, gy0,
+                                               full_bar, parity);
     } else {
         __syncthreads();
         // one warp polls the mbarrier; the others sleep at the CTA barrier
         if (tid < 32) mbar_wait(full_bar, parity);
         __syncthreads();
+        B200_BOX_STAGE(1);
     }
+    B200_BOX_STAGE(2);
 
     // ---- phase A: the pass along axis ndim-2, tin -> mid ----------------------
     for (int item = warp; item < ITEMS_A; item += NWARPS) {
         const int rg = item >> 1, half = item & 1;
         const int cv = (half * 32 + lane) * 4;
-        const float *s = tin + rg * RA * PX + cv;
-        float2 acc[RA][2];
+        if constexpr (BOX) {
+            // integer box filter: rows are widened to float as they are loaded (box_load4), every output row is
+            // stored as soon as it is complete -- the stored first pass, trunc(sum / size) exactly as
+            // box_quotient_bits() rounds it, kept as a float (scalar FADD / FFMA as in the one-pass kernels)
+            const TS *s = tin + rg * RA * PX + cv;
+            float *d = mid + rg * RA * PI + cv;
+            auto quot = [&](float sum) { return fmaf(sum + p.qc0, p.qinv, 12582912.f) - 12582912.f; };
+            auto put = [&](int j, float2 a, float2 b) {
+                *reinterpret_cast<float4 *>(d + j * PI) = make_float4(quot(a.x), quot(a.y), quot(b.x), quot(b.y));
+            };
+            if constexpr (SLIDE) {
+                // running column sums: row j + 1 = row j + (the row entering the window - the row leaving it);
+                // the L1 rows of the window stay in registers, so every staged row is loaded and widened once
+                float4 v[RA + L1 - 1];
+                v[0] = box_load4<TS>(s);
+                float2 r0 = make_float2(v[0].x, v[0].y), r1 = make_float2(v[0].z, v[0].w);
 #pragma unroll
-        for (int j = 0; j < RA; ++j) acc[j][0] = acc[j][1] = make_float2(0.f, 0.f);
+                for (int i = 1; i < L1; ++i) {
+                    v[i] = box_load4<TS>(s + i * PX);
+                    r0 = __fadd2_rn(r0, make_float2(v[i].x, v[i].y));
+                    r1 = __fadd2_rn(r1, make_float2(v[i].z, v[i].w));
+                }
+                put(0, r0, r1);
 #pragma unroll
-        for (int i = 0; i < RA + L1 - 1; ++i) {
-            const float4 v = *reinterpret_cast<const float4 *>(s + i * PX);
+                for (int j = 1; j < RA; ++j) {
+                    v[j + L1 - 1] = box_load4<TS>(s + (j + L1 - 1) * PX);
+                    const float4 vn = v[j + L1 - 1], vo = v[j - 1];
+                    const float2 m1 = make_float2(-1.f, -1.f);
+                    r0 = __fadd2_rn(r0, __ffma2_rn(make_float2(vo.x, vo.y), m1, make_float2(vn.x, vn.y)));
+                    r1 = __fadd2_rn(r1, __ffma2_rn(make_float2(vo.z, vo.w), m1, make_float2(vn.z, vn.w)));
+                    put(j, r0, r1);
+                }
+            } else {
+                float2 acc[RA][2];
 #pragma unroll
-            for (int j = 0; j < RA; ++j) {
-                const int k = i - j;
-                if (k >= 0 && k < L1) {
-                    const float wk = p.w1[k];
-                    const float2 w2 = make_float2(wk, wk);
-                    acc[j][0] = __ffma2_rn(make_float2(v.x, v.y), w2, acc[j][0]);
-                    acc[j][1] = __ffma2_rn(make_float2(v.z, v.w), w2, acc[j][1]);
+                for (int j = 0; j < RA; ++j) acc[j][0] = acc[j][1] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < RA + L1 - 1; ++i) {
+                    const float4 v = box_load4<TS>(s + i * PX);
+#pragma unroll
+                    for (int j = 0; j < RA; ++j) {
+                        const int k = i - j;
+                        if (k >= 0 && k < L1) {
+                            const float2 w2 = make_float2(p.w1[k], p.w1[k]);
+                            acc[j][0] = __ffma2_rn(make_float2(v.x, v.y), w2, acc[j][0]);
+                            acc[j][1] = __ffma2_rn(make_float2(v.z, v.w), w2, acc[j][1]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < RA; ++j) put(j, acc[j][0], acc[j][1]);
+            }
+        } else {
+            const float *s = tile + rg * RA * PX + cv;
+            float2 acc[RA][2];
+#pragma unroll
+            for (int j = 0; j < RA; ++j) acc[j][0] = acc[j][1] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < RA + L1 - 1; ++i) {
+                const float4 v = *reinterpret_cast<const float4 *>(s + i * PX);
+#pragma unroll
+                for (int j = 0; j < RA; ++j) {
+                    const int k = i - j;
+                    if (k >= 0 && k < L1) {
+                        const float wk = p.w1[k];
+                        const float2 w2 = make_float2(wk, wk);
+                        acc[j][0] = __ffma2_rn(make_float2(v.x, v.y), w2, acc[j][0]);
+                        acc[j][1] = __ffma2_rn(make_float2(v.z, v.w), w2, acc[j][1]);
+                    }
                 }
             }
-        }
-        if constexpr (ALIAS) __syncthreads();   // every warp has read its rows of tin
-        float *d = mid + rg * RA * PI + cv;
+            if constexpr (ALIAS) __syncthreads();   // every warp has read its rows of tin
+            float *d = mid + rg * RA * PI + cv;
 #pragma unroll
-        for (int j = 0; j < RA; ++j)
-            *reinterpret_cast<float4 *>(d + j * PI) = make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y);
+            for (int j = 0; j < RA; ++j)
+                *reinterpret_cast<float4 *>(d + j * PI) =
+                    make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y);
+        }
     }
     // ---- phase B: the pass along the contiguous axis, mid -> out ---------------
     // Warp w owns rows [4w, 4w + 4) of the tile from here to the end: their intermediate values were
@@ -283,7 +395,8 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tin, in
         // for the CTA, and an SM has 32 -- two resident CTAs instead of four)
         pair_barrier<NWARPS / 2>(warp >> 1);
     }
-    const bool bulk = TMA && p.epilogue == B200_EPI_STORE;
+    B200_BOX_STAGE(3);
+    const bool bulk = BOX || (TMA && p.epilogue == B200_EPI_STORE);
     const int tile_cols = min(nx - x0, p.ncg * 16);   // columns of this tile inside the array
     const int rw = 4 * warp;                           // first tile row of this warp
     float *const wrows = mid + rw * PI;
@@ -293,11 +406,11 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tin, in
     // the tap loops hides their latency but keeps 32 more registers live: 104 registers, 2 CTAs per SM instead
     // of 3, and every fused launch -- C2 included -- ran 10-15 % slower on the B200.)
     constexpr bool EARLY_PREV = false;
-    float4 pv[4][2];
-    auto load_prev = [&]() {
+    [[maybe_unused]] float4 pv[4][2];
+    [[maybe_unused]] auto load_prev = [&]() {
         const bool reads_out = epilogue_reads_out(p.epilogue);
         const int nvec = tile_cols >> 2;
-        const float *const dst0 = p.out + ((int64_t)z * ny + y0 + rw) * nx + x0;
+        const float *const dst0 = static_cast<const float *>(p.out) + ((int64_t)z * ny + y0 + rw) * nx + x0;
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
@@ -321,9 +434,29 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tin, in
         if (live) {
 #pragma unroll
             for (int b = 0; b < NF / 4; ++b) {
+                if constexpr (SLIDE) {
+                    if (4 * b + 3 < NTX - L1) continue;     // in front of every window
+                }
                 const float4 v = *reinterpret_cast<const float4 *>(srow + 4 * b);
                 f[4 * b] = v.x; f[4 * b + 1] = v.y; f[4 * b + 2] = v.z; f[4 * b + 3] = v.w;
             }
+            if constexpr (SLIDE) {
+                // running row sums over the window [i + LEAD, i + NTX) of output i
+                constexpr int LEAD = NTX - L1;
+                static_assert(LEAD >= 0 && LEAD < 16, "alignment zeros in front of the contiguous window");
+                float rs = f[LEAD];
+#pragma unroll
+                for (int t = LEAD + 1; t < NTX; ++t) rs += f[t];
+                float r[16];
+                r[0] = rs;
+#pragma unroll
+                for (int i = 1; i < 16; ++i) {
+                    rs += f[i + NTX - 1] - f[i + LEAD - 1];
+                    r[i] = rs;
+                }
+#pragma unroll
+                for (int h = 0; h < 4; ++h) res[h] = make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]);
+            } else {
             float2 e[8], o[9];
 #pragma unroll
             for (int i = 0; i < 8; ++i) e[i] = make_float2(0.f, 0.f);
@@ -351,29 +484,49 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tin, in
                 res[h].z = e[2 * h + 1].x + o[2 * h + 1].y;
                 res[h].w = e[2 * h + 1].y + o[2 * h + 2].x;
             }
+            }
         }
         __syncwarp();      // every window of this pass has been read
+        B200_BOX_STAGE(4);
         if (live) {
+            if constexpr (BOX) {
+                // quotients in the storage type, packed at the head of the row: output column c of the tile
+                // sits at element c of a TS row (pass 0 fills the first 128 elements = at most 256 bytes,
+                // below float column 128 where the windows of pass 1 start)
+                TS *orow = reinterpret_cast<TS *>(wrows + rl * PI) + cg * 16;
 #pragma unroll
-            for (int h = 0; h < 4; ++h) *reinterpret_cast<float4 *>(srow + 4 * h) = res[h];
+                for (int h = 0; h < 2; ++h) {
+                    const float s8[8] = {res[2 * h].x, res[2 * h].y, res[2 * h].z, res[2 * h].w,
+                                         res[2 * h + 1].x, res[2 * h + 1].y, res[2 * h + 1].z, res[2 * h + 1].w};
+                    store_box_quotients<float, TS, 8>(orow + 8 * h, s8, p.qinv, p.qc0);
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) *reinterpret_cast<float4 *>(srow + 4 * h) = res[h];
+            }
         }
     }
+    B200_BOX_STAGE(5);
     if (bulk) fence_proxy_async();   // the stores above become visible to the bulk-copy engine
     __syncwarp();
+    B200_BOX_STAGE(6);
     if (bulk) {
         if (lane < 4 && y0 + rw + lane < ny) {
-            bulk_store_row(p.out + ((int64_t)z * ny + y0 + rw + lane) * nx + x0, wrows + lane * PI, tile_cols * 4);
+            bulk_store_row(static_cast<TS *>(p.out) + ((int64_t)z * ny + y0 + rw + lane) * nx + x0, wrows + lane * PI,
+                           tile_cols * (int)sizeof(TS));
             bulk_store_wait_read();    // the rows must stay intact until the engine has read them
         }
         return;
     }
-    if constexpr (TMA) {
+    if constexpr (BOX) {
+        return;
+    } else if constexpr (TMA) {
         // 16-byte vectors, lanes along the row: coalesced read-modify-write with the epilogue.  All eight
         // loads of the previous values (4 rows x 2 vectors per lane) are issued before the first is used:
         // one round trip to L2 / HBM per tile instead of eight in a row.
         if constexpr (!EARLY_PREV) load_prev();
         const int nvec = tile_cols >> 2;
-        float *const dst0 = p.out + ((int64_t)z * ny + y0 + rw) * nx + x0;
+        float *const dst0 = static_cast<float *>(p.out) + ((int64_t)z * ny + y0 + rw) * nx + x0;
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
@@ -389,21 +542,23 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tin, in
                 }
             }
         return;
-    }
-    const bool reads_out = epilogue_reads_out(p.epilogue);
-    for (int rr = 0; rr < 4 && y0 + rw + rr < ny; ++rr) {
-        const float *srcr = wrows + rr * PI;
-        float *dst = p.out + ((int64_t)z * ny + y0 + rw + rr) * nx + x0;
-        if (p.epilogue == B200_EPI_STORE) {
-            for (int c = lane; c < tile_cols; c += 32) dst[c] = srcr[c];
-        } else {
-            for (int c = lane; c < tile_cols; c += 32)
-                dst[c] = apply_epilogue<float>(p.epilogue, reads_out ? dst[c] : 0.f, srcr[c]);
+    } else {
+        const bool reads_out = epilogue_reads_out(p.epilogue);
+        for (int rr = 0; rr < 4 && y0 + rw + rr < ny; ++rr) {
+            const float *srcr = wrows + rr * PI;
+            float *dst = static_cast<float *>(p.out) + ((int64_t)z * ny + y0 + rw + rr) * nx + x0;
+            if (p.epilogue == B200_EPI_STORE) {
+                for (int c = lane; c < tile_cols; c += 32) dst[c] = srcr[c];
+            } else {
+                for (int c = lane; c < tile_cols; c += 32)
+                    dst[c] = apply_epilogue<float>(p.epilogue, reads_out ? dst[c] : 0.f, srcr[c]);
+            }
         }
     }
 }
 
-template <int L1, int NTX, int TYO, int NWARPS, int RA, bool ALIAS, int MINB, bool TMA>
+template <int L1, int NTX, int TYO, int NWARPS, int RA, bool ALIAS, int MINB, bool TMA, typename TS = float,
+          bool SLIDE = false>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
 corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Corr2dParams p)
 {
@@ -420,11 +575,11 @@ corr2d_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         if (threadIdx.x == 0) {
             mbar_init(&full_bar, 1);
             fence_barrier_init();
-            mbar_arrive_expect_tx(&full_bar, (uint32_t)(TYIN * PX * (int)sizeof(float)));
+            mbar_arrive_expect_tx(&full_bar, (uint32_t)(TYIN * PX * (int)sizeof(TS)));
             tma_load_3d(tin, &tmap, &full_bar, x0 - p.lo2, y0 - p.lo1, z);
         }
     }
-    fused_tile<L1, NTX, TYO, NWARPS, RA, ALIAS, TMA>(p, tin, row_src, col_src, &full_bar, 0u, x0, y0, z);
+    fused_tile<L1, NTX, TYO, NWARPS, RA, ALIAS, TMA, TS, SLIDE>(p, tin, row_src, col_src, &full_bar, 0u, x0, y0, z);
 }
 
 // The same tiles on a PERSISTENT grid (as many CTAs as fit the device, each walking the tile list with
@@ -484,7 +639,8 @@ struct FusedCfg {
     int tyo, nwarps, ra, alias, minb;
 };
 
-template <int L1, int NTX, int TYO, int NWARPS, int RA, bool ALIAS, int MINB, bool TMA>
+template <int L1, int NTX, int TYO, int NWARPS, int RA, bool ALIAS, int MINB, bool TMA, typename TS = float,
+          bool SLIDE = false>
 static int launch_fused_cfg(const Corr2dArgs &a, const Corr2dParams &p0)
 {
     constexpr int NCG = (kFusedPX - (NTX - 1)) / 16;
@@ -498,22 +654,25 @@ static int launch_fused_cfg(const Corr2dArgs &a, const Corr2dParams &p0)
     if (a.outer > 65535 || p.y_tiles > 65535) return -1;   // grid = (x tiles, y tiles, planes)
     const size_t in_bytes = (size_t)TYIN * kFusedPX * sizeof(float);
     const size_t mid_bytes = (size_t)TYO * kFusedPI * sizeof(float);
-    const size_t smem = (ALIAS ? (in_bytes > mid_bytes ? in_bytes : mid_bytes) : in_bytes + mid_bytes) + 128;
+    const size_t smem = std::is_same<TS, float>::value
+                            ? (ALIAS ? (in_bytes > mid_bytes ? in_bytes : mid_bytes) : in_bytes + mid_bytes) + 128
+                            : (size_t)box_raw_bytes<TS>(TYIN) + mid_bytes + 128;
     if (smem + 2048 > kSmemPerSm) return -1;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if constexpr (TMA) {
         uint64_t dims[3] = {(uint64_t)a.nx, (uint64_t)a.ny, (uint64_t)a.outer};
-        uint64_t strides[2] = {(uint64_t)a.nx * 4, (uint64_t)a.nx * 4 * (uint64_t)a.ny};
+        uint64_t strides[2] = {(uint64_t)a.nx * sizeof(TS), (uint64_t)a.nx * sizeof(TS) * (uint64_t)a.ny};
         uint32_t bx[3] = {(uint32_t)kFusedPX, (uint32_t)TYIN, 1u};
-        if (encode_tensor_map(&tmap, B200_F32, (void *)a.in, 3, dims, strides, bx) != 0) return -1;
+        if (encode_tensor_map(&tmap, dtype_code<TS>(), (void *)a.in, 3, dims, strides, bx) != 0) return -1;
     }
-    auto kern = corr2d_fused_kernel<L1, NTX, TYO, NWARPS, RA, ALIAS, MINB, TMA>;
+    auto kern = corr2d_fused_kernel<L1, NTX, TYO, NWARPS, RA, ALIAS, MINB, TMA, TS, SLIDE>;
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn - 2048));
     kern<<<dim3((unsigned)p.x_tiles, (unsigned)p.y_tiles, (unsigned)a.outer), NWARPS * 32, smem, a.stream>>>(tmap, p);
     B200_CUDA_TRY(cudaGetLastError());
     count_launch();
-    note_kernel(TMA ? "corr2d_fused_tma_f32" : "corr2d_fused_ldg_f32");
+    if constexpr (std::is_same<TS, float>::value) note_kernel(TMA ? "corr2d_fused_tma_f32" : "corr2d_fused_ldg_f32");
+    else note_kernel(sizeof(TS) == 2 ? "uniform2d_fused_tma_u16" : "uniform2d_fused_tma_u8");
     return B200_OK;
 }
 
@@ -592,10 +751,13 @@ static bool fused_pair_compiled(int l1, int ntx)
     return false;
 }
 
-static void fused_geometry(int nw2, int origin2, int *lo2_al, int *lead, int *ntx)
+// `align` = elements per 16 bytes: the staged box starts lo2_al columns in front of the tile, and TMA wants
+// the byte offset of that column to be a multiple of 16 (a float tile: 4 elements; uint16: 8; uint8: 16 --
+// a misaligned inner coordinate faults with "illegal instruction")
+static void fused_geometry(int nw2, int origin2, int *lo2_al, int *lead, int *ntx, int align = 4)
 {
     const int lo2 = nw2 / 2 + origin2;
-    *lo2_al = (lo2 + 3) / 4 * 4;
+    *lo2_al = (lo2 + align - 1) / align * align;
     *lead = *lo2_al - lo2;
     *ntx = *lead + nw2;
 }
@@ -619,7 +781,7 @@ int launch_corr2d_fused(const Corr2dArgs &a)
 
     Corr2dParams p;
     memset(&p, 0, sizeof(p));
-    p.in = (const float *)a.in; p.out = (float *)a.out;
+    p.in = a.in; p.out = a.out;
     p.outer = (int)a.outer; p.ny = (int)a.ny; p.nx = (int)a.nx;
     p.lo1 = a.nw1 / 2 + a.origin1; p.mode1 = a.mode1; p.hi1 = a.nw1 - 1 - p.lo1;
     p.lo2 = lo2_al; p.mode2 = a.mode2; p.hi2 = ntx - 1 - lo2_al;
@@ -638,6 +800,86 @@ int launch_corr2d_fused(const Corr2dArgs &a)
     B200_FUSED_PAIRS(X)
 #undef X
     return -1;
+}
+
+// ---------------------------------------------------------------------------
+// the exact integer box filter (uniform_filter on u8 / u16) along the last two axes in one launch
+// ---------------------------------------------------------------------------
+// isotropic odd sizes with origin 0 (the (L1, NTX) geometry of the gaussian pairs); the running-sum
+// form costs the same for every size
+#define B200_BOX_PAIRS_U16(X) X(3, 10) X(5, 11) X(7, 12) X(9, 13) X(11, 14) X(13, 15) X(15, 16) X(17, 17)
+#define B200_BOX_PAIRS_U8(X) X(3, 18) X(5, 19) X(7, 20) X(9, 21) X(11, 22) X(13, 23) X(15, 24) X(17, 25)
+
+int uniform2d_fused_eligible(int dtype, int64_t ny, int64_t nx, int size1, int origin1, int mode1, int size2, int origin2,
+                             int mode2, double cval)
+{
+    if (dtype != B200_U16 && dtype != B200_U8) return 0;
+    if (size1 != size2 || origin1 != 0 || origin2 != 0 || !(size1 & 1)) return 0;
+    if (ny < 1 || nx < 1 || ny >= (1ll << 31) || nx >= (1ll << 31)) return 0;
+    if ((nx * (dtype == B200_U16 ? 2 : 1)) % 16) return 0;          // TMA rows and bulk row stores
+    if (!uniform_box_ok(dtype, size1, mode1, cval) || !uniform_box_ok(dtype, size2, mode2, cval)) return 0;
+    int lo2_al, lead, ntx;
+    fused_geometry(size2, 0, &lo2_al, &lead, &ntx, dtype == B200_U16 ? 8 : 16);
+#define X(A, B) if (size1 == A && ntx == B) return 1;
+    if (dtype == B200_U16) {
+        B200_BOX_PAIRS_U16(X)
+    } else {
+        B200_BOX_PAIRS_U8(X)
+    }
+#undef X
+    return 0;
+}
+
+static int launch_uniform2d_u16(const Corr2dArgs &a, const Corr2dParams &p, int ntx)
+{
+    // B200_BOX2D_SLIDE=0: the direct form (one add per tap) of the 7-wide filter, kept for the A/B
+    if (env_int("B200_BOX2D_SLIDE", 1) == 0 && a.nw1 == 7 && ntx == 12)
+        return launch_fused_cfg<7, 12, 32, 8, 8, true, 4, true, unsigned short, false>(a, p);
+#define X(A, B) \
+    if (a.nw1 == A && ntx == B) return launch_fused_cfg<A, B, 32, 8, 8, true, 4, true, unsigned short, true>(a, p);
+    B200_BOX_PAIRS_U16(X)
+#undef X
+    return -1;
+}
+
+static int launch_uniform2d_u8(const Corr2dArgs &a, const Corr2dParams &p, int ntx)
+{
+#define X(A, B) \
+    if (a.nw1 == A && ntx == B) return launch_fused_cfg<A, B, 32, 8, 8, true, 4, true, unsigned char, true>(a, p);
+    B200_BOX_PAIRS_U8(X)
+#undef X
+    return -1;
+}
+
+int launch_uniform2d_fused(const Uniform2dArgs &u)
+{
+    if (!uniform2d_fused_eligible(u.dtype, u.ny, u.nx, u.size1, u.origin1, u.mode1, u.size2, u.origin2, u.mode2, u.cval))
+        return -1;
+    if (u.outer >= (1ll << 31) || ((uintptr_t)u.in & 15) || ((uintptr_t)u.out & 15) || (u.flags & B200_FLAG_NO_TMA))
+        return -1;
+    int lo2_al, lead, ntx;
+    fused_geometry(u.size2, u.origin2, &lo2_al, &lead, &ntx, u.dtype == B200_U16 ? 8 : 16);
+    Corr2dArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = u.in; a.out = u.out; a.dtype = u.dtype; a.outer = u.outer; a.ny = u.ny; a.nx = u.nx;
+    a.nw1 = u.size1; a.nw2 = u.size2; a.mode1 = u.mode1; a.mode2 = u.mode2; a.cval = u.cval;
+    a.epilogue = B200_EPI_STORE; a.flags = u.flags; a.stream = u.stream;
+    Corr2dParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = u.in; p.out = u.out;
+    p.outer = (int)u.outer; p.ny = (int)u.ny; p.nx = (int)u.nx;
+    p.lo1 = u.size1 / 2; p.mode1 = u.mode1; p.hi1 = u.size1 - 1 - p.lo1;
+    p.lo2 = lo2_al; p.mode2 = u.mode2; p.hi2 = ntx - 1 - lo2_al;
+    p.epilogue = B200_EPI_STORE;
+    p.cval = (float)u.cval;
+    p.qinv = 1.0f / (float)u.size1;
+    p.qc0 = 0.5f - 0.5f * (float)u.size1;
+#ifdef B200_BOX_DEBUG
+    p.dbg = env_int("B200_BOX_DBG", 0);
+#endif
+    for (int i = 0; i < u.size1; ++i) p.w1[i] = 1.f;
+    for (int i = 0; i < u.size2; ++i) p.w2[lead + i] = 1.f;
+    return u.dtype == B200_U16 ? launch_uniform2d_u16(a, p, ntx) : launch_uniform2d_u8(a, p, ntx);
 }
 
 }  // namespace b200

@@ -140,8 +140,20 @@ def _launch_correlate1d(src, dst, shape, np_dtype, axis, weights, mode, cval, or
 
 def _launch_correlate1d_pair(src, dst, shape, np_dtype, ps1, ps2, cval, epilogue=_lib.EPI_STORE, flags=None):
     """The passes ``ps1`` (axis ndim-2) and ``ps2`` (axis ndim-1) in one launch
-    (corr2d_fused.cu); bit-identical to the two launches."""
+    (corr2d_fused.cu); bit-identical to the two launches.  Two correlations
+    (float32) or two box filters (uint8 / uint16)."""
     lib = _lib.load()
+    if ps1.kind == "uniform":
+        if epilogue != _lib.EPI_STORE:
+            raise RuntimeError("only correlation passes have a fused epilogue")
+        with _on_device(src):
+            rc = lib.b200_uniform_filter1d_pair(
+                src.data_ptr(), dst.data_ptr(), _dtype_code(np_dtype), len(shape), _lib.i64_array(shape),
+                int(ps1.size), _lib.mode_code(ps1.mode), int(ps1.origin),
+                int(ps2.size), _lib.mode_code(ps2.mode), int(ps2.origin),
+                float(cval), int(_default_flags if flags is None else flags), _stream_ptr(src))
+        _lib.check(rc)
+        return
     (w1, p1), (w2, p2) = ps1.prepared, ps2.prepared
     with _on_device(src):
         rc = lib.b200_correlate1d_pair(
@@ -162,16 +174,26 @@ def set_pair_fusion(on):
     return old
 
 
-def _pair_eligible(shape, np_dtype, ps1, ps2, flags=None):
+def _pair_eligible(shape, np_dtype, ps1, ps2, flags=None, cval=0.0, aligned=True):
     """Can the consecutive passes ``ps1``, ``ps2`` run as one fused launch?  Depends
     on the dtype, the LAST TWO extents and the two filters only -- never on the
-    leading extents, so every slab / chunk of a volume takes the same path."""
-    if not _FUSE_PAIRS or np_dtype != np.float32 or len(shape) < 2:
+    leading extents, so every slab / chunk of a volume takes the same path.
+    ``aligned`` = the buffers of the chain start on 16-byte boundaries (the
+    integer box pair has no plain-load variant)."""
+    if not _FUSE_PAIRS or len(shape) < 2:
         return False
-    if ps1.kind != "corr" or ps2.kind != "corr" or ps1.axis != len(shape) - 2 or ps2.axis != len(shape) - 1:
+    if ps1.kind != ps2.kind or ps1.axis != len(shape) - 2 or ps2.axis != len(shape) - 1:
         return False
     fl = _default_flags if flags is None else flags
     if fl & (_lib.FLAG_EXACT | _lib.FLAG_NO_TMA):
+        return False
+    if ps1.kind == "uniform":
+        if not aligned or np_dtype not in (np.uint8, np.uint16):
+            return False
+        return bool(_lib.load().b200_uniform_filter1d_pair_eligible(
+            _dtype_code(np_dtype), len(shape), _lib.i64_array(shape), int(ps1.size), int(ps1.origin),
+            _lib.mode_code(ps1.mode), int(ps2.size), int(ps2.origin), _lib.mode_code(ps2.mode), float(cval)))
+    if ps1.kind != "corr" or np_dtype != np.float32:
         return False
     return bool(_lib.load().b200_correlate1d_pair_eligible(
         _dtype_code(np_dtype), len(shape), _lib.i64_array(shape), len(ps1.weights), int(ps1.origin),
@@ -181,20 +203,20 @@ def _pair_eligible(shape, np_dtype, ps1, ps2, flags=None):
 _steps_cache = {}
 
 
-def _chain_steps(passes, shape, np_dtype, flags=None, axis0_local=True):
+def _chain_steps(passes, shape, np_dtype, flags=None, axis0_local=True, cval=0.0, aligned=True):
     """Group the 1-D passes of a chain into launches: ``[(pass,)]`` or, where the
     fused kernel applies, ``[(pass, pass)]`` for the passes along the last two
     axes.  ``axis0_local`` = False says axis 0 reaches beyond the resident planes
     (slab halos / streamed chunks): a pass along axis 0 then stays on its own."""
     key = (tuple(ps.sig for ps in passes), len(shape), tuple(shape[-2:]), np_dtype, flags, _default_flags,
-           axis0_local, _FUSE_PAIRS)
+           axis0_local, _FUSE_PAIRS, float(cval), bool(aligned))
     hit = _steps_cache.get(key)
     if hit is not None:
         return hit
     steps, i = [], 0
     while i < len(passes):
         if (i + 1 < len(passes) and (axis0_local or passes[i].axis != 0)
-                and _pair_eligible(shape, np_dtype, passes[i], passes[i + 1], flags)):
+                and _pair_eligible(shape, np_dtype, passes[i], passes[i + 1], flags, cval, aligned)):
             steps.append((passes[i], passes[i + 1]))
             i += 2
         else:
@@ -487,7 +509,8 @@ def _run_chain(x_tensor, shape, np_dtype, passes, cval, out_tensor, final_epilog
     of scipy's 9 passes -- same arithmetic, computed once."""
     scratch = scratch if scratch is not None else []
     src, src_pad = x_tensor, pad
-    steps = _chain_steps(passes, shape, np_dtype, flags, axis0_local=tuple(pad) == (0, 0))
+    steps = _chain_steps(passes, shape, np_dtype, flags, axis0_local=tuple(pad) == (0, 0), cval=cval,
+                         aligned=(x_tensor.data_ptr() | out_tensor.data_ptr()) % 16 == 0)
     targets = _chain_targets(len(steps), final_epilogue)
     sig = ()
     for i, step in enumerate(steps):

@@ -566,7 +566,8 @@ class ShardedVolume:
             # passes along the last two axes pair up into one fused launch where the kernel exists
             # (never the axis-0 pass of a sharded volume: it reaches into the neighbours' planes)
             fuse_ok = hasattr(be, "correlate1d_pair")
-            steps = (_nd._chain_steps(passes, shape, dt, flags, axis0_local=self.world == 1) if fuse_ok
+            steps = (_nd._chain_steps(passes, shape, dt, flags, axis0_local=self.world == 1, cval=plan.cval)
+                     if fuse_ok
                      else [(ps,) for ps in passes])
             targets = _nd._chain_targets(len(steps), op)
             sig = ()

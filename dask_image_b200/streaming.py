@@ -243,7 +243,7 @@ class HostVolume:
             d_out = [torch.empty((C,) + tail, dtype=h_in.dtype, device=dev) for _ in range(nslot)]
             need = 0
             for passes, op in plan.chains:
-                nsteps = len(_nd._chain_steps(passes, (C,) + tail, dt, axis0_local=False))
+                nsteps = len(_nd._chain_steps(passes, (C,) + tail, dt, axis0_local=False, cval=plan.cval))
                 for tgt in _nd._chain_targets(nsteps, op):
                     if tgt != "out":
                         need = max(need, tgt + 1)
@@ -378,7 +378,7 @@ def _run_out_of_core(self, plan, h_in, h_out, lo, hi, ring, budget_bytes):
     plane_bytes = max(1, int(np.prod(tail, dtype=np.int64)) * dt.itemsize)
     need = 0
     for passes, op in plan.chains:
-        nsteps = len(_nd._chain_steps(passes, (2,) + tail, dt, axis0_local=False))
+        nsteps = len(_nd._chain_steps(passes, (2,) + tail, dt, axis0_local=False, cval=plan.cval))
         for tgt in _nd._chain_targets(nsteps, op):
             if tgt != "out":
                 need = max(need, tgt + 1)

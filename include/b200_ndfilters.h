@@ -187,6 +187,27 @@ int b200_uniform_filter1d_halo_eligible(int dtype, int64_t n, int64_t inner,
                                         int64_t size, int64_t origin, int mode,
                                         double cval);
 
+/* Two consecutive b200_uniform_filter1d passes in ONE launch: along axis ndim-2
+ * (size1, mode1, origin1), then along axis ndim-1 (size2, mode2, origin2) -- the
+ * tail of scipy's uniform_filter loop (scipy/ndimage/_filters.py:1613-1617: one
+ * uniform_filter1d per axis, each pass stored in the array dtype).  uint8 /
+ * uint16 only: the first pass's trunc(sum / size) is taken in shared memory
+ * exactly as the stored pass would hold it, so the result is bit-identical to
+ * the two calls at half their HBM traffic.  Needs equal odd sizes, origin 0,
+ * rows that are 16-byte multiples and 16-byte aligned pointers; returns
+ * B200_EINVAL ("not eligible") otherwise.  The _eligible query is host-only and
+ * depends on the dtype, the last two extents and the filters alone. */
+int b200_uniform_filter1d_pair(const void *in, void *out, int dtype, int ndim,
+                               const int64_t *shape, int64_t size1, int mode1,
+                               int64_t origin1, int64_t size2, int mode2,
+                               int64_t origin2, double cval, unsigned flags,
+                               void *stream);
+int b200_uniform_filter1d_pair_eligible(int dtype, int ndim,
+                                        const int64_t *shape, int64_t size1,
+                                        int64_t origin1, int mode1,
+                                        int64_t size2, int64_t origin2,
+                                        int mode2, double cval);
+
 /* replaces _nd_image.correlate (scipy/ndimage/_filters.py:1305); `weights` has
  * shape `wshape` (ndim entries, C order), taps with |w| <= DBL_EPSILON are
  * skipped as scipy does; convolve = flipped weights + adjusted origins,

@@ -165,3 +165,104 @@ def test_pair_abi_direct_and_not_eligible(b200):
     bad = ndimage._Pass("corr", 2, "mirror", weights=np.ones(19))
     with pytest.raises(RuntimeError, match="not eligible"):
         ndimage._launch_correlate1d_pair(x, out, a.shape, a.dtype, ps1, bad, 0.0)
+
+
+# ---- the exact integer box filter along the last two axes in one launch -----------------------------
+# rows are 16-byte multiples (the pair is TMA-staged only); ragged tiles in both directions
+BOX_SHAPES = {
+    np.uint16: [(40, 64), (33, 264), (70, 520), (3, 37, 104), (2, 130, 248), (5, 8, 8), (2, 2, 65, 304), (1, 300, 16)],
+    np.uint8: [(40, 64), (33, 272), (70, 528), (3, 37, 112), (2, 130, 256), (5, 16, 16), (2, 2, 65, 304)],
+}
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint8])
+def test_fused_box_pair_bit_exact(b200, dtype, mode):
+    """uniform_filter on u8 / u16: the box passes along the last two axes run as ONE launch and the result is
+    bit-exact against scipy's (oracle) and equal to the pass-by-pass path."""
+    import scipy.ndimage as ndi
+
+    info = np.iinfo(dtype)
+    for shape in BOX_SHAPES[dtype]:
+        rng = np.random.default_rng(hash((shape, mode, info.max)) % (2 ** 32))
+        a = rng.integers(0, info.max + 1, shape).astype(dtype)
+        a.flat[:: 7] = info.max          # the largest window sums
+        d = dev(b200, a)
+        for size in (3, 5, 7, 9, 11, 13, 15, 17):
+            cval = 7.0 if mode == "constant" else 0.0
+            fused, k, nf, plain, npl = both(b200, b200.ndimage.uniform_filter, d, size, mode=mode, cval=cval)
+            assert k == "uniform2d_fused_tma_" + np.dtype(dtype).name.replace("int", ""), (k, shape, size)
+            assert nf == npl - 1 and nf == len(shape) - 1
+            ref = ndi.uniform_filter(a, size, mode=mode, cval=cval)
+            assert np.array_equal(fused, plain), (shape, size, int((fused != plain).sum()))
+            assert_parity(fused, ref, exact=True, what="%s size=%d" % (shape, size))
+
+
+def test_fused_box_pair_direct_form_equals_running_sums(b200, monkeypatch):
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, 65536, (3, 70, 520)).astype(np.uint16)
+    d = dev(b200, a)
+    want = b200.ndimage.uniform_filter(d, 7).to_numpy()
+    monkeypatch.setenv("B200_BOX2D_SLIDE", "0")
+    got = b200.ndimage.uniform_filter(d, 7).to_numpy()
+    assert np.array_equal(got, want)
+
+
+def test_fused_box_pair_eligibility(b200):
+    """What does NOT take the pair (and still gives scipy's values pass by pass): even sizes, origins, unequal
+    sizes, rows that are not 16-byte multiples, floats, signed types, constant mode with a non-integer cval."""
+    import scipy.ndimage as ndi
+
+    from dask_image_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 65536, (3, 40, 64)).astype(np.uint16)
+    cases = [
+        (a, dict(size=4)), (a, dict(size=7, origin=1)), (a, dict(size=(3, 7, 5))),
+        (a[:, :, :63].copy(), dict(size=7)), (a.astype(np.int16), dict(size=7)),
+        (a, dict(size=7, mode="constant", cval=0.5)),
+    ]
+    for arr, kw in cases:
+        got = b200.ndimage.uniform_filter(dev(b200, arr), **kw).to_numpy()
+        assert not _lib.last_kernel().startswith("uniform2d_fused"), kw
+        assert_parity(got, ndi.uniform_filter(arr, **kw), exact=True, what=str(kw))
+    # sizes (1, 7, 7): the first axis is skipped, the pair still applies; (7, 7, 1) leaves no pair
+    got = b200.ndimage.uniform_filter(dev(b200, a), (1, 7, 7)).to_numpy()
+    assert _lib.last_kernel() == "uniform2d_fused_tma_u16"
+    assert_parity(got, ndi.uniform_filter(a, (1, 7, 7)), exact=True)
+    lib = _lib.load()
+    sh = _lib.i64_array(a.shape)
+    assert lib.b200_uniform_filter1d_pair_eligible(2, 3, sh, 7, 0, 2, 7, 0, 2, 0.0) == 1
+    assert lib.b200_uniform_filter1d_pair_eligible(8, 3, sh, 7, 0, 2, 7, 0, 2, 0.0) == 0      # float32
+    assert lib.b200_uniform_filter1d_pair_eligible(2, 3, sh, 7, 0, 2, 9, 0, 2, 0.0) == 0
+    assert lib.b200_uniform_filter1d_pair_eligible(2, 3, sh, 19, 0, 2, 19, 0, 2, 0.0) == 0    # not compiled
+    assert lib.b200_uniform_filter1d_pair_eligible(2, 1, _lib.i64_array(a.shape[:1]), 7, 0, 2, 7, 0, 2, 0.0) == 0
+
+
+def test_fused_box_pair_unaligned_base_pointer_takes_two_launches(b200):
+    import scipy.ndimage as ndi
+    import torch
+
+    from dask_image_b200 import _lib
+
+    rng = np.random.default_rng(6)
+    a = rng.integers(0, 65536, (2, 40, 64)).astype(np.uint16)
+    flat = torch.from_numpy(np.concatenate([np.zeros(1, np.uint16), a.reshape(-1)])).cuda()
+    x = b200.B200Array(flat[1:].view(a.shape))             # base pointer 2 bytes off a 16-byte boundary
+    assert x.tensor.data_ptr() % 16 == 2
+    got = b200.ndimage.uniform_filter(x, 7).to_numpy()
+    assert not _lib.last_kernel().startswith("uniform2d_fused")
+    assert_parity(got, ndi.uniform_filter(a, 7), exact=True)
+
+
+def test_fused_box_pair_in_sharded_and_host_volumes(b200):
+    """The same pair inside the slab engine (one rank) and the streamed host volume."""
+    import scipy.ndimage as ndi
+
+    rng = np.random.default_rng(8)
+    a = rng.integers(0, 65536, (24, 72, 136)).astype(np.uint16)
+    ref = ndi.uniform_filter(a, 7)
+    v = b200.ShardedVolume.from_global(a)
+    assert_parity(b200.ndfilters.uniform_filter(v, 7).gather(), ref, exact=True)
+    h = b200.HostVolume(a, chunk_bytes=8 * 72 * 136 * 2)
+    assert_parity(b200.ndfilters.uniform_filter(h, 7).to_numpy(), ref, exact=True)
