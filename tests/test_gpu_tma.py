@@ -275,10 +275,20 @@ def test_config3_uniform_u16_volume(b200):
     from dask_image_b200 import _lib
 
     a = np.random.default_rng(1234).integers(0, 65536, (136, 200, 264), dtype=np.uint16)
+    ref = ndi.uniform_filter(a, 7)
     _lib.launch_count(reset=True)
     got = b200.ndfilters.uniform_filter(dev(b200, a), size=7)
-    assert _lib.launch_count() == 3 and _lib.last_kernel() == "uniform1d_tma_contig_u16"
-    assert_parity(got.to_numpy(), ndi.uniform_filter(a, 7), exact=True)
+    # the axis-0 pass + the fused pair along the last two axes (corr2d_fused.cu)
+    assert _lib.launch_count() == 2 and _lib.last_kernel() == "uniform2d_fused_tma_u16"
+    assert_parity(got.to_numpy(), ref, exact=True)
+    old = b200.ndimage.set_pair_fusion(False)
+    try:
+        _lib.launch_count(reset=True)
+        got = b200.ndfilters.uniform_filter(dev(b200, a), size=7)
+        assert _lib.launch_count() == 3 and _lib.last_kernel() == "uniform1d_tma_contig_u16"
+        assert_parity(got.to_numpy(), ref, exact=True)
+    finally:
+        b200.ndimage.set_pair_fusion(old)
 
 
 # ---------------------------------------------------------------------------

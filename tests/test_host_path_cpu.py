@@ -40,6 +40,12 @@ def cpu_path(monkeypatch):
 
     def corr_pair(src, dst, shape, np_dtype, ps1, ps2, cval, epilogue=_lib.EPI_STORE, flags=None):
         # the fused launch IS the two passes, the intermediate stored in the array dtype
+        if ps1.kind == "uniform":
+            assert epilogue == _lib.EPI_STORE and np.dtype(np_dtype) in (np.uint8, np.uint16)
+            calls.append(("uniform_pair", ps1.axis, ps2.axis, ps1.size, ps2.size))
+            mid = orc.uniform_filter1d(_view(src, shape), ps1.size, ps1.axis, ps1.mode, cval, ps1.origin)
+            _view(dst, shape)[...] = orc.uniform_filter1d(mid, ps2.size, ps2.axis, ps2.mode, cval, ps2.origin)
+            return
         calls.append(("pair", ps1.axis, ps2.axis, len(ps1.weights), len(ps2.weights), epilogue))
         mid = orc.correlate1d(_view(src, shape), ps1.weights, ps1.axis, ps1.mode, cval, ps1.origin)
         r = orc.correlate1d(mid, ps2.weights, ps2.axis, ps2.mode, cval, ps2.origin)
@@ -230,3 +236,36 @@ def test_ndfilters_layer_chunked_equals_whole_array_scipy(cpu_path, dtype):
             np.testing.assert_array_equal(np.asarray(b200.ndfilters.sobel(d, axis=1).compute()), ndi.sobel(a, axis=1))
             np.testing.assert_array_equal(np.asarray(b200.ndfilters.maximum_filter(d, size=3).compute()),
                                           ndi.maximum_filter(a, size=3))
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_integer_box_filter_pairs_the_last_two_axes(cpu_path, dtype):
+    """uniform_filter on uint8 / uint16 with equal odd sizes, origin 0 and 16-byte rows: one axis-0 pass and ONE
+    pair launch; anything else stays pass by pass.  Values are scipy's either way."""
+    rng = np.random.default_rng(23)
+    a = _data(rng, (6, 10, 32), dtype)
+    x = _array.B200Array.from_numpy(a)
+    del cpu_path[:]
+    _same(ndimage.uniform_filter(x, 7), ndi.uniform_filter(a, 7))
+    assert cpu_path == [("uniform", 0, 7), ("uniform_pair", 1, 2, 7, 7)]
+    del cpu_path[:]
+    _same(ndimage.uniform_filter(x, (1, 3, 3), mode="constant", cval=2.0),
+          ndi.uniform_filter(a, (1, 3, 3), mode="constant", cval=2.0))
+    assert cpu_path == [("uniform_pair", 1, 2, 3, 3)]
+    for kw in (dict(size=4), dict(size=(3, 5, 7)), dict(size=5, origin=1), dict(size=19),
+               dict(size=3, mode="constant", cval=0.5)):
+        del cpu_path[:]
+        _same(ndimage.uniform_filter(x, **kw), ndi.uniform_filter(a, **kw))
+        assert all(c[0] == "uniform" for c in cpu_path) and len(cpu_path) == 3, (kw, cpu_path)
+    # rows that are not 16-byte multiples
+    b = np.ascontiguousarray(a[:, :, :27])
+    del cpu_path[:]
+    _same(ndimage.uniform_filter(_array.B200Array.from_numpy(b), 7), ndi.uniform_filter(b, 7))
+    assert [c[0] for c in cpu_path] == ["uniform"] * 3
+    old = ndimage.set_pair_fusion(False)
+    try:
+        del cpu_path[:]
+        _same(ndimage.uniform_filter(x, 7), ndi.uniform_filter(a, 7))
+        assert [c[0] for c in cpu_path] == ["uniform"] * 3
+    finally:
+        ndimage.set_pair_fusion(old)

@@ -48,7 +48,7 @@ def main():
             want = uo.clone()
             rows = [("two launches", t2)]
             for slide in ("1", "0"):
-                if slide == "0" and size != 7:
+                if slide == "0" and (size != 7 or code != "uint16"):     # the direct form exists for uint16, size 7
                     continue
                 os.environ["B200_BOX2D_SLIDE"] = slide
                 uo.zero_()
