@@ -99,24 +99,30 @@ __device__ __forceinline__ int ext_index32(int i, int n, int mode)
 // ran at 90 % of the shared-memory pipe) and is widened in registers where phase A reads it: an
 // integer v < 2^23 is the low mantissa of 2^23 + v, i.e. one byte permute and one exact subtraction
 // per element, no I2F.
-template <typename TS>
+// MAGIC: leave the elements as 2^23 + v (no subtraction): differences of two such values are exact, which is
+// all the running sums need once the first window has been summed
+template <typename TS, bool MAGIC = false>
 __device__ __forceinline__ float4 box_load4(const TS *ptr)
 {
-    constexpr float kTwo23 = 8388608.f;
+    auto widen = [](uint32_t bits) {
+        const float f = __uint_as_float(bits);        // 2^23 + v
+        if constexpr (MAGIC) return f;
+        else return f - 8388608.f;
+    };
     float4 v;
     if constexpr (sizeof(TS) == 2) {
         const uint2 w = *reinterpret_cast<const uint2 *>(ptr);
-        v.x = __uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7410)) - kTwo23;
-        v.y = __uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7432)) - kTwo23;
-        v.z = __uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7410)) - kTwo23;
-        v.w = __uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7432)) - kTwo23;
+        v.x = widen(__byte_perm(w.x, 0x4B000000u, 0x7410));
+        v.y = widen(__byte_perm(w.x, 0x4B000000u, 0x7432));
+        v.z = widen(__byte_perm(w.y, 0x4B000000u, 0x7410));
+        v.w = widen(__byte_perm(w.y, 0x4B000000u, 0x7432));
     } else {
         static_assert(sizeof(TS) == 1, "8- or 16-bit storage");
         const uint32_t w = *reinterpret_cast<const uint32_t *>(ptr);
-        v.x = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)) - kTwo23;
-        v.y = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)) - kTwo23;
-        v.z = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)) - kTwo23;
-        v.w = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)) - kTwo23;
+        v.x = widen(__byte_perm(w, 0x4B000000u, 0x7440));
+        v.y = widen(__byte_perm(w, 0x4B000000u, 0x7441));
+        v.z = widen(__byte_perm(w, 0x4B000000u, 0x7442));
+        v.w = widen(__byte_perm(w, 0x4B000000u, 0x7443));
     }
     return v;
 }
@@ -300,26 +306,31 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tile, i
             // box_quotient_bits() rounds it, kept as a float (scalar FADD / FFMA as in the one-pass kernels)
             const TS *s = tin + rg * RA * PX + cv;
             float *d = mid + rg * RA * PI + cv;
-            auto quot = [&](float sum) { return fmaf(sum + p.qc0, p.qinv, 12582912.f) - 12582912.f; };
+            auto quot = [&](float sum) {
+                return fmaf(SLIDE ? sum : sum + p.qc0, p.qinv, 12582912.f) - 12582912.f;   // (SLIDE: qc0 is in the sum)
+            };
             auto put = [&](int j, float2 a, float2 b) {
                 *reinterpret_cast<float4 *>(d + j * PI) = make_float4(quot(a.x), quot(a.y), quot(b.x), quot(b.y));
             };
             if constexpr (SLIDE) {
                 // running column sums: row j + 1 = row j + (the row entering the window - the row leaving it);
-                // the L1 rows of the window stay in registers, so every staged row is loaded and widened once
+                // the L1 rows of the window stay in registers, so every staged row is loaded once.  Rows are kept
+                // as 2^23 + v (one byte permute per element): the first window is summed as r <- (r + row) - 2^23,
+                // every step exact, and the differences of the sliding steps cancel the offset.  The sum carries
+                // the quotient epilogue's pre-add qc0 = -(size - 1) / 2 (an integer for odd sizes) from the start.
                 float4 v[RA + L1 - 1];
-                v[0] = box_load4<TS>(s);
-                float2 r0 = make_float2(v[0].x, v[0].y), r1 = make_float2(v[0].z, v[0].w);
+                const float2 k2 = make_float2(-8388608.f, -8388608.f);
+                float2 r0 = make_float2(p.qc0, p.qc0), r1 = r0;
 #pragma unroll
-                for (int i = 1; i < L1; ++i) {
-                    v[i] = box_load4<TS>(s + i * PX);
-                    r0 = __fadd2_rn(r0, make_float2(v[i].x, v[i].y));
-                    r1 = __fadd2_rn(r1, make_float2(v[i].z, v[i].w));
+                for (int i = 0; i < L1; ++i) {
+                    v[i] = box_load4<TS, true>(s + i * PX);
+                    r0 = __fadd2_rn(__fadd2_rn(r0, make_float2(v[i].x, v[i].y)), k2);
+                    r1 = __fadd2_rn(__fadd2_rn(r1, make_float2(v[i].z, v[i].w)), k2);
                 }
                 put(0, r0, r1);
 #pragma unroll
                 for (int j = 1; j < RA; ++j) {
-                    v[j + L1 - 1] = box_load4<TS>(s + (j + L1 - 1) * PX);
+                    v[j + L1 - 1] = box_load4<TS, true>(s + (j + L1 - 1) * PX);
                     const float4 vn = v[j + L1 - 1], vo = v[j - 1];
                     const float2 m1 = make_float2(-1.f, -1.f);
                     r0 = __fadd2_rn(r0, __ffma2_rn(make_float2(vo.x, vo.y), m1, make_float2(vn.x, vn.y)));
@@ -444,7 +455,7 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tile, i
                 // running row sums over the window [i + LEAD, i + NTX) of output i
                 constexpr int LEAD = NTX - L1;
                 static_assert(LEAD >= 0 && LEAD < 16, "alignment zeros in front of the contiguous window");
-                float rs = f[LEAD];
+                float rs = f[LEAD] + p.qc0;          // (the quotient epilogue's pre-add rides on the running sum)
 #pragma unroll
                 for (int t = LEAD + 1; t < NTX; ++t) rs += f[t];
                 float r[16];
@@ -498,7 +509,14 @@ __device__ __forceinline__ void fused_tile(const Corr2dParams &p, float *tile, i
                 for (int h = 0; h < 2; ++h) {
                     const float s8[8] = {res[2 * h].x, res[2 * h].y, res[2 * h].z, res[2 * h].w,
                                          res[2 * h + 1].x, res[2 * h + 1].y, res[2 * h + 1].z, res[2 * h + 1].w};
-                    store_box_quotients<float, TS, 8>(orow + 8 * h, s8, p.qinv, p.qc0);
+                    if constexpr (SLIDE) {
+                        uint32_t q8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) q8[i] = __float_as_uint(fmaf(s8[i], p.qinv, 12582912.f));
+                        pack_box_quotients<TS, 8>(orow + 8 * h, q8);
+                    } else {
+                        store_box_quotients<float, TS, 8>(orow + 8 * h, s8, p.qinv, p.qc0);
+                    }
                 }
             } else {
 #pragma unroll

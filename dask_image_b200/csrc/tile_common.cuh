@@ -198,13 +198,11 @@ __device__ __forceinline__ uint32_t box_quotient_bits(T s, T qinv, T qc0)
     return __float_as_uint(fmaf((float)s + (float)qc0, (float)qinv, 12582912.f));
 }
 
-template <typename T, typename TS, int N>
-__device__ __forceinline__ void store_box_quotients(TS *dst, const T (&s)[N], T qinv, T qc0)
+// N quotients (the low bits of q[i]) packed to the storage type and written with one store
+template <typename TS, int N>
+__device__ __forceinline__ void pack_box_quotients(TS *dst, const uint32_t (&q)[N])
 {
     static_assert(N == 4 || N == 8, "4 or 8 outputs per store");
-    uint32_t q[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) q[i] = box_quotient_bits<T>(s[i], qinv, qc0);
     if constexpr (sizeof(TS) == 2) {
         uint32_t w[N / 2];
 #pragma unroll
@@ -222,6 +220,15 @@ __device__ __forceinline__ void store_box_quotients(TS *dst, const T (&s)[N], T 
         if constexpr (N == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
         else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
     }
+}
+
+template <typename T, typename TS, int N>
+__device__ __forceinline__ void store_box_quotients(TS *dst, const T (&s)[N], T qinv, T qc0)
+{
+    uint32_t q[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = box_quotient_bits<T>(s[i], qinv, qc0);
+    pack_box_quotients<TS, N>(dst, q);
 }
 
 // 32-byte global stores/loads (sm_100 STG.E.256 / LDG.E.256): a contiguous-axis

@@ -143,6 +143,9 @@ def _launch_correlate1d_pair(src, dst, shape, np_dtype, ps1, ps2, cval, epilogue
     (corr2d_fused.cu); bit-identical to the two launches.  Two correlations
     (float32) or two box filters (uint8 / uint16)."""
     lib = _lib.load()
+    if ps1.kind == "uniform" and np.dtype(np_dtype) == np.float32:
+        # the float box filter IS a correlation with `size` taps of 1 / size (corr1d_tma.cu: launch_uniform1d_fast)
+        ps1, ps2 = _box_as_corr(ps1), _box_as_corr(ps2)
     if ps1.kind == "uniform":
         if epilogue != _lib.EPI_STORE:
             raise RuntimeError("only correlation passes have a fused epilogue")
@@ -165,6 +168,20 @@ def _launch_correlate1d_pair(src, dst, shape, np_dtype, ps1, ps2, cval, epilogue
 
 
 _FUSE_PAIRS = os.environ.get("B200_FUSE_PAIRS", "1") not in ("", "0")
+_box_corr_cache = {}
+
+
+def _box_as_corr(ps):
+    """The correlation pass a float32 box-filter pass is computed as: ``size`` taps of ``1 / size`` (the values
+    launch_uniform1d_fast() hands to the one-pass kernels)."""
+    key = (ps.axis, ps.mode, ps.size, ps.origin)
+    hit = _box_corr_cache.get(key)
+    if hit is None:
+        if len(_box_corr_cache) >= 256:
+            _box_corr_cache.clear()
+        hit = _box_corr_cache[key] = _Pass("corr", ps.axis, ps.mode, weights=np.full(ps.size, 1.0 / ps.size),
+                                           origin=ps.origin)
+    return hit
 
 
 def set_pair_fusion(on):
@@ -187,6 +204,12 @@ def _pair_eligible(shape, np_dtype, ps1, ps2, flags=None, cval=0.0, aligned=True
     fl = _default_flags if flags is None else flags
     if fl & (_lib.FLAG_EXACT | _lib.FLAG_NO_TMA):
         return False
+    if ps1.kind == "uniform" and np_dtype == np.float32:
+        if ps1.size < 2 or ps2.size < 2:
+            return False
+        return bool(_lib.load().b200_correlate1d_pair_eligible(
+            _dtype_code(np_dtype), len(shape), _lib.i64_array(shape), int(ps1.size), int(ps1.origin),
+            int(ps2.size), int(ps2.origin)))
     if ps1.kind == "uniform":
         if not aligned or np_dtype not in (np.uint8, np.uint16):
             return False

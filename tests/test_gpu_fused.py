@@ -266,3 +266,30 @@ def test_fused_box_pair_in_sharded_and_host_volumes(b200):
     assert_parity(b200.ndfilters.uniform_filter(v, 7).gather(), ref, exact=True)
     h = b200.HostVolume(a, chunk_bytes=8 * 72 * 136 * 2)
     assert_parity(b200.ndfilters.uniform_filter(h, 7).to_numpy(), ref, exact=True)
+
+
+@pytest.mark.parametrize("mode", ["reflect", "constant", "wrap"])
+def test_fused_float_box_pair(b200, mode):
+    """float32 uniform_filter: the box filter is a correlation with taps 1 / size, so its last two passes take the
+    float32 pair kernel -- bit-identical to the pass-by-pass path, within the fp32 tolerance of scipy."""
+    import scipy.ndimage as ndi
+
+    for shape in [(40, 64), (3, 37, 100), (2, 130, 244), (2, 33, 63)]:
+        rng = np.random.default_rng(hash((shape, mode)) % (2 ** 32))
+        a = (rng.random(shape) * 5 - 1).astype(np.float32)
+        d = dev(b200, a)
+        for size in (3, 5, 7, 9, 15, 21, 33):
+            fused, k, nf, plain, npl = both(b200, b200.ndimage.uniform_filter, d, size, mode=mode, cval=0.3)
+            assert k.startswith("corr2d_fused_"), (k, shape, size)
+            assert nf == npl - 1 and nf == len(shape) - 1
+            assert np.array_equal(fused, plain), (shape, size, int((fused != plain).sum()))
+            assert_parity(fused, ndi.uniform_filter(a, size, mode=mode, cval=0.3), what="%s size=%d" % (shape, size),
+                          data=a)
+    # even sizes / origins / unequal sizes: no pair
+    from dask_image_b200 import _lib
+
+    a3 = np.random.default_rng(4).random((4, 40, 64)).astype(np.float32)
+    for kw in (dict(size=4), dict(size=7, origin=1), dict(size=(3, 7, 5))):
+        got = b200.ndimage.uniform_filter(dev(b200, a3), **kw).to_numpy()
+        assert not _lib.last_kernel().startswith("corr2d_fused"), kw
+        assert_parity(got, ndi.uniform_filter(a3, **kw), data=a3)

@@ -41,7 +41,7 @@ def cpu_path(monkeypatch):
     def corr_pair(src, dst, shape, np_dtype, ps1, ps2, cval, epilogue=_lib.EPI_STORE, flags=None):
         # the fused launch IS the two passes, the intermediate stored in the array dtype
         if ps1.kind == "uniform":
-            assert epilogue == _lib.EPI_STORE and np.dtype(np_dtype) in (np.uint8, np.uint16)
+            assert epilogue == _lib.EPI_STORE and np.dtype(np_dtype) in (np.uint8, np.uint16, np.float32)
             calls.append(("uniform_pair", ps1.axis, ps2.axis, ps1.size, ps2.size))
             mid = orc.uniform_filter1d(_view(src, shape), ps1.size, ps1.axis, ps1.mode, cval, ps1.origin)
             _view(dst, shape)[...] = orc.uniform_filter1d(mid, ps2.size, ps2.axis, ps2.mode, cval, ps2.origin)
@@ -269,3 +269,18 @@ def test_integer_box_filter_pairs_the_last_two_axes(cpu_path, dtype):
         assert [c[0] for c in cpu_path] == ["uniform"] * 3
     finally:
         ndimage.set_pair_fusion(old)
+
+
+def test_float_box_filter_pairs_the_last_two_axes(cpu_path):
+    a = np.random.default_rng(29).random((6, 10, 19)).astype(np.float32)
+    x = _array.B200Array.from_numpy(a)
+    del cpu_path[:]
+    _same(ndimage.uniform_filter(x, 5), ndi.uniform_filter(a, 5))
+    assert cpu_path == [("uniform", 0, 5), ("uniform_pair", 1, 2, 5, 5)]
+    del cpu_path[:]
+    _same(ndimage.uniform_filter(x, (5, 4, 4)), ndi.uniform_filter(a, (5, 4, 4)))
+    assert [c[0] for c in cpu_path] == ["uniform"] * 3
+    d = _array.B200Array.from_numpy(a.astype(np.float64))
+    del cpu_path[:]
+    _same(ndimage.uniform_filter(d, 5), ndi.uniform_filter(a.astype(np.float64), 5))
+    assert [c[0] for c in cpu_path] == ["uniform"] * 3
