@@ -101,9 +101,10 @@ def main():
                              r"corr1d_strided_ldg_kernelIffLi128ELi8ELi4ELi3ELi1E"],
         "corr1d_contig.o": [r"corr1d_contig_static_kernelIfLi17ELb0E", r"corr1d_contig_static_kernelItLi16ELb0E",
                             r"corr1d_contig_tma_kernelIffLi0ELi1E"],
-        "corr2d_fused.o": [r"corr2d_fused_kernelILi17ELi17ELi32ELi8ELi8ELb1ELi4ELb1E",
-                           r"corr2d_fused_kernelILi33ELi33ELi32ELi8ELi8ELb1ELi2ELb1E",
-                           r"corr2d_fused_kernelILi17ELi17ELi32ELi8ELi8ELb1ELi4ELb0E"],
+        "corr2d_fused.o": [r"corr2d_fused_kernelILi17ELi17ELi32ELi8ELi8ELb1ELi4ELb1EfLb0E",
+                           r"corr2d_fused_kernelILi33ELi33ELi32ELi8ELi8ELb1ELi2ELb1EfLb0E",
+                           r"corr2d_fused_kernelILi17ELi17ELi32ELi8ELi8ELb1ELi4ELb0EfLb0E",
+                           r"corr2d_fused_kernelILi7ELi12ELi32ELi8ELi8ELb1ELi4ELb1EtLb1E"],
         "corrnd_tiled.o": [r"corrnd_static_kernelILi9ELb0E"],
         "corr1d_int.o": [r"corr1d_int_strided_kernelItLi1E"],
         "corrnd_int.o": [r"corrnd_int_kernelItE"],
