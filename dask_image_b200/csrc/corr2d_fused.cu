@@ -740,6 +740,8 @@ static int launch_fused_taps(const Corr2dArgs &a, const Corr2dParams &p)
     case 3: return launch_fused_cfg<L1, NTX, 32, 8, 8, true, 4, TMA>(a, p);
     case 4: return launch_fused_cfg<L1, NTX, 16, 4, 8, true, 6, TMA>(a, p);
     case 6: return launch_fused_cfg<L1, NTX, 64, 16, 8, true, 1, TMA>(a, p);
+    case 7: return launch_fused_cfg<L1, NTX, 24, 6, 8, true, 5, TMA>(a, p);   // 24 rows x 6 warps, 5 CTAs / SM
+    case 8: return launch_fused_cfg<L1, NTX, 24, 6, 8, true, 4, TMA>(a, p);
     default: break;
     }
 #else
@@ -749,9 +751,10 @@ static int launch_fused_taps(const Corr2dArgs &a, const Corr2dParams &p)
     if constexpr (TMA && 2 * (2 * fused_buffer_floats(L1, 32, 8) * 4 + 128 + 2560) <= (int)kSmemPerSm) {
         if (env_int("B200_FUSED_PERSIST", 0) && a.epilogue == B200_EPI_STORE) return launch_fused_persist<L1, NTX>(a, p);
     }
-    // short filters: 4 CTAs of 8 warps per SM (<= 64 registers); from 25 taps on the pass is FP32-issue
-    // bound, the tiles are bigger and 3 resident CTAs with more registers do better (B200 sweep)
-    return launch_fused_cfg<L1, NTX, 32, 8, 8, true, (NTX < 25 ? 4 : 2), TMA>(a, p);
+    // 64 registers for every filter length: 4 CTAs of 8 warps per SM below 25 taps; from 25 taps on shared memory
+    // admits 3 CTAs either way, and the 64-register code still runs 0-10 % faster than the 72-register one
+    // (B200 sweeps at 1024^3 and 512 x 2048^2, profiles/r2_sweep_fused_minb_*.log)
+    return launch_fused_cfg<L1, NTX, 32, 8, 8, true, 4, TMA>(a, p);
 }
 
 // (L1, NTX) pairs with a compiled kernel: the two passes of an isotropic odd

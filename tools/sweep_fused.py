@@ -18,7 +18,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dask_image_b200 import _lib, ndimage  # noqa: E402
 
 VARIANTS = {0: "default (32x8w RA8 alias)", 1: "32x8w RA8 noalias minb2", 2: "32x8w RA8 alias minb2",
-            3: "32x8w RA8 alias minb4", 4: "16x4w RA8 alias minb6", 6: "64x16w RA8 alias minb1"}
+            3: "32x8w RA8 alias minb4", 4: "16x4w RA8 alias minb6", 6: "64x16w RA8 alias minb1",
+            7: "24x6w RA8 alias minb5", 8: "24x6w RA8 alias minb4"}
+if os.environ.get("SWEEP_VARIANTS"):
+    VARIANTS = {int(v): VARIANTS[int(v)] for v in os.environ["SWEEP_VARIANTS"].split(",")}
 
 
 def timeit(fn, reps):
