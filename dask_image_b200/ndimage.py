@@ -10,6 +10,7 @@ every step as a hand-written sm_100a kernel through the C ABI
 exactly as scipy does, so integer results are bit-identical.
 """
 import numbers
+import operator
 import os
 
 import numpy as np
@@ -591,20 +592,43 @@ def _gaussian_passes(ndim, sigma, order, mode, truncate, radius=None, axes=None)
 
 
 def _check_axes(axes, ndim):
+    """scipy/ndimage/_ni_support.py:110-126 (a negative scalar is normalised as well)."""
     if axes is None:
         return tuple(range(ndim))
     if np.isscalar(axes):
         axes = (axes,)
+    elif not np.iterable(axes):
+        raise ValueError("axes must be an integer, iterable of integers, or None")
     out = []
     for ax in axes:
-        if not isinstance(ax, numbers.Integral):
-            raise ValueError("axes must be integers")
-        if ax < -ndim or ax >= ndim:
+        ax = operator.index(ax)      # TypeError for anything that is not an integer, as scipy
+        if ax < -ndim or ax > ndim - 1:
             raise ValueError("specified axis: %d is out of range" % ax)
-        out.append(int(ax) % ndim)
+        out.append(ax % ndim if ax < 0 else ax)
     if len(set(out)) != len(out):
         raise ValueError("axes must be unique")
     return tuple(out)
+
+
+def _expand_origin(ndim, axes, origin):
+    """scipy/ndimage/_filters.py:516-525: one origin per listed axis, 0 on the axes that are not filtered."""
+    origins = _per_axis(origin, len(axes))
+    if len(axes) < ndim:
+        full = [0] * ndim
+        for og, ax in zip(origins, axes):
+            full[ax] = og
+        origins = full
+    return origins
+
+
+def _expand_footprint(ndim, axes, footprint, name="footprint"):
+    """scipy/ndimage/_filters.py:528-540: singleton dimensions on the axes that are not filtered.  (As in scipy
+    the window's dimensions land on the listed axes in INCREASING axis order.)"""
+    if len(axes) < ndim:
+        if footprint.ndim != len(axes):
+            raise RuntimeError("%s.ndim (%d) must match len(axes) (%d)" % (name, footprint.ndim, len(axes)))
+        footprint = np.expand_dims(footprint, tuple(ax for ax in range(ndim) if ax not in axes))
+    return footprint
 
 
 class _Plan:
@@ -687,18 +711,18 @@ def _derivative_kwargs(kwargs):
 
 
 def _plan_gaussian_gradient_magnitude(ndim, sigma, mode="reflect", cval=0.0, axes=None, **kwargs):
+    """scipy/ndimage/_filters.py:1143-1250.  ``axes`` selects the axes a derivative is taken along (in the order
+    given, one ``mode`` each); every derivative is a full ``gaussian_filter`` call with ``sigma`` exactly as
+    given, i.e. per axis of the ARRAY -- scipy does not re-map it onto ``axes`` here."""
     truncate, radius = _derivative_kwargs(kwargs)
     axes = _check_axes(axes, ndim)
-    if len(axes) != ndim:
-        raise NotImplementedError("axes subsets are not supported (the reference never passes them)")
     modes = _per_axis(mode, len(axes))
-    sigmas = _per_axis(sigma, len(axes))
     chains = []
     for i, ax in enumerate(axes):
-        order = [0] * len(axes)
-        order[i] = 1
-        passes = _gaussian_passes(ndim, sigmas, order, modes[i], truncate, radius, axes)
-        if len(axes) == 1 or i == len(axes) - 1:
+        order = [0] * ndim
+        order[ax] = 1
+        passes = _gaussian_passes(ndim, sigma, order, modes[i], truncate, radius)
+        if i == len(axes) - 1:
             op = _lib.EPI_SQ_ACC_SQRT
         elif i == 0:
             op = _lib.EPI_SQ_STORE
@@ -709,17 +733,23 @@ def _plan_gaussian_gradient_magnitude(ndim, sigma, mode="reflect", cval=0.0, axe
 
 
 def _plan_gaussian_laplace(ndim, sigma, mode="reflect", cval=0.0, axes=None, **kwargs):
+    """scipy/ndimage/_filters.py:985-1030,1075-1139.  With fewer ``axes`` than dimensions ``sigma`` has one
+    entry per listed axis and is 0 (= no smoothing) elsewhere; with all of them it is taken per axis of the
+    array, whatever the order of ``axes`` (scipy's rule, kept as it is)."""
     truncate, radius = _derivative_kwargs(kwargs)
     axes = _check_axes(axes, ndim)
-    if len(axes) != ndim:
-        raise NotImplementedError("axes subsets are not supported (the reference never passes them)")
     modes = _per_axis(mode, len(axes))
     sigmas = _per_axis(sigma, len(axes))
+    if len(axes) < ndim:
+        full = [0] * ndim
+        for sg, ax in zip(sigmas, axes):
+            full[ax] = sg
+        sigmas = full
     chains = []
     for i, ax in enumerate(axes):
-        order = [0] * len(axes)
-        order[i] = 2
-        passes = _gaussian_passes(ndim, sigmas, order, modes[i], truncate, radius, axes)
+        order = [0] * ndim
+        order[ax] = 2
+        passes = _gaussian_passes(ndim, sigmas, order, modes[i], truncate, radius)
         chains.append((passes, _lib.EPI_STORE if i == 0 else _lib.EPI_ACC))
     return _Plan(chains, cval=cval)
 
@@ -750,29 +780,26 @@ def _plan_sobel(ndim, axis=-1, mode="reflect", cval=0.0):
     return _plan_edge(ndim, axis, mode, cval, [1.0, 2.0, 1.0])
 
 
-def _plan_correlate_nd(ndim, np_dtype, weights, mode="reflect", cval=0.0, origin=0, convolution=False):
+def _plan_correlate_nd(ndim, np_dtype, weights, mode="reflect", cval=0.0, origin=0, convolution=False, axes=None):
+    w, origins = _prepare_nd_weights(ndim, np_dtype, weights, origin, convolution, axes)
     if not isinstance(mode, str) and np.iterable(mode):
         raise RuntimeError("A sequence of modes is not supported")
-    w, origins = _prepare_nd_weights(ndim, np_dtype, weights, origin, convolution)
     _lib.mode_code(mode)
     return _Plan(nd=(w, origins, mode), cval=cval)
 
 
 def _plan_minmax(ndim, is_max, size=None, footprint=None, mode="reflect", cval=0.0, origin=0, axes=None):
-    """scipy/ndimage/_filters.py:1669-1773 (_min_or_max_filter): a box (``size``,
-    or an all-true footprint) is separable -> one 1-D pass per axis with size > 1;
+    """scipy/ndimage/_filters.py:1738-1830 (_min_or_max_filter): a box (``size``,
+    or an all-true footprint) is separable -> one 1-D pass per listed axis with size > 1;
     any other footprint is a direct N-D scan of its true positions."""
     axes = _check_axes(axes, ndim)
-    if len(axes) != ndim:
-        raise NotImplementedError("axes subsets are not supported (the reference never passes them)")
+    k = len(axes)
     if footprint is None:
         if size is None:
             raise RuntimeError("no footprint provided")
         separable = True
     else:
         footprint = np.asarray(_weights_to_host(footprint), dtype=bool)
-        if footprint.ndim != ndim:
-            raise RuntimeError("footprint.ndim (%d) must match len(axes) (%d)" % (footprint.ndim, ndim))
         if not footprint.any():
             raise ValueError("All-zero footprint is not supported.")
         if footprint.all():
@@ -781,24 +808,27 @@ def _plan_minmax(ndim, is_max, size=None, footprint=None, mode="reflect", cval=0
             separable = False
     kind = "max" if is_max else "min"
     if separable:
-        sizes, origins, modes = _per_axis(size, ndim), _per_axis(origin, ndim), _per_axis(mode, ndim)
+        origins, sizes, modes = _per_axis(origin, k), _per_axis(size, k), _per_axis(mode, k)
         passes = []
-        for ax in range(ndim):
-            sz, og = int(sizes[ax]), int(origins[ax])
-            if sz < 1:
-                raise RuntimeError("incorrect filter size")
-            if sz > 1:
-                if (sz // 2 + og < 0) or (sz // 2 + og >= sz):
-                    raise ValueError("invalid origin")
-                _lib.mode_code(modes[ax])
-                passes.append(_Pass(kind, ax, modes[ax], size=sz, origin=og))
+        for i, ax in enumerate(axes):
+            if not sizes[i] > 1:
+                continue
+            sz, og = int(sizes[i]), int(origins[i])
+            if (sz // 2 + og < 0) or (sz // 2 + og >= sz):
+                raise ValueError("invalid origin")
+            _lib.mode_code(modes[i])
+            passes.append(_Pass(kind, ax, modes[i], size=sz, origin=og))
         return _Plan([(passes, _lib.EPI_STORE)] if passes else [], cval=cval)
+    footprint = _expand_footprint(ndim, axes, footprint)
+    origins = [int(o) for o in _expand_origin(ndim, axes, origin)]
+    fshape = [s for s in footprint.shape if s > 0]
+    if len(fshape) != ndim or footprint.ndim != ndim:
+        raise RuntimeError("footprint.ndim (%d) must match len(axes) (%d)" % (footprint.ndim, k))
+    for og, lenf in zip(origins, fshape):
+        if (lenf // 2 + og < 0) or (lenf // 2 + og >= lenf):
+            raise ValueError("invalid origin")
     if not isinstance(mode, str) and np.iterable(mode):
         raise RuntimeError("A sequence of modes is not supported for non-separable footprints")
-    origins = [int(o) for o in _per_axis(origin, ndim)]
-    for og, lenf in zip(origins, footprint.shape):
-        if (og < -(lenf // 2)) or (og > (lenf - 1) // 2):
-            raise ValueError("invalid origin")
     _lib.mode_code(mode)
     fp = np.ascontiguousarray(footprint)
     return _Plan(nd=(fp, origins, mode), cval=cval, extreme=(fp, origins, mode, bool(is_max)))
@@ -890,17 +920,19 @@ def _weights_to_host(weights):
     return np.asarray(weights)
 
 
-def _prepare_nd_weights(ndim, np_dtype, weights, origin, convolution):
-    """scipy/ndimage/_filters.py:1271-1292: float64 weights; for convolution
-    flip every axis and negate origins (one more on even-length axes)."""
+def _prepare_nd_weights(ndim, np_dtype, weights, origin, convolution, axes=None):
+    """scipy/ndimage/_filters.py:1271-1292: float64 weights, expanded with singleton dimensions when ``axes``
+    lists fewer axes than the array has; for convolution flip every axis and negate origins (one more on
+    even-length axes)."""
     w = _weights_to_host(weights)
     if w.dtype.kind == "c" or np_dtype.kind == "c":
         raise RuntimeError("complex data is not supported")
-    w = np.asarray(w, dtype=np.float64)
+    axes = _check_axes(axes, ndim)
+    w = _expand_footprint(ndim, axes, np.asarray(w, dtype=np.float64), "weights")
+    origins = [int(o) for o in _expand_origin(ndim, axes, origin)]
     wshape = [s for s in w.shape if s > 0]
     if len(wshape) != ndim or w.ndim != ndim:
-        raise RuntimeError("weights.ndim (%d) must match len(axes) (%d)" % (len(wshape), ndim))
-    origins = [int(o) for o in _per_axis(origin, ndim)]
+        raise RuntimeError("weights.ndim (%d) must match len(axes) (%d)" % (len(wshape), len(axes)))
     if convolution:
         w = w[tuple([slice(None, None, -1)] * w.ndim)]
         for i in range(ndim):
@@ -914,22 +946,22 @@ def _prepare_nd_weights(ndim, np_dtype, weights, origin, convolution):
     return np.ascontiguousarray(w), origins
 
 
-def _correlate_or_convolve(input, weights, output, mode, cval, origin, convolution):
+def _correlate_or_convolve(input, weights, output, mode, cval, origin, convolution, axes=None):
     x = as_b200(input)
     _zero_dim_guard(x)
-    plan = _plan_correlate_nd(x.ndim, x.dtype, weights, mode, cval, origin, convolution)
+    plan = _plan_correlate_nd(x.ndim, x.dtype, weights, mode, cval, origin, convolution, axes)
     out = _output_or_new(output, x)
     return _execute(plan, x, out)
 
 
-def correlate(input, weights, output=None, mode="reflect", cval=0.0, origin=0):
+def correlate(input, weights, output=None, mode="reflect", cval=0.0, origin=0, *, axes=None):
     """scipy.ndimage.correlate (scipy/ndimage/_filters.py:1312-1380)."""
-    return _correlate_or_convolve(input, weights, output, mode, cval, origin, False)
+    return _correlate_or_convolve(input, weights, output, mode, cval, origin, False, axes)
 
 
-def convolve(input, weights, output=None, mode="reflect", cval=0.0, origin=0):
+def convolve(input, weights, output=None, mode="reflect", cval=0.0, origin=0, *, axes=None):
     """scipy.ndimage.convolve (scipy/ndimage/_filters.py:1383-1499)."""
-    return _correlate_or_convolve(input, weights, output, mode, cval, origin, True)
+    return _correlate_or_convolve(input, weights, output, mode, cval, origin, True, axes)
 
 
 # --------------------------------------------------------------------------
