@@ -705,14 +705,14 @@ def gaussian_laplace(input, sigma, mode="reflect", cval=0.0, *, axes=None, **kwa
     return vol._run_plan(_nd._cached_plan(_nd._plan_gaussian_laplace, vol.ndim, (sigma, mode, cval, axes,), kwargs))
 
 
-def correlate(input, weights, mode="reflect", cval=0.0, origin=0):
+def correlate(input, weights, mode="reflect", cval=0.0, origin=0, *, axes=None):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_correlate_nd(vol.ndim, vol.dtype, weights, mode, cval, origin, False))
+    return vol._run_plan(_nd._plan_correlate_nd(vol.ndim, vol.dtype, weights, mode, cval, origin, False, axes))
 
 
-def convolve(input, weights, mode="reflect", cval=0.0, origin=0):
+def convolve(input, weights, mode="reflect", cval=0.0, origin=0, *, axes=None):
     vol = _check(input)
-    return vol._run_plan(_nd._plan_correlate_nd(vol.ndim, vol.dtype, weights, mode, cval, origin, True))
+    return vol._run_plan(_nd._plan_correlate_nd(vol.ndim, vol.dtype, weights, mode, cval, origin, True, axes))
 
 
 def laplace(input, mode="reflect", cval=0.0, *, axes=None):

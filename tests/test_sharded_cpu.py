@@ -53,6 +53,11 @@ def _cases():
             ("minimum_filter", u16, dict(size=(5, 1, 3), mode=mode, origin=(1, 0, -1), cval=9.0)),
             ("maximum_filter", f32, dict(footprint=np.array([[[1, 0, 1]], [[0, 1, 0]], [[1, 1, 0]]], bool),
                                          mode=mode, cval=0.4)),
+            # scipy's `axes=` travels through **kwargs of the reference's wrappers (ref:_gaussian.py:119-123,147-151)
+            ("gaussian_gradient_magnitude", u16, dict(sigma=1.0, mode=mode, axes=(2, 0))),
+            # (the reference expands sigma to one entry per array axis, ref:_gaussian.py:22-44, which scipy's
+            # gaussian_laplace only accepts together with ALL axes: a permutation changes the summation order)
+            ("gaussian_laplace", f32, dict(sigma=(0.9, 1.3, 0.6), mode=mode, axes=(2, 0, 1), cval=0.2)),
         ]
     return cases
 
@@ -61,9 +66,9 @@ def _reference(name, a, kw):
     from oracle import oracle as orc
     import scipy.ndimage as ndi
 
-    if hasattr(orc, name):
+    if hasattr(orc, name) and "axes" not in kw:
         return getattr(orc, name)(a, **kw)
-    return getattr(ndi, name)(a, **kw)          # laplace / sobel / prewitt: scipy itself
+    return getattr(ndi, name)(a, **kw)          # laplace / sobel / prewitt / `axes=`: scipy itself
 
 
 def _worker(rank, world, port, q):
