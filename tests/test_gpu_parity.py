@@ -273,6 +273,34 @@ def test_per_axis_modes_and_axes(b200):
     assert_parity(got.to_numpy(), ndi.uniform_filter(a, 5, axes=(1,)))
 
 
+@pytest.mark.parametrize("dt", ["float32", "float64", "uint16"])
+def test_axes_subsets(b200, dt):
+    """scipy's `axes=` (scipy/ndimage/_filters.py:516-553,1126-1139,1181-1195,1271-1292,1738-1830): derivative
+    chains along the listed axes only, N-D windows expanded with singleton dimensions."""
+    rng = np.random.default_rng(15)
+    a = (rng.random((18, 21, 40)) * 200).astype(dt)
+    exact = np.dtype(dt).kind != "f"
+    d = dev(b200, a)
+    for axes in [(0,), (2, 0), (1, 2), (2, 1, 0), ()]:
+        k = len(axes)
+        got = b200.ndimage.gaussian_gradient_magnitude(d, 1.2, axes=axes, mode="nearest")
+        assert_parity(got.to_numpy(), ndi.gaussian_gradient_magnitude(a, 1.2, axes=axes, mode="nearest"), exact=exact,
+                      data=a)
+        got = b200.ndimage.gaussian_laplace(d, [0.8, 1.5, 1.1][:k], axes=axes)
+        assert_parity(got.to_numpy(), ndi.gaussian_laplace(a, [0.8, 1.5, 1.1][:k], axes=axes), exact=exact, data=a)
+        got = b200.ndimage.minimum_filter(d, size=[3, 2, 5][:k], axes=axes)
+        assert_parity(got.to_numpy(), ndi.minimum_filter(a, size=[3, 2, 5][:k], axes=axes), exact=True)
+        if k:
+            w = rng.random((3, 4, 5)[:k]) - 0.3
+            got = b200.ndimage.convolve(d, w, axes=axes, mode="wrap", origin=[1, -1, 0][:k])
+            assert_parity(got.to_numpy(), ndi.convolve(a, w, axes=axes, mode="wrap", origin=[1, -1, 0][:k]),
+                          exact=exact, data=a)
+            fp = rng.random((3, 2, 3)[:k]) > 0.4
+            fp.flat[0], fp.flat[-1] = True, False
+            got = b200.ndimage.maximum_filter(d, footprint=fp, axes=axes, mode="mirror")
+            assert_parity(got.to_numpy(), ndi.maximum_filter(a, footprint=fp, axes=axes, mode="mirror"), exact=True)
+
+
 @pytest.mark.parametrize("name", ["laplace", "prewitt", "sobel"])
 @pytest.mark.parametrize("dt", ["float64", "float32", "int16", "uint8"])
 def test_three_tap_compositions(b200, name, dt):
