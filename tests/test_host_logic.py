@@ -69,6 +69,26 @@ def test_abi_argument_errors_without_gpu():
         _lib.mode_code("bogus")
 
 
+def test_plain_c_program_uses_the_abi(tmp_path):
+    """The boundary is a C ABI: the header is C99 (no C++ / torch types in any signature), a C program links
+    against the library and gets the documented status codes from argument validation -- no Python, no GPU
+    (tests/native/abi_check.c)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    _lib.load()
+    src = os.path.join(ROOT, "tests", "native", "abi_check.c")
+    exe = str(tmp_path / "abi_check")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                           "-I", os.path.join(ROOT, "include"), src, "-o", exe, _lib.LIB_PATH,
+                           "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)])
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0 and "abi_check: ok" in run.stdout, run.stdout + run.stderr
+
+
 # ---- gaussian taps -----------------------------------------------------------
 @pytest.mark.parametrize("order", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("sigma", [0.5, 1.0, 2.0, 3.0, 4.0, 7.3])
