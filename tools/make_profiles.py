@@ -52,6 +52,13 @@ def raw_page(rep):
 def main():
     tag = sys.argv[1]
     os.makedirs(PROF, exist_ok=True)
+    if tag == "--sass-only":        # regenerate profiles/sass/ from dask_image_b200/build/*.o, nothing else
+        return dump_sass()
+    summaries(tag)
+    dump_sass()
+
+
+def summaries(tag):
     md = ["# ncu --set full summaries, round %s" % tag, "",
           "Captured with `ncu --set full --clock-control none --import-source on` under gpurun on a B200 "
           "(one launch per kernel, after the same command had run clean without ncu).  ncu serialises and "
@@ -91,7 +98,10 @@ def main():
         f.write("\n".join(md) + "\n")
     with open(traffic_path, "w") as f:
         json.dump(traffic, f, indent=1, sort_keys=True)
-    # SASS listings of the hot kernels
+
+
+def dump_sass():
+    """SASS listings of the hot kernels (cuobjdump of the object files of the in-tree build)."""
     sass_dir = os.path.join(PROF, "sass")
     os.makedirs(sass_dir, exist_ok=True)
     wanted = {
@@ -102,7 +112,7 @@ def main():
         "corr1d_contig.o": [r"corr1d_contig_static_kernelIfLi17ELb0E", r"corr1d_contig_static_kernelItLi16ELb0E",
                             r"corr1d_contig_tma_kernelIffLi0ELi1E"],
         "corr2d_fused.o": [r"corr2d_fused_kernelILi17ELi17ELi32ELi8ELi8ELb1ELi4ELb1EfLb0E",
-                           r"corr2d_fused_kernelILi33ELi33ELi32ELi8ELi8ELb1ELi2ELb1EfLb0E",
+                           r"corr2d_fused_kernelILi33ELi33ELi32ELi8ELi8ELb1ELi4ELb1EfLb0E",
                            r"corr2d_fused_kernelILi17ELi17ELi32ELi8ELi8ELb1ELi4ELb0EfLb0E",
                            r"corr2d_fused_kernelILi7ELi12ELi32ELi8ELi8ELb1ELi4ELb1EtLb1E"],
         "corrnd_tiled.o": [r"corrnd_static_kernelILi9ELb0E"],
