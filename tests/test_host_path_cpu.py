@@ -284,3 +284,33 @@ def test_float_box_filter_pairs_the_last_two_axes(cpu_path):
     del cpu_path[:]
     _same(ndimage.uniform_filter(d, 5), ndi.uniform_filter(a.astype(np.float64), 5))
     assert [c[0] for c in cpu_path] == ["uniform"] * 3
+
+
+def test_chunk_functions_are_thread_safe(cpu_path):
+    """dask's threaded scheduler calls the chunk function from a thread pool (SURVEY 8b "Threading"): the plan /
+    taps / pass-grouping caches are shared, filled concurrently and wiped when full -- results must not depend on it."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    rng = np.random.default_rng(41)
+    chunks = [_data(rng, (9, 10, 11), dt) for dt in (np.float32, np.uint16, np.float64, np.int16) for _ in range(4)]
+    sigmas = [0.6 + 0.1 * i for i in range(12)]
+
+    def work(i):
+        a = chunks[i % len(chunks)]
+        x = _array.B200Array.from_numpy(a)
+        s = sigmas[i % len(sigmas)]
+        with np.errstate(all="ignore"):
+            got = [ndimage.gaussian_filter(x, s).to_numpy(), ndimage.gaussian_laplace(x, s, mode="wrap").to_numpy(),
+                   ndimage.uniform_filter(x, 3 + i % 3).to_numpy()]
+            ref = [ndi.gaussian_filter(a, s), ndi.gaussian_laplace(a, s, mode="wrap"), ndi.uniform_filter(a, 3 + i % 3)]
+        return all(np.array_equal(g, r) for g, r in zip(got, ref))
+
+    old = ndimage._PLAN_CACHE_MAX, ndimage._TAPS_CACHE_MAX
+    ndimage._PLAN_CACHE_MAX, ndimage._TAPS_CACHE_MAX = 8, 8      # force the caches to be wiped while in use
+    try:
+        ndimage._plan_cache.clear()
+        ndimage._taps_cache.clear()
+        with ThreadPoolExecutor(8) as pool:
+            assert all(pool.map(work, range(96)))
+    finally:
+        ndimage._PLAN_CACHE_MAX, ndimage._TAPS_CACHE_MAX = old
