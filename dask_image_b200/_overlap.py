@@ -13,6 +13,7 @@ trimmed off again.  It drives the per-chunk drop-in boundary (the functions in
 ``dask_image_b200.ndimage``) with the same kwargs dask would pass.
 """
 import itertools
+import numbers
 
 import torch
 
@@ -44,6 +45,9 @@ class HaloChunked:
     def dtype(self):
         return self._array.dtype
 
+    def __len__(self):
+        return len(self._array)
+
     def compute(self):
         return self._array
 
@@ -52,8 +56,16 @@ class HaloChunked:
 
     def __getitem__(self, key):
         sub = self._array[key]
-        dropped = self.ndim - sub.ndim
-        return HaloChunked(sub, self.chunksize[dropped:]) if sub.ndim else sub
+        if not sub.ndim:
+            return sub
+        keys = key if isinstance(key, tuple) else (key,)
+        if all(isinstance(k, numbers.Integral) for k in keys):
+            chunks = self.chunksize[len(keys):]             # d[i]: the leading axes are dropped
+        elif key is None:
+            chunks = (1,) + self.chunksize                  # d[None]: a new leading axis
+        else:
+            chunks = sub.shape                              # anything else: one chunk
+        return HaloChunked(sub, chunks)
 
     def astype(self, dtype):
         return HaloChunked(self._array.astype(dtype), self.chunksize)
