@@ -15,6 +15,14 @@ from test_host_path_cpu import cpu_path  # noqa: F401  (fixture)
 assert register_with_dask_image(), "the reference (dask_image) must be importable next to the dask stand-in"
 
 
+@pytest.fixture(autouse=True)
+def _reset_data_scale():
+    from dask.array.utils import DATA_SCALE
+
+    DATA_SCALE[0] = 0.0
+    yield
+
+
 if not torch.cuda.is_available():
     # arrays created while the reference's test modules are COLLECTED (parametrize lists) need host buffers too
     from dask_image_b200 import _array

@@ -27,6 +27,7 @@ class _Host:
 
 def from_array(a, chunks=None):
     a = np.asarray(a)
+    utils.note_data(a)
     if chunks is None:
         chunks = a.shape
     return Array(B200Array.from_numpy(np.ascontiguousarray(a)), chunks)

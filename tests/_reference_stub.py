@@ -29,6 +29,49 @@ def reference_root():
     return None
 
 
+def reference_tests_dir():
+    """The reference's own ndfilters test files: in the reference tree, or the copy build() puts next to
+    baseline/_ref (git-ignored)."""
+    for path in ("/root/reference/tests", os.path.join(ROOT, "baseline", "_ref_tests")):
+        d = os.path.join(path, "test_dask_image", "test_ndfilters")
+        if os.path.isfile(os.path.join(d, "test__gaussian.py")):
+            return d
+    return None
+
+
+# what of the reference's ndfilters suite applies to a non-numpy chunk type and the hot path (the rest: test__conv.py
+# passes numpy weights, which the reference rejects for any other chunk type, ref:dask_image/dispatch/_utils.py:23-25;
+# median / rank / percentile / generic filters are out of scope, SURVEY.md 8)
+REFERENCE_TESTS_SELECTION = (
+    "(not test__order or minimum_filter or maximum_filter) and "
+    "(not test__threshold or gaussian or invalid_threshold_method) and "
+    "not test__conv and not test__generic and not cupy")
+REFERENCE_TESTS_COUNT = 321      # reference v2025.11.0
+
+
+def run_reference_tests(tmp_path, files=None, expr=REFERENCE_TESTS_SELECTION, timeout=900):
+    """Start the reference's test files in a pytest subprocess with the dask stand-in (tests/_dask_stub) and the
+    plugin that keeps the arithmetic on the oracle when there is no GPU.  Returns (returncode, passed, output tail)."""
+    import re
+    import subprocess
+
+    here = os.path.join(ROOT, "tests")
+    tests_dir = reference_tests_dir()
+    ini = os.path.join(str(tmp_path), "pytest.ini")
+    with open(ini, "w") as f:
+        f.write("[pytest]\nmarkers = cupy\n")        # not the reference's `--flake8` addopts
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(here, "_dask_stub"), reference_root(), ROOT, here])
+    targets = [os.path.join(tests_dir, f) for f in files] if files else [tests_dir]
+    cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-p", "b200_refsuite_plugin",
+           "-c", ini, "--rootdir", str(tmp_path)] + targets
+    if expr:
+        cmd += ["-k", expr]
+    run = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=str(tmp_path))
+    m = re.search(r"(\d+) passed", run.stdout)
+    return run.returncode, int(m.group(1)) if m else 0, run.stdout[-3000:] + run.stderr[-2000:]
+
+
 def unavailable_reason():
     """None when the reference can be driven through the stub, else why not."""
     if importlib.util.find_spec("dask") is not None:

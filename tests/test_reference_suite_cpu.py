@@ -15,21 +15,13 @@ ref:tests/.../test_cupy_ndfilters.py:27-30; tests/test_reference_wrappers_cpu.py
 median / rank / percentile / generic filters are out of scope.
 Runs only where /root/reference exists (the build container).
 """
-import os
-import re
-import subprocess
-import sys
-
 import pytest
 
 import _reference_stub
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
-REF_TESTS = "/root/reference/tests/test_dask_image/test_ndfilters"
-
-pytestmark = pytest.mark.skipif(_reference_stub.unavailable_reason() is not None or not os.path.isdir(REF_TESTS),
-                                reason="needs /root/reference (build container) and no real dask")
+pytestmark = pytest.mark.skipif(_reference_stub.unavailable_reason() is not None
+                                or _reference_stub.reference_tests_dir() is None,
+                                reason="needs the reference tree (build container) and no real dask")
 
 SELECTION = [
     # (file, -k expression, tests that must pass: the counts of reference v2025.11.0 -- 321 in all)
@@ -43,18 +35,12 @@ SELECTION = [
 ]
 
 
-@pytest.mark.parametrize("fname, expr, at_least", SELECTION, ids=[s[0] for s in SELECTION])
-def test_reference_test_file_passes_with_b200_chunks(tmp_path, fname, expr, at_least):
-    (tmp_path / "pytest.ini").write_text("[pytest]\nmarkers = cupy\n")     # not the reference's `--flake8` addopts
-    env = dict(os.environ)
-    env["PYTHONPATH"] = os.pathsep.join([os.path.join(HERE, "_dask_stub"), "/root/reference", ROOT, HERE])
-    env["B200_REPLICATE_BELOW"] = "0"
-    cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-p", "b200_refsuite_plugin",
-           "-c", str(tmp_path / "pytest.ini"), "--rootdir", str(tmp_path), os.path.join(REF_TESTS, fname)]
-    if expr:
-        cmd += ["-k", expr]
-    run = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=str(tmp_path))
-    tail = run.stdout[-3000:] + run.stderr[-2000:]
-    assert run.returncode == 0, tail
-    m = re.search(r"(\d+) passed", run.stdout)
-    assert m and int(m.group(1)) >= at_least and "failed" not in run.stdout.splitlines()[-1], tail
+@pytest.mark.parametrize("fname, expr, count", SELECTION, ids=[s[0] for s in SELECTION])
+def test_reference_test_file_passes_with_b200_chunks(tmp_path, fname, expr, count):
+    rc, passed, tail = _reference_stub.run_reference_tests(tmp_path, [fname], expr)
+    assert rc == 0 and passed == count, tail
+
+
+def test_selection_expression_counts():
+    """The one-run form used on the GPU (tests/test_gpu_reference_tests.py) selects the same tests."""
+    assert sum(s[2] for s in SELECTION) == _reference_stub.REFERENCE_TESTS_COUNT
