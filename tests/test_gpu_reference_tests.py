@@ -20,4 +20,13 @@ pytestmark = [pytest.mark.gpu,
 
 def test_reference_ndfilters_tests_pass_on_the_kernels(tmp_path):
     rc, passed, tail = _reference_stub.run_reference_tests(tmp_path)
+    try:        # keep the reference suite's own summary with the session's records (copied to profiles/)
+        import os
+
+        out = os.path.join(_reference_stub.ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "reference_tests_on_gpu.log"), "w") as f:
+            f.write(tail)
+    except OSError:
+        pass
     assert rc == 0 and passed == _reference_stub.REFERENCE_TESTS_COUNT, tail
