@@ -14,15 +14,19 @@ from ._gaussian import (gaussian, gaussian_filter, gaussian_gradient_magnitude,
 from ._order import maximum_filter, minimum_filter
 from ._smooth import uniform_filter
 from ._threshold import threshold_local
+from ._unsupported import (OutOfScopeError, generic_filter, median_filter, percentile_filter,
+                           rank_filter)
 
 __all__ = [
     "convolve", "correlate", "laplace", "prewitt", "sobel", "gaussian", "gaussian_filter",
     "gaussian_gradient_magnitude", "gaussian_laplace", "uniform_filter", "threshold_local",
     "minimum_filter", "maximum_filter",
+    # present under the reference's names, raising OutOfScopeError (rank statistics / Python callables: SURVEY 8)
+    "generic_filter", "median_filter", "rank_filter", "percentile_filter", "OutOfScopeError",
 ]
 
 for _f in (convolve, correlate, laplace, prewitt, sobel, gaussian, gaussian_filter,
            gaussian_gradient_magnitude, gaussian_laplace, uniform_filter, threshold_local,
-           minimum_filter, maximum_filter):
+           minimum_filter, maximum_filter, generic_filter, median_filter, rank_filter, percentile_filter):
     _f.__module__ = __name__
 del _f

@@ -7,6 +7,7 @@ the correlation path (arbitrary Python callables / rank filters) and raise."""
 import numpy as np
 
 from . import _gaussian, _smooth
+from ._unsupported import OutOfScopeError
 
 __all__ = ["threshold_local"]
 
@@ -21,8 +22,8 @@ def threshold_local(image, block_size, method='gaussian', offset=0, mode='reflec
     if method == 'generic':
         if not callable(param):
             raise ValueError("Must include a valid function to use as the 'param' keyword argument.")
-        raise NotImplementedError("method='generic' runs an arbitrary Python callable per voxel; "
-                                  "it is outside the B200 correlation path")
+        raise OutOfScopeError("method='generic' runs an arbitrary Python callable per voxel; "
+                              "it is outside the B200 correlation path")
     elif method == 'gaussian':
         if param is None:
             sigma = (np.array(np.asarray(block_size)).astype(float) - 1) / 6.0
@@ -34,7 +35,7 @@ def threshold_local(image, block_size, method='gaussian', offset=0, mode='reflec
         size = int(size) if size.ndim == 0 else tuple(int(s) for s in size)
         thresh_image = _smooth.uniform_filter(image, size, mode=mode, cval=cval)
     elif method == 'median':
-        raise NotImplementedError("method='median' is a rank filter; it is outside the B200 correlation path")
+        raise OutOfScopeError("method='median' is a rank filter; it is outside the B200 correlation path")
     else:
         raise ValueError("Invalid method specified. Please use `generic`, `gaussian`, `mean`, or `median`.")
     return thresh_image - offset

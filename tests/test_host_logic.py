@@ -467,3 +467,21 @@ def test_order_filter_params(name, err_type, size, footprint, origin):
     # reference: test__order.py:20-66 -- all raised before any dispatch / compute
     with pytest.raises(err_type):
         getattr(dask_image_b200.ndfilters, name)(_Shape2D(), size=size, footprint=footprint, origin=origin)
+
+
+def test_out_of_scope_entry_points_raise_one_clear_error():
+    """dask_image.ndfilters names outside the correlation path exist and raise OutOfScopeError
+    (a NotImplementedError) -- never an AttributeError, never a silent CPU fallback."""
+    from dask_image_b200 import ndfilters
+
+    reference_all = {"convolve", "correlate", "laplace", "prewitt", "sobel", "gaussian", "gaussian_filter",
+                     "gaussian_gradient_magnitude", "gaussian_laplace", "generic_filter", "minimum_filter",
+                     "median_filter", "maximum_filter", "rank_filter", "percentile_filter", "uniform_filter",
+                     "threshold_local"}                      # ref:dask_image/ndfilters/__init__.py:3-21
+    assert reference_all <= set(ndfilters.__all__)
+    for name in ("generic_filter", "median_filter", "rank_filter", "percentile_filter"):
+        f = getattr(ndfilters, name)
+        assert f.__name__ == name and f.__module__ == "dask_image_b200.ndfilters"
+        with pytest.raises(ndfilters.OutOfScopeError, match=name):
+            f(object(), size=3)
+    assert issubclass(ndfilters.OutOfScopeError, NotImplementedError)
