@@ -89,8 +89,46 @@ class B200Array:
     def empty_like(self):
         return B200Array(torch.empty_like(self.tensor))
 
+    @classmethod
+    def from_device_array(cls, obj):
+        """Zero-copy view of another library's device array: anything that speaks DLPack (``__dlpack__``: cupy,
+        torch, jax, numba >= 0.55) or the CUDA Array Interface (``__cuda_array_interface__``: cupy, numba, rmm).
+        The buffer must be C-contiguous (it is copied on the device otherwise); ``obj`` is kept alive by the view.
+        This is how chunks of the reference's cupy backend (dask_image/dispatch/_dispatch_ndfilters.py:132-139) enter
+        this path without a round trip through the host."""
+        if isinstance(obj, torch.Tensor):
+            return cls(obj)
+        if hasattr(obj, "__dlpack__"):
+            return cls(torch.from_dlpack(obj))
+        cai = getattr(obj, "__cuda_array_interface__", None)
+        if cai is None:
+            raise TypeError("expected a device array exposing __dlpack__ or __cuda_array_interface__")
+        dt = np.dtype(cai["typestr"])
+        torch_dtype(dt)
+        if dt.kind == "u" and dt.itemsize > 1:
+            # torch reads the interface for the signed types only: take the bits, view them back
+            signed = dict(cai, typestr=np.dtype("i%d" % dt.itemsize).str)
+            proxy = type("_CAI", (), {"__cuda_array_interface__": signed, "_owner": obj})()
+            return cls(torch.as_tensor(proxy, device="cuda").view(torch_dtype(dt)))
+        return cls(torch.as_tensor(obj, device="cuda"))
+
     def to_numpy(self):
         return self.tensor.cpu().numpy()
+
+    # ---- zero-copy export to other GPU libraries -----------------------------
+    def __dlpack__(self, *args, **kwargs):
+        return self.tensor.__dlpack__(*args, **kwargs)
+
+    def __dlpack_device__(self):
+        return self.tensor.__dlpack_device__()
+
+    @property
+    def __cuda_array_interface__(self):
+        """CUDA Array Interface v3 (``cupy.asarray(x)`` / ``numba.cuda.as_cuda_array(x)`` view the buffer in place)."""
+        if self.tensor.device.type != "cuda":
+            raise AttributeError("__cuda_array_interface__")
+        return {"shape": self.shape, "typestr": self.dtype.str, "strides": None, "version": 3,
+                "data": (self.tensor.data_ptr() if self.size else 0, False)}
 
     def __array__(self, dtype=None, copy=None):
         a = self.to_numpy()
@@ -180,6 +218,9 @@ def as_b200(x, like=None):
         return x
     if isinstance(x, torch.Tensor):
         return B200Array(x)
+    if not isinstance(x, np.ndarray) and (hasattr(x, "__cuda_array_interface__") or (
+            hasattr(x, "__dlpack_device__") and x.__dlpack_device__()[0] == 2)):      # 2 = kDLCUDA
+        return B200Array.from_device_array(x)
     dev = like.device if like is not None else None
     return B200Array.from_numpy(np.asarray(x), device=dev)
 

@@ -273,6 +273,46 @@ def test_per_axis_modes_and_axes(b200):
     assert_parity(got.to_numpy(), ndi.uniform_filter(a, 5, axes=(1,)))
 
 
+class _CaiProducer:
+    """A device array that speaks only the CUDA Array Interface (as numba / rmm buffers do)."""
+
+    def __init__(self, tensor, np_dtype):
+        self._t, self._dt = tensor, np.dtype(np_dtype)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": tuple(self._t.shape), "typestr": self._dt.str, "strides": None, "version": 3,
+                "data": (self._t.data_ptr(), False)}
+
+
+@pytest.mark.parametrize("dt", ["float32", "uint16", "uint8", "int16", "float64"])
+def test_zero_copy_interop_with_other_gpu_libraries(b200, dt):
+    """Chunks of another GPU backend (the reference's is cupy, ref:_dispatch_ndfilters.py:132-139) enter and leave
+    without a host round trip: DLPack and the CUDA Array Interface, both directions, same device pointer."""
+    import torch
+
+    a = (np.random.default_rng(3).random((12, 40)) * 200).astype(dt)
+    d = dev(b200, a)
+    ptr = d.tensor.data_ptr()
+    # export: DLPack and CAI consumers see the same buffer
+    assert torch.from_dlpack(d).data_ptr() == ptr
+    cai = d.__cuda_array_interface__
+    assert cai["data"] == (ptr, False) and cai["shape"] == a.shape and np.dtype(cai["typestr"]) == a.dtype
+    if a.dtype.kind != "u" or a.dtype.itemsize == 1:      # torch reads the interface for the signed types only
+        assert torch.as_tensor(d, device="cuda").data_ptr() == ptr
+    # import: a CAI-only producer and a DLPack producer, no copy, correct dtype, and the filter runs on it
+    prod = _CaiProducer(d.tensor, a.dtype)
+    for src in (prod, d.tensor):
+        v = b200.as_b200(src)
+        assert isinstance(v, b200.B200Array) and v.dtype == a.dtype and v.shape == a.shape
+        assert v.tensor.data_ptr() == ptr
+        got = b200.ndfilters.uniform_filter(v, 3).to_numpy()
+        assert_parity(got, ndi.uniform_filter(a, 3), exact=a.dtype.kind != "f")
+    assert b200.B200Array.from_device_array(prod).tensor.data_ptr() == ptr
+    with pytest.raises(TypeError):
+        b200.B200Array.from_device_array(a)
+
+
 @pytest.mark.parametrize("dt", ["float32", "float64", "uint16"])
 def test_axes_subsets(b200, dt):
     """scipy's `axes=` (scipy/ndimage/_filters.py:516-553,1126-1139,1181-1195,1271-1292,1738-1830): derivative

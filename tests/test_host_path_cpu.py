@@ -314,3 +314,14 @@ def test_chunk_functions_are_thread_safe(cpu_path):
             assert all(pool.map(work, range(96)))
     finally:
         ndimage._PLAN_CACHE_MAX, ndimage._TAPS_CACHE_MAX = old
+
+
+def test_dlpack_export_is_zero_copy(cpu_path):
+    """B200Array forwards the DLPack protocol of its buffer (consumers such as cupy / torch / jax view it in place);
+    the CUDA Array Interface is only offered for device buffers."""
+    x = _array.B200Array.from_numpy(np.arange(12, dtype=np.int16).reshape(3, 4))
+    t = torch.from_dlpack(x)
+    assert t.data_ptr() == x.tensor.data_ptr() and tuple(t.shape) == (3, 4) and t.dtype == torch.int16
+    assert not hasattr(x, "__cuda_array_interface__")
+    with pytest.raises(TypeError):
+        _array.B200Array.from_device_array(np.zeros(3))
