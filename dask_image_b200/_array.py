@@ -98,9 +98,11 @@ class B200Array:
         this path without a round trip through the host."""
         if isinstance(obj, torch.Tensor):
             return cls(obj)
-        if hasattr(obj, "__dlpack__"):
-            return cls(torch.from_dlpack(obj))
         cai = getattr(obj, "__cuda_array_interface__", None)
+        if cai is None and hasattr(obj, "__dlpack__") and hasattr(obj, "__dlpack_device__"):
+            if int(obj.__dlpack_device__()[0]) != 2:      # kDLCUDA
+                raise TypeError("expected an array in CUDA device memory (use B200Array.from_numpy for host data)")
+            return cls(torch.from_dlpack(obj))
         if cai is None:
             raise TypeError("expected a device array exposing __dlpack__ or __cuda_array_interface__")
         dt = np.dtype(cai["typestr"])

@@ -285,6 +285,19 @@ class _CaiProducer:
                 "data": (self._t.data_ptr(), False)}
 
 
+class _DlpackProducer:
+    """A device array that speaks only DLPack."""
+
+    def __init__(self, tensor):
+        self._t = tensor
+
+    def __dlpack__(self, *args, **kwargs):
+        return self._t.__dlpack__(*args, **kwargs)
+
+    def __dlpack_device__(self):
+        return self._t.__dlpack_device__()
+
+
 @pytest.mark.parametrize("dt", ["float32", "uint16", "uint8", "int16", "float64"])
 def test_zero_copy_interop_with_other_gpu_libraries(b200, dt):
     """Chunks of another GPU backend (the reference's is cupy, ref:_dispatch_ndfilters.py:132-139) enter and leave
@@ -302,7 +315,7 @@ def test_zero_copy_interop_with_other_gpu_libraries(b200, dt):
         assert torch.as_tensor(d, device="cuda").data_ptr() == ptr
     # import: a CAI-only producer and a DLPack producer, no copy, correct dtype, and the filter runs on it
     prod = _CaiProducer(d.tensor, a.dtype)
-    for src in (prod, d.tensor):
+    for src in (prod, _DlpackProducer(d.tensor), d.tensor):
         v = b200.as_b200(src)
         assert isinstance(v, b200.B200Array) and v.dtype == a.dtype and v.shape == a.shape
         assert v.tensor.data_ptr() == ptr
