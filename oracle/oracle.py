@@ -1,10 +1,13 @@
 """CPU oracle for the dask-image ndfilters hot path -- TEST INFRASTRUCTURE ONLY.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg
-may import this module; the product package (``dask_image_b200``) never does.
+may import this module (and ``oracle/reference_arm.py``, the reference's own public API for that leg); the product
+package (``dask_image_b200``) never does.
 
-Layers restated here (parity status: PINNED against scipy 1.18.1, see
-``tests/test_oracle.py`` and ``tests/golden/``):
+Layers restated here (parity status: PINNED -- against scipy 1.18.1 run here, ``tests/test_oracle.py`` and
+``tests/golden/``, and against the REFERENCE ITSELF run here: the unmodified ``dask_image.ndfilters`` imports with a
+stand-in for ``dask.utils.Dispatch``, the one name it needs from dask, and reproduces every golden output and this
+module's ``map_overlap_emulated`` results bit for bit, ``tests/test_reference_wrappers_cpu.py``):
 
 * the three compiled loops of scipy's ``_nd_image`` module -> ``ni_oracle.c``
   (loaded through ctypes below);

@@ -6,6 +6,10 @@ fixtures; this script is committed so they can be regenerated:
 
     python tests/golden/make_golden.py
 
+The stored outputs are also what the REFERENCE ITSELF computes (its wrappers + numpy registrations, imported
+unmodified with a stand-in for dask.utils.Dispatch): tests/test_reference_wrappers_cpu.py::
+test_goldens_are_the_reference_outputs recomputes every public-function case that way and requires bit equality.
+
 Parametrisations follow the reference's own tests
 (tests/test_dask_image/test_ndfilters/test__gaussian.py:125-196,
 test__smooth.py:80-99, test__conv.py:117-191) plus a dtype sweep.
