@@ -245,3 +245,52 @@ def test_goldens_are_the_reference_outputs(ref_ndfilters):
                 np.testing.assert_array_equal(got, want, err_msg=spec["name"] + " chunked")
                 chunked += 1
     assert checked > 300 and chunked > 250, (checked, chunked)
+
+
+def test_integration_md_registration_snippet_works(cpu_path):  # noqa: F811
+    """The patch INTEGRATION.md section 1 proposes to a dask-image maintainer, taken from the document verbatim and
+    executed inside the reference's ``dask_image/dispatch/_dispatch_ndfilters.py`` namespace: lazy registration
+    keyed on the ``dask_image_b200`` top-level module, fired by the first B200Array chunk."""
+    import os
+    import re
+    import sys
+    import types
+
+    import dask_image_b200 as b200
+    from dask_image_b200.dispatch._dispatcher import _Base
+
+    text = open(os.path.join(_reference_stub.ROOT, "INTEGRATION.md")).read()
+    section = text[text.index("## 1. The registration a maintainer adds"):text.index("## 2.")]
+    snippet = re.search(r"```python\n(.*?)```", section, re.S).group(1)
+    assert "register_lazy(\"dask_image_b200\"" in snippet
+
+    root = _reference_stub.reference_root()
+    dask, utils = types.ModuleType("dask"), types.ModuleType("dask.utils")
+    utils.Dispatch = _Base
+    dask.utils = utils
+    saved = {k: sys.modules.get(k) for k in ("dask", "dask.utils")}
+    sys.modules["dask"], sys.modules["dask.utils"] = dask, utils
+    sys.path.insert(0, root)
+    before = set(sys.modules)
+    try:
+        import dask_image.ndfilters as ref
+        from dask_image.dispatch import _dispatch_ndfilters as tables
+
+        d = b200.from_array(np.arange(48, dtype=np.float32).reshape(6, 8), chunks=(3, 4))
+        with pytest.raises(TypeError):                   # nothing registered for B200Array yet
+            tables.dispatch_gaussian_filter(d)
+        exec(compile(snippet, "INTEGRATION.md#1", "exec"), tables.__dict__)
+        got = np.asarray(ref.gaussian_filter(d, 1.0).compute())
+        np.testing.assert_array_equal(got, ndi.gaussian_filter(np.arange(48, dtype=np.float32).reshape(6, 8), 1.0))
+        assert tables.dispatch_uniform_filter(d) is b200.ndimage.uniform_filter
+        assert tables.dispatch_maximum_filter(d) is b200.ndimage.maximum_filter
+    finally:
+        sys.path.remove(root)
+        for name in set(sys.modules) - before:
+            if name == "dask_image" or name.startswith("dask_image."):
+                del sys.modules[name]
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
